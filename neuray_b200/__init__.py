@@ -1,0 +1,12 @@
+"""neuray_b200 -- B200-native (sm_100a) implementation of NeuRay's per-ray rendering hot path.
+
+Drop-in surface:
+    neuray_b200.render_ops      mirrors reference network/render_ops.py (same 12 function names)
+    neuray_b200.renderer        NeuralRayBaseRenderer-compatible render_by_depth / render_impl / render
+    neuray_b200.patch           installs both into an importable reference tree (render.py / run_training.py unchanged)
+
+All arithmetic runs in hand-written CUDA kernels behind the C-ABI declared in include/neuray_b200.h
+(libneuray_b200.so, loaded with ctypes).  There is no CPU or PyTorch fallback: calling any op without the
+built library, or with non-CUDA tensors, raises.
+"""
+__version__ = "0.1.0"

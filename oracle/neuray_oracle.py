@@ -1,0 +1,463 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for NeuRay's per-ray rendering hot path.
+
+A functional fp32 restatement (plain torch tensor arithmetic on the CPU, explicit bilinear taps, no
+nn.Module, no F.grid_sample) of the algorithm in the reference (liuyuan-pal/NeuRay @ 17a52d3):
+
+    network/render_ops.py:4-229       ray geometry, sampling, reprojection, gather, compositing, resample
+    network/ops.py:14-34              interpolate_feats (grid_sample wrapper)
+    network/dist_decoder.py:6-140     mixture-of-logistics visibility decoder
+    network/aggregate_net.py:8-68     aggregation front-end
+    network/ibrnet.py:7-102,239-369   IBRNetWithNeuRay + ray self-attention
+    network/renderer.py:67-83,127-254 render_by_depth / render_impl / render chunk loop
+
+Pinning: the reference ships no tests or golden vectors for this path, so the
+oracle is pinned against outputs of the reference itself, run in the build container by
+oracle/gen_golden.py and committed under tests/golden/ (checked by tests/test_oracle_golden.py).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this file.  The product path (neuray_b200/) never does.
+
+Weights are passed as a flat dict keyed by the reference's state-dict names, e.g.
+'dist_decoder.mean_decoder.0.weight', 'agg_net.agg_impl.base_fc.0.weight'.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------------------------------
+# small helpers
+
+
+def _lin(W, name, x):
+    """y = x @ weight^T + bias for the Linear called `name` (bias optional)."""
+    y = x @ W[name + ".weight"].t()
+    b = W.get(name + ".bias")
+    return y if b is None else y + b
+
+
+def _elu(x):
+    return torch.where(x > 0, x, torch.expm1(x))
+
+
+def _softplus(x):
+    # torch.nn.Softplus(beta=1, threshold=20)
+    return torch.where(x > 20, x, torch.log1p(torch.exp(x)))
+
+
+def _sigmoid(x):
+    return 1.0 / (1.0 + torch.exp(-x))
+
+
+# --------------------------------------------------------------------------------------------------
+# render_ops.py
+
+
+def coords2rays(coords, poses, Ks):
+    """render_ops.py:4-25.  coords [n,rn,2], poses [n,3,4] (world->cam), Ks [n,3,3]."""
+    n, rn, _ = coords.shape
+    Rt = poses[:, :, :3].transpose(1, 2)              # cam->world rotation  [n,3,3]
+    centre = -(Rt @ poses[:, :, 3:])                   # camera centre        [n,3,1]
+    hom = torch.cat([coords, torch.ones(n, rn, 1, dtype=torch.float32)], 2)  # [n,rn,3]
+    cam = torch.inverse(Ks)[:, None] @ hom[..., None]  # [n,rn,3,1]
+    world = Rt[:, None] @ cam + centre[:, None]
+    centres = centre[:, None, :, 0].expand(n, rn, 3)
+    # the reference subtracts the centre again instead of skipping the add (render_ops.py:22-23)
+    directions = world[..., 0] - centres
+    return centres, directions
+
+
+def depth2points(que_imgs_info, que_depth):
+    """render_ops.py:27-39."""
+    o, d = coords2rays(que_imgs_info["coords"], que_imgs_info["poses"], que_imgs_info["Ks"])
+    pts = o[:, :, None] + d[:, :, None] * que_depth[..., None]
+    dn = que_depth.shape[-1]
+    view_dir = -d / torch.linalg.norm(d, dim=2, keepdim=True)
+    return pts, view_dir[:, :, None].expand(-1, -1, dn, -1).contiguous()
+
+
+def depth2dists(depth):
+    """render_ops.py:41-44."""
+    tail = torch.full_like(depth[..., :1], 1e6)
+    return torch.cat([depth[..., 1:] - depth[..., :-1], tail], -1)
+
+
+def depth2inv_dists(depth, depth_range):
+    """render_ops.py:46-52."""
+    a = (-1 / depth_range[:, 0])[:, None, None]
+    b = (-1 / depth_range[:, 1])[:, None, None]
+    return depth2dists((-1 / depth - a) / (b - a))
+
+
+def _unnormalise(g, size, align_corners):
+    if align_corners:
+        return (g + 1) / 2 * (size - 1)
+    return ((g + 1) * size - 1) / 2
+
+
+def bilinear_sample(feats, pts, h=None, w=None, padding_mode="zeros", align_corners=False):
+    """ops.py:14-34 (interpolate_feats) with F.grid_sample(mode='bilinear') written out tap by tap.
+
+    feats [b,c,fh,fw]; pts [b,n,2] in pixel units of an (h,w) image -> [b,n,c].
+    """
+    b, c, fh, fw = feats.shape
+    if h is None and w is None:
+        h, w = fh, fw
+    gx = pts[..., 0] / (w - 1) * 2 - 1
+    gy = pts[..., 1] / (h - 1) * 2 - 1
+    ix = _unnormalise(gx, fw, align_corners)
+    iy = _unnormalise(gy, fh, align_corners)
+    if padding_mode == "border":
+        ix = ix.clamp(0, fw - 1)
+        iy = iy.clamp(0, fh - 1)
+    x0 = torch.floor(ix)
+    y0 = torch.floor(iy)
+    tx = ix - x0
+    ty = iy - y0
+    flat = feats.reshape(b, c, fh * fw)
+    out = torch.zeros(b, c, pts.shape[1], dtype=torch.float32)
+    for dy, dx, wgt in ((0, 0, (1 - tx) * (1 - ty)), (0, 1, tx * (1 - ty)),
+                        (1, 0, (1 - tx) * ty), (1, 1, tx * ty)):
+        xi = x0 + dx
+        yi = y0 + dy
+        inside = (xi >= 0) & (xi <= fw - 1) & (yi >= 0) & (yi <= fh - 1)
+        idx = (yi.clamp(0, fh - 1) * fw + xi.clamp(0, fw - 1)).long()   # [b,n]
+        tap = torch.gather(flat, 2, idx[:, None, :].expand(b, c, -1))   # [b,c,n]
+        out = out + tap * (wgt * inside.float())[:, None, :]
+    return out.permute(0, 2, 1)
+
+
+def interpolate_feature_map(ray_feats, coords, mask, h, w, border_type="border"):
+    """render_ops.py:54-70."""
+    fh, fw = ray_feats.shape[-2:]
+    same = (fh == h) and (fw == w)
+    return bilinear_sample(ray_feats, coords, h, w, border_type, same) * mask.float()[..., None]
+
+
+def alpha_values2hit_prob(alpha):
+    """render_ops.py:72-80."""
+    keep = torch.cat([torch.ones_like(alpha[..., :1]), 1.0 - alpha + 1e-10], -1)
+    return alpha * torch.cumprod(keep, -1)[..., :-1]
+
+
+def project_points_coords(pts, Rt, K):
+    """render_ops.py:82-104.  pts [pn,3] -> pix [rfn,pn,2], valid [rfn,pn], depth [rfn,pn,1]."""
+    rfn = Rt.shape[0]
+    P = K @ Rt                                                         # [rfn,3,4]
+    bottom = torch.zeros(rfn, 1, 4)
+    bottom[:, :, 3] = 1
+    H = torch.cat([P, bottom], 1)
+    hom = torch.cat([pts, torch.ones(pts.shape[0], 1)], 1)
+    cam = (H[:, None] @ hom[None, :, :, None])[:, :, :3, 0]           # [rfn,pn,3]
+    z = cam[:, :, 2:].clone()
+    degenerate = z.abs() < 1e-4
+    z[degenerate] = 1e-3
+    return cam[:, :, :2] / z, ~degenerate[..., 0], z
+
+
+def project_points_directions(poses, points):
+    """render_ops.py:106-115."""
+    centre = -(poses[:, :, :3].transpose(1, 2) @ poses[:, :, 3:])     # [rfn,3,1]
+    d = points[None] - centre.transpose(1, 2)
+    return -d / torch.linalg.norm(d, dim=2, keepdim=True).clamp_min(1e-5)
+
+
+def project_points_ref_views(ref_imgs_info, que_points):
+    """render_ops.py:117-130."""
+    pix, ok, z = project_points_coords(que_points, ref_imgs_info["poses"], ref_imgs_info["Ks"])
+    h, w = ref_imgs_info["imgs"].shape[-2:]
+    outside = (pix[..., 0] < -0.5) | (pix[..., 0] >= w - 0.5) | (pix[..., 1] < -0.5) | (pix[..., 1] >= h - 0.5)
+    return project_points_directions(ref_imgs_info["poses"], que_points), pix, z, ok & ~outside
+
+
+def project_points_dict(ref_imgs_info, que_pts):
+    """render_ops.py:132-144."""
+    qn, rn, dn, _ = que_pts.shape
+    pdir, pix, z, ok = project_points_ref_views(ref_imgs_info, que_pts.reshape(-1, 3))
+    rfn, _, h, w = ref_imgs_info["imgs"].shape
+    d = {
+        "dir": pdir, "pts": pix, "depth": z, "mask": ok.float(),
+        "ray_feats": interpolate_feature_map(ref_imgs_info["ray_feats"], pix, ok, h, w),
+        "rgb": interpolate_feature_map(ref_imgs_info["imgs"], pix, ok, h, w),
+    }
+    return {k: v.reshape(rfn, qn, rn, dn, -1) for k, v in d.items()}
+
+
+def sample_depth(depth_range, coords, sample_num, random_sample=False, jitter=None):
+    """render_ops.py:146-170.  `jitter` (qn,rn,dn-2 uniform[0,1)) replaces torch.rand when random_sample."""
+    qn, rn, _ = coords.shape
+    near, far = depth_range[:, 0], depth_range[:, 1]
+    dn = sample_num
+    assert dn > 2
+    span = 1 / far - 1 / near
+    step = span / (dn - 1)
+    k = torch.arange(1, dn - 1, dtype=torch.float32)[None, None, :]
+    if random_sample:
+        k = k + (jitter - 0.5) * 0.999
+    else:
+        k = k + torch.zeros(qn, rn, dn - 2)
+    ticks = torch.cat([torch.zeros(qn, rn, 1), step[:, None, None] * k, span[:, None, None].expand(qn, rn, 1)], -1)
+    depth = 1 / (1 / near[:, None, None] + ticks)
+    nxt = torch.cat([depth[..., 1:], torch.full((qn, rn, 1), 1e6)], -1)
+    return depth, nxt - depth
+
+
+def fine_sample_u(fdn):
+    """render_ops.py:199-202: deterministic bin-centre quantiles used at eval time."""
+    step = 1 / fdn
+    return 0.5 * step + torch.arange(fdn) * step
+
+
+def sample_fine_depth(depth, hit_prob, depth_range, sample_num, random_sample, u=None):
+    """render_ops.py:172-229 (inv_mode=True).  `u` [qn,rn,fdn] replaces torch.rand when random_sample."""
+    a = -1 / depth_range[0, 0]
+    b = -1 / depth_range[0, 1]
+    t = (-1 / depth - a) / (b - a)
+    edges = torch.cat([t[..., :1], (t[..., 1:] + t[..., :-1]) / 2, t[..., -1:]], -1)   # dn+1
+    p = hit_prob + 1e-5
+    pdf = p / p.sum(-1, keepdim=True)
+    cdf = torch.cat([torch.zeros_like(pdf[..., :1]), torch.cumsum(pdf, -1)], -1)        # dn+1
+    if not random_sample:
+        u = fine_sample_u(sample_num).expand(*cdf.shape[:-1], sample_num)
+    u = u.contiguous()
+    hi = torch.searchsorted(cdf, u, right=True)
+    lo = (hi - 1).clamp_min(0)
+    hi = hi.clamp_max(cdf.shape[-1] - 1)
+    c0, c1 = torch.gather(cdf, -1, lo), torch.gather(cdf, -1, hi)
+    e0, e1 = torch.gather(edges, -1, lo), torch.gather(edges, -1, hi)
+    den = c1 - c0
+    den = torch.where(den < 1e-5, torch.ones_like(den), den)
+    tf = e0 + (u - c0) / den * (e1 - e0)
+    return -1 / (tf * (b - a) + a)
+
+
+# --------------------------------------------------------------------------------------------------
+# dist_decoder.py
+
+
+def dist_decoder_forward(W, pre, feats, use_vis, bias_val=0.05):
+    """dist_decoder.py:99-107.  `pre` = 'dist_decoder' | 'fine_dist_decoder'."""
+    def trunk(name):
+        h = _elu(_lin(W, f"{pre}.{name}.0", feats))
+        h = _elu(_lin(W, f"{pre}.{name}.2", h))
+        return _lin(W, f"{pre}.{name}.4", h)
+    mean = _softplus(trunk("mean_decoder"))
+    var = _softplus(trunk("var_decoder")) + bias_val                            # AddBias (ops.py:78-84)
+    aw = _sigmoid(trunk("aw_decoder"))
+    vis = _sigmoid(trunk("vis_decoder")) if use_vis else None
+    return mean, var, vis, aw
+
+
+def get_near_far_points(depth, interval, depth_range, is_ref):
+    """dist_decoder.py:6-51 (fixed_interval=False)."""
+    shape = (-1,) + (1,) * (depth.dim() - 1)
+    a = (-1 / depth_range[:, 0]).reshape(shape)
+    b = (-1 / depth_range[:, 1]).reshape(shape)
+    t = (-1 / depth.clamp(min=1e-5) - a) / (b - a)
+    half = interval / 2
+    if is_ref:
+        before = torch.cat([half[..., :1], half[..., :-1]], -1)
+        return t - before, t + half
+    first = t[..., :1] - half[..., :1]
+    last = t[..., -1:] + half[..., -1:]
+    edges = torch.cat([first, (t[..., :-1] + t[..., 1:]) / 2, last], -1)
+    return edges[..., :-1], edges[..., 1:]
+
+
+def compute_prob(depth, interval, mean, var, vis, aw, is_ref, depth_range, use_vis):
+    """dist_decoder.py:109-140."""
+    lo, hi = get_near_far_points(depth, interval, depth_range, is_ref)
+    mix = torch.cat([aw, 1 - aw], -1)
+    c0 = 0.5 + 0.5 * torch.tanh((lo[..., None] - mean) * var)
+    c1 = 0.5 + 0.5 * torch.tanh((hi[..., None] - mean) * var)
+    if use_vis:
+        c0, c1 = c0 * vis, c1 * vis
+    visibility = ((1 - c0) * mix).sum(-1)
+    hit = ((c1 - c0) * mix).sum(-1)
+    alpha = torch.log(hit / (visibility - hit + 1e-5) + 1e-5)
+    return alpha, visibility, hit
+
+
+# --------------------------------------------------------------------------------------------------
+# ibrnet.py / aggregate_net.py
+
+
+def posenc_table(n_samples, d_hid=16):
+    """ibrnet.py:305-313 (float64 numpy table cast to fp32)."""
+    pos = np.arange(n_samples, dtype=np.float64)[:, None]
+    j = np.arange(d_hid)[None, :]
+    ang = pos / np.power(10000, 2 * (j // 2) / d_hid)
+    ang[:, 0::2] = np.sin(ang[:, 0::2])
+    ang[:, 1::2] = np.cos(ang[:, 1::2])
+    return torch.from_numpy(ang).float()[None]
+
+
+def weighted_mean_var(x, w):
+    """ibrnet.py:112-116."""
+    m = (x * w).sum(2, keepdim=True)
+    return m, (w * (x - m) ** 2).sum(2, keepdim=True)
+
+
+def ray_attention(W, pre, x, row_mask):
+    """ibrnet.py:52-102 + 7-27: 4 heads, d_k = d_v = 4, temperature 2, post-LN (eps 1e-6)."""
+    B, L, _ = x.shape
+    nh, dk = 4, 4
+    q = (x @ W[f"{pre}.w_qs.weight"].t()).view(B, L, nh, dk).transpose(1, 2)
+    k = (x @ W[f"{pre}.w_ks.weight"].t()).view(B, L, nh, dk).transpose(1, 2)
+    v = (x @ W[f"{pre}.w_vs.weight"].t()).view(B, L, nh, dk).transpose(1, 2)
+    logits = (q / (dk ** 0.5)) @ k.transpose(2, 3)                     # [B,nh,Lq,Lk]
+    # mask [B,L,1] -> [B,1,L,1]: broadcasts over KEYS, i.e. it blanks whole query rows (ibrnet.py:20)
+    logits = logits.masked_fill(row_mask[:, None] == 0, -1e9)
+    a = torch.softmax(logits, -1)
+    o = (a @ v).transpose(1, 2).reshape(B, L, nh * dk)
+    o = o @ W[f"{pre}.fc.weight"].t() + x
+    return F.layer_norm(o, (16,), W[f"{pre}.layer_norm.weight"], W[f"{pre}.layer_norm.bias"], 1e-6)
+
+
+def ibrnet_forward(W, pre, rgb_feat, neuray_feat, ray_diff, mask, pos_enc):
+    """ibrnet.py:315-369.  rgb_feat [R,dn,rfn,35], neuray_feat [...,32], ray_diff [...,4], mask [...,1]."""
+    nv = rgb_feat.shape[2]
+    dfeat = _elu(_lin(W, f"{pre}.ray_dir_fc.2", _elu(_lin(W, f"{pre}.ray_dir_fc.0", ray_diff))))
+    rgb_in = rgb_feat[..., :3]
+    rgb_feat = rgb_feat + dfeat
+    weight = mask / (mask.sum(2, keepdim=True) + 1e-8)
+
+    gate = _lin(W, f"{pre}.neuray_fc.2", _elu(_lin(W, f"{pre}.neuray_fc.0", neuray_feat)))
+    weight0 = _sigmoid(gate) * weight
+    m0, v0 = weighted_mean_var(rgb_feat, weight0)
+    m1, v1 = weighted_mean_var(rgb_feat, weight)
+    glob = torch.cat([m0, v0, m1, v1], -1).expand(-1, -1, nv, -1)
+
+    x = torch.cat([glob, rgb_feat, neuray_feat], -1)                    # 140 + 35 + 32 = 207
+    x = _elu(_lin(W, f"{pre}.base_fc.2", _elu(_lin(W, f"{pre}.base_fc.0", x))))
+
+    xv = _elu(_lin(W, f"{pre}.vis_fc.2", _elu(_lin(W, f"{pre}.vis_fc.0", x * weight))))
+    x_res, vis = xv[..., :-1], xv[..., -1:]
+    vis = _sigmoid(vis) * mask
+    x = x + x_res
+    vis = _sigmoid(_lin(W, f"{pre}.vis_fc2.2", _elu(_lin(W, f"{pre}.vis_fc2.0", x * vis)))) * mask
+    weight = vis / (vis.sum(2, keepdim=True) + 1e-8)
+
+    m, v = weighted_mean_var(x, weight)
+    g = torch.cat([m.squeeze(2), v.squeeze(2), weight.mean(2)], -1)     # 65
+    g = _elu(_lin(W, f"{pre}.geometry_fc.2", _elu(_lin(W, f"{pre}.geometry_fc.0", g))))
+    n_valid = mask.sum(2)                                                # [R,dn,1]
+    g = g + pos_enc
+    g = ray_attention(W, f"{pre}.ray_attention", g, (n_valid > 1).float())
+    sigma = torch.relu(_lin(W, f"{pre}.out_geometry_fc.2", _elu(_lin(W, f"{pre}.out_geometry_fc.0", g))))
+    sigma = sigma.masked_fill(n_valid < 1, 0.0)
+
+    c = torch.cat([x, vis, ray_diff], -1)                                # 37
+    c = _elu(_lin(W, f"{pre}.rgb_fc.0", c))
+    c = _elu(_lin(W, f"{pre}.rgb_fc.2", c))
+    c = _lin(W, f"{pre}.rgb_fc.4", c)
+    c = c.masked_fill(mask == 0, -1e9)
+    blend = torch.softmax(c, 2)
+    return torch.cat([(rgb_in * blend).sum(2), sigma], -1)
+
+
+def agg_net_forward(W, pre, prj, que_dir, pos_enc):
+    """aggregate_net.py:34-68.  Returns density [qn,rn,dn], colours [qn,rn,dn,3]."""
+    rfn, qn, rn, dn, _ = prj["mask"].shape
+    hit = (prj["hit_prob"] - 0.5) * 2
+    vis = (prj["vis"] - 0.5) * 2
+    emb = torch.cat([prj["ray_feats"], hit, vis], -1)
+    emb = _lin(W, f"{pre}.prob_embed.2", torch.relu(_lin(W, f"{pre}.prob_embed.0", emb)))
+
+    def to_rays(t):  # [rfn,qn,rn,dn,c] -> [qn*rn,dn,rfn,c]
+        return t.reshape(rfn, qn * rn, dn, -1).permute(1, 2, 0, 3)
+    diff = prj["dir"] - que_dir[None]
+    dot = (prj["dir"] * que_dir[None]).sum(-1, keepdim=True)
+    out = ibrnet_forward(W, f"{pre}.agg_impl", to_rays(torch.cat([prj["rgb"], prj["img_feats"]], -1)),
+                         to_rays(emb), to_rays(torch.cat([diff, dot], -1)), to_rays(prj["mask"]), pos_enc)
+    return out[..., 3].reshape(qn, rn, dn), out[..., :3].reshape(qn, rn, dn, 3)
+
+
+# --------------------------------------------------------------------------------------------------
+# renderer.py
+
+
+DEFAULT_CFG = {
+    "use_hierarchical_sampling": False, "fine_depth_sample_num": 64, "fine_depth_use_all": False,
+    "ray_batch_num": 2048, "depth_sample_num": 64, "use_ray_mask": True, "ray_mask_view_num": 2,
+    "ray_mask_point_num": 8, "render_depth": False,
+    "dist_decoder_use_vis": True, "fine_dist_decoder_use_vis": True,
+    "agg_sample_num": 64, "fine_agg_sample_num": 64, "dist_decoder_bias_val": 0.05, "fine_dist_decoder_bias_val": 0.05,
+}
+
+
+def render_by_depth(W, cfg, que_depth, que, ref, is_train, is_fine, keep=None):
+    """renderer.py:168-203 (+ predict_proj_ray_prob :67-83, get_img_feats :127-135, network_rendering :157-166).
+
+    `keep`: optional dict that receives intermediate tensors (for stage-level parity tests).
+    """
+    que_dists = depth2inv_dists(que_depth, que["depth_range"])
+    que_pts, que_dir = depth2points(que, que_depth)
+    prj = project_points_dict(ref, que_pts)
+    rfn, qn, rn, dn, _ = prj["mask"].shape
+
+    dec = "fine_dist_decoder" if is_fine else "dist_decoder"
+    mean, var, vis, aw = dist_decoder_forward(W, dec, prj["ray_feats"], cfg[dec + "_use_vis"], cfg[dec + "_bias_val"])
+    # compute_prob is always the COARSE decoder's method (renderer.py:75) -> its use_vis flag decides
+    _, visibility, hit = compute_prob(prj["depth"].squeeze(-1), que_dists[None], mean, var, vis, aw, True,
+                                      ref["depth_range"], cfg["dist_decoder_use_vis"])
+    prj["vis"] = visibility.reshape(rfn, qn, rn, dn, 1) * prj["mask"]
+    prj["hit_prob"] = hit.reshape(rfn, qn, rn, dn, 1) * prj["mask"]
+
+    h, w = ref["imgs"].shape[-2:]
+    prj["img_feats"] = interpolate_feature_map(ref["img_feats"], prj["pts"].reshape(rfn, -1, 2),
+                                               prj["mask"].reshape(rfn, -1), h, w).reshape(rfn, qn, rn, dn, -1)
+
+    agg = "fine_agg_net" if is_fine else "agg_net"
+    pos_enc = posenc_table(cfg["fine_agg_sample_num" if is_fine else "agg_sample_num"])
+    density, colors = agg_net_forward(W, agg, prj, que_dir, pos_enc)
+    alpha = 1.0 - torch.exp(-torch.relu(density))
+    hit_prob = alpha_values2hit_prob(alpha)
+    out = {"pixel_colors_nr": (hit_prob[..., None] * colors).sum(2), "hit_prob_nr": hit_prob}
+    if "imgs" in que:
+        out["pixel_colors_gt"] = bilinear_sample(que["imgs"], que["coords"], align_corners=True)
+    if cfg["use_ray_mask"]:
+        seen = prj["mask"].int().sum(0) > cfg["ray_mask_view_num"]          # qn,rn,dn,1
+        out["ray_mask"] = (seen.sum(2) > cfg["ray_mask_point_num"])[..., 0]
+    if cfg["render_depth"]:
+        out["render_depth"] = (hit_prob * que_depth).sum(-1)
+    if keep is not None:
+        keep.update({"que_dists": que_dists, "que_pts": que_pts, "que_dir": que_dir, "density": density,
+                     "colors": colors, **{"prj_" + k: v for k, v in prj.items()}})
+    return out
+
+
+def render_impl(W, cfg, que, ref, is_train, fine_u=None, fine_depth_override=None):
+    """renderer.py:205-226.  `fine_u`: training-time uniforms for sample_fine_depth; `fine_depth_override`
+    injects externally computed (sorted) fine-pass depths (searchsorted is discontinuous)."""
+    que_depth, _ = sample_depth(que["depth_range"], que["coords"], cfg["depth_sample_num"], False)
+    out = render_by_depth(W, cfg, que_depth, que, ref, is_train, False)
+    if cfg["use_hierarchical_sampling"]:
+        if fine_depth_override is not None:
+            fd = fine_depth_override
+        else:
+            fd = sample_fine_depth(que_depth, out["hit_prob_nr"].detach(), que["depth_range"],
+                                   cfg["fine_depth_sample_num"], is_train, fine_u)
+            if cfg["fine_depth_use_all"]:
+                fd = torch.cat([que_depth, fd], -1)
+            fd = torch.sort(fd, -1)[0]
+        out["que_depth_fine"] = fd                                              # oracle-only extra
+        for k, v in render_by_depth(W, cfg, fd, que, ref, is_train, True).items():
+            out[k + "_fine"] = v
+    out["que_depth"] = que_depth                                                # oracle-only extra
+    return out
+
+
+def render(W, cfg, que, ref, is_train, ray_batch_num=None):
+    """renderer.py:237-254: python chunk loop (image_encoder / vis_encoder are upstream, not part of the path)."""
+    que = dict(que)
+    coords = que["coords"]
+    step = ray_batch_num or cfg["ray_batch_num"]
+    chunks = {}
+    for s in range(0, coords.shape[1], step):
+        que["coords"] = coords[:, s:s + step]
+        for k, v in render_impl(W, cfg, que, ref, is_train).items():
+            if is_train or not k.startswith("hit_prob"):
+                chunks.setdefault(k, []).append(v)
+    return {k: torch.cat(v, 1) for k, v in chunks.items()}
