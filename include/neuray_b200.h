@@ -1,0 +1,153 @@
+/*
+ * neuray_b200 C-ABI  (libneuray_b200.so)
+ *
+ * The reference (liuyuan-pal/NeuRay) is pure Python/PyTorch: it has no FFI or operator-plugin layer, so there is
+ * no existing binding to replace.  The drop-in boundary is therefore the reference's Python API for the per-ray
+ * rendering path (network/render_ops.py, NeuralRayBaseRenderer.render_by_depth / render_impl / render) and THIS
+ * header is the native interface a maintainer binds underneath it (ctypes stub in INTEGRATION.md; the in-tree
+ * binding is neuray_b200/_lib.py).  Each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch types; every pointer is a DEVICE pointer to contiguous fp32 unless stated otherwise
+ *   - the caller allocates every output and workspace; nothing is allocated or freed across the ABI
+ *   - every call is enqueued on `stream` (a cudaStream_t passed as void*) and never synchronises the host
+ *   - returns 0 on success, a negative NR_E_* code on failure; nr_last_error() gives a thread-local message
+ *   - one query view per call (qn == 1), exactly like every call site in the reference
+ *   - sm_100a only; there is no CPU fallback
+ */
+#ifndef NEURAY_B200_H
+#define NEURAY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NR_ABI_VERSION 1
+
+#define NR_OK 0
+#define NR_E_INVALID (-1)   /* bad argument (null pointer, unsupported shape) */
+#define NR_E_CUDA (-2)      /* a CUDA runtime call / launch failed */
+#define NR_E_UNSUPPORTED (-3)
+
+#define NR_MAX_VIEWS 32     /* reference views per call */
+#define NR_MAX_SAMPLES 256  /* depth samples per ray per pass */
+#define NR_POINT_REC 20     /* floats per point in the point-kernel -> ray-kernel record */
+
+int nr_abi_version(void);
+const char* nr_last_error(void);
+
+/* ---- weight layout --------------------------------------------------------------------------------------
+ * Host code packs one flat fp32 buffer per pass (coarse / fine) in the order the kernels stage it.  The
+ * offsets (in floats) come from the library so that host and device cannot disagree. */
+typedef struct NrWeightLayout {
+  int32_t total_point;      /* floats in the point-kernel weight buffer */
+  int32_t total_ray;        /* floats in the ray-kernel weight buffer (without pos_encoding) */
+  /* point kernel, dist-decoder heads (mean, var, aw, vis): block h at dd_head + h*dd_head_stride */
+  int32_t dd_head, dd_head_stride;
+  int32_t dd_l0_w, dd_l0_b, dd_l1_w, dd_l1_b, dd_l2_w, dd_l2_b;   /* offsets inside a head block */
+  /* group B */
+  int32_t grp_b, pe0_w, pe0_b, pe1_w, pe1_b, rd0_w, rd0_b, rd1_w, rd1_b, nf0_w, nf0_b, nf1_w, nf1_b, grp_b_size;
+  /* group C */
+  int32_t hoist_w, hoist_b, base0_w, base1_w, base1_b;
+  /* group D1 */
+  int32_t grp_d1, vis0_w, vis0_b, vis1_w, vis1_b, vis1l_w, vis1l_b, v20_w, v20_b, v21_w, v21_b,
+          rgb0_w, rgb0_b, rgb1_w, rgb1_b, rgb2_w, rgb2_b, grp_d1_size;
+  /* group D2 */
+  int32_t grp_d2, geo0_w, geo0_b, geo1_w, geo1_b, grp_d2_size;
+  /* ray kernel */
+  int32_t wq, wk, wv, wfc, ln_w, ln_b, og0_w, og0_b, og1_w, og1_b;
+} NrWeightLayout;
+
+int nr_weight_layout(NrWeightLayout* out);
+
+/* ---- per-frame packing ---------------------------------------------------------------------------------- */
+
+/* NCHW -> channel-last repack of the reference views' maps, once per frame.
+ *   ray_feats, img_feats : [rfn,32,fh,fw]   (reference: ref_imgs_info['ray_feats'|'img_feats'], renderer.py:229-231)
+ *   imgs                 : [rfn,3,h,w]
+ *   out_feat             : [rfn,fh,fw,64]   ray_feats in channels 0..31, img_feats in 32..63 (256 B per texel)
+ *   out_rgb              : [rfn,h,w,4]      rgb + zero pad (16 B per texel)                                      */
+int nr_pack_feature_maps(const float* ray_feats, const float* img_feats, const float* imgs, int rfn, int h, int w,
+                         int fh, int fw, float* out_feat, float* out_rgb, void* stream);
+
+/* ---- fused render pass ---------------------------------------------------------------------------------- */
+
+typedef struct NrPassParams {
+  /* query rays */
+  const float* coords;       /* [rn,2] pixel (x,y) */
+  const float* que_depth;    /* [rn,dn] sample depths of this pass (sorted along dn) */
+  const float* que_cam;      /* [24]: R^T row-major (9) | camera centre (3) | K^-1 row-major (9) | near, far, 0 */
+  int32_t rn, dn;
+  /* reference views */
+  const float* feat;         /* [rfn,fh,fw,64]  from nr_pack_feature_maps */
+  const float* rgb;          /* [rfn,h,w,4] */
+  const float* view_params;  /* [rfn,20]: K@Rt row-major (12) | camera centre (3) | -1/near, -1/far | pad(3) */
+  int32_t rfn, h, w, fh, fw;
+  /* weights of this pass */
+  const float* w_point;      /* NrWeightLayout.total_point floats */
+  const float* w_ray;        /* NrWeightLayout.total_ray floats */
+  const float* pos_enc;      /* [dn,16] sinusoid table (reference ibrnet.py:305-313) */
+  int32_t use_vis;           /* 1: compute_prob multiplies the CDFs by the decoder's vis head (dist_decoder.py:127) */
+  float var_bias;            /* AddBias value of the variance head (dist_decoder.py:78, ops.py:78-84) */
+  /* ray_mask thresholds (renderer.py:195-198) */
+  int32_t ray_mask_view_num, ray_mask_point_num;
+  /* workspace: rn*dn*NR_POINT_REC floats */
+  float* point_rec;
+  /* outputs (any may be NULL to skip) */
+  float* pixel_colors;       /* [rn,3]   pixel_colors_nr */
+  float* hit_prob;           /* [rn,dn]  hit_prob_nr */
+  float* render_depth;       /* [rn] */
+  uint8_t* ray_mask;         /* [rn] bool */
+  /* optional fused hierarchical resampling (sample_fine_depth + sort, render_ops.py:172-229, renderer.py:205-213) */
+  int32_t fine_dn;           /* 0: off */
+  int32_t fine_use_all;      /* 1: merge the coarse depths in (fine_depth_use_all) -> dn + fine_dn samples */
+  const float* fine_u;       /* quantiles: [fine_dn] if fine_u_stride == 0, else [rn,fine_dn] with that row stride */
+  int32_t fine_u_stride;
+  float* fine_depth;         /* [rn, fine_dn (+dn)] sorted */
+} NrPassParams;
+
+/* One render_by_depth (reference renderer.py:168-203): depth2inv_dists + depth2points + project_points_dict +
+ * predict_proj_ray_prob + get_img_feats + network_rendering (+ ray_mask, render_depth), and optionally the
+ * following sample_fine_depth.  Two kernels: point kernel (per point x view) and ray kernel (per ray). */
+int nr_render_pass_fwd(const NrPassParams* p, void* stream);
+
+/* Only the point kernel / only the ray kernel (profiling and stage-level tests). */
+int nr_point_kernel(const NrPassParams* p, void* stream);
+int nr_ray_kernel(const NrPassParams* p, void* stream);
+
+/* Stage-level debug tap of the point kernel: per (view, point) rows of
+ * [mask, z, hit, vis, pix_x, pix_y, dir(3), rgb(3), ray_feats(32), img_feats(32)] = 76 floats.  dbg: [rfn,rn*dn,76] */
+int nr_point_kernel_debug(const NrPassParams* p, float* dbg, void* stream);
+
+/* ---- stand-alone render_ops (reference network/render_ops.py; same names in neuray_b200/render_ops.py) ------- */
+
+/* sample_depth (render_ops.py:146-170).  jitter: NULL or [rn,dn-2] uniforms in [0,1). */
+int nr_sample_depth(float near, float far, int rn, int dn, const float* jitter, float* depth, float* dists, void* stream);
+/* coords2rays (render_ops.py:4-25), one camera.  cam as NrPassParams.que_cam. */
+int nr_coords2rays(const float* coords, const float* cam, int rn, float* centers, float* directions, void* stream);
+/* depth2points (render_ops.py:27-39) */
+int nr_depth2points(const float* coords, const float* cam, const float* depth, int rn, int dn, float* pts, float* dirs, void* stream);
+/* depth2dists (render_ops.py:41-44) over rows of length dn */
+int nr_depth2dists(const float* depth, int rows, int dn, float* dists, void* stream);
+/* depth2inv_dists (render_ops.py:46-52) */
+int nr_depth2inv_dists(const float* depth, float near, float far, int rows, int dn, float* dists, void* stream);
+/* alpha_values2hit_prob (render_ops.py:72-80) */
+int nr_alpha_values2hit_prob(const float* alpha, int rows, int dn, float* hit, void* stream);
+/* project_points_ref_views (render_ops.py:82-130): pts [pn,3] -> dir [rfn,pn,3], pix [rfn,pn,2], depth [rfn,pn],
+ * mask [rfn,pn] (1.0/0.0); valid_z (may be NULL) = project_points_coords' own validity flag. */
+int nr_project_points(const float* pts, int pn, const float* view_params, int rfn, int h, int w, float* dir, float* pix,
+                      float* depth, float* mask, float* valid_z, void* stream);
+/* interpolate_feats (ops.py:14-34) on an NCHW map: feats [b,c,fh,fw], pts [b,n,2] -> out [b,n,c];
+ * border: 1 = 'border', 0 = 'zeros'; mask (may be NULL) [b,n] multiplies the result (interpolate_feature_map). */
+int nr_interpolate_feats(const float* feats, const float* pts, const float* mask, int b, int c, int fh, int fw, int n,
+                         float h, float w, int border, int align_corners, float* out, void* stream);
+/* sample_fine_depth (render_ops.py:172-229, inv_mode) followed by the caller-visible sort (renderer.py:210-213). */
+int nr_sample_fine_depth(const float* depth, const float* hit_prob, float near, float far, int rn, int dn, int fine_dn,
+                         const float* u, int u_stride, int use_all, int do_sort, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEURAY_B200_H */

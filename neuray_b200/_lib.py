@@ -1,0 +1,120 @@
+"""ctypes binding of libneuray_b200.so (C-ABI declared in include/neuray_b200.h).
+
+The library is the product: if it is missing the import of this module still succeeds (so that CPU-only host
+logic can be imported), but the first call that needs it raises -- there is no PyTorch or CPU fallback.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libneuray_b200.so")
+
+NR_POINT_REC = 20
+NR_MAX_VIEWS = 32
+NR_MAX_SAMPLES = 256
+
+
+class NrWeightLayout(C.Structure):
+    _names = ("total_point total_ray dd_head dd_head_stride dd_l0_w dd_l0_b dd_l1_w dd_l1_b dd_l2_w dd_l2_b "
+              "grp_b pe0_w pe0_b pe1_w pe1_b rd0_w rd0_b rd1_w rd1_b nf0_w nf0_b nf1_w nf1_b grp_b_size "
+              "hoist_w hoist_b base0_w base1_w base1_b "
+              "grp_d1 vis0_w vis0_b vis1_w vis1_b vis1l_w vis1l_b v20_w v20_b v21_w v21_b rgb0_w rgb0_b rgb1_w rgb1_b "
+              "rgb2_w rgb2_b grp_d1_size grp_d2 geo0_w geo0_b geo1_w geo1_b grp_d2_size "
+              "wq wk wv wfc ln_w ln_b og0_w og0_b og1_w og1_b").split()
+    _fields_ = [(n, C.c_int32) for n in _names]
+
+
+class NrPassParams(C.Structure):
+    _fields_ = [
+        ("coords", C.c_void_p), ("que_depth", C.c_void_p), ("que_cam", C.c_void_p),
+        ("rn", C.c_int32), ("dn", C.c_int32),
+        ("feat", C.c_void_p), ("rgb", C.c_void_p), ("view_params", C.c_void_p),
+        ("rfn", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("fh", C.c_int32), ("fw", C.c_int32),
+        ("w_point", C.c_void_p), ("w_ray", C.c_void_p), ("pos_enc", C.c_void_p),
+        ("use_vis", C.c_int32), ("var_bias", C.c_float),
+        ("ray_mask_view_num", C.c_int32), ("ray_mask_point_num", C.c_int32),
+        ("point_rec", C.c_void_p),
+        ("pixel_colors", C.c_void_p), ("hit_prob", C.c_void_p), ("render_depth", C.c_void_p), ("ray_mask", C.c_void_p),
+        ("fine_dn", C.c_int32), ("fine_use_all", C.c_int32), ("fine_u", C.c_void_p), ("fine_u_stride", C.c_int32),
+        ("fine_depth", C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); mirrors include/neuray_b200.h one to one (tests/test_abi.py checks the header against this)
+_vp, _i, _f = C.c_void_p, C.c_int, C.c_float
+SIGNATURES = {
+    "nr_abi_version": (C.c_int, []),
+    "nr_last_error": (C.c_char_p, []),
+    "nr_weight_layout": (C.c_int, [C.POINTER(NrWeightLayout)]),
+    "nr_pack_feature_maps": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "nr_render_pass_fwd": (C.c_int, [C.POINTER(NrPassParams), _vp]),
+    "nr_point_kernel": (C.c_int, [C.POINTER(NrPassParams), _vp]),
+    "nr_ray_kernel": (C.c_int, [C.POINTER(NrPassParams), _vp]),
+    "nr_point_kernel_debug": (C.c_int, [C.POINTER(NrPassParams), _vp, _vp]),
+    "nr_sample_depth": (C.c_int, [_f, _f, _i, _i, _vp, _vp, _vp, _vp]),
+    "nr_coords2rays": (C.c_int, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "nr_depth2points": (C.c_int, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "nr_depth2dists": (C.c_int, [_vp, _i, _i, _vp, _vp]),
+    "nr_depth2inv_dists": (C.c_int, [_vp, _f, _f, _i, _i, _vp, _vp]),
+    "nr_alpha_values2hit_prob": (C.c_int, [_vp, _i, _i, _vp, _vp]),
+    "nr_project_points": (C.c_int, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nr_interpolate_feats": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _i, _i, _vp, _vp]),
+    "nr_sample_fine_depth": (C.c_int, [_vp, _vp, _f, _f, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
+}
+
+_lib = None
+_layout = None
+
+
+class NeurayB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library; raises if it has not been built (python -m neuray_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NeurayB200Error(
+                f"{LIB_PATH} not found: build the CUDA extension with `python -m neuray_b200.build` "
+                "(there is no CPU / PyTorch fallback for the rendering path)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        if handle.nr_abi_version() != 1:
+            raise NeurayB200Error("libneuray_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().nr_last_error()
+        raise NeurayB200Error(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def weight_layout():
+    global _layout
+    if _layout is None:
+        lay = NrWeightLayout()
+        check(lib().nr_weight_layout(C.byref(lay)), "nr_weight_layout")
+        _layout = lay
+    return _layout
+
+
+def ptr(t):
+    """Device pointer of a contiguous fp32/uint8 CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NeurayB200Error("neuray_b200 ops need CUDA tensors (no CPU fallback)")
+    if not t.is_contiguous():
+        raise NeurayB200Error("neuray_b200 ops need contiguous tensors")
+    return t.data_ptr()
+
+
+def stream_of(t):
+    import torch
+    return torch.cuda.current_stream(t.device).cuda_stream

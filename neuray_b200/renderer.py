@@ -1,0 +1,281 @@
+"""Host side of the per-ray rendering path: the reference's NeuralRayBaseRenderer API over the fused CUDA kernels.
+
+Mirrors reference network/renderer.py:24-254 for the hot path:
+
+    render_by_depth   :168-203      one point-kernel + one ray-kernel launch (nr_render_pass_fwd)
+    fine_render_impl  :205-215      the resampling is fused into the coarse pass' ray kernel
+    render_impl       :217-226
+    render            :228-254      chunk loop; per-frame NCHW -> channel-last repack hoisted out of it
+
+Two ways to use it:
+  * `NeuralRayRenderPath` -- a self-contained nn.Module holding the hot path's parameters under the reference's
+    state-dict names (loads a reference checkpoint with strict=False); `render()` takes encoder outputs.
+  * `neuray_b200.patch.install()` -- rebinds the same functions onto the reference's own NeuralRayBaseRenderer so
+    render.py / run_training.py run unchanged.
+
+The functions below are written against "owner": any nn.Module that has `.cfg` (reference base_cfg keys) and the
+sub-modules dist_decoder / agg_net (/ fine_dist_decoder / fine_agg_net) with the reference's parameter names.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib, modules
+from .render_ops import fine_sample_u, interpolate_feats, sample_depth
+from .weights import camera_block, pack_pass_weights, posenc_table, view_param_block
+
+PACK_KEY = "_nr_frame_pack"
+
+base_cfg = {
+    "vis_encoder_type": "default", "vis_encoder_cfg": {},
+    "dist_decoder_type": "mixture_logistics", "dist_decoder_cfg": {},
+    "agg_net_type": "default", "agg_net_cfg": {},
+    "use_hierarchical_sampling": False, "fine_agg_net_cfg": {}, "fine_dist_decoder_cfg": {},
+    "fine_depth_sample_num": 64, "fine_depth_use_all": False,
+    "ray_batch_num": 2048, "depth_sample_num": 64, "alpha_value_ground_state": -15,
+    "use_dr_prediction": False, "use_nr_color_for_dr": False, "use_self_hit_prob": False,
+    "use_ray_mask": True, "ray_mask_view_num": 2, "ray_mask_point_num": 8,
+    "render_depth": False,
+}
+
+
+class FramePack:
+    """Per-frame device data shared by every chunk and both passes: channel-last maps + per-view parameters."""
+
+    def __init__(self, ref_imgs_info):
+        imgs = ref_imgs_info["imgs"]
+        rf, imf = ref_imgs_info["ray_feats"], ref_imgs_info["img_feats"]
+        if not imgs.is_cuda:
+            raise _lib.NeurayB200Error("the rendering path needs CUDA tensors (no CPU fallback)")
+        rfn, _, h, w = imgs.shape
+        if rf.shape != imf.shape or rf.shape[1] != 32:
+            raise _lib.NeurayB200Error(f"ray_feats {tuple(rf.shape)} and img_feats {tuple(imf.shape)} must both be [rfn,32,fh,fw]")
+        if rfn > _lib.NR_MAX_VIEWS:
+            raise _lib.NeurayB200Error(f"at most {_lib.NR_MAX_VIEWS} reference views per call, got {rfn}")
+        fh, fw = rf.shape[-2:]
+        dev = imgs.device
+        self.rfn, self.h, self.w, self.fh, self.fw = rfn, h, w, fh, fw
+        self.feat = torch.empty(rfn, fh, fw, 64, dtype=torch.float32, device=dev)
+        self.rgb = torch.empty(rfn, h, w, 4, dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().nr_pack_feature_maps(
+            _lib.ptr(rf.detach().contiguous().float()), _lib.ptr(imf.detach().contiguous().float()),
+            _lib.ptr(imgs.detach().contiguous().float()), rfn, h, w, fh, fw, _lib.ptr(self.feat), _lib.ptr(self.rgb),
+            _lib.stream_of(imgs)), "nr_pack_feature_maps")
+        self.view_params = view_param_block(ref_imgs_info["poses"].float(), ref_imgs_info["Ks"].float(),
+                                            ref_imgs_info["depth_range"].float())
+        self.src = (rf.data_ptr(), imf.data_ptr(), imgs.data_ptr(), rf._version, imf._version)
+
+    def matches(self, ref_imgs_info):
+        rf, imf, imgs = ref_imgs_info["ray_feats"], ref_imgs_info["img_feats"], ref_imgs_info["imgs"]
+        return self.src == (rf.data_ptr(), imf.data_ptr(), imgs.data_ptr(), rf._version, imf._version)
+
+
+def frame_pack(ref_imgs_info):
+    pack = ref_imgs_info.get(PACK_KEY)
+    if pack is None or not pack.matches(ref_imgs_info):
+        pack = FramePack(ref_imgs_info)
+        ref_imgs_info[PACK_KEY] = pack
+    return pack
+
+
+def _pass_modules(owner, is_fine):
+    return (owner.fine_dist_decoder, owner.fine_agg_net, "fine_dist_decoder", "fine_agg_net") if is_fine else \
+        (owner.dist_decoder, owner.agg_net, "dist_decoder", "agg_net")
+
+
+def pass_weights(owner, is_fine, dn, device):
+    """Packed weights of one pass, cached on the owner and re-packed when any parameter changed (optimizer steps
+    bump tensor._version)."""
+    dec, agg, dec_name, agg_name = _pass_modules(owner, is_fine)
+    params = {f"{dec_name}.{k}": v for k, v in dec.named_parameters()}
+    params.update({f"{agg_name}.{k}": v for k, v in agg.named_parameters()})
+    stamp = tuple((v.data_ptr(), v._version) for v in params.values()) + (str(device),)
+    cache = owner.__dict__.setdefault("_nr_wcache", {})
+    hit = cache.get(is_fine)
+    if hit is None or hit[0] != stamp:
+        wp, wr = pack_pass_weights(params, dec_name, agg_name, device)
+        hit = (stamp, wp, wr, {})
+        cache[is_fine] = hit
+    pe = hit[3].get(dn)
+    if pe is None:
+        n_samples = agg.agg_impl.n_samples
+        if n_samples != dn:
+            # the reference fails with a broadcast error here (ibrnet.py:356); keep that behaviour explicit
+            raise _lib.NeurayB200Error(
+                f"{agg_name}: pos_encoding was built for sample_num={n_samples} but the pass has {dn} samples per ray")
+        pe = posenc_table(dn).to(device).contiguous()
+        hit[3][dn] = pe
+    return hit[1], hit[2], pe
+
+
+def _check_supported(owner):
+    cfg = owner.cfg
+    if cfg.get("use_dr_prediction", False):
+        raise NotImplementedError("use_dr_prediction (direct rendering / SH fit) is outside the B200 hot path (SURVEY.md 8f)")
+
+
+def run_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine=None, want_hit=True):
+    """One fused pass.  que_depth [1,rn,dn].  `fine`: None or dict(dn=, use_all=, u=, u_stride=) to also emit the
+    next pass' depths.  Returns dict with pixel_colors [1,rn,3], hit_prob [1,rn,dn], render_depth [1,rn],
+    ray_mask [1,rn] (bool) and optionally fine_depth [1,rn,M]."""
+    _check_supported(owner)
+    cfg = owner.cfg
+    coords = que_imgs_info["coords"]
+    if coords.shape[0] != 1:
+        raise _lib.NeurayB200Error("one query view per call (qn == 1), like every call site of the reference")
+    dev = coords.device
+    pack = frame_pack(ref_imgs_info)
+    que_depth = que_depth.detach().contiguous().float()
+    _, rn, dn = que_depth.shape
+    if dn > _lib.NR_MAX_SAMPLES:
+        raise _lib.NeurayB200Error(f"at most {_lib.NR_MAX_SAMPLES} samples per ray per pass, got {dn}")
+    dec, agg, _, _ = _pass_modules(owner, is_fine)
+    w_point, w_ray, pos_enc = pass_weights(owner, is_fine, dn, dev)
+    cam = camera_block(que_imgs_info["poses"][0].float(), que_imgs_info["Ks"][0].float(), que_imgs_info["depth_range"][0].float())
+    coords_c = coords[0].detach().contiguous().float()
+
+    out = {
+        "pixel_colors": torch.empty(1, rn, 3, dtype=torch.float32, device=dev),
+        "hit_prob": torch.empty(1, rn, dn, dtype=torch.float32, device=dev) if (want_hit or fine) else None,
+        "render_depth": torch.empty(1, rn, dtype=torch.float32, device=dev),
+        "ray_mask": torch.empty(1, rn, dtype=torch.uint8, device=dev),
+    }
+    rec = torch.empty(rn * dn * _lib.NR_POINT_REC, dtype=torch.float32, device=dev)
+    p = _lib.NrPassParams()
+    p.coords, p.que_depth, p.que_cam = _lib.ptr(coords_c), _lib.ptr(que_depth), _lib.ptr(cam)
+    p.rn, p.dn = rn, dn
+    p.feat, p.rgb, p.view_params = _lib.ptr(pack.feat), _lib.ptr(pack.rgb), _lib.ptr(pack.view_params)
+    p.rfn, p.h, p.w, p.fh, p.fw = pack.rfn, pack.h, pack.w, pack.fh, pack.fw
+    p.w_point, p.w_ray, p.pos_enc = _lib.ptr(w_point), _lib.ptr(w_ray), _lib.ptr(pos_enc)
+    # compute_prob is always the COARSE decoder's method (reference renderer.py:75): its use_vis decides
+    p.use_vis = 1 if owner.dist_decoder.cfg["use_vis"] else 0
+    if p.use_vis and not dec.cfg["use_vis"]:
+        raise _lib.NeurayB200Error("coarse dist_decoder has use_vis but the active decoder has no vis head (the reference fails too)")
+    p.var_bias = float(dec.cfg["bias_val"])
+    p.ray_mask_view_num, p.ray_mask_point_num = int(cfg["ray_mask_view_num"]), int(cfg["ray_mask_point_num"])
+    p.point_rec = _lib.ptr(rec)
+    p.pixel_colors, p.hit_prob = _lib.ptr(out["pixel_colors"]), _lib.ptr(out["hit_prob"])
+    p.render_depth, p.ray_mask = _lib.ptr(out["render_depth"]), _lib.ptr(out["ray_mask"])
+    if fine:
+        m = fine["dn"] + (dn if fine["use_all"] else 0)
+        out["fine_depth"] = torch.empty(1, rn, m, dtype=torch.float32, device=dev)
+        p.fine_dn, p.fine_use_all = int(fine["dn"]), 1 if fine["use_all"] else 0
+        p.fine_u, p.fine_u_stride, p.fine_depth = _lib.ptr(fine["u"]), int(fine["u_stride"]), _lib.ptr(out["fine_depth"])
+    _lib.check(_lib.lib().nr_render_pass_fwd(C.byref(p), _lib.stream_of(coords)), "nr_render_pass_fwd")
+    out["ray_mask"] = out["ray_mask"].bool()
+    return out
+
+
+def _finish_outputs(owner, res, que_depth, que_imgs_info):
+    cfg = owner.cfg
+    outputs = {"pixel_colors_nr": res["pixel_colors"], "hit_prob_nr": res["hit_prob"]}
+    if "imgs" in que_imgs_info:
+        outputs["pixel_colors_gt"] = interpolate_feats(que_imgs_info["imgs"], que_imgs_info["coords"], align_corners=True)
+    if cfg["use_ray_mask"]:
+        outputs["ray_mask"] = res["ray_mask"]
+    if cfg["render_depth"]:
+        outputs["render_depth"] = res["render_depth"]
+    return outputs
+
+
+def render_by_depth(self, que_depth, que_imgs_info, ref_imgs_info, is_train, is_fine):
+    """reference renderer.py:168-203."""
+    if is_train and self.cfg["use_self_hit_prob"]:
+        raise NotImplementedError("use_self_hit_prob (finetuning-only self visibility) is not on the B200 path yet (SURVEY.md 8f)")
+    res = run_pass(self, que_depth, que_imgs_info, ref_imgs_info, is_fine)
+    return _finish_outputs(self, res, que_depth, que_imgs_info)
+
+
+def _fine_request(self, rn, is_train, device):
+    fdn = int(self.cfg["fine_depth_sample_num"])
+    if is_train:
+        u = torch.rand([1, rn, fdn]).to(device).contiguous()       # CPU generator, as reference render_ops.py:205-209
+        return {"dn": fdn, "use_all": bool(self.cfg["fine_depth_use_all"]), "u": u, "u_stride": fdn}
+    return {"dn": fdn, "use_all": bool(self.cfg["fine_depth_use_all"]), "u": fine_sample_u(fdn, device), "u_stride": 0}
+
+
+def fine_render_impl(self, coarse_render_info, que_imgs_info, ref_imgs_info, is_train):
+    """reference renderer.py:205-215 (stand-alone form: resample with the CUDA sample_fine_depth, then a fine pass)."""
+    from .render_ops import sample_fine_depth
+    fine_depth = sample_fine_depth(coarse_render_info["depth"], coarse_render_info["hit_prob"].detach(),
+                                   que_imgs_info["depth_range"], self.cfg["fine_depth_sample_num"], is_train)
+    if self.cfg["fine_depth_use_all"]:
+        que_depth = torch.sort(torch.cat([coarse_render_info["depth"], fine_depth], -1), -1)[0]
+    else:
+        que_depth = torch.sort(fine_depth, -1)[0]
+    return render_by_depth(self, que_depth, que_imgs_info, ref_imgs_info, is_train, True)
+
+
+def render_impl(self, que_imgs_info, ref_imgs_info, is_train):
+    """reference renderer.py:217-226: coarse pass, fused resampling, fine pass."""
+    if is_train and self.cfg["use_self_hit_prob"]:
+        raise NotImplementedError("use_self_hit_prob (finetuning-only self visibility) is not on the B200 path yet (SURVEY.md 8f)")
+    que_depth, _ = sample_depth(que_imgs_info["depth_range"], que_imgs_info["coords"], self.cfg["depth_sample_num"], False)
+    hier = bool(self.cfg["use_hierarchical_sampling"])
+    rn = que_imgs_info["coords"].shape[1]
+    fine = _fine_request(self, rn, is_train, que_depth.device) if hier else None
+    res = run_pass(self, que_depth, que_imgs_info, ref_imgs_info, False, fine=fine)
+    outputs = _finish_outputs(self, res, que_depth, que_imgs_info)
+    if hier:
+        res_f = run_pass(self, res["fine_depth"], que_imgs_info, ref_imgs_info, True)
+        for k, v in _finish_outputs(self, res_f, res["fine_depth"], que_imgs_info).items():
+            outputs[k + "_fine"] = v
+    return outputs
+
+
+def render_chunks(self, que_imgs_info, ref_imgs_info, is_train):
+    """The chunk loop of reference renderer.py:236-254 (everything after the encoders)."""
+    frame_pack(ref_imgs_info)
+    ray_batch_num = self.cfg["ray_batch_num"]
+    coords = que_imgs_info["coords"]
+    ray_num = coords.shape[1]
+    render_info_all = {}
+    for ray_id in range(0, ray_num, ray_batch_num):
+        que_imgs_info["coords"] = coords[:, ray_id:ray_id + ray_batch_num]
+        render_info = render_impl(self, que_imgs_info, ref_imgs_info, is_train)
+        for k, v in render_info.items():
+            if is_train or (not k.startswith("hit_prob")):
+                render_info_all.setdefault(k, []).append(v)
+    que_imgs_info["coords"] = coords
+    return {k: (v[0] if len(v) == 1 else torch.cat(v, 1)) for k, v in render_info_all.items()}
+
+
+def render(self, que_imgs_info, ref_imgs_info, is_train):
+    """reference renderer.py:228-254, for an owner that has the reference's encoders."""
+    ref_img_feats = self.image_encoder(ref_imgs_info["imgs"])
+    ref_imgs_info["img_feats"] = ref_img_feats
+    ref_imgs_info["ray_feats"] = self.vis_encoder(ref_imgs_info["ray_feats"], ref_img_feats)
+    if is_train and self.cfg["use_self_hit_prob"]:
+        que_img_feats = self.image_encoder(que_imgs_info["imgs"])
+        que_imgs_info["ray_feats"] = self.vis_encoder(que_imgs_info["ray_feats"], que_img_feats)
+    return render_chunks(self, que_imgs_info, ref_imgs_info, is_train)
+
+
+class NeuralRayRenderPath(nn.Module):
+    """The hot path as a stand-alone module: parameters under the reference's state-dict names, kernels for the math.
+
+    `render(que_imgs_info, ref_imgs_info, is_train)` expects ref_imgs_info to already hold the encoder outputs
+    'ray_feats' and 'img_feats' [rfn,32,H/4,W/4] (reference renderer.py:229-231 produces them; the CNN encoders are
+    out of scope)."""
+    base_cfg = base_cfg
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = {**self.base_cfg, **cfg}
+        self.dist_decoder = modules.name2dist_decoder[self.cfg["dist_decoder_type"]](self.cfg["dist_decoder_cfg"])
+        self.agg_net = modules.name2agg_net[self.cfg["agg_net_type"]](self.cfg["agg_net_cfg"])
+        if self.cfg["use_hierarchical_sampling"]:
+            self.fine_dist_decoder = modules.name2dist_decoder[self.cfg["dist_decoder_type"]](self.cfg["fine_dist_decoder_cfg"])
+            self.fine_agg_net = modules.name2agg_net[self.cfg["agg_net_type"]](self.cfg["fine_agg_net_cfg"])
+
+    render_by_depth = render_by_depth
+    fine_render_impl = fine_render_impl
+    render_impl = render_impl
+
+    def render(self, que_imgs_info, ref_imgs_info, is_train):
+        return render_chunks(self, dict(que_imgs_info), ref_imgs_info, is_train)
+
+    def forward(self, data):
+        is_train = "eval" not in data
+        return self.render(data["que_imgs_info"].copy(), data["ref_imgs_info"].copy(), is_train)

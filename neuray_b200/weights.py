@@ -1,0 +1,135 @@
+"""Packing of the reference's parameters into the flat buffers the kernels stage to shared memory.
+
+Source: any mapping {state-dict name -> tensor} with the reference's names, e.g.
+`dict(renderer.named_parameters())` of a reference NeuralRayBaseRenderer, or of neuray_b200.renderer.NeuralRayRenderPath.
+The layout (offsets in floats) is owned by the library: `_lib.weight_layout()` (include/neuray_b200.h, NrWeightLayout).
+"PyTorch is plumbing": only cat / transpose / copy here, no arithmetic.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def posenc_table(n_samples, d_hid=16):
+    """Sinusoid table of reference network/ibrnet.py:305-313 (built in float64 numpy, cast to fp32) -> [n,16]."""
+    pos = np.arange(n_samples, dtype=np.float64)[:, None]
+    j = np.arange(d_hid)[None, :]
+    table = pos / np.power(10000, 2 * (j // 2) / d_hid)
+    table[:, 0::2] = np.sin(table[:, 0::2])
+    table[:, 1::2] = np.cos(table[:, 1::2])
+    return torch.from_numpy(table).float()
+
+
+def _put(buf, off, t):
+    t = t.detach().reshape(-1).to(buf.dtype)
+    buf[off:off + t.numel()] = t
+
+
+def pack_pass_weights(params, dec, agg, device=None):
+    """Returns (w_point [total_point], w_ray [total_ray]) for one pass.
+
+    params: mapping name -> tensor; dec: 'dist_decoder' | 'fine_dist_decoder'; agg: 'agg_net' | 'fine_agg_net'.
+    A decoder without a vis head (use_vis False) leaves that head block zero.
+    """
+    L = _lib.weight_layout()
+    g = lambda name: params[name]
+    device = device if device is not None else g(f"{dec}.mean_decoder.0.weight").device
+    wp = torch.zeros(L.total_point, dtype=torch.float32, device=device)
+    wr = torch.zeros(L.total_ray, dtype=torch.float32, device=device)
+
+    for hi, head in enumerate(("mean_decoder", "var_decoder", "aw_decoder", "vis_decoder")):
+        if f"{dec}.{head}.0.weight" not in params:
+            continue
+        base = L.dd_head + hi * L.dd_head_stride
+        _put(wp, base + L.dd_l0_w, g(f"{dec}.{head}.0.weight").t())
+        _put(wp, base + L.dd_l0_b, g(f"{dec}.{head}.0.bias"))
+        _put(wp, base + L.dd_l1_w, g(f"{dec}.{head}.2.weight").t())
+        _put(wp, base + L.dd_l1_b, g(f"{dec}.{head}.2.bias"))
+        _put(wp, base + L.dd_l2_w, g(f"{dec}.{head}.4.weight"))          # [outs,32] row-major
+        _put(wp, base + L.dd_l2_b, g(f"{dec}.{head}.4.bias"))
+
+    b = L.grp_b
+    _put(wp, b + L.pe0_w, g(f"{agg}.prob_embed.0.weight").t())
+    _put(wp, b + L.pe0_b, g(f"{agg}.prob_embed.0.bias"))
+    _put(wp, b + L.pe1_w, g(f"{agg}.prob_embed.2.weight").t())
+    _put(wp, b + L.pe1_b, g(f"{agg}.prob_embed.2.bias"))
+    ib = f"{agg}.agg_impl"
+    _put(wp, b + L.rd0_w, g(f"{ib}.ray_dir_fc.0.weight").t())
+    _put(wp, b + L.rd0_b, g(f"{ib}.ray_dir_fc.0.bias"))
+    rd1 = torch.zeros(16, 36, dtype=torch.float32, device=device)
+    rd1[:, :35] = g(f"{ib}.ray_dir_fc.2.weight").detach().t()
+    _put(wp, b + L.rd1_w, rd1)
+    _put(wp, b + L.rd1_b, g(f"{ib}.ray_dir_fc.2.bias"))
+    _put(wp, b + L.nf0_w, g(f"{ib}.neuray_fc.0.weight").t())
+    _put(wp, b + L.nf0_b, g(f"{ib}.neuray_fc.0.bias"))
+    _put(wp, b + L.nf1_w, g(f"{ib}.neuray_fc.2.weight"))
+    _put(wp, b + L.nf1_b, g(f"{ib}.neuray_fc.2.bias"))
+
+    w0 = g(f"{ib}.base_fc.0.weight")                                      # [64, 207] = [glob 140 | rgb_feat 35 | neuray 32]
+    _put(wp, L.hoist_w, w0[:, :140].t())
+    _put(wp, L.hoist_b, g(f"{ib}.base_fc.0.bias"))
+    _put(wp, L.base0_w, w0[:, 140:].t())
+    _put(wp, L.base1_w, g(f"{ib}.base_fc.2.weight").t())
+    _put(wp, L.base1_b, g(f"{ib}.base_fc.2.bias"))
+
+    d = L.grp_d1
+    _put(wp, d + L.vis0_w, g(f"{ib}.vis_fc.0.weight").t())
+    _put(wp, d + L.vis0_b, g(f"{ib}.vis_fc.0.bias"))
+    v1w, v1b = g(f"{ib}.vis_fc.2.weight"), g(f"{ib}.vis_fc.2.bias")       # [33,32], [33]
+    _put(wp, d + L.vis1_w, v1w[:32].t())
+    _put(wp, d + L.vis1_b, v1b[:32])
+    _put(wp, d + L.vis1l_w, v1w[32])
+    _put(wp, d + L.vis1l_b, v1b[32:])
+    _put(wp, d + L.v20_w, g(f"{ib}.vis_fc2.0.weight").t())
+    _put(wp, d + L.v20_b, g(f"{ib}.vis_fc2.0.bias"))
+    _put(wp, d + L.v21_w, g(f"{ib}.vis_fc2.2.weight"))
+    _put(wp, d + L.v21_b, g(f"{ib}.vis_fc2.2.bias"))
+    _put(wp, d + L.rgb0_w, g(f"{ib}.rgb_fc.0.weight").t())
+    _put(wp, d + L.rgb0_b, g(f"{ib}.rgb_fc.0.bias"))
+    _put(wp, d + L.rgb1_w, g(f"{ib}.rgb_fc.2.weight").t())
+    _put(wp, d + L.rgb1_b, g(f"{ib}.rgb_fc.2.bias"))
+    _put(wp, d + L.rgb2_w, g(f"{ib}.rgb_fc.4.weight"))
+    _put(wp, d + L.rgb2_b, g(f"{ib}.rgb_fc.4.bias"))
+
+    e = L.grp_d2
+    _put(wp, e + L.geo0_w, g(f"{ib}.geometry_fc.0.weight").t())
+    _put(wp, e + L.geo0_b, g(f"{ib}.geometry_fc.0.bias"))
+    _put(wp, e + L.geo1_w, g(f"{ib}.geometry_fc.2.weight").t())
+    _put(wp, e + L.geo1_b, g(f"{ib}.geometry_fc.2.bias"))
+
+    at = f"{ib}.ray_attention"
+    _put(wr, L.wq, g(f"{at}.w_qs.weight").t())
+    _put(wr, L.wk, g(f"{at}.w_ks.weight").t())
+    _put(wr, L.wv, g(f"{at}.w_vs.weight").t())
+    _put(wr, L.wfc, g(f"{at}.fc.weight").t())
+    _put(wr, L.ln_w, g(f"{at}.layer_norm.weight"))
+    _put(wr, L.ln_b, g(f"{at}.layer_norm.bias"))
+    _put(wr, L.og0_w, g(f"{ib}.out_geometry_fc.0.weight").t())
+    _put(wr, L.og0_b, g(f"{ib}.out_geometry_fc.0.bias"))
+    _put(wr, L.og1_w, g(f"{ib}.out_geometry_fc.2.weight"))
+    _put(wr, L.og1_b, g(f"{ib}.out_geometry_fc.2.bias"))
+    return wp, wr
+
+
+def camera_block(pose, K, depth_range):
+    """que_cam [24] = R^T (9) | centre (3) | K^-1 (9) | near, far, 0, built with the reference's own torch
+    expressions (render_ops.py:14-20) so the rounding matches."""
+    rot = pose[:, :3].t()
+    centre = -(rot @ pose[:, 3:])
+    kinv = torch.inverse(K)
+    pad = torch.zeros(1, dtype=torch.float32, device=pose.device)
+    return torch.cat([rot.reshape(-1), centre.reshape(-1), kinv.reshape(-1), depth_range.reshape(-1)[:2], pad]).contiguous()
+
+
+def view_param_block(poses, Ks, depth_range=None):
+    """view_params [rfn,20] = K@Rt (12) | centre (3) | -1/near, -1/far | pad (3)  (render_ops.py:95, 112; dist_decoder.py:17-20)."""
+    rfn = poses.shape[0]
+    KRt = Ks @ poses
+    centre = -(poses[:, :, :3].transpose(1, 2) @ poses[:, :, 3:])
+    if depth_range is None:
+        inv = torch.zeros(rfn, 2, dtype=torch.float32, device=poses.device)
+    else:
+        inv = -1 / depth_range
+    pad = torch.zeros(rfn, 3, dtype=torch.float32, device=poses.device)
+    return torch.cat([KRt.reshape(rfn, 12), centre.reshape(rfn, 3), inv, pad], 1).contiguous()

@@ -1,0 +1,78 @@
+"""CPU: the C-ABI library loads and exports exactly what include/neuray_b200.h declares; host-side packing logic."""
+import os
+import re
+
+import pytest
+import torch
+
+from neuray_b200 import _lib, synthetic, weights
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "neuray_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return set(re.findall(r"\b(nr_[a-z0-9_]+)\s*\(", src))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    names = header_functions()
+    assert names == set(_lib.SIGNATURES), names ^ set(_lib.SIGNATURES)
+    handle = _lib.lib()
+    for n in names:
+        assert getattr(handle, n) is not None
+    assert handle.nr_abi_version() == 1
+
+
+def test_weight_layout_is_consistent():
+    L = _lib.weight_layout()
+    assert L.total_point > 0 and L.total_ray == 1348
+    assert L.dd_head_stride == 2180 and L.grp_b == 4 * 2180
+    for name in ("grp_b", "hoist_w", "base0_w", "base1_w", "grp_d1", "grp_d2"):
+        assert getattr(L, name) % 4 == 0, name          # 16-byte alignment for 128-bit staging copies
+    assert L.grp_d2 + L.grp_d2_size == L.total_point
+
+
+def test_pack_covers_every_parameter_exactly_once():
+    """Give every parameter element a unique value; after packing, each value must appear exactly once."""
+    cfg = {"use_hierarchical_sampling": True}
+    W = synthetic.make_weights(cfg)
+    for pre_d, pre_a in (("dist_decoder", "agg_net"), ("fine_dist_decoder", "fine_agg_net")):
+        params = {k: v for k, v in W.items() if k.startswith(pre_d + ".") or k.startswith(pre_a + ".")}
+        counter = 1.0
+        uniq = {}
+        for k in sorted(params):
+            n = params[k].numel()
+            uniq[k] = torch.arange(counter, counter + n, dtype=torch.float32).reshape(params[k].shape)
+            counter += n
+        wp, wr = weights.pack_pass_weights(uniq, pre_d, pre_a, torch.device("cpu"))
+        packed = torch.cat([wp, wr])
+        vals = packed[packed != 0]
+        assert vals.numel() == int(counter - 1), (vals.numel(), counter - 1)
+        assert torch.equal(torch.sort(vals)[0], torch.arange(1.0, counter))
+
+
+def test_pack_spot_checks():
+    cfg = {"dist_decoder_cfg": {"use_vis": False}}
+    W = synthetic.make_weights(cfg)
+    L = _lib.weight_layout()
+    wp, wr = weights.pack_pass_weights(W, "dist_decoder", "agg_net", torch.device("cpu"))
+    w = W["agg_net.agg_impl.base_fc.0.weight"]
+    assert wp[L.hoist_w + 5 * 64 + 7] == w[7, 5]                  # WT[k][j] = W[j][k]
+    assert wp[L.base0_w + 3 * 64 + 9] == w[9, 140 + 3]
+    assert wp[L.grp_d1 + L.vis1l_w + 4] == W["agg_net.agg_impl.vis_fc.2.weight"][32, 4]
+    assert wr[L.wq + 2 * 16 + 5] == W["agg_net.agg_impl.ray_attention.w_qs.weight"][5, 2]
+    vis_block = wp[L.dd_head + 3 * L.dd_head_stride: L.dd_head + 4 * L.dd_head_stride]
+    assert float(vis_block.abs().sum()) == 0.0                     # no vis head when use_vis is False
+
+
+def test_ops_refuse_cpu_tensors():
+    from neuray_b200 import render_ops
+    with pytest.raises(_lib.NeurayB200Error):
+        render_ops.depth2dists(torch.rand(1, 4, 8))
+
+
+def test_posenc_matches_oracle():
+    import neuray_oracle as orc
+    assert torch.equal(weights.posenc_table(48), orc.posenc_table(48)[0])
