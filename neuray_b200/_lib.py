@@ -65,6 +65,16 @@ SIGNATURES = {
 _lib = None
 _layout = None
 
+# bookkeeping for bench.py: number of CUDA kernels this package launched, and (when PROFILE is a list) CUDA-event
+# pairs around every point-kernel launch, recorded on the launching stream
+LAUNCHES = 0
+PROFILE = None
+
+
+def count_launches(n):
+    global LAUNCHES
+    LAUNCHES += n
+
 
 class NeurayB200Error(RuntimeError):
     pass

@@ -24,6 +24,11 @@ def _c(t):
     return t.contiguous().float()
 
 
+def _ck(rc, what):
+    _lib.check(rc, what)
+    _lib.count_launches(1)
+
+
 def coords2rays(coords, poses, Ks):
     """reference render_ops.py:4-25.  coords [n,rn,2], poses [n,3,4], Ks [n,3,3] -> centers, directions [n,rn,3]."""
     n, rn, _ = coords.shape
@@ -33,7 +38,7 @@ def coords2rays(coords, poses, Ks):
     zero_range = torch.zeros(2, dtype=torch.float32, device=coords.device)
     for i in range(n):
         cam = camera_block(poses[i].float(), Ks[i].float(), zero_range)
-        _lib.check(_lib.lib().nr_coords2rays(_lib.ptr(coords[i]), _lib.ptr(cam), rn, _lib.ptr(centers[i]), _lib.ptr(dirs[i]),
+        _ck(_lib.lib().nr_coords2rays(_lib.ptr(coords[i]), _lib.ptr(cam), rn, _lib.ptr(centers[i]), _lib.ptr(dirs[i]),
                                              _lib.stream_of(coords)), "nr_coords2rays")
     return centers, dirs
 
@@ -48,7 +53,7 @@ def depth2points(que_imgs_info, que_depth):
     zero_range = torch.zeros(2, dtype=torch.float32, device=coords.device)
     for i in range(qn):
         cam = camera_block(que_imgs_info["poses"][i].float(), que_imgs_info["Ks"][i].float(), zero_range)
-        _lib.check(_lib.lib().nr_depth2points(_lib.ptr(coords[i]), _lib.ptr(cam), _lib.ptr(que_depth[i]), rn, dn,
+        _ck(_lib.lib().nr_depth2points(_lib.ptr(coords[i]), _lib.ptr(cam), _lib.ptr(que_depth[i]), rn, dn,
                                               _lib.ptr(pts[i]), _lib.ptr(dirs[i]), _lib.stream_of(coords)), "nr_depth2points")
     return pts, dirs
 
@@ -58,7 +63,7 @@ def depth2dists(depth):
     depth = _c(depth)
     out = torch.empty_like(depth)
     dn = depth.shape[-1]
-    _lib.check(_lib.lib().nr_depth2dists(_lib.ptr(depth), depth.numel() // dn, dn, _lib.ptr(out), _lib.stream_of(depth)),
+    _ck(_lib.lib().nr_depth2dists(_lib.ptr(depth), depth.numel() // dn, dn, _lib.ptr(out), _lib.stream_of(depth)),
                "nr_depth2dists")
     return out
 
@@ -70,7 +75,7 @@ def depth2inv_dists(depth, depth_range):
     qn, rn, dn = depth.shape
     dr = depth_range.detach().float().cpu()
     for i in range(qn):
-        _lib.check(_lib.lib().nr_depth2inv_dists(_lib.ptr(depth[i]), float(dr[i, 0]), float(dr[i, 1]), rn, dn, _lib.ptr(out[i]),
+        _ck(_lib.lib().nr_depth2inv_dists(_lib.ptr(depth[i]), float(dr[i, 0]), float(dr[i, 1]), rn, dn, _lib.ptr(out[i]),
                                                  _lib.stream_of(depth)), "nr_depth2inv_dists")
     return out
 
@@ -85,7 +90,7 @@ def interpolate_feats(feats, points, h=None, w=None, padding_mode="zeros", align
         h, w = ch, cw
     n = points.shape[1]
     out = torch.empty(b, n, f, dtype=torch.float32, device=feats.device)
-    _lib.check(_lib.lib().nr_interpolate_feats(_lib.ptr(feats), _lib.ptr(points), None, b, f, ch, cw, n, float(h), float(w),
+    _ck(_lib.lib().nr_interpolate_feats(_lib.ptr(feats), _lib.ptr(points), None, b, f, ch, cw, n, float(h), float(w),
                                                1 if padding_mode == "border" else 0, 1 if align_corners else 0,
                                                _lib.ptr(out), _lib.stream_of(feats)), "nr_interpolate_feats")
     return out
@@ -99,7 +104,7 @@ def interpolate_feature_map(ray_feats, coords, mask, h, w, border_type="border")
     n = coords.shape[1]
     out = torch.empty(rfn, n, f, dtype=torch.float32, device=ray_feats.device)
     align = 1 if (fh == h and fw == w) else 0
-    _lib.check(_lib.lib().nr_interpolate_feats(_lib.ptr(ray_feats), _lib.ptr(coords), _lib.ptr(maskf), rfn, f, fh, fw, n,
+    _ck(_lib.lib().nr_interpolate_feats(_lib.ptr(ray_feats), _lib.ptr(coords), _lib.ptr(maskf), rfn, f, fh, fw, n,
                                                float(h), float(w), 1 if border_type == "border" else 0, align,
                                                _lib.ptr(out), _lib.stream_of(ray_feats)), "nr_interpolate_feats")
     return out
@@ -110,7 +115,7 @@ def alpha_values2hit_prob(alpha_values):
     a = _c(alpha_values)
     out = torch.empty_like(a)
     dn = a.shape[-1]
-    _lib.check(_lib.lib().nr_alpha_values2hit_prob(_lib.ptr(a), a.numel() // dn, dn, _lib.ptr(out), _lib.stream_of(a)),
+    _ck(_lib.lib().nr_alpha_values2hit_prob(_lib.ptr(a), a.numel() // dn, dn, _lib.ptr(out), _lib.stream_of(a)),
                "nr_alpha_values2hit_prob")
     return out
 
@@ -126,7 +131,7 @@ def _project(pts, poses, Ks, h, w, want_dir):
     mask = torch.empty(rfn, pn, dtype=torch.float32, device=dev)
     valid = torch.empty(rfn, pn, dtype=torch.float32, device=dev)
     d = torch.empty(rfn, pn, 3, dtype=torch.float32, device=dev) if want_dir else None
-    _lib.check(_lib.lib().nr_project_points(_lib.ptr(pts), pn, _lib.ptr(vp), rfn, int(h), int(w), _lib.ptr(d), _lib.ptr(pix),
+    _ck(_lib.lib().nr_project_points(_lib.ptr(pts), pn, _lib.ptr(vp), rfn, int(h), int(w), _lib.ptr(d), _lib.ptr(pix),
                                             _lib.ptr(depth), _lib.ptr(mask), _lib.ptr(valid), _lib.stream_of(pts)),
                "nr_project_points")
     return d, pix, depth, mask, valid
@@ -176,7 +181,7 @@ def sample_depth(depth_range, coords, sample_num, random_sample):
     # the uniforms come from torch's generator exactly like the reference's torch.rand(..., device=device)
     jitter = torch.rand(qn, rn, dn - 2, dtype=torch.float32, device=dev) if random_sample else None
     for i in range(qn):
-        _lib.check(_lib.lib().nr_sample_depth(float(dr[i, 0]), float(dr[i, 1]), rn, dn,
+        _ck(_lib.lib().nr_sample_depth(float(dr[i, 0]), float(dr[i, 1]), rn, dn,
                                               _lib.ptr(jitter[i]) if jitter is not None else None,
                                               _lib.ptr(depth[i]), _lib.ptr(dists[i]), _lib.stream_of(coords)), "nr_sample_depth")
     return depth, dists
@@ -207,7 +212,7 @@ def sample_fine_depth(depth, hit_prob, depth_range, sample_num, random_sample, i
         stride = 0
     for i in range(qn):
         ui = u[i] if random_sample else u
-        _lib.check(_lib.lib().nr_sample_fine_depth(_lib.ptr(depth[i]), _lib.ptr(hit_prob[i]), near, far, rn, dn, fdn,
+        _ck(_lib.lib().nr_sample_fine_depth(_lib.ptr(depth[i]), _lib.ptr(hit_prob[i]), near, far, rn, dn, fdn,
                                                    _lib.ptr(ui), stride, 0, 0, _lib.ptr(out[i]), _lib.stream_of(depth)),
                    "nr_sample_fine_depth")
     return out

@@ -62,6 +62,7 @@ class FramePack:
             _lib.ptr(rf.detach().contiguous().float()), _lib.ptr(imf.detach().contiguous().float()),
             _lib.ptr(imgs.detach().contiguous().float()), rfn, h, w, fh, fw, _lib.ptr(self.feat), _lib.ptr(self.rgb),
             _lib.stream_of(imgs)), "nr_pack_feature_maps")
+        _lib.count_launches(2)
         self.view_params = view_param_block(ref_imgs_info["poses"].float(), ref_imgs_info["Ks"].float(),
                                             ref_imgs_info["depth_range"].float())
         self.src = (rf.data_ptr(), imf.data_ptr(), imgs.data_ptr(), rf._version, imf._version)
@@ -162,7 +163,18 @@ def run_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine=None,
         out["fine_depth"] = torch.empty(1, rn, m, dtype=torch.float32, device=dev)
         p.fine_dn, p.fine_use_all = int(fine["dn"]), 1 if fine["use_all"] else 0
         p.fine_u, p.fine_u_stride, p.fine_depth = _lib.ptr(fine["u"]), int(fine["u_stride"]), _lib.ptr(out["fine_depth"])
-    _lib.check(_lib.lib().nr_render_pass_fwd(C.byref(p), _lib.stream_of(coords)), "nr_render_pass_fwd")
+    stream = _lib.stream_of(coords)
+    if _lib.PROFILE is not None:
+        # bench.py: time the dominant kernel alone, with CUDA events on the launching stream
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(_lib.lib().nr_point_kernel(C.byref(p), stream), "nr_point_kernel")
+        e1.record()
+        _lib.check(_lib.lib().nr_ray_kernel(C.byref(p), stream), "nr_ray_kernel")
+        _lib.PROFILE.append((e0, e1, rn * dn))
+    else:
+        _lib.check(_lib.lib().nr_render_pass_fwd(C.byref(p), stream), "nr_render_pass_fwd")
+    _lib.count_launches(2)
     out["ray_mask"] = out["ray_mask"].bool()
     return out
 
