@@ -82,6 +82,12 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def cpu_threads():
+    """Threads for the CPU arm: all host cores up to 32 -- beyond that torch's intra-op pool only adds contention on
+    this op mix (128 threads measured 27x slower than 8 on the same rays, profiles/r1_notes.md)."""
+    return max(1, min(os.cpu_count() or 1, int(os.environ.get("NR_CPU_THREADS", "32"))))
+
+
 def oracle_throughput(wl, n_rays, steps, warmup, threads):
     """ray-samples/s of the CPU oracle on `n_rays` rays of the workload (same maps, same weights)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -113,7 +119,7 @@ def run_reference(args):
     if rank != 0:
         return
     h, w, rfn, dn_c, dn_f, desc = WORKLOADS[args.workload]
-    threads = os.cpu_count() or 1
+    threads = cpu_threads()
     n_rays = args.ref_rays
     v, t = oracle_throughput(args.workload, n_rays, args.steps, max(1, min(args.warmup, 1)), threads)
     sample = f"{n_rays} rays x ({dn_c}+{dn_f}) samples of the workload per step (a contiguous stretch of image rows)"
@@ -245,7 +251,7 @@ def run_b200(args):
 
     cpu = None
     if not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = cpu_threads()
         v, t = oracle_throughput(args.workload, args.cpu_rays, 1, 1, threads)
         cpu = {"value": v, "unit": "ray-samples/s", "cores": threads, "kind": "port",
                "sample": f"{args.cpu_rays} rays x ({dn_c}+{dn_f}) samples of the same workload, 1 warm-up + 1 timed pass, {t:.1f} s"}
@@ -285,8 +291,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="black_800", choices=sorted(WORKLOADS))
     ap.add_argument("--ray-batch", type=int, default=65536)
-    ap.add_argument("--cpu-rays", type=int, default=1024, help="rays of the workload timed on the CPU oracle (cpu_baseline)")
-    ap.add_argument("--ref-rays", type=int, default=1024, help="rays per step for --impl reference")
+    ap.add_argument("--cpu-rays", type=int, default=512, help="rays of the workload timed on the CPU oracle (cpu_baseline)")
+    ap.add_argument("--ref-rays", type=int, default=512, help="rays per step for --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

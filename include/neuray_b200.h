@@ -147,6 +147,13 @@ int nr_interpolate_feats(const float* feats, const float* pts, const float* mask
 int nr_sample_fine_depth(const float* depth, const float* hit_prob, float near, float far, int rn, int dn, int fine_dn,
                          const float* u, int u_stride, int use_all, int do_sort, float* out, void* stream);
 
+/* ---- diagnostics ------------------------------------------------------------------------------------------- */
+
+/* Self-test of the tcgen05 layer primitive the point kernel uses: D[128,n] = A[128,k] * W[n,k]^T with A staged in
+ * TMEM and W in swizzled shared memory; mode 0 = one TF32 pass, 1 = 3xTF32 (fp32-accurate).  (n,k) in
+ * {(32,32),(64,64),(16,64)}. */
+int nr_tc_selftest(const float* A, const float* W, float* D, int n, int k, int mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

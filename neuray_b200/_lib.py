@@ -60,6 +60,7 @@ SIGNATURES = {
     "nr_project_points": (C.c_int, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nr_interpolate_feats": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _i, _i, _vp, _vp]),
     "nr_sample_fine_depth": (C.c_int, [_vp, _vp, _f, _f, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "nr_tc_selftest": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
 }
 
 _lib = None

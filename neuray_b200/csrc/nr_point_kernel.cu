@@ -102,35 +102,56 @@ struct Frag {
       for (int i = 0; i < TR; ++i) acc[i][j] = v;
     }
   }
-  // accumulate k = 0..KN-1; activations from tile `tA` (row stride ld), columns colA0+k; weights sW[k*OUT + j]
-  template <int KN, int ld>
+  // one k step: activations at ap (rows r0..) / ap2 (rows r0+4..), weights at wp (row k of WT)
+  __device__ __forceinline__ void step(const float* __restrict__ ap, const float* __restrict__ ap2, const float* __restrict__ wp) {
+    float a[TR];
+    {
+      const float4 t = *reinterpret_cast<const float4*>(ap);
+      a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w;
+    }
+    if constexpr (TR == 8) {
+      const float4 t = *reinterpret_cast<const float4*>(ap2);
+      a[4] = t.x; a[5] = t.y; a[6] = t.z; a[7] = t.w;
+    }
+    float w[NC];
+    {
+      const float4 t = *reinterpret_cast<const float4*>(wp + ja);
+      w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+    }
+    if constexpr (TCH == 2) {
+      const float4 t = *reinterpret_cast<const float4*>(wp + jb);
+      w[4] = t.x; w[5] = t.y; w[6] = t.z; w[7] = t.w;
+    }
+#pragma unroll
+    for (int i = 0; i < TR; ++i)
+#pragma unroll
+      for (int j = 0; j < NC; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+  }
+  // accumulate k = 0..KN-1; activations from tile `tA` (row stride ld), columns colA0+k (colA0 % 4 == 0, so the
+  // row swizzle is constant inside each group of 4 columns); weights sW[k*OUT + j].  The k loop is a real loop
+  // (groups of 4, unrolled by UNR groups): fully unrolling every layer made the kernel ~700 KB of SASS and the
+  // warps starved on instruction fetch (ncu: stall_no_instruction 3.1 per issue, profiles/r1_point_kernel_v0).
+  template <int KN, int ld, int UNR = 2>
   __device__ __forceinline__ void mac(const float* __restrict__ tA, int colA0, const float* __restrict__ sW) {
+    constexpr int KQ = KN / 4, KT = KN % 4;
+#pragma unroll UNR
+    for (int kq = 0; kq < KQ; ++kq) {
+      const int col0 = colA0 + 4 * kq;
+      const int sw = swz(col0);
+      const float* ap = tA + col0 * ld + (r0 ^ sw);
+      const float* ap2 = tA + col0 * ld + ((r0 + 4) ^ sw);
+      const float* wp = sW + 4 * kq * OUT;
 #pragma unroll
-    for (int k = 0; k < KN; ++k) {
-      const int col = colA0 + k;
-      const float* ap = tA + col * ld;
-      float a[TR];
-      {
-        const float4 t = *reinterpret_cast<const float4*>(ap + (r0 ^ swz(col)));
-        a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w;
-      }
-      if constexpr (TR == 8) {
-        const float4 t = *reinterpret_cast<const float4*>(ap + ((r0 + 4) ^ swz(col)));
-        a[4] = t.x; a[5] = t.y; a[6] = t.z; a[7] = t.w;
-      }
-      float w[NC];
-      {
-        const float4 t = *reinterpret_cast<const float4*>(sW + k * OUT + ja);
-        w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
-      }
-      if constexpr (TCH == 2) {
-        const float4 t = *reinterpret_cast<const float4*>(sW + k * OUT + jb);
-        w[4] = t.x; w[5] = t.y; w[6] = t.z; w[7] = t.w;
-      }
+      for (int i = 0; i < 4; ++i) step(ap + i * ld, ap2 + i * ld, wp + i * OUT);
+    }
+    if constexpr (KT > 0) {
+      const int col0 = colA0 + 4 * KQ;
+      const int sw = swz(col0);
+      const float* ap = tA + col0 * ld + (r0 ^ sw);
+      const float* ap2 = tA + col0 * ld + ((r0 + 4) ^ sw);
+      const float* wp = sW + 4 * KQ * OUT;
 #pragma unroll
-      for (int i = 0; i < TR; ++i)
-#pragma unroll
-        for (int j = 0; j < NC; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+      for (int i = 0; i < KT; ++i) step(ap + i * ld, ap2 + i * ld, wp + i * OUT);
     }
   }
   // epi(col j, first row r (multiple of 4), float4 of the 4 consecutive rows)
@@ -317,6 +338,7 @@ __global__ void __launch_bounds__(NT, 1) point_kernel(const KParams kp) {
     // ---------------- phase 3: dist decoder heads + compute_prob (dist_decoder.py:99-140) ----------------
     float hv[4][2];   // head outputs of this thread's row
     const int n_heads = pp.use_vis ? 4 : 3;
+#pragma unroll 1
     for (int hd = 0; hd < n_heads; ++hd) {
       __syncthreads();   // gather stores visible / previous head done with wbuf + H
       stage(c, W + lay::DD_HEAD + hd * lay::DD_HEAD_STRIDE, lay::DD_HEAD_STRIDE);
@@ -483,15 +505,15 @@ __global__ void __launch_bounds__(NT, 1) point_kernel(const KParams kp) {
       f.setup(c);
       f.zero();
       __syncthreads();
-      stage(c, W + lay::HOIST_W, 70 * 64);
+      stage(c, W + lay::HOIST_W, 72 * 64);
       __syncthreads();
-      if (f.r0 < P) f.mac<70, LDP>(tGLOB, 0, c.wbuf);
+      if (f.r0 < P) f.mac<72, LDP>(tGLOB, 0, c.wbuf);
       __syncthreads();
-      stage(c, W + lay::HOIST_W + 70 * 64, 70 * 64 + 64);
+      stage(c, W + lay::HOIST_W + 72 * 64, 68 * 64 + 64);
       __syncthreads();
       if (f.r0 < P) {
-        f.mac<70, LDP>(tGLOB, 70, c.wbuf);
-        const float* __restrict__ hb = c.wbuf + 70 * 64;
+        f.mac<68, LDP>(tGLOB, 72, c.wbuf);
+        const float* __restrict__ hb = c.wbuf + 68 * 64;
         f.store([&](int col, int r4, float4 v4) {
           const float b = hb[col];
           at4<LDP>(tG, col, r4) = make_float4(v4.x + b, v4.y + b, v4.z + b, v4.w + b);
@@ -519,7 +541,7 @@ __global__ void __launch_bounds__(NT, 1) point_kernel(const KParams kp) {
             f.acc[4 * half + 0][j] = g.x; f.acc[4 * half + 1][j] = g.y; f.acc[4 * half + 2][j] = g.z; f.acc[4 * half + 3][j] = g.w;
           }
         }
-        f.mac<67, LD>(tA, 0, c.wbuf);
+        f.mac<67, LD, 1>(tA, 0, c.wbuf);
         f.store([&](int col, int r4, float4 v4) { at4<LD>(tH, col, r4) = elu4(v4); });
       }
     }

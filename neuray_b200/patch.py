@@ -1,0 +1,39 @@
+"""Installs the B200 path into an importable reference tree so that its own entry points (render.py,
+run_training.py, eval.py) run unchanged:
+
+    import neuray_b200.patch as patch
+    patch.install()            # before the reference builds its network
+    ...                        # the reference's code, untouched
+
+What is rebound:
+  * every function of network/render_ops.py  -> neuray_b200.render_ops (also inside network.renderer's and
+    network.init_net's namespaces, which star-/name-import them)
+  * NeuralRayBaseRenderer.render_by_depth / fine_render_impl / render_impl / render -> neuray_b200.renderer
+Constructors, cfg keys, sub-module and state-dict names, and the output dict stay the reference's own.
+The IBRNetWithNeuRay.pos_encoding attribute pinned to cuda:0 (ibrnet.py:312) is no longer used on the path: the
+kernels get a per-device table built by neuray_b200.weights.posenc_table.
+"""
+import importlib
+
+from . import render_ops, renderer
+
+
+def install():
+    ref_ops = importlib.import_module("network.render_ops")
+    ref_renderer = importlib.import_module("network.renderer")
+    targets = [ref_ops, ref_renderer]
+    try:
+        targets.append(importlib.import_module("network.init_net"))
+    except Exception:      # init_net needs inplace_abn / kornia; the rendering path does not
+        pass
+    for name in render_ops.__all__:
+        fn = getattr(render_ops, name)
+        for mod in targets:
+            if hasattr(mod, name):
+                setattr(mod, name, fn)
+    base = ref_renderer.NeuralRayBaseRenderer
+    base.render_by_depth = renderer.render_by_depth
+    base.fine_render_impl = renderer.fine_render_impl
+    base.render_impl = renderer.render_impl
+    base.render = renderer.render
+    return base
