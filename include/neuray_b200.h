@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NR_ABI_VERSION 1
+#define NR_ABI_VERSION 2
 
 #define NR_OK 0
 #define NR_E_INVALID (-1)   /* bad argument (null pointer, unsupported shape) */
@@ -61,6 +61,12 @@ typedef struct NrWeightLayout {
 } NrWeightLayout;
 
 int nr_weight_layout(NrWeightLayout* out);
+
+/* Layout of the tensor-core weight buffer (floats; details in csrc/nr_common.cuh namespace tcl). */
+typedef struct NrTcLayout {
+  int32_t total, stage, head0, pe0, pe1, b0, b1, v01, v2r;
+} NrTcLayout;
+int nr_tc_layout(NrTcLayout* out);
 
 /* ---- per-frame packing ---------------------------------------------------------------------------------- */
 
@@ -106,6 +112,9 @@ typedef struct NrPassParams {
   const float* fine_u;       /* quantiles: [fine_dn] if fine_u_stride == 0, else [rn,fine_dn] with that row stride */
   int32_t fine_u_stride;
   float* fine_depth;         /* [rn, fine_dn (+dn)] sorted */
+  /* tensor-core weights of this pass (NrTcLayout.total floats: hi/lo tf32 parts, pre-swizzled).  NULL selects the
+   * fp32 SIMT point kernel; non-NULL the tcgen05 point kernel. */
+  const float* w_tc;
 } NrPassParams;
 
 /* One render_by_depth (reference renderer.py:168-203): depth2inv_dists + depth2points + project_points_dict +

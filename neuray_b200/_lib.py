@@ -9,6 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libneuray_b200.so")
 
+ABI_VERSION = 2
 NR_POINT_REC = 20
 NR_MAX_VIEWS = 32
 NR_MAX_SAMPLES = 256
@@ -37,7 +38,12 @@ class NrPassParams(C.Structure):
         ("pixel_colors", C.c_void_p), ("hit_prob", C.c_void_p), ("render_depth", C.c_void_p), ("ray_mask", C.c_void_p),
         ("fine_dn", C.c_int32), ("fine_use_all", C.c_int32), ("fine_u", C.c_void_p), ("fine_u_stride", C.c_int32),
         ("fine_depth", C.c_void_p),
+        ("w_tc", C.c_void_p),
     ]
+
+
+class NrTcLayout(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in "total stage head0 pe0 pe1 b0 b1 v01 v2r".split()]
 
 
 # name -> (restype, argtypes); mirrors include/neuray_b200.h one to one (tests/test_abi.py checks the header against this)
@@ -46,6 +52,7 @@ SIGNATURES = {
     "nr_abi_version": (C.c_int, []),
     "nr_last_error": (C.c_char_p, []),
     "nr_weight_layout": (C.c_int, [C.POINTER(NrWeightLayout)]),
+    "nr_tc_layout": (C.c_int, [C.POINTER(NrTcLayout)]),
     "nr_pack_feature_maps": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "nr_render_pass_fwd": (C.c_int, [C.POINTER(NrPassParams), _vp]),
     "nr_point_kernel": (C.c_int, [C.POINTER(NrPassParams), _vp]),
@@ -94,7 +101,7 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.nr_abi_version() != 1:
+        if handle.nr_abi_version() != ABI_VERSION:
             raise NeurayB200Error("libneuray_b200.so ABI version mismatch")
         _lib = handle
     return _lib
@@ -113,6 +120,12 @@ def weight_layout():
         check(lib().nr_weight_layout(C.byref(lay)), "nr_weight_layout")
         _layout = lay
     return _layout
+
+
+def tc_layout():
+    lay = NrTcLayout()
+    check(lib().nr_tc_layout(C.byref(lay)), "nr_tc_layout")
+    return lay
 
 
 def ptr(t):

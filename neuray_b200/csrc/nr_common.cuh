@@ -116,6 +116,29 @@ static_assert(GRP_B % 4 == 0 && HOIST_W % 4 == 0 && BASE0_W % 4 == 0 && BASE1_W 
 }  // namespace lay
 
 // ------------------------------------------------------------------------------------------------------------
+// Tensor-core weight buffer (w_tc): every tcgen05 layer's W^T as hi / lo tf32 parts, K padded and re-ordered to the
+// kernel's A-column order, pre-swizzled into K-major SWIZZLE_128B tiles of 32-wide K slabs, grouped into the 16 KB
+// ring stages the producer warp streams (offsets in floats).  Inside a stage:
+//   head h   : L0 hi 0 | L0 lo 1024 | L1 hi 2048 | L1 lo 3072                     (N 32, K 32)
+//   PE0      : hi slabs 0,1024 | lo slabs 2048,3072                              (N 32, K 34 -> 40)
+//   PE1      : hi 0 | lo 1024                                                     (N 32, K 32)
+//   B0 + s   : slab s of base_fc.0: hi 0 | lo 2048                                (N 64, K 67 -> 72 = 35+5 | 32)
+//   B1       : hi slabs 0,1024 | lo slabs 2048,3072                              (N 32, K 64)
+//   V01      : vis_fc.0 hi 0 | lo 1024 | vis_fc.2[:32] hi 2048 | lo 3072
+//   V2R      : vis_fc2.0 hi 0 | lo 1024 | rgb_fc.0 hi slabs 2048,2560 | lo slabs 3072,3584   (N 16, K 37 -> 40)
+namespace tcl {
+constexpr int STAGE = 4096;
+constexpr int HEAD0 = 0;
+constexpr int PE0 = 4 * STAGE;
+constexpr int PE1 = PE0 + STAGE;
+constexpr int B0 = PE1 + 2048;
+constexpr int B1 = B0 + 3 * STAGE;
+constexpr int V01 = B1 + STAGE;
+constexpr int V2R = V01 + STAGE;
+constexpr int TOTAL = V2R + STAGE;
+}  // namespace tcl
+
+// ------------------------------------------------------------------------------------------------------------
 // math used by both kernels
 
 // exp(x)-1 through the SFU: absolute error ~1e-7 for x<=0 (expm1f would cost ~20 instructions, and ELU runs

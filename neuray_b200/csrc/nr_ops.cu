@@ -244,6 +244,13 @@ int nr_weight_layout(NrWeightLayout* o) {
   return NR_OK;
 }
 
+int nr_tc_layout(NrTcLayout* o) {
+  NR_CHECK_ARG(o != nullptr, "out");
+  o->total = tcl::TOTAL; o->stage = tcl::STAGE; o->head0 = tcl::HEAD0; o->pe0 = tcl::PE0; o->pe1 = tcl::PE1; o->b0 = tcl::B0;
+  o->b1 = tcl::B1; o->v01 = tcl::V01; o->v2r = tcl::V2R;
+  return NR_OK;
+}
+
 int nr_pack_feature_maps(const float* ray_feats, const float* img_feats, const float* imgs, int rfn, int h, int w, int fh,
                          int fw, float* out_feat, float* out_rgb, void* stream) {
   NR_CHECK_ARG(ray_feats && img_feats && imgs && out_feat && out_rgb, "null device pointer");

@@ -17,13 +17,14 @@ The functions below are written against "owner": any nn.Module that has `.cfg` (
 sub-modules dist_decoder / agg_net (/ fine_dist_decoder / fine_agg_net) with the reference's parameter names.
 """
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
 
 from . import _lib, modules
 from .render_ops import fine_sample_u, interpolate_feats, sample_depth
-from .weights import camera_block, pack_pass_weights, posenc_table, view_param_block
+from .weights import camera_block, pack_pass_weights, pack_tc_weights, posenc_table, view_param_block
 
 PACK_KEY = "_nr_frame_pack"
 
@@ -96,7 +97,8 @@ def pass_weights(owner, is_fine, dn, device):
     hit = cache.get(is_fine)
     if hit is None or hit[0] != stamp:
         wp, wr = pack_pass_weights(params, dec_name, agg_name, device)
-        hit = (stamp, wp, wr, {})
+        wt = pack_tc_weights(params, dec_name, agg_name, device)
+        hit = (stamp, wp, wr, {}, wt)
         cache[is_fine] = hit
     pe = hit[3].get(dn)
     if pe is None:
@@ -107,7 +109,7 @@ def pass_weights(owner, is_fine, dn, device):
                 f"{agg_name}: pos_encoding was built for sample_num={n_samples} but the pass has {dn} samples per ray")
         pe = posenc_table(dn).to(device).contiguous()
         hit[3][dn] = pe
-    return hit[1], hit[2], pe
+    return hit[1], hit[2], pe, hit[4]
 
 
 def _check_supported(owner):
@@ -132,7 +134,7 @@ def run_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine=None,
     if dn > _lib.NR_MAX_SAMPLES:
         raise _lib.NeurayB200Error(f"at most {_lib.NR_MAX_SAMPLES} samples per ray per pass, got {dn}")
     dec, agg, _, _ = _pass_modules(owner, is_fine)
-    w_point, w_ray, pos_enc = pass_weights(owner, is_fine, dn, dev)
+    w_point, w_ray, pos_enc, w_tc = pass_weights(owner, is_fine, dn, dev)
     cam = camera_block(que_imgs_info["poses"][0].float(), que_imgs_info["Ks"][0].float(), que_imgs_info["depth_range"][0].float())
     coords_c = coords[0].detach().contiguous().float()
 
@@ -149,6 +151,8 @@ def run_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine=None,
     p.feat, p.rgb, p.view_params = _lib.ptr(pack.feat), _lib.ptr(pack.rgb), _lib.ptr(pack.view_params)
     p.rfn, p.h, p.w, p.fh, p.fw = pack.rfn, pack.h, pack.w, pack.fh, pack.fw
     p.w_point, p.w_ray, p.pos_enc = _lib.ptr(w_point), _lib.ptr(w_ray), _lib.ptr(pos_enc)
+    # NR_POINT_KERNEL=simt selects the fp32 SIMT point kernel (development A/B switch); default: tcgen05 point kernel
+    p.w_tc = None if os.environ.get("NR_POINT_KERNEL", "tc") == "simt" else _lib.ptr(w_tc)
     # compute_prob is always the COARSE decoder's method (reference renderer.py:75): its use_vis decides
     p.use_vis = 1 if owner.dist_decoder.cfg["use_vis"] else 0
     if p.use_vis and not dec.cfg["use_vis"]:

@@ -112,6 +112,77 @@ def pack_pass_weights(params, dec, agg, device=None):
     return wp, wr
 
 
+_SWZ_CACHE = {}
+
+
+def _sw128_perm(n_rows, device):
+    """perm[n*32+k] = float index of element (n,k) inside a K-major SWIZZLE_128B tile of 32-wide fp32 rows
+    (csrc/nr_tc.cuh sw128_index): 8-row atoms of 1024 B, 16-byte chunk index XORed with the row index mod 8."""
+    key = (n_rows, str(device))
+    if key not in _SWZ_CACHE:
+        n = torch.arange(n_rows)[:, None]
+        k = torch.arange(32)[None, :]
+        idx = (n >> 3) * 256 + (n & 7) * 32 + ((((k >> 2) ^ (n & 7)) << 2) | (k & 3))
+        _SWZ_CACHE[key] = idx.reshape(-1).to(device)
+    return _SWZ_CACHE[key]
+
+
+def _tc_tiles(wmat, k_cols):
+    """wmat [N, K] fp32 (already in the kernel's K order, un-padded) -> (hi, lo) flat tensors of ceil(k_cols/32)
+    swizzled slabs each; hi = w with the low 13 mantissa bits cleared (exact tf32), lo = w - hi (exact in fp32)."""
+    n, k = wmat.shape
+    slabs = (k_cols + 31) // 32
+    full = torch.zeros(n, slabs * 32, dtype=torch.float32, device=wmat.device)
+    full[:, :k] = wmat.detach().float()
+    hi = (full.view(torch.int32) & -8192).view(torch.float32)          # 0xffffe000
+    lo = full - hi
+    perm = _sw128_perm(n, wmat.device)
+    out = []
+    for part in (hi, lo):
+        tiles = torch.empty(slabs, n * 32, dtype=torch.float32, device=wmat.device)
+        for s_ in range(slabs):
+            tiles[s_, perm] = part[:, 32 * s_:32 * s_ + 32].reshape(-1)
+        out.append(tiles.reshape(-1))
+    return out
+
+
+def pack_tc_weights(params, dec, agg, device=None):
+    """Tensor-core weight buffer of one pass (layout: csrc/nr_common.cuh namespace tcl / NrTcLayout)."""
+    T = _lib.tc_layout()
+    g = lambda name: params[name]
+    device = device if device is not None else g(f"{dec}.mean_decoder.0.weight").device
+    buf = torch.zeros(T.total, dtype=torch.float32, device=device)
+
+    def put(off, wmat, k_cols, lo_off):
+        hi, lo = _tc_tiles(wmat.to(device), k_cols)
+        buf[off:off + hi.numel()] = hi
+        buf[off + lo_off:off + lo_off + lo.numel()] = lo
+
+    for hi_, head in enumerate(("mean_decoder", "var_decoder", "aw_decoder", "vis_decoder")):
+        if f"{dec}.{head}.0.weight" not in params:
+            continue
+        base = T.head0 + hi_ * T.stage
+        put(base, g(f"{dec}.{head}.0.weight"), 32, 1024)
+        put(base + 2048, g(f"{dec}.{head}.2.weight"), 32, 1024)
+    ib = f"{agg}.agg_impl"
+    put(T.pe0, g(f"{agg}.prob_embed.0.weight"), 40, 2048)                 # [32, 34] -> K 40
+    put(T.pe1, g(f"{agg}.prob_embed.2.weight"), 32, 1024)
+    w0 = g(f"{ib}.base_fc.0.weight").detach().float().to(device)        # [64, 207]
+    b0 = torch.zeros(64, 72, dtype=torch.float32, device=device)          # K order: rgb_feat 35 | 5 zeros | neuray_feat 32
+    b0[:, :35] = w0[:, 140:175]
+    b0[:, 40:72] = w0[:, 175:207]
+    hi, lo = _tc_tiles(b0, 72)
+    for s_ in range(3):
+        buf[T.b0 + s_ * T.stage: T.b0 + s_ * T.stage + 2048] = hi[s_ * 2048:(s_ + 1) * 2048]
+        buf[T.b0 + s_ * T.stage + 2048: T.b0 + (s_ + 1) * T.stage] = lo[s_ * 2048:(s_ + 1) * 2048]
+    put(T.b1, g(f"{ib}.base_fc.2.weight"), 64, 2048)
+    put(T.v01, g(f"{ib}.vis_fc.0.weight"), 32, 1024)
+    put(T.v01 + 2048, g(f"{ib}.vis_fc.2.weight")[:32], 32, 1024)
+    put(T.v2r, g(f"{ib}.vis_fc2.0.weight"), 32, 1024)
+    put(T.v2r + 2048, g(f"{ib}.rgb_fc.0.weight"), 40, 1024)               # [16, 37] -> K 40, two 512-float slabs
+    return buf
+
+
 def camera_block(pose, K, depth_range):
     """que_cam [24] = R^T (9) | centre (3) | K^-1 (9) | near, far, 0, built with the reference's own torch
     expressions (render_ops.py:14-20) so the rounding matches."""

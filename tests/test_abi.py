@@ -22,7 +22,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     handle = _lib.lib()
     for n in names:
         assert getattr(handle, n) is not None
-    assert handle.nr_abi_version() == 1
+    assert handle.nr_abi_version() == _lib.ABI_VERSION
 
 
 def test_weight_layout_is_consistent():
@@ -76,3 +76,30 @@ def test_ops_refuse_cpu_tensors():
 def test_posenc_matches_oracle():
     import neuray_oracle as orc
     assert torch.equal(weights.posenc_table(48), orc.posenc_table(48)[0])
+
+
+def test_tc_weight_pack_roundtrip():
+    """Un-swizzle the packed tensor-core tiles and check hi + lo == W exactly, hi is tf32-exact, K padding is zero."""
+    cfg = {"use_hierarchical_sampling": False}
+    W = synthetic.make_weights(cfg)
+    T = _lib.tc_layout()
+    buf = weights.pack_tc_weights(W, "dist_decoder", "agg_net", torch.device("cpu"))
+    assert buf.numel() == T.total == 47104
+
+    def unswz(flat, n):                # [slabs*n*32] -> [n, slabs*32]
+        slabs = flat.numel() // (n * 32)
+        perm = weights._sw128_perm(n, torch.device("cpu"))
+        return torch.cat([flat[s * n * 32:(s + 1) * n * 32][perm].reshape(n, 32) for s in range(slabs)], 1)
+
+    w = W["agg_net.agg_impl.base_fc.2.weight"]                      # [32, 64], stage B1: hi 0..2048, lo 2048..4096
+    hi, lo = unswz(buf[T.b1:T.b1 + 2048], 32), unswz(buf[T.b1 + 2048:T.b1 + 4096], 32)
+    assert torch.equal(hi + lo, w)
+    assert torch.equal((hi.view(torch.int32) & 8191), torch.zeros_like(hi, dtype=torch.int32))
+    w0 = W["agg_net.agg_impl.base_fc.0.weight"]
+    rec = torch.cat([unswz(buf[T.b0 + s * T.stage:T.b0 + s * T.stage + 2048], 64) +
+                     unswz(buf[T.b0 + s * T.stage + 2048:T.b0 + (s + 1) * T.stage], 64) for s in range(3)], 1)   # [64, 96]
+    assert torch.equal(rec[:, :35], w0[:, 140:175]) and torch.equal(rec[:, 40:72], w0[:, 175:207])
+    assert float(rec[:, 35:40].abs().sum()) == 0.0 and float(rec[:, 72:].abs().sum()) == 0.0
+    wr = W["agg_net.agg_impl.rgb_fc.0.weight"]                      # [16, 37] at V2R+2048 (hi, two 512 slabs), lo at +1024
+    rec = unswz(buf[T.v2r + 2048:T.v2r + 3072], 16) + unswz(buf[T.v2r + 3072:T.v2r + 4096], 16)
+    assert torch.equal(rec[:, :37], wr) and float(rec[:, 37:].abs().sum()) == 0.0

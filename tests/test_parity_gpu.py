@@ -1,6 +1,7 @@
 """GPU parity: the CUDA path (through the C-ABI) against the golden vectors of the unmodified reference and
 against the CPU oracle.  Tolerance = BASELINE.json north_star: 1e-4 abs / 1e-3 rel, fp32."""
 import ctypes as C
+import os
 
 import pytest
 import torch
@@ -60,7 +61,7 @@ def test_point_kernel_stage_tap(name):
         depth = depth.cuda().contiguous()
         _, rn, dn = depth.shape
         pack = renderer.frame_pack(ref)
-        wp, wr, pe = renderer.pass_weights(net, is_fine, dn, depth.device)
+        wp, wr, pe, wt = renderer.pass_weights(net, is_fine, dn, depth.device)
         from neuray_b200.weights import camera_block
         cam = camera_block(que["poses"][0], que["Ks"][0], que["depth_range"][0])
         rec = torch.empty(rn * dn * 20, device="cuda")
@@ -75,6 +76,7 @@ def test_point_kernel_stage_tap(name):
         p.use_vis = 1 if net.dist_decoder.cfg["use_vis"] else 0
         p.var_bias = dec.cfg["bias_val"]
         p.point_rec = rec.data_ptr()
+        p.w_tc = None if os.environ.get("NR_POINT_KERNEL", "tc") == "simt" else wt.data_ptr()
         _lib.check(_lib.lib().nr_point_kernel_debug(C.byref(p), dbg.data_ptr(), None), "debug")
         torch.cuda.synchronize()
         d = dbg.reshape(pack.rfn, 1, rn, dn, 76)
