@@ -130,6 +130,10 @@ int nr_ray_kernel(const NrPassParams* p, void* stream);
  * [mask, z, hit, vis, pix_x, pix_y, dir(3), rgb(3), ray_feats(32), img_feats(32)] = 76 floats.  dbg: [rfn,rn*dn,76] */
 int nr_point_kernel_debug(const NrPassParams* p, float* dbg, void* stream);
 
+/* Diagnostics: the tensor-core point kernel with clock64() stamps at its phase boundaries (CTA 0, the lead thread of
+ * each 128-row block): timing[tile < 64][2][32] device buffer of int64. */
+int nr_point_kernel_timing(const NrPassParams* p, long long* timing, void* stream);
+
 /* ---- stand-alone render_ops (reference network/render_ops.py; same names in neuray_b200/render_ops.py) ------- */
 
 /* sample_depth (render_ops.py:146-170).  jitter: NULL or [rn,dn-2] uniforms in [0,1). */

@@ -58,6 +58,7 @@ SIGNATURES = {
     "nr_point_kernel": (C.c_int, [C.POINTER(NrPassParams), _vp]),
     "nr_ray_kernel": (C.c_int, [C.POINTER(NrPassParams), _vp]),
     "nr_point_kernel_debug": (C.c_int, [C.POINTER(NrPassParams), _vp, _vp]),
+    "nr_point_kernel_timing": (C.c_int, [C.POINTER(NrPassParams), _vp, _vp]),
     "nr_sample_depth": (C.c_int, [_f, _f, _i, _i, _vp, _vp, _vp, _vp]),
     "nr_coords2rays": (C.c_int, [_vp, _vp, _i, _vp, _vp, _vp]),
     "nr_depth2points": (C.c_int, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),

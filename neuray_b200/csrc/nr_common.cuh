@@ -141,9 +141,22 @@ constexpr int TOTAL = V2R + STAGE;
 // ------------------------------------------------------------------------------------------------------------
 // math used by both kernels
 
-// exp(x)-1 through the SFU: absolute error ~1e-7 for x<=0 (expm1f would cost ~20 instructions, and ELU runs
-// ~470 times per (point,view) row)
-__device__ __forceinline__ float elu(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+// ELU = x > 0 ? x : exp(x) - 1, five instructions and no branch:
+//   * exp through ex2.approx.ftz (FMUL + MUFU; __expf's non-ftz path adds a compare and two predicated multiplies per
+//     call for denormal results, which only matter below exp(-87) where ELU is -1 either way); abs error ~1e-7
+//   * the select is a selp on a setp, never a divergent branch around the MUFU (the ternary form compiled to one and
+//     serialised the 32-wide epilogues; profiles/r1_phase_timing.md)
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float elu(float x) {
+  const float e = ex2_ftz(x * 1.4426950408889634f) - 1.f;
+  float y;
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, 0f00000000;\n\tselp.f32 %0, %1, %2, p;\n\t}" : "=f"(y) : "f"(x), "f"(e));
+  return y;
+}
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 __device__ __forceinline__ float softplusf_(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 // 0.5 + 0.5 tanh(x), accurate to ~1e-7 absolute (tanh.approx is only ~5e-4)

@@ -204,6 +204,7 @@ __global__ void fine_depth_kernel(const float* __restrict__ depth, const float* 
 // implemented in nr_point_kernel.cu / nr_ray_kernel.cu
 int launch_point_kernel(const NrPassParams* p, float* dbg, cudaStream_t stream);
 int launch_ray_kernel(const NrPassParams* p, cudaStream_t stream);
+void set_point_kernel_timing(long long* buf);
 
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
@@ -267,6 +268,13 @@ int nr_point_kernel(const NrPassParams* p, void* stream) { return launch_point_k
 int nr_point_kernel_debug(const NrPassParams* p, float* dbg, void* stream) {
   NR_CHECK_ARG(dbg != nullptr, "dbg");
   return launch_point_kernel(p, dbg, (cudaStream_t)stream);
+}
+int nr_point_kernel_timing(const NrPassParams* p, long long* timing, void* stream) {
+  NR_CHECK_ARG(timing != nullptr && p != nullptr && p->w_tc != nullptr, "timing buffer / tensor-core weights required");
+  set_point_kernel_timing(timing);
+  const int rc = launch_point_kernel(p, nullptr, (cudaStream_t)stream);
+  set_point_kernel_timing(nullptr);
+  return rc;
 }
 int nr_ray_kernel(const NrPassParams* p, void* stream) { return launch_ray_kernel(p, (cudaStream_t)stream); }
 int nr_render_pass_fwd(const NrPassParams* p, void* stream) {

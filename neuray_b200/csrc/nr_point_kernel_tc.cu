@@ -40,11 +40,14 @@ constexpr int C_SCAL = 0, C_A = 24, C_RF = 60, C_PP = 100, N_COLS = 126;
 constexpr int OFF_ARENA = OFF_RING + NBUF * RING_STAGE;
 constexpr int OFF_WBUF = OFF_ARENA + N_COLS * LD;
 constexpr int WBUF = 4608;
-constexpr int OFF_SW = OFF_WBUF + WBUF;
+constexpr int OFF_WBUF2 = OFF_WBUF + WBUF;
+constexpr int OFF_SW = OFF_WBUF2 + WBUF;
 constexpr int SW = 2048;
-constexpr int OFF_BAR = OFF_SW + SW;              // 8 mbarriers (64 B) + tmem base
+constexpr int OFF_GEO = OFF_SW + SW;              // per-point ray geometry, double buffered: [2][8][LDP]
+constexpr int GEO = 2 * 8 * LDP;
+constexpr int OFF_BAR = OFF_GEO + GEO;            // 12 mbarriers (96 B) + tmem base
 constexpr int SMEM_FLOATS = OFF_BAR + 32;
-constexpr size_t SMEM_BYTES = size_t(SMEM_FLOATS) * 4 + 1024;   // + slack for the manual 1024-byte alignment
+constexpr size_t SMEM_BYTES = size_t(SMEM_FLOATS) * 4;
 
 enum { S_MASK = 0, S_Z, S_HIT, S_VIS, S_W1, S_W0, S_VISA, S_VIS2, S_W2, S_DD0, S_DD1, S_DD2, S_DD3, S_R, S_G, S_B,
        S_LOGIT, S_IX, S_IY, S_PT0 };
@@ -68,10 +71,20 @@ constexpr int T_AHI = 0, T_ALO = 80, T_D = 160;
 struct KParams {
   NrPassParams p;
   float* dbg;
+  long long* timing;   // optional: clock64() at phase boundaries, CTA 0, threads 0 and 128: [tile][2][32]
   int P, n_tiles, n_heads;
 };
 
 __device__ __forceinline__ void sync_compute() { tc::named_sync(1, NT); }
+
+// asynchronous staging of SIMT-layer weights (cp.async, 16 B per request): issued a phase ahead, waited for at use
+__device__ __forceinline__ void stage_async(float* dst, const float* __restrict__ src, int n, int tid) {
+  for (int i = tid * 4; i < n; i += NT * 4)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(tc::smem_u32(dst + i)), "l"(src + i) : "memory");
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // Everything a compute thread needs to drive its block's tensor-core layers.
 struct Blk {
@@ -84,50 +97,67 @@ struct Blk {
   uint32_t wi;                  // weight stages consumed so far (same sequence in every thread)
   int blk;
   bool leader;
+  bool issuer_warp;             // warp 0 of the block (warp-uniform): one elected lane of it issues the MMAs
+  long long* tk;                // diagnostics: where run_layer drops clock64() stamps (nullptr: off)
 };
 
 // Layer issue + completion wait, executed by all 128 threads of the block after they wrote their A columns.
-//   chunks c < nlin read A columns a0 + 8c, the remaining ones atail + 8(c - nlin); B chunk c lives in slab c/4 at
-//   byte offset (c%4)*32; slab s of the hi / lo tile is at stage_rel(s) (stage index relative to b.wi) + off_hi/lo + s'*slab_bytes
-template <int N>
-__device__ __forceinline__ void run_layer(Blk& b, int nch, int a0, int nlin, int atail,
-                                          int n_stages,             // ring stages this layer reads (1, or 3 for base_fc.0)
-                                          int slabs_per_stage, uint32_t off_hi, uint32_t off_lo, uint32_t slab_bytes,
-                                          bool wait_full, bool release) {
+//   NCH K-chunks of 8; chunks c < NLIN read A columns A0 + 8c, the rest ATAIL + 8(c - NLIN); B chunk c lives in slab c/4
+//   at byte offset (c%4)*32 inside the slab; a layer reads NSTG ring stages: one (all slabs in it, SLAB bytes apart) or
+//   one slab per stage (base_fc.0).  Everything is a template constant so that the single issuing lane executes ~4
+//   instructions per MMA (a runtime-parameterised loop cost ~140 cycles per MMA: dependent scalar code on one lane).
+template <int N, int NCH, int A0, int NLIN, int ATAIL, int NSTG, uint32_t OFF_HI, uint32_t OFF_LO, uint32_t SLAB, bool WAIT_FULL, bool RELEASE>
+__device__ __forceinline__ void run_layer(Blk& b) {
+  if (b.tk && b.leader) b.tk[0] = clock64();
   tc::tmem_st_wait();
   tc::fence_before_thread_sync();
   tc::named_sync(2 + b.blk, 128);
-  if (b.leader) {
+  if (b.tk && b.leader) b.tk[2] = clock64();
+  if (b.issuer_warp) {                       // warp-uniform branch; one elected lane issues
     tc::fence_after_thread_sync();
-    if (wait_full)
-      for (int s = 0; s < n_stages; ++s) {
-        const uint32_t i = b.wi + s;
-        tc::mbar_wait(b.wfull + (i % NBUF), (i / NBUF) & 1);
-      }
-    constexpr uint32_t idesc = tc::idesc_tf32(N);
-    bool acc = false;
-#pragma unroll 1
-    for (int ps = 0; ps < 3; ++ps) {
-      const uint32_t abase = (ps == 1) ? b.mAlo : b.mAhi;
-      const uint32_t boff = (ps == 2) ? off_lo : off_hi;
-#pragma unroll 1
-      for (int c = 0; c < nch; ++c) {
-        const int acol = c < nlin ? a0 + 8 * c : atail + 8 * (c - nlin);
-        const int slab = c >> 2;
-        const uint32_t stage = (b.wi + slab / slabs_per_stage) % NBUF;
-        const uint32_t baddr = b.ring_addr + stage * (RING_STAGE * 4) + boff + (slab % slabs_per_stage) * slab_bytes + (c & 3) * 32;
-        tc::mma_tf32_ts(b.mD, abase + acol, tc::smem_desc_sw128(baddr), idesc, acc);
-        acc = true;
-      }
+    const uint32_t st0 = b.wi % NBUF;
+    if (WAIT_FULL) {
+#pragma unroll
+      for (int s = 0; s < NSTG; ++s) tc::mbar_wait(b.wfull + ((st0 + s) % NBUF), ((b.wi + s) / NBUF) & 1);
     }
-    if (release)
-      for (int s = 0; s < n_stages; ++s) tc::mma_commit(b.wempty + ((b.wi + s) % NBUF));
-    tc::mma_commit(b.mma_bar);
+    if (b.tk && b.leader) b.tk[3] = clock64();
+    if (tc::elect_one()) {
+      constexpr uint32_t idesc = tc::idesc_tf32(N);
+      uint64_t dhi[NSTG], dlo[NSTG];
+#pragma unroll
+      for (int s = 0; s < NSTG; ++s) {
+        const uint32_t base = b.ring_addr + ((st0 + s) % NBUF) * (RING_STAGE * 4);
+        dhi[s] = tc::smem_desc_sw128(base + OFF_HI);
+        dlo[s] = tc::smem_desc_sw128(base + OFF_LO);
+      }
+#pragma unroll
+      for (int ps = 0; ps < 3; ++ps) {
+        const uint32_t abase = (ps == 1) ? b.mAlo : b.mAhi;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          constexpr int dummy = 0;
+          const int acol = c < NLIN ? A0 + 8 * c : ATAIL + 8 * (c - NLIN);
+          const int slab = c >> 2;
+          const int stg = NSTG == 1 ? 0 : slab;
+          const uint32_t inc = ((NSTG == 1 ? slab * SLAB : 0u) + (c & 3) * 32) >> 4;
+          tc::mma_tf32_ts(b.mD, abase + acol, (ps == 2 ? dlo[stg] : dhi[stg]) + inc, idesc, (ps | c) != 0);
+          (void)dummy;
+        }
+      }
+      if (RELEASE) {
+#pragma unroll
+        for (int s = 0; s < NSTG; ++s) tc::mma_commit(b.wempty + ((st0 + s) % NBUF));
+      }
+      tc::mma_commit(b.mma_bar);
+    }
+    __syncwarp();
+    if (b.tk && b.leader) b.tk[4] = clock64();
   }
-  if (release) b.wi += n_stages;
+  if (RELEASE) b.wi += NSTG;
   tc::mbar_wait(b.mma_bar, b.phase);
   b.phase ^= 1;
   tc::fence_after_thread_sync();
+  if (b.tk && b.leader) b.tk[5] = clock64();
 }
 
 // D columns [c0, c0+16) of this thread's row
@@ -135,6 +165,13 @@ __device__ __forceinline__ void load_d16(const Blk& b, int c0, float* v) {
   tc::tmem_ld16(b.tD + c0, v);
   tc::tmem_ld_wait();
 }
+// D columns [c0, c0+32): both loads in flight before the single wait
+__device__ __forceinline__ void load_d32(const Blk& b, int c0, float* v) {
+  tc::tmem_ld16(b.tD + c0, v);
+  tc::tmem_ld16(b.tD + c0 + 16, v + 16);
+  tc::tmem_ld_wait();
+}
+__device__ __forceinline__ void store_a32(const Blk& b, int col, const float* v);
 // 16 activations -> A columns [col, col+16) (hi and lo parts)
 __device__ __forceinline__ void store_a16(const Blk& b, int col, const float* v) {
   uint32_t hi[16], lo[16];
@@ -144,10 +181,25 @@ __device__ __forceinline__ void store_a16(const Blk& b, int col, const float* v)
   tc::tmem_st16(b.tAlo + col, lo);
 }
 
+__device__ __forceinline__ void store_a32(const Blk& b, int col, const float* v) {
+  store_a16(b, col, v);
+  store_a16(b, col + 16, v + 16);
+}
+// bias vector (shared memory, 16-byte aligned) added to 32 values with 128-bit loads
+__device__ __forceinline__ void add_bias32(float* x, const float* __restrict__ bias) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 t = *reinterpret_cast<const float4*>(bias + 4 * q);
+    x[4 * q] += t.x; x[4 * q + 1] += t.y; x[4 * q + 2] += t.z; x[4 * q + 3] += t.w;
+  }
+}
+
 template <bool DEBUG>
 __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp) {
-  extern __shared__ uint8_t smem_raw[];
-  float* const smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (SWIZZLE_128B tiles) comes from the declaration: the kernel has no static shared memory, so
+  // the dynamic window starts at the CTA's shared base.  (Rounding the pointer up by hand made every access a generic
+  // LD/ST instead of LDS/STS.)
+  extern __shared__ __align__(1024) float smem[];
   const NrPassParams& pp = kp.p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -158,7 +210,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
   uint64_t* const wfull = bars;             // [NBUF]
   uint64_t* const wempty = bars + NBUF;     // [NBUF]
   uint64_t* const mma_bars = bars + 2 * NBUF;   // [2]
-  uint32_t* const tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2 * NBUF + 2);
+  uint64_t* const pfull = bars + 2 * NBUF + 2;  // [2] per-point geometry of the next tile (producer warp -> compute warps)
+  uint64_t* const pempty = bars + 2 * NBUF + 4; // [2]
+  uint32_t* const tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2 * NBUF + 6);
+  float* const geo = smem + OFF_GEO;
 
   const int P = kp.P, rfn = pp.rfn, ROWS = P * rfn, dn = pp.dn;
   const int N = pp.rn * dn;
@@ -171,6 +226,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
     for (int i = 0; i < NBUF; ++i) { tc::mbar_init(wfull + i, 1); tc::mbar_init(wempty + i, 2); }
     tc::mbar_init(mma_bars + 0, 1);
     tc::mbar_init(mma_bars + 1, 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(pfull + i, 1); tc::mbar_init(pempty + i, 1); }
     tc::fence_mbar_init();
   }
   if (warp == 0) tc::tmem_alloc<512>(tmem_base_s);
@@ -193,11 +249,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
   tc::fence_after_thread_sync();
   const uint32_t tmem_base = *tmem_base_s;
 
-  // ---------------- producer warp: stream the tensor-core weights through the ring ----------------
+  // ---------------- producer warp: per-point ray geometry one tile ahead + the tensor-core weight stream ----------------
   if (warp == NT / 32) {
-    if (lane == 0) {
-      uint32_t i = 0;
-      for (int tile = blockIdx.x; tile < kp.n_tiles; tile += gridDim.x) {
+    // depth2points / depth2inv_dists for the P points of a tile (reference render_ops.py:27-52), one lane per point
+    auto geometry = [&](int tile, int j) {
+      const int buf = j & 1;
+      if (j >= 2) tc::mbar_wait(pempty + buf, ((j >> 1) - 1) & 1);
+      float* __restrict__ g = geo + buf * 8 * LDP;
+      const int n = tile * P + lane;
+      float px = 0.f, py = 0.f, pz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f, ihp = 0.f, ihc = 0.f;
+      if (lane < P && n < N) {
+        const float* __restrict__ cam = pp.que_cam;
+        const int ray = n / dn, s = n - ray * dn;
+        const float cx = __ldg(pp.coords + 2 * ray), cy = __ldg(pp.coords + 2 * ray + 1);
+        float cm[3], d[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) cm[i] = fmaf(cam[12 + 3 * i + 1], cy, cam[12 + 3 * i] * cx) + cam[12 + 3 * i + 2];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float wld = fmaf(cam[3 * i + 2], cm[2], fmaf(cam[3 * i + 1], cm[1], cam[3 * i] * cm[0])) + cam[9 + i];
+          d[i] = wld - cam[9 + i];   // the reference adds the centre and subtracts it again (render_ops.py:22-23)
+        }
+        const float z = __ldg(pp.que_depth + n);
+        px = fmaf(d[0], z, cam[9]); py = fmaf(d[1], z, cam[10]); pz = fmaf(d[2], z, cam[11]);
+        const float nrm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        qx = -d[0] / nrm; qy = -d[1] / nrm; qz = -d[2] / nrm;
+        const float a = -1.f / cam[21], bb = -1.f / cam[22];
+        const float tcur = (-1.f / z - a) / (bb - a);
+        float dc = 1e6f;
+        if (s + 1 < dn) dc = (-1.f / __ldg(pp.que_depth + n + 1) - a) / (bb - a) - tcur;
+        float dp = dc;
+        if (s > 0) dp = tcur - (-1.f / __ldg(pp.que_depth + n - 1) - a) / (bb - a);
+        ihc = dc * 0.5f; ihp = dp * 0.5f;
+      }
+      g[P_X * LDP + lane] = px; g[P_Y * LDP + lane] = py; g[P_Z * LDP + lane] = pz;
+      g[P_QX * LDP + lane] = qx; g[P_QY * LDP + lane] = qy; g[P_QZ * LDP + lane] = qz;
+      g[P_IHP * LDP + lane] = ihp; g[P_IHC * LDP + lane] = ihc;
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(pfull + buf);
+    };
+    uint32_t i = 0;
+    int j = 0;
+    if (blockIdx.x < kp.n_tiles) geometry(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < kp.n_tiles; tile += gridDim.x, ++j) {
+      if (tile + int(gridDim.x) < kp.n_tiles) geometry(tile + gridDim.x, j + 1);
+      if (lane == 0) {
         for (int s = 0; s < stages_per_tile; ++s, ++i) {
           // stage sequence: heads [0,n_heads) | pe0 | pe1 | base0 slab 0,1,2 | base1 | vis0+vis1 | vis_fc2.0+rgb_fc.0
           int src, bytes = RING_STAGE * 4;
@@ -213,18 +309,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
           tc::bulk_g2s(ring + buf * RING_STAGE, pp.w_tc + src, bytes, wfull + buf);
         }
       }
+      __syncwarp();
     }
   } else {
     // ---------------- compute warps ----------------
     pk::Ctx c;
     c.sm = arena;
     c.wbuf = smem + OFF_WBUF;
+    float* const wbufA = smem + OFF_WBUF;
+    float* const wbufB = smem + OFF_WBUF2;
     c.tid = tid; c.lane = lane; c.warp = warp;
 
     float* const tS = arena + C_SCAL * LD;
     float* const tA = arena + C_A * LD;
     float* const tRF = arena + C_RF * LD;
-    float* const parr = tS + S_PT0 * LD;
+    float* const pnv = tS + S_PT0 * LD;          // per-point #valid views
     float* const tPP = arena + C_PP * LD;
     float* const tGLOB = tPP + PP_GLOB;
     float* const tG = tPP + PP_G;
@@ -237,11 +336,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
     const int r = tid;
     const bool row_ok = r < ROWS;
     const int v = row_ok ? r / P : 0;
-    const int p = r - v * P;
+    const int p = row_ok ? r - v * P : 0;   // padding rows (r >= ROWS) alias point 0: they only ever produce unused values
 
     Blk b;
     b.blk = warp >> 2;
     b.leader = (tid & 127) == 0;
+    b.issuer_warp = (__shfl_sync(0xffffffffu, warp, 0) & 3) == 0;
     {
       const uint32_t col0 = tmem_base + 256 * b.blk;
       const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
@@ -253,44 +353,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
     b.ring_addr = tc::smem_u32(ring);
     b.phase = 0;
     b.wi = 0;
+    b.tk = nullptr;
 
-    for (int tile = blockIdx.x; tile < kp.n_tiles; tile += gridDim.x) {
+    int tile_it = 0;
+#define NR_TICK(id)                                                                                   \
+  if (kp.timing != nullptr && blockIdx.x == 0 && (tid & 127) == 0 && tile_it < 64)                    \
+    kp.timing[(tile_it * 2 + (tid >> 7)) * 32 + (id)] = clock64();
+    for (int tile = blockIdx.x; tile < kp.n_tiles; tile += gridDim.x, ++tile_it) {
       const int n0 = tile * P;
       sync_compute();
+      NR_TICK(0)
+      // SIMT-layer weights of this tile: hoisted base_fc.0 halves now (group 1 -> buffer A, group 2 -> buffer B)
+      stage_async(wbufA, W + lay::HOIST_W, 72 * 64, tid);
+      stage_async(wbufB, W + lay::HOIST_W + 72 * 64, 68 * 64 + 64, tid);
 
-      // ---------------- phase 0: per-point ray geometry ----------------
-      if (tid < P) {
-        const int n = n0 + tid;
-        float px = 0.f, py = 0.f, pz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f, ihp = 0.f, ihc = 0.f;
-        if (n < N) {
-          const float* __restrict__ cam = pp.que_cam;
-          const int ray = n / dn, s = n - ray * dn;
-          const float cx = __ldg(pp.coords + 2 * ray), cy = __ldg(pp.coords + 2 * ray + 1);
-          float cm[3], d[3];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) cm[i] = fmaf(cam[12 + 3 * i + 1], cy, cam[12 + 3 * i] * cx) + cam[12 + 3 * i + 2];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const float wld = fmaf(cam[3 * i + 2], cm[2], fmaf(cam[3 * i + 1], cm[1], cam[3 * i] * cm[0])) + cam[9 + i];
-            d[i] = wld - cam[9 + i];
-          }
-          const float z = __ldg(pp.que_depth + n);
-          px = fmaf(d[0], z, cam[9]); py = fmaf(d[1], z, cam[10]); pz = fmaf(d[2], z, cam[11]);
-          const float nrm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-          qx = -d[0] / nrm; qy = -d[1] / nrm; qz = -d[2] / nrm;
-          const float a = -1.f / cam[21], bb = -1.f / cam[22];
-          const float tcur = (-1.f / z - a) / (bb - a);
-          float dc = 1e6f;
-          if (s + 1 < dn) dc = (-1.f / __ldg(pp.que_depth + n + 1) - a) / (bb - a) - tcur;
-          float dp = dc;
-          if (s > 0) dp = tcur - (-1.f / __ldg(pp.que_depth + n - 1) - a) / (bb - a);
-          ihc = dc * 0.5f; ihp = dp * 0.5f;
-        }
-        parr[P_X * LDP + tid] = px; parr[P_Y * LDP + tid] = py; parr[P_Z * LDP + tid] = pz;
-        parr[P_QX * LDP + tid] = qx; parr[P_QY * LDP + tid] = qy; parr[P_QZ * LDP + tid] = qz;
-        parr[P_IHP * LDP + tid] = ihp; parr[P_IHC * LDP + tid] = ihc;
-      }
-      sync_compute();
+      // ---------------- phase 0: per-point ray geometry comes from the producer warp, one tile ahead ----------------
+      if (tile_it >= 1 && tid == 0) tc::mbar_arrive(pempty + ((tile_it - 1) & 1));   // previous tile's buffer is free
+      tc::mbar_wait(pfull + (tile_it & 1), (tile_it >> 1) & 1);
+      const float* __restrict__ parr = geo + (tile_it & 1) * 8 * LDP;
+      NR_TICK(1)
 
       // ---------------- phase 1: projection into the row's view + rgb taps ----------------
       float dbg_px = 0.f, dbg_py = 0.f, dbg_dir[3] = {0.f, 0.f, 0.f};
@@ -341,39 +422,60 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
         at<LD>(tA, 0, r) = cr; at<LD>(tA, 1, r) = cg; at<LD>(tA, 2, r) = cb;
       }
       sync_compute();
+      NR_TICK(2)
 
       // ---------------- phase 2: 64-channel bilinear gather, 16 lanes x float4 per texel ----------------
+      // Each half-warp fetches one row's texels (4 taps x 256 contiguous bytes); four rows are batched so that 16
+      // independent 128-bit loads are in flight per lane before the first blend (the un-batched loop exposed one L2
+      // round trip per row: 12.9 k cycles per tile, profiles/r1_phase_timing.md).
       {
         const int hw = lane >> 4, l = lane & 15;
-        for (int rr = warp * 2 + hw; rr < ROWS; rr += 16) {
-          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (at<LD>(tS, S_MASK, rr) != 0.f) {
-            const int vv = rr / P;
-            const float ix = at<LD>(tS, S_IX, rr), iy = at<LD>(tS, S_IY, rr);
-            const float x0f = floorf(ix), y0f = floorf(iy);
-            const int x0 = int(x0f), y0 = int(y0f);
-            const int x1 = min(x0 + 1, fw - 1), y1 = min(y0 + 1, fh - 1);
-            const float we = ix - x0f, ww = (x0f + 1.f) - ix, ws = iy - y0f, wn = (y0f + 1.f) - iy;
-            const float* __restrict__ base = pp.feat + size_t(vv) * fh * fw * 64 + 4 * l;
-            const float4 t00 = ldg4(base + (size_t(y0) * fw + x0) * 64), t01 = ldg4(base + (size_t(y0) * fw + x1) * 64);
-            const float4 t10 = ldg4(base + (size_t(y1) * fw + x0) * 64), t11 = ldg4(base + (size_t(y1) * fw + x1) * 64);
-            const float w00 = ww * wn, w01 = we * wn, w10 = ww * ws, w11 = we * ws;
-            o.x = t00.x * w00 + t01.x * w01 + t10.x * w10 + t11.x * w11;
-            o.y = t00.y * w00 + t01.y * w01 + t10.y * w10 + t11.y * w11;
-            o.z = t00.z * w00 + t01.z * w01 + t10.z * w10 + t11.z * w11;
-            o.w = t00.w * w00 + t01.w * w01 + t10.w * w10 + t11.w * w11;
+        for (int rb = warp * 2 + hw; rb < ROWS; rb += 64) {
+          float4 t[4][4];
+          float wq[4][4];
+          bool on[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int rr = rb + 16 * u;
+            on[u] = rr < ROWS && at<LD>(tS, S_MASK, rr < ROWS ? rr : 0) != 0.f;
+            if (on[u]) {
+              const int vv = rr / P;
+              const float ix = at<LD>(tS, S_IX, rr), iy = at<LD>(tS, S_IY, rr);
+              const float x0f = floorf(ix), y0f = floorf(iy);
+              const int x0 = int(x0f), y0 = int(y0f);
+              const int x1 = min(x0 + 1, fw - 1), y1 = min(y0 + 1, fh - 1);
+              const float we = ix - x0f, ww = (x0f + 1.f) - ix, ws = iy - y0f, wn = (y0f + 1.f) - iy;
+              const float* __restrict__ base = pp.feat + size_t(vv) * fh * fw * 64 + 4 * l;
+              t[u][0] = ldg4(base + (size_t(y0) * fw + x0) * 64); t[u][1] = ldg4(base + (size_t(y0) * fw + x1) * 64);
+              t[u][2] = ldg4(base + (size_t(y1) * fw + x0) * 64); t[u][3] = ldg4(base + (size_t(y1) * fw + x1) * 64);
+              wq[u][0] = ww * wn; wq[u][1] = we * wn; wq[u][2] = ww * ws; wq[u][3] = we * ws;
+            }
           }
-          if (l < 8) {
-            at<LD>(tRF, 4 * l + 0, rr) = o.x; at<LD>(tRF, 4 * l + 1, rr) = o.y;
-            at<LD>(tRF, 4 * l + 2, rr) = o.z; at<LD>(tRF, 4 * l + 3, rr) = o.w;
-          } else {
-            const int cc = 3 + 4 * (l - 8);
-            at<LD>(tA, cc + 0, rr) = o.x; at<LD>(tA, cc + 1, rr) = o.y;
-            at<LD>(tA, cc + 2, rr) = o.z; at<LD>(tA, cc + 3, rr) = o.w;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int rr = rb + 16 * u;
+            if (rr < ROWS) {
+              float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (on[u]) {
+                o.x = t[u][0].x * wq[u][0] + t[u][1].x * wq[u][1] + t[u][2].x * wq[u][2] + t[u][3].x * wq[u][3];
+                o.y = t[u][0].y * wq[u][0] + t[u][1].y * wq[u][1] + t[u][2].y * wq[u][2] + t[u][3].y * wq[u][3];
+                o.z = t[u][0].z * wq[u][0] + t[u][1].z * wq[u][1] + t[u][2].z * wq[u][2] + t[u][3].z * wq[u][3];
+                o.w = t[u][0].w * wq[u][0] + t[u][1].w * wq[u][1] + t[u][2].w * wq[u][2] + t[u][3].w * wq[u][3];
+              }
+              if (l < 8) {
+                at<LD>(tRF, 4 * l + 0, rr) = o.x; at<LD>(tRF, 4 * l + 1, rr) = o.y;
+                at<LD>(tRF, 4 * l + 2, rr) = o.z; at<LD>(tRF, 4 * l + 3, rr) = o.w;
+              } else {
+                const int cc = 3 + 4 * (l - 8);
+                at<LD>(tA, cc + 0, rr) = o.x; at<LD>(tA, cc + 1, rr) = o.y;
+                at<LD>(tA, cc + 2, rr) = o.z; at<LD>(tA, cc + 3, rr) = o.w;
+              }
+            }
           }
         }
       }
       sync_compute();
+      NR_TICK(3)
 
       // ---------------- phase 3: dist decoder on the tensor cores ----------------
       // A[0:32] <- ray_feats of this row
@@ -384,30 +486,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
         for (int j = 0; j < 16; ++j) x[j] = at<LD>(tRF, c0 + j, r);
         store_a16(b, c0, x);
       }
+      NR_TICK(4)
       float hv[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll 1
       for (int hd = 0; hd < n_heads; ++hd) {
         const float* __restrict__ hw_ = sw + SW_HEAD + hd * SW_HEAD_STRIDE;
-        run_layer<32>(b, 4, 0, 4, 0, 1, 1, 0, 1024 * 4, 0, true, false);           // L0: A[0:32]
+        run_layer<32, 4, 0, 4, 0, 1, 0, 1024 * 4, 0, true, false>(b);           // L0: A[0:32]
+        {
+          float x[32];
+          load_d32(b, 0, x);
+          add_bias32(x, hw_);
 #pragma unroll
-        for (int c0 = 0; c0 < 32; c0 += 16) {
-          float x[16];
-          load_d16(b, c0, x);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) x[j] = elu(x[j] + hw_[c0 + j]);
-          store_a16(b, 32 + c0, x);
+          for (int j = 0; j < 32; ++j) x[j] = elu(x[j]);
+          store_a32(b, 32, x);
         }
-        run_layer<32>(b, 4, 32, 4, 0, 1, 1, 2048 * 4, 3072 * 4, 0, false, true);   // L1: A[32:64]
+        run_layer<32, 4, 32, 4, 0, 1, 2048 * 4, 3072 * 4, 0, false, true>(b);   // L1: A[32:64]
         float o0 = hw_[128], o1 = hw_[129];
+        {
+          float x[32];
+          load_d32(b, 0, x);
+          add_bias32(x, hw_ + 32);
 #pragma unroll
-        for (int c0 = 0; c0 < 32; c0 += 16) {
-          float x[16];
-          load_d16(b, c0, x);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a = elu(x[j] + hw_[32 + c0 + j]);
-            o0 = fmaf(hw_[64 + c0 + j], a, o0);
-            o1 = fmaf(hw_[96 + c0 + j], a, o1);
+          for (int q = 0; q < 8; ++q) {
+            const float4 wa = *reinterpret_cast<const float4*>(hw_ + 64 + 4 * q);
+            const float4 wb = *reinterpret_cast<const float4*>(hw_ + 96 + 4 * q);
+            const float a0 = elu(x[4 * q]), a1 = elu(x[4 * q + 1]), a2 = elu(x[4 * q + 2]), a3 = elu(x[4 * q + 3]);
+            o0 = fmaf(wa.w, a3, fmaf(wa.z, a2, fmaf(wa.y, a1, fmaf(wa.x, a0, o0))));
+            o1 = fmaf(wb.w, a3, fmaf(wb.z, a2, fmaf(wb.y, a1, fmaf(wb.x, a0, o1))));
           }
         }
         // (explicit selects keep hv in registers: a dynamically indexed array would live in local memory)
@@ -416,6 +521,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
         else if (hd == 2) { hv[2][0] = o0; hv[2][1] = o1; }
         else { hv[3][0] = o0; hv[3][1] = o1; }
       }
+      NR_TICK(5)
       float hit = 0.f, visib = 0.f;
       {
         const float* __restrict__ vp = pp.view_params + v * 20;
@@ -453,34 +559,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
         x[0] = (hit - 0.5f) * 2.f; x[1] = (visib - 0.5f) * 2.f;
         store_a16(b, 64, x);                                                         // A[64:72] = hit', vis', 0...
       }
-      run_layer<32>(b, 5, 0, 4, 64, 1, 2, 0, 2048 * 4, 4096, true, true);            // prob_embed.0: K = 32 + 8
+      run_layer<32, 5, 0, 4, 64, 1, 0, 2048 * 4, 4096, true, true>(b);            // prob_embed.0: K = 32 + 8
+      {
+        float x[32];
+        load_d32(b, 0, x);
+        add_bias32(x, sw + SW_PE0B);
 #pragma unroll
-      for (int c0 = 0; c0 < 32; c0 += 16) {
-        float x[16];
-        load_d16(b, c0, x);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j] + sw[SW_PE0B + c0 + j], 0.f);
-        store_a16(b, 32 + c0, x);
+        for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+        store_a32(b, 32, x);
       }
-      run_layer<32>(b, 4, 32, 4, 0, 1, 1, 0, 1024 * 4, 0, true, true);               // prob_embed.2
+      NR_TICK(6)
+      run_layer<32, 4, 32, 4, 0, 1, 0, 1024 * 4, 0, true, true>(b);               // prob_embed.2
       float gate;
       {
         float h8[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) h8[j] = sw[SW_NF0B + j];
+        {
+          float x[32];
+          load_d32(b, 0, x);
+          add_bias32(x, sw + SW_PE1B);                                               // neuray_feat
 #pragma unroll
-        for (int c0 = 0; c0 < 32; c0 += 16) {
-          float x[16];
-          load_d16(b, c0, x);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            x[j] += sw[SW_PE1B + c0 + j];                                            // neuray_feat
-            const float4 wa = *reinterpret_cast<const float4*>(sw + SW_NF0W + (c0 + j) * 8);
-            const float4 wb = *reinterpret_cast<const float4*>(sw + SW_NF0W + (c0 + j) * 8 + 4);
+          for (int j = 0; j < 32; ++j) {
+            const float4 wa = *reinterpret_cast<const float4*>(sw + SW_NF0W + j * 8);
+            const float4 wb = *reinterpret_cast<const float4*>(sw + SW_NF0W + j * 8 + 4);
             h8[0] = fmaf(wa.x, x[j], h8[0]); h8[1] = fmaf(wa.y, x[j], h8[1]); h8[2] = fmaf(wa.z, x[j], h8[2]); h8[3] = fmaf(wa.w, x[j], h8[3]);
             h8[4] = fmaf(wb.x, x[j], h8[4]); h8[5] = fmaf(wb.y, x[j], h8[5]); h8[6] = fmaf(wb.z, x[j], h8[6]); h8[7] = fmaf(wb.w, x[j], h8[7]);
           }
-          store_a16(b, 40 + c0, x);                                                  // base_fc.0 input columns 40..71
+          store_a32(b, 40, x);                                                       // base_fc.0 input columns 40..71
         }
         gate = sw[SW_NF1B];
 #pragma unroll
@@ -521,6 +627,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
           tc::tmem_st8(b.tAlo + 32, lo8);
         }
       }
+      NR_TICK(7)
       sync_compute();
       {
         float msum = 0.f;
@@ -528,14 +635,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
         const float w1 = mrow / (msum + 1e-8f);
         at<LD>(tS, S_W1, r) = w1;
         at<LD>(tS, S_W0, r) = sigmoidf_(gate) * w1;
-        if (v == 0 && row_ok) parr[P_NV * LDP + p] = msum;
+        if (v == 0 && row_ok) pnv[p] = msum;
       }
       sync_compute();
 
+      NR_TICK(8)
       // ---------------- phase 5: weighted mean/var over views of rgb_feat, twice ----------------
       for (int it = tid; it < P * 35; it += NT) {
         const int f = it / P, q = it - f * P;
         float m0 = 0.f, m1 = 0.f;
+#pragma unroll 8
         for (int vv = 0; vv < rfn; ++vv) {
           const int rr = vv * P + q;
           const float x = at<LD>(tA, f, rr);
@@ -543,6 +652,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
           m1 = fmaf(x, at<LD>(tS, S_W1, rr), m1);
         }
         float v0 = 0.f, v1 = 0.f;
+#pragma unroll 8
         for (int vv = 0; vv < rfn; ++vv) {
           const int rr = vv * P + q;
           const float x = at<LD>(tA, f, rr);
@@ -553,21 +663,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
         at<LDP>(tGLOB, 70 + f, q) = m1; at<LDP>(tGLOB, 105 + f, q) = v1;
       }
 
+      NR_TICK(9)
       // ---------------- phase 6: hoisted base_fc.0 on the 140 view-invariant inputs (SIMT, per point) ----------------
       {
         Frag<64, 4, 2> f;
         f.setup(c);
         f.zero();
+        stage_wait<1>();                       // group 1 (first 72 rows of W_hoist^T) has landed
         sync_compute();
-        pk::stage(c, W + lay::HOIST_W, 72 * 64);
+        if (f.r0 < P) f.mac<72, LDP>(tGLOB, 0, wbufA);
+        stage_wait<0>();                       // group 2
         sync_compute();
-        if (f.r0 < P) f.mac<72, LDP>(tGLOB, 0, c.wbuf);
-        sync_compute();
-        pk::stage(c, W + lay::HOIST_W + 72 * 64, 68 * 64 + 64);
-        sync_compute();
+        stage_async(wbufA, W + lay::GRP_D2 + lay::GEO0_W, 65 * 64 + 64, tid);      // group 3: geometry_fc.0 -> buffer A
         if (f.r0 < P) {
-          f.mac<68, LDP>(tGLOB, 72, c.wbuf);
-          const float* __restrict__ hb = c.wbuf + 68 * 64;
+          f.mac<68, LDP>(tGLOB, 72, wbufB);
+          const float* __restrict__ hb = wbufB + 68 * 64;
           f.store([&](int col, int r4, float4 v4) {
             const float bv = hb[col];
             at4<LDP>(tG, col, r4) = make_float4(v4.x + bv, v4.y + bv, v4.z + bv, v4.w + bv);
@@ -575,65 +685,79 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
         }
       }
       sync_compute();
+      stage_async(wbufB, W + lay::GRP_D2 + lay::GEO1_W, 64 * 16 + 16, tid);        // group 4: geometry_fc.2 -> buffer B
 
+      NR_TICK(10)
       // ---------------- phase 7: base_fc on the tensor cores ----------------
-      run_layer<64>(b, 9, 0, 9, 0, 3, 1, 0, 2048 * 4, 0, true, true);               // base_fc.0: K = 72, three ring stages
+      run_layer<64, 9, 0, 9, 0, 3, 0, 2048 * 4, 0, true, true>(b);               // base_fc.0: K = 72, three ring stages
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 16) {
-        float x[16];
-        load_d16(b, c0, x);
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        float x[32];
+        load_d32(b, c0, x);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = elu(x[j] + at<LDP>(tG, c0 + j, p));
-        store_a16(b, c0, x);
+        for (int j = 0; j < 32; ++j) x[j] = elu(x[j] + at<LDP>(tG, c0 + j, p));
+        store_a32(b, c0, x);
       }
-      run_layer<32>(b, 8, 0, 8, 0, 1, 2, 0, 2048 * 4, 4096, true, true);            // base_fc.2: K = 64
+      NR_TICK(11)
+      run_layer<32, 8, 0, 8, 0, 1, 0, 2048 * 4, 4096, true, true>(b);            // base_fc.2: K = 64
       float xr[32];
+      load_d32(b, 0, xr);
+      add_bias32(xr, sw + SW_B1B);
 #pragma unroll
-      for (int c0 = 0; c0 < 32; c0 += 16) {
-        load_d16(b, c0, xr + c0);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) xr[c0 + j] = elu(xr[c0 + j] + sw[SW_B1B + c0 + j]);
-        store_a16(b, c0, xr + c0);
-      }
+      for (int j = 0; j < 32; ++j) xr[j] = elu(xr[j]);
+      store_a32(b, 0, xr);
 
+      NR_TICK(12)
       // ---------------- phase 8: vis_fc, vis_fc2, rgb_fc ----------------
       const float w1row = at<LD>(tS, S_W1, r);
-      run_layer<32>(b, 4, 0, 4, 0, 1, 1, 0, 1024 * 4, 0, true, false);               // vis_fc.0 (row scale folded into the epilogue)
+      if (kp.timing != nullptr && blockIdx.x == 0 && tile_it < 64) b.tk = kp.timing + (tile_it * 2 + (tid >> 7)) * 32 + 22;
+      run_layer<32, 4, 0, 4, 0, 1, 0, 1024 * 4, 0, true, false>(b);               // vis_fc.0 (row scale folded into the epilogue)
+      b.tk = nullptr;
       float lg = sw[SW_V1LB];
+      {
+        float x[32];
+        load_d32(b, 0, x);
+        NR_TICK(29)
 #pragma unroll
-      for (int c0 = 0; c0 < 32; c0 += 16) {
-        float x[16];
-        load_d16(b, c0, x);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          x[j] = elu(fmaf(w1row, x[j], sw[SW_V0B + c0 + j]));
-          lg = fmaf(sw[SW_V1LW + c0 + j], x[j], lg);
+        for (int q = 0; q < 8; ++q) {
+          const float4 bb = *reinterpret_cast<const float4*>(sw + SW_V0B + 4 * q);
+          const float4 wl = *reinterpret_cast<const float4*>(sw + SW_V1LW + 4 * q);
+          x[4 * q] = elu(fmaf(w1row, x[4 * q], bb.x)); x[4 * q + 1] = elu(fmaf(w1row, x[4 * q + 1], bb.y));
+          x[4 * q + 2] = elu(fmaf(w1row, x[4 * q + 2], bb.z)); x[4 * q + 3] = elu(fmaf(w1row, x[4 * q + 3], bb.w));
+          lg = fmaf(wl.w, x[4 * q + 3], fmaf(wl.z, x[4 * q + 2], fmaf(wl.y, x[4 * q + 1], fmaf(wl.x, x[4 * q], lg))));
         }
-        store_a16(b, 32 + c0, x);
+        NR_TICK(28)
+        store_a32(b, 32, x);
       }
+      NR_TICK(13)
       const float visa = sigmoidf_(elu(lg)) * mrow;
-      run_layer<32>(b, 4, 32, 4, 0, 1, 1, 2048 * 4, 3072 * 4, 0, false, true);       // vis_fc.2 outputs 0..31 (residual)
+      run_layer<32, 4, 32, 4, 0, 1, 2048 * 4, 3072 * 4, 0, false, true>(b);       // vis_fc.2 outputs 0..31 (residual)
+      {
+        float x[32];
+        load_d32(b, 0, x);
+        add_bias32(x, sw + SW_V1B);
 #pragma unroll
-      for (int c0 = 0; c0 < 32; c0 += 16) {
-        float x[16];
-        load_d16(b, c0, x);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          xr[c0 + j] += elu(x[j] + sw[SW_V1B + c0 + j]);
-          at<LD>(tRF, c0 + j, r) = xr[c0 + j];                                       // x for the second view reduction
+        for (int j = 0; j < 32; ++j) {
+          xr[j] += elu(x[j]);
+          at<LD>(tRF, j, r) = xr[j];                                                 // x for the second view reduction
         }
-        store_a16(b, c0, xr + c0);
+        store_a32(b, 0, xr);
       }
-      run_layer<32>(b, 4, 0, 4, 0, 1, 1, 0, 1024 * 4, 0, true, false);               // vis_fc2.0
+      NR_TICK(14)
+      run_layer<32, 4, 0, 4, 0, 1, 0, 1024 * 4, 0, true, false>(b);               // vis_fc2.0
       float vis2;
       {
         float l2 = sw[SW_V21B];
+        {
+          float x[32];
+          load_d32(b, 0, x);
 #pragma unroll
-        for (int c0 = 0; c0 < 32; c0 += 16) {
-          float x[16];
-          load_d16(b, c0, x);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) l2 = fmaf(sw[SW_V21W + c0 + j], elu(fmaf(visa, x[j], sw[SW_V20B + c0 + j])), l2);
+          for (int q = 0; q < 8; ++q) {
+            const float4 bb = *reinterpret_cast<const float4*>(sw + SW_V20B + 4 * q);
+            const float4 wl = *reinterpret_cast<const float4*>(sw + SW_V21W + 4 * q);
+            l2 = fmaf(wl.x, elu(fmaf(visa, x[4 * q], bb.x)), l2); l2 = fmaf(wl.y, elu(fmaf(visa, x[4 * q + 1], bb.y)), l2);
+            l2 = fmaf(wl.z, elu(fmaf(visa, x[4 * q + 2], bb.z)), l2); l2 = fmaf(wl.w, elu(fmaf(visa, x[4 * q + 3], bb.w)), l2);
+          }
         }
         vis2 = sigmoidf_(l2) * mrow;
         at<LD>(tS, S_VIS2, r) = vis2;
@@ -643,7 +767,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
         x[0] = vis2; x[1] = dd[0]; x[2] = dd[1]; x[3] = dd[2]; x[4] = dd[3];
         store_a16(b, 32, x);                                                         // A[32:40] = vis, ray_diff, 0
       }
-      run_layer<16>(b, 5, 0, 4, 32, 1, 2, 2048 * 4, 3072 * 4, 2048, false, true);    // rgb_fc.0: K = 32 + 8, N = 16
+      NR_TICK(15)
+      run_layer<16, 5, 0, 4, 32, 1, 2048 * 4, 3072 * 4, 2048, false, true>(b);    // rgb_fc.0: K = 32 + 8, N = 16
       {
         float x[16];
         load_d16(b, 0, x);
@@ -663,6 +788,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
         for (int j = 0; j < 8; ++j) l3 = fmaf(sw[SW_RGB2W + j], elu(h8[j]), l3);
         at<LD>(tS, S_LOGIT, r) = mrow == 0.f ? -1e9f : l3;
       }
+      NR_TICK(16)
       sync_compute();
       {
         float s = 0.f;
@@ -671,6 +797,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
       }
       sync_compute();
 
+      NR_TICK(17)
       // ---------------- phase 9: per-point softmax blend + second weighted mean/var ----------------
       if (tid < P) {
         const int q = tid;
@@ -684,14 +811,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
           cr = fmaf(e, at<LD>(tS, S_R, rr), cr); cg = fmaf(e, at<LD>(tS, S_G, rr), cg); cb = fmaf(e, at<LD>(tS, S_B, rr), cb);
         }
         at<LDP>(tGOUT, 16, q) = cr / den; at<LDP>(tGOUT, 17, q) = cg / den; at<LDP>(tGOUT, 18, q) = cb / den;
-        at<LDP>(tGOUT, 19, q) = parr[P_NV * LDP + q];
+        at<LDP>(tGOUT, 19, q) = pnv[q];
       }
       for (int it = tid; it < P * 33; it += NT) {
         const int f = it / P, q = it - f * P;
         if (f < 32) {
           float m = 0.f;
+#pragma unroll 8
           for (int vv = 0; vv < rfn; ++vv) m = fmaf(at<LD>(tRF, f, vv * P + q), at<LD>(tS, S_W2, vv * P + q), m);
           float vr = 0.f;
+#pragma unroll 8
           for (int vv = 0; vv < rfn; ++vv) {
             const float x = at<LD>(tRF, f, vv * P + q);
             vr = fmaf(at<LD>(tS, S_W2, vv * P + q), (x - m) * (x - m), vr);
@@ -704,32 +833,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
         }
       }
 
+      NR_TICK(18)
       // ---------------- phase 10: geometry_fc per point (SIMT) ----------------
-      sync_compute();
-      pk::stage(c, W + lay::GRP_D2 + lay::GEO0_W, 65 * 64 + 64);
+      stage_wait<1>();                         // group 3
       sync_compute();
       {
         Frag<64, 4, 2> f;
         f.setup(c);
         if (f.r0 < P) {
-          f.init_bias(c.wbuf + 65 * 64);
-          f.mac<65, LDP>(tGVEC, 0, c.wbuf);
+          f.init_bias(wbufA + 65 * 64);
+          f.mac<65, LDP>(tGVEC, 0, wbufA);
           f.store([&](int col, int r4, float4 v4) { at4<LDP>(tGHID, col, r4) = elu4(v4); });
         }
       }
-      sync_compute();
-      pk::stage(c, W + lay::GRP_D2 + lay::GEO1_W, 64 * 16 + 16);
+      NR_TICK(19)
+      stage_wait<0>();                         // group 4
       sync_compute();
       {
         Frag<16, 4, 1> f;
         f.setup(c);
         if (f.r0 < P) {
-          f.init_bias(c.wbuf + 64 * 16);
-          f.mac<64, LDP>(tGHID, 0, c.wbuf);
+          f.init_bias(wbufB + 64 * 16);
+          f.mac<64, LDP>(tGHID, 0, wbufB);
           f.store([&](int col, int r4, float4 v4) { at4<LDP>(tGOUT, col, r4) = elu4(v4); });
         }
       }
       sync_compute();
+      NR_TICK(20)
       {
         const int cnt = min(P, N - n0) * REC;
         float* __restrict__ dst = pp.point_rec + size_t(n0) * REC;
@@ -738,6 +868,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
           dst[i] = at<LDP>(tGOUT, cc, q);
         }
       }
+      NR_TICK(21)
     }
   }
 
@@ -749,10 +880,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
 
 }  // namespace pkt
 
+static long long* g_timing = nullptr;   // diagnostics only (nr_point_kernel_timing)
+void set_point_kernel_timing(long long* buf) { g_timing = buf; }
+
 int launch_point_kernel_tc(const NrPassParams* p, float* dbg, cudaStream_t stream) {
   pkt::KParams kp;
   kp.p = *p;
   kp.dbg = dbg;
+  kp.timing = g_timing;
   kp.P = (pkt::LD / p->rfn) & ~3;
   if (kp.P > pkt::LDP) kp.P = pkt::LDP;
   const long long N = (long long)p->rn * p->dn;

@@ -1,0 +1,56 @@
+"""Per-phase critical-path timing of the tensor-core point kernel (clock64 stamps, CTA 0).  usage: phase_timing.py [rays]"""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from neuray_b200 import _lib, renderer, synthetic  # noqa: E402
+from neuray_b200.weights import camera_block  # noqa: E402
+
+rays = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+h, w, rfn, dn_c, dn_f, _ = bench.WORKLOADS["black_800"]
+cfg = bench.model_cfg(dn_c, dn_f)
+que, ref = synthetic.make_scene(h, w, rfn, seed=0, smooth=2, with_que_imgs=False)
+n = que["coords"].shape[1]
+start = (n // 2 // w) * w
+que = synthetic.slice_rays(que, start, start + rays)
+W = synthetic.make_weights(cfg, seed=0)
+net = renderer.NeuralRayRenderPath(cfg)
+net.load_state_dict(W, strict=True)
+net.cuda()
+dq, dr = synthetic.to_device(que, "cuda"), synthetic.to_device(ref, "cuda")
+out = net.render_impl(dq, dr, False)          # warm-up, builds caches
+depth = renderer.sample_depth(dq["depth_range"], dq["coords"], dn_c, False)[0]
+pack = renderer.frame_pack(dr)
+wp, wr, pe, wt = renderer.pass_weights(net, False, dn_c, depth.device)
+cam = camera_block(dq["poses"][0], dq["Ks"][0], dq["depth_range"][0])
+rec = torch.empty(rays * dn_c * 20, device="cuda")
+timing = torch.zeros(64 * 2 * 32, dtype=torch.int64, device="cuda")
+p = _lib.NrPassParams()
+coords = dq["coords"][0].contiguous()
+p.coords, p.que_depth, p.que_cam, p.rn, p.dn = coords.data_ptr(), depth.data_ptr(), cam.data_ptr(), rays, dn_c
+p.feat, p.rgb, p.view_params = pack.feat.data_ptr(), pack.rgb.data_ptr(), pack.view_params.data_ptr()
+p.rfn, p.h, p.w, p.fh, p.fw = pack.rfn, pack.h, pack.w, pack.fh, pack.fw
+p.w_point, p.w_ray, p.pos_enc, p.w_tc = wp.data_ptr(), wr.data_ptr(), pe.data_ptr(), wt.data_ptr()
+p.use_vis, p.var_bias, p.point_rec = 0, 0.05, rec.data_ptr()
+_lib.check(_lib.lib().nr_point_kernel_timing(C.byref(p), timing.data_ptr(), None), "timing")
+torch.cuda.synchronize()
+t = timing.cpu().reshape(64, 2, 32)
+names = ["start", "geo-wait", "ph1 proj", "ph2 gather", "RF->A", "dd heads", "cprob+pe0", "pe1+nf+raydir", "w1 syncs", "R1", "hoist", "base0",
+         "base1", "vis0", "vis1", "v20", "rgb0", "w2 syncs", "ph9", "geo0", "geo1", "output"]
+for blk in (0, 1):
+    d = (t[4:40, blk, 1:22] - t[4:40, blk, 0:21]).double().mean(0)
+    tot = (t[4:40, blk, 21] - t[4:40, blk, 0]).double().mean()
+    print(f"block {blk}: tile total {tot:.0f} cycles")
+    print("  " + "  ".join(f"{names[i + 1]}:{d[i]:.0f}" for i in range(21)))
+for blk in (0, 1):
+    m = t[4:40, blk].double()
+    print(f"block {blk} vis_fc.0 layer: st_wait+bar {float((m[:,24]-m[:,22]).mean()):.0f}  wfull-wait {float((m[:,25]-m[:,24]).mean()):.0f}  "
+          f"issue+commit {float((m[:,26]-m[:,25]).mean()):.0f}  mma-wait {float((m[:,27]-m[:,26]).mean()):.0f}  "
+          f"ld32 {float((m[:,29]-m[:,27]).mean()):.0f}  epilogue {float((m[:,28]-m[:,29]).mean()):.0f}  store_a32 {float((m[:,13]-m[:,28]).mean()):.0f}")
+gap = (t[5:40, 0, 0] - t[4:39, 0, 21]).double().mean()
+print(f"gap between tiles {gap:.0f}")
