@@ -83,9 +83,10 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_threads():
-    """Threads for the CPU arm: all host cores up to 32 -- beyond that torch's intra-op pool only adds contention on
-    this op mix (128 threads measured 27x slower than 8 on the same rays, profiles/r1_notes.md)."""
-    return max(1, min(os.cpu_count() or 1, int(os.environ.get("NR_CPU_THREADS", "32"))))
+    """Threads for the CPU arm: the measured optimum on the GPU box's 128-core host is 16 (8: 61 k, 16: 67 k, 32: 63 k,
+    64: 22 k, 128: 1.6 k ray-samples/s on the same rays, profiles/README.md): beyond that torch's intra-op pool only adds
+    contention on this op mix of many small tensors."""
+    return max(1, min(os.cpu_count() or 1, int(os.environ.get("NR_CPU_THREADS", "16"))))
 
 
 def oracle_throughput(wl, n_rays, steps, warmup, threads):
@@ -268,11 +269,11 @@ def run_b200(args):
                 "ms_per_step": t_e2e / args.steps * 1e3},
         "gpu_launches": launches,
         "clocks": sampler.summary(),
-        "roofline": {"bound": "tensor", "kernel": "nr::pk::point_kernel", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+        "roofline": {"bound": "tensor", "kernel": "nr::pkt::point_kernel_tc", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": f"{peaks_src} bf16_tflops_sustained",
                      "flops_per_ray_sample": fl, "launches": n_launch, "avg_launch_ms": sum(pk_ms) / max(n_launch, 1),
                      "share_of_step": pk_time / t_res,
-                     "note": "fp32 SIMT FFMA kernel today (no tcgen05 yet): fraction is of the tensor-pipe peak it will move to"},
+                     "note": "dense layers on tcgen05 with 3xTF32 (3 MMAs per algorithmic one); the kernel is epilogue/latency bound, not tensor-pipe bound (profiles/README.md)"},
         "roofline_gather": {"bound": "hbm", "achieved": gather_gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gather_gbs / peak_hbm,
                             "bytes_per_ray_sample": rfn * 1072,
                             "note": "gather runs inside the point kernel; algorithmic bytes / point-kernel time"},

@@ -665,27 +665,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
 
       NR_TICK(9)
       // ---------------- phase 6: hoisted base_fc.0 on the 140 view-invariant inputs (SIMT, per point) ----------------
+      // 32 points x 64 outputs x K 140: every thread takes a 4-point x 8-output register tile over one quarter of K
+      // (K split 36|36|36|32 across the four warp pairs), then the three upper partial sums are added in a fixed order
+      // (deterministic).  The previous 64-thread version was 11.7 k cycles of the 96 k-cycle tile.
       {
         Frag<64, 4, 2> f;
-        f.setup(c);
+        const int ks = tid >> 6;                      // K quarter (warp-uniform)
+        f.r0 = ((tid & 63) >> 3) * 4;                 // points r0..r0+3
+        f.ja = (tid & 7) * 4;
+        f.jb = 32 + f.ja;
         f.zero();
-        stage_wait<1>();                       // group 1 (first 72 rows of W_hoist^T) has landed
-        sync_compute();
-        if (f.r0 < P) f.mac<72, LDP>(tGLOB, 0, wbufA);
-        stage_wait<0>();                       // group 2
-        sync_compute();
-        stage_async(wbufA, W + lay::GRP_D2 + lay::GEO0_W, 65 * 64 + 64, tid);      // group 3: geometry_fc.0 -> buffer A
+        stage_wait<0>();                              // groups 1,2: both halves of W_hoist^T have landed
+        sync_compute();                               // (also: the view reductions above are complete)
         if (f.r0 < P) {
-          f.mac<68, LDP>(tGLOB, 72, wbufB);
-          const float* __restrict__ hb = wbufB + 68 * 64;
+          if (ks == 0) f.mac<36, LDP>(tGLOB, 0, wbufA);
+          else if (ks == 1) f.mac<36, LDP>(tGLOB, 36, wbufA + 36 * 64);
+          else if (ks == 2) f.mac<36, LDP>(tGLOB, 72, wbufB);
+          else f.mac<32, LDP>(tGLOB, 108, wbufB + 36 * 64);
+        }
+        float hb[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hb[j] = wbufB[68 * 64 + (j < 4 ? f.ja : f.jb - 4) + j];
+        sync_compute();                               // all reads of the weight buffers and of GLOB are done
+        float* const part = wbufA;                    // partials of K quarters 1,2 -> wbufA, quarter 3 -> the dead GLOB tile
+        if (f.r0 < P && ks > 0) {
+          float* dst = ks == 3 ? tGLOB : part + (ks - 1) * 64 * LDP;
+          f.store([&](int col, int r4, float4 v4) { at4<LDP>(dst, col, r4) = v4; });
+        }
+        sync_compute();
+        if (f.r0 < P && ks == 0) {
+          int jj = 0;
           f.store([&](int col, int r4, float4 v4) {
-            const float bv = hb[col];
-            at4<LDP>(tG, col, r4) = make_float4(v4.x + bv, v4.y + bv, v4.z + bv, v4.w + bv);
+            const float4 p1 = at4<LDP>(part, col, r4), p2 = at4<LDP>(part + 64 * LDP, col, r4), p3 = at4<LDP>(tGLOB, col, r4);
+            const float bv = hb[jj++];
+            at4<LDP>(tG, col, r4) = make_float4(((v4.x + p1.x) + p2.x) + p3.x + bv, ((v4.y + p1.y) + p2.y) + p3.y + bv,
+                                                ((v4.z + p1.z) + p2.z) + p3.z + bv, ((v4.w + p1.w) + p2.w) + p3.w + bv);
           });
         }
       }
       sync_compute();
-      stage_async(wbufB, W + lay::GRP_D2 + lay::GEO1_W, 64 * 16 + 16, tid);        // group 4: geometry_fc.2 -> buffer B
+      stage_async(wbufA, W + lay::GRP_D2 + lay::GEO0_W, 65 * 64 + 64, tid);      // group 3: geometry_fc.0 -> buffer A
+      stage_async(wbufB, W + lay::GRP_D2 + lay::GEO1_W, 64 * 16 + 16, tid);      // group 4: geometry_fc.2 -> buffer B
 
       NR_TICK(10)
       // ---------------- phase 7: base_fc on the tensor cores ----------------
@@ -834,28 +854,69 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
       }
 
       NR_TICK(18)
-      // ---------------- phase 10: geometry_fc per point (SIMT) ----------------
-      stage_wait<1>();                         // group 3
+      // ---------------- phase 10: geometry_fc per point (SIMT, K split across warp pairs / warps) ----------------
+      stage_wait<0>();                         // groups 3,4
       sync_compute();
       {
-        Frag<64, 4, 2> f;
-        f.setup(c);
+        Frag<64, 4, 2> f;                      // geometry_fc.0: 65 -> 64, K split 20|16|16|13
+        const int ks = tid >> 6;
+        f.r0 = ((tid & 63) >> 3) * 4;
+        f.ja = (tid & 7) * 4;
+        f.jb = 32 + f.ja;
+        f.zero();
         if (f.r0 < P) {
-          f.init_bias(wbufA + 65 * 64);
-          f.mac<65, LDP>(tGVEC, 0, wbufA);
-          f.store([&](int col, int r4, float4 v4) { at4<LDP>(tGHID, col, r4) = elu4(v4); });
+          if (ks == 0) f.mac<20, LDP>(tGVEC, 0, wbufA);
+          else if (ks == 1) f.mac<16, LDP>(tGVEC, 20, wbufA + 20 * 64);
+          else if (ks == 2) f.mac<16, LDP>(tGVEC, 36, wbufA + 36 * 64);
+          else f.mac<13, LDP>(tGVEC, 52, wbufA + 52 * 64);
+        }
+        float gb[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gb[j] = wbufA[65 * 64 + (j < 4 ? f.ja : f.jb - 4) + j];
+        sync_compute();                        // weights (wbufA) and GVEC fully consumed
+        float* const part = wbufA;             // quarters 1,2 -> wbufA, quarter 3 -> the dead GVEC tile
+        if (f.r0 < P && ks > 0) {
+          float* dst = ks == 3 ? tGVEC : part + (ks - 1) * 64 * LDP;
+          f.store([&](int col, int r4, float4 v4) { at4<LDP>(dst, col, r4) = v4; });
+        }
+        sync_compute();
+        if (f.r0 < P && ks == 0) {
+          int jj = 0;
+          f.store([&](int col, int r4, float4 v4) {
+            const float4 p1 = at4<LDP>(part, col, r4), p2 = at4<LDP>(part + 64 * LDP, col, r4), p3 = at4<LDP>(tGVEC, col, r4);
+            const float bv = gb[jj++];
+            at4<LDP>(tGHID, col, r4) = elu4(make_float4(((v4.x + p1.x) + p2.x) + p3.x + bv, ((v4.y + p1.y) + p2.y) + p3.y + bv,
+                                                         ((v4.z + p1.z) + p2.z) + p3.z + bv, ((v4.w + p1.w) + p2.w) + p3.w + bv));
+          });
         }
       }
       NR_TICK(19)
-      stage_wait<0>();                         // group 4
       sync_compute();
       {
-        Frag<16, 4, 1> f;
-        f.setup(c);
-        if (f.r0 < P) {
-          f.init_bias(wbufB + 64 * 16);
-          f.mac<64, LDP>(tGHID, 0, wbufB);
-          f.store([&](int col, int r4, float4 v4) { at4<LDP>(tGOUT, col, r4) = elu4(v4); });
+        Frag<16, 4, 1> f;                      // geometry_fc.2: 64 -> 16, one K slice of 8 per warp
+        const int ks = warp;
+        f.r0 = (lane >> 2) * 4;
+        f.ja = (lane & 3) * 4;
+        f.jb = 0;
+        f.zero();
+        if (f.r0 < P) f.mac<8, LDP>(tGHID, 8 * ks, wbufB + 8 * ks * 16);
+        const float4 gb = *reinterpret_cast<const float4*>(wbufB + 64 * 16 + f.ja);
+        float* const part = wbufA;             // 7 partial tiles [16][LDP]
+        if (f.r0 < P && ks > 0) f.store([&](int col, int r4, float4 v4) { at4<LDP>(part + (ks - 1) * 16 * LDP, col, r4) = v4; });
+        sync_compute();
+        if (f.r0 < P && ks == 0) {
+          int jj = 0;
+          f.store([&](int col, int r4, float4 v4) {
+            float4 acc = v4;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+              const float4 pk_ = at4<LDP>(part + k * 16 * LDP, col, r4);
+              acc.x += pk_.x; acc.y += pk_.y; acc.z += pk_.z; acc.w += pk_.w;
+            }
+            const float bv = jj == 0 ? gb.x : jj == 1 ? gb.y : jj == 2 ? gb.z : gb.w;
+            ++jj;
+            at4<LDP>(tGOUT, col, r4) = elu4(make_float4(acc.x + bv, acc.y + bv, acc.z + bv, acc.w + bv));
+          });
         }
       }
       sync_compute();
