@@ -118,21 +118,13 @@ def _check_supported(owner):
         raise NotImplementedError("use_dr_prediction (direct rendering / SH fit) is outside the B200 hot path (SURVEY.md 8f)")
 
 
-def run_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine=None, want_hit=True):
-    """One fused pass.  que_depth [1,rn,dn].  `fine`: None or dict(dn=, use_all=, u=, u_stride=) to also emit the
-    next pass' depths.  Returns dict with pixel_colors [1,rn,3], hit_prob [1,rn,dn], render_depth [1,rn],
-    ray_mask [1,rn] (bool) and optionally fine_depth [1,rn,M]."""
-    _check_supported(owner)
+def _launch_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine, want_hit):
+    """Enqueues the two kernels of one pass; returns the raw output dict (ray_mask as uint8)."""
     cfg = owner.cfg
     coords = que_imgs_info["coords"]
-    if coords.shape[0] != 1:
-        raise _lib.NeurayB200Error("one query view per call (qn == 1), like every call site of the reference")
     dev = coords.device
     pack = frame_pack(ref_imgs_info)
-    que_depth = que_depth.detach().contiguous().float()
     _, rn, dn = que_depth.shape
-    if dn > _lib.NR_MAX_SAMPLES:
-        raise _lib.NeurayB200Error(f"at most {_lib.NR_MAX_SAMPLES} samples per ray per pass, got {dn}")
     dec, agg, _, _ = _pass_modules(owner, is_fine)
     w_point, w_ray, pos_enc, w_tc = pass_weights(owner, is_fine, dn, dev)
     cam = camera_block(que_imgs_info["poses"][0].float(), que_imgs_info["Ks"][0].float(), que_imgs_info["depth_range"][0].float())
@@ -142,7 +134,7 @@ def run_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine=None,
         "pixel_colors": torch.empty(1, rn, 3, dtype=torch.float32, device=dev),
         "hit_prob": torch.empty(1, rn, dn, dtype=torch.float32, device=dev) if (want_hit or fine) else None,
         "render_depth": torch.empty(1, rn, dtype=torch.float32, device=dev),
-        "ray_mask": torch.empty(1, rn, dtype=torch.uint8, device=dev),
+        "ray_mask_u8": torch.empty(1, rn, dtype=torch.uint8, device=dev),
     }
     rec = torch.empty(rn * dn * _lib.NR_POINT_REC, dtype=torch.float32, device=dev)
     p = _lib.NrPassParams()
@@ -161,7 +153,7 @@ def run_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine=None,
     p.ray_mask_view_num, p.ray_mask_point_num = int(cfg["ray_mask_view_num"]), int(cfg["ray_mask_point_num"])
     p.point_rec = _lib.ptr(rec)
     p.pixel_colors, p.hit_prob = _lib.ptr(out["pixel_colors"]), _lib.ptr(out["hit_prob"])
-    p.render_depth, p.ray_mask = _lib.ptr(out["render_depth"]), _lib.ptr(out["ray_mask"])
+    p.render_depth, p.ray_mask = _lib.ptr(out["render_depth"]), _lib.ptr(out["ray_mask_u8"])
     if fine:
         m = fine["dn"] + (dn if fine["use_all"] else 0)
         out["fine_depth"] = torch.empty(1, rn, m, dtype=torch.float32, device=dev)
@@ -179,7 +171,46 @@ def run_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine=None,
     else:
         _lib.check(_lib.lib().nr_render_pass_fwd(C.byref(p), stream), "nr_render_pass_fwd")
     _lib.count_launches(2)
-    out["ray_mask"] = out["ray_mask"].bool()
+    return out
+
+
+def run_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine=None, want_hit=True):
+    """One fused pass.  que_depth [1,rn,dn].  `fine`: None or dict(dn=, use_all=, u=, u_stride=) to also emit the
+    next pass' depths.  Returns dict with pixel_colors [1,rn,3], hit_prob [1,rn,dn], render_depth [1,rn],
+    ray_mask [1,rn] (bool) and optionally fine_depth [1,rn,M].
+
+    When gradients are being recorded and the reference feature maps or any parameter of the pass require them, the
+    outputs are attached to autograd through autograd_path.RenderPassFn (forward values still come from the kernels)."""
+    _check_supported(owner)
+    coords = que_imgs_info["coords"]
+    if coords.shape[0] != 1:
+        raise _lib.NeurayB200Error("one query view per call (qn == 1), like every call site of the reference")
+    que_depth = que_depth.detach().contiguous().float()
+    _, rn, dn = que_depth.shape
+    if dn > _lib.NR_MAX_SAMPLES:
+        raise _lib.NeurayB200Error(f"at most {_lib.NR_MAX_SAMPLES} samples per ray per pass, got {dn}")
+    dec, agg, dec_name, agg_name = _pass_modules(owner, is_fine)
+    rf, imf = ref_imgs_info["ray_feats"], ref_imgs_info["img_feats"]
+    named = [(f"{dec_name}.{k}", v) for k, v in dec.named_parameters()] + [(f"{agg_name}.{k}", v) for k, v in agg.named_parameters()]
+    needs_grad = torch.is_grad_enabled() and (rf.requires_grad or imf.requires_grad or any(v.requires_grad for _, v in named))
+    launch = lambda: _launch_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine, want_hit)
+    if not needs_grad:
+        out = launch()
+    else:
+        from .autograd_path import RenderPassFn
+        meta = {
+            "names": [n for n, _ in named], "dec": dec_name, "agg": agg_name,
+            "cfgv": {"use_vis_prob": bool(owner.dist_decoder.cfg["use_vis"]), "var_bias": float(dec.cfg["bias_val"])},
+            "que_depth": que_depth, "coords": coords.detach().float(), "que_pose": que_imgs_info["poses"].detach().float(),
+            "que_K": que_imgs_info["Ks"].detach().float(), "que_range": que_imgs_info["depth_range"].detach().float(),
+            "ref": {k: ref_imgs_info[k].detach().float() for k in ("poses", "Ks", "depth_range", "imgs")},
+            "pos_enc": posenc_table(dn).to(coords.device),
+        }
+        res = RenderPassFn.apply(launch, meta, rf, imf, *[v for _, v in named])
+        out = {"pixel_colors": res[0], "hit_prob": res[1], "render_depth": res[2], "ray_mask_u8": res[3]}
+        if fine:
+            out["fine_depth"] = res[4]
+    out["ray_mask"] = out.pop("ray_mask_u8").bool()
     return out
 
 
@@ -195,12 +226,23 @@ def _finish_outputs(owner, res, que_depth, que_imgs_info):
     return outputs
 
 
+def _self_hit_prob(self, que_depth, que_imgs_info, is_fine):
+    """a17 predict_self_hit_prob (reference renderer.py:137-155): fine-tuning only; interim PyTorch (autograd_path.py)."""
+    from .autograd_path import self_hit_prob_torch
+    dec, _, dec_name, _ = _pass_modules(self, is_fine)
+    P = {f"{dec_name}.{k}": v for k, v in dec.named_parameters()}
+    h, w = que_imgs_info["imgs"].shape[-2:]
+    return self_hit_prob_torch(P, dec_name, bool(dec.cfg["use_vis"]), float(dec.cfg["bias_val"]), que_imgs_info["ray_feats"],
+                               que_imgs_info["coords"], h, w, que_depth, que_imgs_info["depth_range"])
+
+
 def render_by_depth(self, que_depth, que_imgs_info, ref_imgs_info, is_train, is_fine):
     """reference renderer.py:168-203."""
-    if is_train and self.cfg["use_self_hit_prob"]:
-        raise NotImplementedError("use_self_hit_prob (finetuning-only self visibility) is not on the B200 path yet (SURVEY.md 8f)")
     res = run_pass(self, que_depth, que_imgs_info, ref_imgs_info, is_fine)
-    return _finish_outputs(self, res, que_depth, que_imgs_info)
+    outputs = _finish_outputs(self, res, que_depth, que_imgs_info)
+    if is_train and self.cfg["use_self_hit_prob"]:
+        outputs["hit_prob_self"] = _self_hit_prob(self, que_depth, que_imgs_info, is_fine)
+    return outputs
 
 
 def _fine_request(self, rn, is_train, device):
@@ -225,17 +267,21 @@ def fine_render_impl(self, coarse_render_info, que_imgs_info, ref_imgs_info, is_
 
 def render_impl(self, que_imgs_info, ref_imgs_info, is_train):
     """reference renderer.py:217-226: coarse pass, fused resampling, fine pass."""
-    if is_train and self.cfg["use_self_hit_prob"]:
-        raise NotImplementedError("use_self_hit_prob (finetuning-only self visibility) is not on the B200 path yet (SURVEY.md 8f)")
     que_depth, _ = sample_depth(que_imgs_info["depth_range"], que_imgs_info["coords"], self.cfg["depth_sample_num"], False)
     hier = bool(self.cfg["use_hierarchical_sampling"])
     rn = que_imgs_info["coords"].shape[1]
     fine = _fine_request(self, rn, is_train, que_depth.device) if hier else None
     res = run_pass(self, que_depth, que_imgs_info, ref_imgs_info, False, fine=fine)
     outputs = _finish_outputs(self, res, que_depth, que_imgs_info)
+    self_hit = is_train and self.cfg["use_self_hit_prob"]
+    if self_hit:
+        outputs["hit_prob_self"] = _self_hit_prob(self, que_depth, que_imgs_info, False)
     if hier:
         res_f = run_pass(self, res["fine_depth"], que_imgs_info, ref_imgs_info, True)
-        for k, v in _finish_outputs(self, res_f, res["fine_depth"], que_imgs_info).items():
+        fine_out = _finish_outputs(self, res_f, res["fine_depth"], que_imgs_info)
+        if self_hit:
+            fine_out["hit_prob_self"] = _self_hit_prob(self, res["fine_depth"], que_imgs_info, True)
+        for k, v in fine_out.items():
             outputs[k + "_fine"] = v
     return outputs
 

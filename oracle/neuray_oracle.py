@@ -428,6 +428,20 @@ def render_by_depth(W, cfg, que_depth, que, ref, is_train, is_fine, keep=None):
     return out
 
 
+def predict_self_hit_prob(W, cfg, que, que_depth, que_dists, is_fine):
+    """renderer.py:137-155: the query view's own ray_feats decoded along its rays (fine-tuning configs).
+    que must hold 'ray_feats' [qn,32,fh,fw] and 'imgs'."""
+    dec = "fine_dist_decoder" if is_fine else "dist_decoder"
+    h, w = que["imgs"].shape[-2:]
+    mask = torch.ones(que["coords"].shape[:2])
+    feats = interpolate_feature_map(que["ray_feats"], que["coords"], mask, h, w)          # qn,rn,32
+    mean, var, vis, aw = dist_decoder_forward(W, dec, feats, cfg[dec + "_use_vis"], cfg[dec + "_bias_val"])
+    un = lambda t: None if t is None else t.unsqueeze(2)
+    # the decoder's OWN compute_prob here (renderer.py:146), so its own use_vis flag
+    _, _, hit = compute_prob(que_depth, que_dists, un(mean), un(var), un(vis), un(aw), False, que["depth_range"], cfg[dec + "_use_vis"])
+    return hit
+
+
 def render_impl(W, cfg, que, ref, is_train, fine_u=None, fine_depth_override=None):
     """renderer.py:205-226.  `fine_u`: training-time uniforms for sample_fine_depth; `fine_depth_override`
     injects externally computed (sorted) fine-pass depths (searchsorted is discontinuous)."""

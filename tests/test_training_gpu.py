@@ -1,0 +1,80 @@
+"""GPU: training-mode plumbing.  Forward values from the CUDA kernels, gradients through the interim autograd path; both
+checked against the CPU oracle's autograd on the same inputs."""
+import pytest
+import torch
+
+import neuray_oracle as orc
+from gen_golden import flat_cfg
+from neuray_b200 import renderer, synthetic
+
+pytestmark = pytest.mark.gpu
+CFG = {"use_hierarchical_sampling": True, "depth_sample_num": 24, "fine_depth_sample_num": 24, "agg_net_cfg": {"sample_num": 24},
+       "fine_agg_net_cfg": {"sample_num": 24}, "render_depth": True, "dist_decoder_cfg": {"use_vis": False}}
+
+
+def test_gradients_match_oracle():
+    que, ref = synthetic.make_scene(40, 48, 5, seed=6, smooth=2)
+    que = synthetic.slice_rays(que, 300, 396)
+    W = synthetic.make_weights(CFG, seed=8)
+    ocfg = flat_cfg({**renderer.base_cfg, **CFG})
+    gw = torch.randn(1, 96, 3)
+    # oracle (CPU autograd); fine pass on the oracle's own fine depths so that both sides see identical samples
+    Wo = {k: v.clone().requires_grad_(True) for k, v in W.items()}
+    ro = dict(ref)
+    ro["ray_feats"] = ref["ray_feats"].clone().requires_grad_(True)
+    ro["img_feats"] = ref["img_feats"].clone().requires_grad_(True)
+    depth, _ = orc.sample_depth(que["depth_range"], que["coords"], 24, False)
+    oc = orc.render_by_depth(Wo, ocfg, depth, que, ro, True, False)
+    fd = torch.sort(orc.sample_fine_depth(depth, oc["hit_prob_nr"].detach(), que["depth_range"], 24, False), -1)[0]
+    of = orc.render_by_depth(Wo, ocfg, fd, que, ro, True, True)
+    ((oc["pixel_colors_nr"] * gw).sum() + (of["pixel_colors_nr"] * gw).sum() * 0.5 + oc["hit_prob_nr"].pow(2).sum() * 0.1).backward()
+
+    net = renderer.NeuralRayRenderPath(CFG)
+    net.load_state_dict(W, strict=True)
+    net.cuda()
+    dq, dr = synthetic.to_device(que, "cuda"), synthetic.to_device(ref, "cuda")
+    dr["ray_feats"].requires_grad_(True)
+    dr["img_feats"].requires_grad_(True)
+    pc = net.render_by_depth(depth.cuda(), dq, dr, True, False)
+    pf = net.render_by_depth(fd.cuda(), dq, dr, True, True)
+    g = gw.cuda()
+    ((pc["pixel_colors_nr"] * g).sum() + (pf["pixel_colors_nr"] * g).sum() * 0.5 + pc["hit_prob_nr"].pow(2).sum() * 0.1).backward()
+    torch.cuda.synchronize()
+    assert torch.allclose(pc["pixel_colors_nr"].detach().cpu(), oc["pixel_colors_nr"].detach(), atol=1e-4)
+    named = dict(net.named_parameters())
+    checked = 0
+    for k, p in named.items():
+        go = Wo[k].grad
+        if go is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        assert p.grad is not None, k
+        assert torch.allclose(p.grad.cpu(), go, atol=5e-5, rtol=5e-3), (k, (p.grad.cpu() - go).abs().max())
+        checked += 1
+    assert checked > 80
+    for k in ("ray_feats", "img_feats"):
+        assert torch.allclose(dr[k].grad.cpu(), ro[k].grad, atol=5e-5, rtol=5e-3), k
+
+
+def test_training_step_runs_and_updates():
+    """render() in training mode (random fine quantiles, hit_prob outputs kept) + backward + optimizer step + re-render:
+    the packed weight buffers must follow the parameter update."""
+    cfg = dict(CFG, ray_batch_num=4096)
+    que, ref = synthetic.make_scene(40, 48, 8, seed=9, smooth=2)
+    que = synthetic.slice_rays(que, 0, 512)
+    net = renderer.NeuralRayRenderPath(cfg)
+    net.load_state_dict(synthetic.make_weights(cfg, seed=1), strict=True)
+    net.cuda()
+    dq, dr = synthetic.to_device(que, "cuda"), synthetic.to_device(ref, "cuda")
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    out = net.render(dq, dr, True)
+    assert {"hit_prob_nr", "hit_prob_nr_fine", "pixel_colors_nr_fine", "pixel_colors_gt"} <= set(out)
+    loss = ((out["pixel_colors_nr"] - out["pixel_colors_gt"]) ** 2).mean() + ((out["pixel_colors_nr_fine"] - out["pixel_colors_gt_fine"]) ** 2).mean()
+    loss.backward()
+    before = out["pixel_colors_nr"].detach().clone()
+    opt.step()
+    with torch.no_grad():
+        after = net.render(dq, dr, False)["pixel_colors_nr"]
+    torch.cuda.synchronize()
+    assert float((after - before).abs().max()) > 1e-6          # weights re-packed after the step
+    assert all(torch.isfinite(p.grad).all() for p in net.parameters() if p.grad is not None)
