@@ -251,7 +251,7 @@ def run_b200(args):
     n_launch = len(pk_ms)
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only (torchrun pins OMP_NUM_THREADS=1)
         threads = cpu_threads()
         v, t = oracle_throughput(args.workload, args.cpu_rays, 1, 1, threads)
         cpu = {"value": v, "unit": "ray-samples/s", "cores": threads, "kind": "port",
