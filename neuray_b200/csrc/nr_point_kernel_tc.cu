@@ -13,6 +13,8 @@
 //     epilogue overlaps the other block's MMAs; CTA-wide syncs only where views are reduced
 //   * gather, projections, per-view scalar heads, the cross-view reductions and the per-point layers (hoisted
 //     base_fc.0, geometry_fc) stay SIMT exactly as in the SIMT kernel
+#include <stdlib.h>
+
 #include "nr_common.cuh"
 #include "nr_point_common.cuh"
 #include "nr_tc.cuh"
@@ -86,6 +88,43 @@ __device__ __forceinline__ void stage_async(float* dst, const float* __restrict_
 template <int N>
 __device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// The weight stream, driven by ONE thread (thread 0) from inside its own MMA-issue path: before it waits for a stage it
+// issues every stage up to that one (blocking on the ring slot if it has to) and opportunistically up to NBUF-1 further.
+struct Producer {
+  const float* w_tc;
+  float* ring;
+  uint64_t *wfull, *wempty;
+  uint32_t next;          // next stage index to issue
+  uint32_t total;         // iters * stages_per_tile
+  int stages_per_tile, n_heads;
+
+  __device__ __forceinline__ void issue() {
+    const int s = int(next % uint32_t(stages_per_tile));
+    int src, bytes = RING_STAGE * 4;
+    if (s < n_heads) src = tcl::HEAD0 + s * RING_STAGE;
+    else {
+      const int t = s - n_heads;
+      src = t == 0 ? tcl::PE0 : t == 1 ? tcl::PE1 : t <= 4 ? tcl::B0 + (t - 2) * RING_STAGE : t == 5 ? tcl::B1 : t == 6 ? tcl::V01 : tcl::V2R;
+      if (t == 1) bytes = 2048 * 4;
+    }
+    const uint32_t buf = next % NBUF;
+    tc::mbar_arrive_expect_tx(wfull + buf, bytes);
+    tc::bulk_g2s(ring + buf * RING_STAGE, w_tc + src, bytes, wfull + buf);
+    ++next;
+  }
+  // make sure stages [.., last] are in flight; then try to run ahead without blocking
+  __device__ __forceinline__ void feed(uint32_t last) {
+    while (next <= last && next < total) {
+      if (next >= NBUF) tc::mbar_wait(wempty + (next % NBUF), ((next / NBUF) - 1) & 1);
+      issue();
+    }
+    while (next < total && next <= last + (NBUF - 1)) {
+      if (next >= NBUF && !tc::mbar_try_wait(wempty + (next % NBUF), ((next / NBUF) - 1) & 1)) break;
+      issue();
+    }
+  }
+};
+
 // Everything a compute thread needs to drive its block's tensor-core layers.
 struct Blk {
   uint32_t tAhi, tAlo, tD;      // TMEM addresses of this thread's lane quadrant (lane field included)
@@ -98,6 +137,7 @@ struct Blk {
   int blk;
   bool leader;
   bool issuer_warp;             // warp 0 of the block (warp-uniform): one elected lane of it issues the MMAs
+  Producer* prod;               // non-null in the one thread that also feeds the weight ring (point-major kernel)
   long long* tk;                // diagnostics: where run_layer drops clock64() stamps (nullptr: off)
 };
 
@@ -116,6 +156,8 @@ __device__ __forceinline__ void run_layer(Blk& b) {
   if (b.issuer_warp) {                       // warp-uniform branch; one elected lane issues
     tc::fence_after_thread_sync();
     const uint32_t st0 = b.wi % NBUF;
+    if (WAIT_FULL && b.prod != nullptr) b.prod->feed(b.wi + NSTG - 1);   // only thread 0 of the point-major kernel
+    __syncwarp();
     if (WAIT_FULL) {
 #pragma unroll
       for (int s = 0; s < NSTG; ++s) tc::mbar_wait(b.wfull + ((st0 + s) % NBUF), ((b.wi + s) / NBUF) & 1);
@@ -354,6 +396,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
     b.phase = 0;
     b.wi = 0;
     b.tk = nullptr;
+    b.prod = nullptr;
 
     int tile_it = 0;
 #define NR_TICK(id)                                                                                   \
@@ -939,12 +982,64 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
   if (warp == 0) tc::tmem_dealloc<512>(tmem_base);
 }
 
+#include "nr_point_kernel_pm.cuh"
+
 }  // namespace pkt
 
 static long long* g_timing = nullptr;   // diagnostics only (nr_point_kernel_timing)
 void set_point_kernel_timing(long long* buf) { g_timing = buf; }
 
+
+template <int G>
+static int launch_pm(const pkt::KParams& kp0, int sms, cudaStream_t stream) {
+  pkt::KParams kp = kp0;
+  constexpr int PB = 128 / G;
+  const long long N = (long long)kp.p.rn * kp.p.dn;
+  kp.P = PB;
+  kp.n_tiles = int((N + PB - 1) / PB);
+  const int pairs = (kp.n_tiles + pkt::pm::NBLK - 1) / pkt::pm::NBLK;
+  const int grid = pairs < sms ? pairs : sms;
+  static bool attr_done[2] = {false, false};
+  if (kp.dbg) {
+    if (!attr_done[1]) {
+      cudaFuncSetAttribute(pkt::pm::point_kernel_pm<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pkt::pm::SMEM_BYTES));
+      attr_done[1] = true;
+    }
+    pkt::pm::point_kernel_pm<G, true><<<grid, pkt::pm::NTHR, pkt::pm::SMEM_BYTES, stream>>>(kp);
+  } else {
+    if (!attr_done[0]) {
+      cudaFuncSetAttribute(pkt::pm::point_kernel_pm<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pkt::pm::SMEM_BYTES));
+      attr_done[0] = true;
+    }
+    pkt::pm::point_kernel_pm<G, false><<<grid, pkt::pm::NTHR, pkt::pm::SMEM_BYTES, stream>>>(kp);
+  }
+  NR_CHECK_LAUNCH("point_kernel_pm");
+  return NR_OK;
+}
+
+// point-major kernel (nr_point_kernel_pm.cuh); the row-per-(view,point) kernel above stays selectable for A/B runs
+int launch_point_kernel_pm(const NrPassParams* p, float* dbg, cudaStream_t stream) {
+  pkt::KParams kp;
+  kp.p = *p;
+  kp.dbg = dbg;
+  kp.timing = g_timing;
+  kp.n_heads = p->use_vis ? 4 : 3;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (p->rfn <= 4) return launch_pm<4>(kp, sms, stream);
+  if (p->rfn <= 8) return launch_pm<8>(kp, sms, stream);
+  if (p->rfn <= 16) return launch_pm<16>(kp, sms, stream);
+  return launch_pm<32>(kp, sms, stream);
+}
+
 int launch_point_kernel_tc(const NrPassParams* p, float* dbg, cudaStream_t stream) {
+  {
+    // default: the point-major kernel; NR_POINT_KERNEL=tc selects the row-per-(view,point) tensor-core kernel and
+    // NR_POINT_KERNEL=simt (host side: w_tc = NULL) the fp32 SIMT kernel -- development A/B switches only
+    const char* sel = getenv("NR_POINT_KERNEL");
+    if (sel == nullptr || !(sel[0] == 't' && sel[1] == 'c')) return launch_point_kernel_pm(p, dbg, stream);
+  }
   pkt::KParams kp;
   kp.p = *p;
   kp.dbg = dbg;

@@ -144,7 +144,7 @@ def _launch_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine, 
     p.rfn, p.h, p.w, p.fh, p.fw = pack.rfn, pack.h, pack.w, pack.fh, pack.fw
     p.w_point, p.w_ray, p.pos_enc = _lib.ptr(w_point), _lib.ptr(w_ray), _lib.ptr(pos_enc)
     # NR_POINT_KERNEL=simt selects the fp32 SIMT point kernel (development A/B switch); default: tcgen05 point kernel
-    p.w_tc = None if os.environ.get("NR_POINT_KERNEL", "tc") == "simt" else _lib.ptr(w_tc)
+    p.w_tc = None if os.environ.get("NR_POINT_KERNEL", "") == "simt" else _lib.ptr(w_tc)
     # compute_prob is always the COARSE decoder's method (reference renderer.py:75): its use_vis decides
     p.use_vis = 1 if owner.dist_decoder.cfg["use_vis"] else 0
     if p.use_vis and not dec.cfg["use_vis"]:

@@ -76,7 +76,7 @@ def test_point_kernel_stage_tap(name):
         p.use_vis = 1 if net.dist_decoder.cfg["use_vis"] else 0
         p.var_bias = dec.cfg["bias_val"]
         p.point_rec = rec.data_ptr()
-        p.w_tc = None if os.environ.get("NR_POINT_KERNEL", "tc") == "simt" else wt.data_ptr()
+        p.w_tc = None if os.environ.get("NR_POINT_KERNEL", "") == "simt" else wt.data_ptr()
         _lib.check(_lib.lib().nr_point_kernel_debug(C.byref(p), dbg.data_ptr(), None), "debug")
         torch.cuda.synchronize()
         d = dbg.reshape(pack.rfn, 1, rn, dn, 76)

@@ -40,6 +40,16 @@ p.use_vis, p.var_bias, p.point_rec = 0, 0.05, rec.data_ptr()
 _lib.check(_lib.lib().nr_point_kernel_timing(C.byref(p), timing.data_ptr(), None), "timing")
 torch.cuda.synchronize()
 t = timing.cpu().reshape(64, 2, 32)
+if os.environ.get("NR_POINT_KERNEL", "pm") == "pm":
+    t = timing.cpu().reshape(64, 2, 32)
+    nm = ["geom+proj", "gather", "RF->A", "dd heads", "cprob+pe0", "pe1+nf+raydir", "pool1+hoist", "base0", "base1", "vis0", "vis1", "v20",
+          "rgb0", "blend", "pool2+geo+rec"]
+    for blk in (0, 1):
+        d = (t[4:40, blk, 1:16] - t[4:40, blk, 0:15]).double().mean(0)
+        tot = (t[4:40, blk, 15] - t[4:40, blk, 0]).double().mean()
+        print(f"block {blk}: tile (16 points x 8 views = 128 rows) total {tot:.0f} cycles")
+        print("  " + "  ".join(f"{nm[i]}:{d[i]:.0f}" for i in range(15)))
+    sys.exit(0)
 names = ["start", "geo-wait", "ph1 proj", "ph2 gather", "RF->A", "dd heads", "cprob+pe0", "pe1+nf+raydir", "w1 syncs", "R1", "hoist", "base0",
          "base1", "vis0", "vis1", "v20", "rgb0", "w2 syncs", "ph9", "geo0", "geo1", "output"]
 for blk in (0, 1):
