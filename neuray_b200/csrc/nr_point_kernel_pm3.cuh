@@ -1,0 +1,737 @@
+// Point kernel, point-major tensor-core version with THREE 128-row blocks per SM (namespace nr::pkt::pm3).
+//
+// Same row ownership and arithmetic as point_kernel_pm (nr_point_kernel_pm.cuh); what changes is the resource plan, so
+// that a third block fits next to the other two and fills the issue slots they leave idle while they wait for their MMAs:
+//   * tensor memory: 160 columns per block instead of 224.  Activations: hi parts at columns [0,64), lo parts at
+//     [64,128), accumulator at [128,160).  base_fc.0 (N = 64) is issued in two K rounds into one accumulator at
+//     [96,160): round A (the 32 neuray_feat inputs) right after prob_embed.2 while they are still the only live A
+//     operand, round B (the 40 rgb_feat inputs, lo parts at [48,88)) after the first view pooling.  Its epilogue reads
+//     the accumulator half by half and writes base_fc.2's operand over the columns it has already consumed.
+//   * shared memory: the gather is transposed in two channel passes (ray_feats, then img_feats) through a per-warp
+//     [32][36] buffer instead of one [32][68] pass; img_feats stay there until ray_dir_fc needs them.
+//   * 384 threads: three warps per SM sub-partition, i.e. at most 168 registers per thread.
+#pragma once
+
+namespace pm3 {
+
+using pm::bsum;
+using pm::bmax;
+using pm::bsum_vec;
+using pm::own_col;
+using pm::ld_cols;
+
+constexpr int NBLK = 3;
+constexpr int NCOMP = NBLK * 128;
+constexpr int NTHR = NCOMP;
+constexpr int TCOLS = 160;                                    // tensor-memory columns per block
+
+// ---- shared memory map (floats) ----
+constexpr int OFF_RING = 0;                                   // NBUF x RING_STAGE
+constexpr int OFF_WH = OFF_RING + NBUF * RING_STAGE;          // hoisted base_fc.0: WT[140][64] | bias[64]
+constexpr int WH = 140 * 64 + 64;
+constexpr int OFF_WG0 = OFF_WH + WH;                          // geometry_fc.0: WT[65][64] | bias[64]
+constexpr int WG0 = 65 * 64 + 64;
+constexpr int OFF_WG1 = OFF_WG0 + WG0;                        // geometry_fc.2: [16][64] (output-major) | bias[16]
+constexpr int WG1 = 64 * 16 + 16;
+constexpr int OFF_SW = OFF_WG1 + WG1;                         // small resident weights (same layout as point_kernel_tc)
+constexpr int GS_ROW = 68;                                    // padded: the points of a warp read their rows conflict-free
+constexpr int OFF_GS = OFF_SW + SW;                           // hoisted partial sums per point: [NBLK][32][GS_ROW]
+constexpr int GS = NBLK * 32 * GS_ROW;
+constexpr int OFF_STG = OFF_GS + GS;                          // gather transposition: per warp [32 rows][36]
+constexpr int STG_ROW = 36;
+constexpr int STG = (NCOMP / 32) * 32 * STG_ROW;
+constexpr int OFF_BAR = OFF_STG + STG;
+constexpr int SMEM_FLOATS = OFF_BAR + 32;
+constexpr size_t SMEM_BYTES = size_t(SMEM_FLOATS) * 4;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(OFF_WH % 4 == 0 && OFF_WG0 % 4 == 0 && OFF_WG1 % 4 == 0 && OFF_SW % 4 == 0 && OFF_GS % 4 == 0 && OFF_STG % 4 == 0, "alignment");
+
+// Layer issue, executed by all 128 threads of the block after they wrote their A columns (b.tAhi / b.mAhi = column 0 of
+// the block).  K chunk c (of NCH) reads A columns AHI + 8c (c < NLIN) or TAILHI + 8(c - NLIN), lo parts LOOFF columns
+// further, and B chunk CB0 + c of the layer's tiles (slab (CB0+c)/4; one ring stage per slab when NSTG > 1); ACC: the
+// first MMA accumulates onto what is already in D.
+template <int N, int NCH, int AHI, int LOOFF, int NLIN, int TAILHI, int DCOL, int CB0, int NSTG, uint32_t OFF_HI, uint32_t OFF_LO,
+          uint32_t SLAB, bool WAIT_FULL, bool RELEASE, bool ACC>
+__device__ __forceinline__ void issue_layer(Blk& b) {
+  tc::tmem_st_wait();
+  tc::fence_before_thread_sync();
+  tc::named_sync(2 + b.blk, 128);
+  if (b.issuer_warp) {                       // warp-uniform branch; one elected lane issues
+    tc::fence_after_thread_sync();
+    const uint32_t st0 = b.wi % NBUF;
+    if (WAIT_FULL && b.prod != nullptr) b.prod->feed(b.wi + NSTG - 1);
+    __syncwarp();
+    if (WAIT_FULL) {
+#pragma unroll
+      for (int s = 0; s < NSTG; ++s) tc::mbar_wait(b.wfull + ((st0 + s) % NBUF), ((b.wi + s) / NBUF) & 1);
+    }
+    if (tc::elect_one()) {
+      constexpr uint32_t idesc = tc::idesc_tf32(N);
+      uint64_t dhi[NSTG], dlo[NSTG];
+#pragma unroll
+      for (int s = 0; s < NSTG; ++s) {
+        const uint32_t base = b.ring_addr + ((st0 + s) % NBUF) * (RING_STAGE * 4);
+        dhi[s] = tc::smem_desc_sw128(base + OFF_HI);
+        dlo[s] = tc::smem_desc_sw128(base + OFF_LO);
+      }
+#pragma unroll
+      for (int ps = 0; ps < 3; ++ps) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int acol = (c < NLIN ? AHI + 8 * c : TAILHI + 8 * (c - NLIN)) + (ps == 1 ? LOOFF : 0);
+          const int cb = CB0 + c;
+          const int slab = cb >> 2;
+          const int stg = NSTG == 1 ? 0 : slab;
+          const uint32_t inc = ((NSTG == 1 ? slab * SLAB : 0u) + (cb & 3) * 32) >> 4;
+          tc::mma_tf32_ts(b.mAhi + DCOL, b.mAhi + acol, (ps == 2 ? dlo[stg] : dhi[stg]) + inc, idesc, ACC || (ps | c) != 0);
+        }
+      }
+      if (RELEASE) {
+#pragma unroll
+        for (int s = 0; s < NSTG; ++s) tc::mma_commit(b.wempty + ((st0 + s) % NBUF));
+      }
+      tc::mma_commit(b.mma_bar);
+    }
+    __syncwarp();
+  }
+  if (RELEASE) b.wi += NSTG;
+}
+__device__ __forceinline__ void wait_layer(Blk& b) {
+  tc::mbar_wait(b.mma_bar, b.phase);
+  b.phase ^= 1;
+  tc::fence_after_thread_sync();
+}
+// the common case: activations hi [0,64) / lo [64,128), accumulator at 128, one ring stage
+template <int N, int NCH, int AHI, int NLIN, int TAILHI, uint32_t OFF_HI, uint32_t OFF_LO, uint32_t SLAB, bool WAIT_FULL, bool RELEASE>
+__device__ __forceinline__ void run_layer(Blk& b) {
+  issue_layer<N, NCH, AHI, 64, NLIN, TAILHI, 128, 0, 1, OFF_HI, OFF_LO, SLAB, WAIT_FULL, RELEASE, false>(b);
+  wait_layer(b);
+}
+
+__device__ __forceinline__ void ld32(const Blk& b, int col, float* v) {
+  tc::tmem_ld16(b.tAhi + col, v);
+  tc::tmem_ld16(b.tAhi + col + 16, v + 16);
+  tc::tmem_ld_wait();
+}
+__device__ __forceinline__ void ld16(const Blk& b, int col, float* v) {
+  tc::tmem_ld16(b.tAhi + col, v);
+  tc::tmem_ld_wait();
+}
+// 16 / 32 / 8 activations -> hi parts at `hi`, lo parts at `lo`
+__device__ __forceinline__ void st16(const Blk& b, int hi, int lo, const float* v) {
+  uint32_t h[16], l[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) tc::split_tf32(v[j], h[j], l[j]);
+  tc::tmem_st16(b.tAhi + hi, h);
+  tc::tmem_st16(b.tAhi + lo, l);
+}
+__device__ __forceinline__ void st32(const Blk& b, int hi, int lo, const float* v) {
+  st16(b, hi, lo, v);
+  st16(b, hi + 16, lo + 16, v + 16);
+}
+__device__ __forceinline__ void st8(const Blk& b, int hi, int lo, const float* v) {
+  uint32_t h[8], l[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) tc::split_tf32(v[j], h[j], l[j]);
+  tc::tmem_st8(b.tAhi + hi, h);
+  tc::tmem_st8(b.tAhi + lo, l);
+}
+
+template <int G, bool DEBUG>
+__global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
+  extern __shared__ __align__(1024) float smem[];
+  constexpr int PB = 128 / G;          // points per block
+  constexpr int CPL = 64 / G;          // hoist / geometry_fc.0 output columns per lane
+  static_assert(G == 4 || G == 8 || G == 16 || G == 32, "lanes per point");
+  const NrPassParams& pp = kp.p;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  float* const ring = smem + OFF_RING;
+  float* const sWh = smem + OFF_WH;
+  float* const sWg0 = smem + OFF_WG0;
+  float* const sWg1 = smem + OFF_WG1;
+  float* const sw = smem + OFF_SW;
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* const wfull = bars;
+  uint64_t* const wempty = bars + NBUF;
+  uint64_t* const mma_bars = bars + 2 * NBUF;                 // [NBLK]
+  uint32_t* const tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2 * NBUF + NBLK);
+
+  const int rfn = pp.rfn, dn = pp.dn;
+  const int N = pp.rn * dn;
+  const int n_heads = kp.n_heads;
+  const int stages_per_tile = n_heads + 8;
+  const int n_tiles = kp.n_tiles;                              // tiles of PB points
+  const int iters = (n_tiles + int(gridDim.x) * NBLK - 1) / (int(gridDim.x) * NBLK);
+  const float* __restrict__ W = pp.w_point;
+
+  // ---------------- one-time setup ----------------
+  if (tid == 0) {
+    for (int i = 0; i < NBUF; ++i) { tc::mbar_init(wfull + i, 1); tc::mbar_init(wempty + i, NBLK); }
+    for (int i = 0; i < NBLK; ++i) tc::mbar_init(mma_bars + i, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc<512>(tmem_base_s);
+  if (tid < NCOMP) {
+    auto cp = [&](float* dst, int src, int n) { for (int i = tid; i < n; i += NCOMP) dst[i] = __ldg(W + src + i); };
+    for (int hh = 0; hh < 4; ++hh) {
+      const int g = lay::DD_HEAD + hh * lay::DD_HEAD_STRIDE;
+      float* d = sw + SW_HEAD + hh * SW_HEAD_STRIDE;
+      cp(d, g + lay::DD_L0_B, 32); cp(d + 32, g + lay::DD_L1_B, 32); cp(d + 64, g + lay::DD_L2_W, 64); cp(d + 128, g + lay::DD_L2_B, 4);
+    }
+    const int gb = lay::GRP_B, gd = lay::GRP_D1;
+    cp(sw + SW_PE0B, gb + lay::PE0_B, 32); cp(sw + SW_PE1B, gb + lay::PE1_B, 32); cp(sw + SW_RD0W, gb + lay::RD0_W, 64);
+    cp(sw + SW_RD0B, gb + lay::RD0_B, 16); cp(sw + SW_RD1W, gb + lay::RD1_W, 576); cp(sw + SW_RD1B, gb + lay::RD1_B, 36);
+    cp(sw + SW_NF0W, gb + lay::NF0_W, 256); cp(sw + SW_NF0B, gb + lay::NF0_B, 8); cp(sw + SW_NF1W, gb + lay::NF1_W, 8);
+    cp(sw + SW_NF1B, gb + lay::NF1_B, 4); cp(sw + SW_B1B, lay::BASE1_B, 32);
+    cp(sw + SW_V0B, gd + lay::VIS0_B, 32); cp(sw + SW_V1B, gd + lay::VIS1_B, 32); cp(sw + SW_V1LW, gd + lay::VIS1L_W, 32);
+    cp(sw + SW_V1LB, gd + lay::VIS1L_B, 4); cp(sw + SW_V20B, gd + lay::V20_B, 32); cp(sw + SW_V21W, gd + lay::V21_W, 32);
+    cp(sw + SW_V21B, gd + lay::V21_B, 4); cp(sw + SW_RGB0B, gd + lay::RGB0_B, 16); cp(sw + SW_RGB1W, gd + lay::RGB1_W, 128);
+    cp(sw + SW_RGB1B, gd + lay::RGB1_B, 8); cp(sw + SW_RGB2W, gd + lay::RGB2_W, 8); cp(sw + SW_RGB2B, gd + lay::RGB2_B, 4);
+    cp(sWh, lay::HOIST_W, WH);                                                    // WT[140][64] | bias[64] are contiguous
+    cp(sWg0, lay::GRP_D2 + lay::GEO0_W, WG0);
+    for (int i = tid; i < 64 * 16; i += NCOMP) sWg1[(i & 15) * 64 + (i >> 4)] = __ldg(W + lay::GRP_D2 + lay::GEO1_W + i);   // WT[64][16] -> [16][64]
+    cp(sWg1 + 64 * 16, lay::GRP_D2 + lay::GEO1_B, 16);
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem_base = *tmem_base_s;
+
+  {
+    // ---------------- compute warps (thread 0 also feeds the weight ring, see Producer) ----------------
+    const int fh = pp.fh, fw = pp.fw, h = pp.h, w = pp.w;
+    const bool feat_align = (fh == h && fw == w);
+    const int v = lane % G;                         // view of this row (>= rfn: padding lane)
+    const int pl = (tid & 127) / G;                 // point inside the block
+    const int lane0 = lane - v;                     // first lane of this point's group
+    float* const stg = smem + OFF_STG + warp * 32 * STG_ROW;
+    float* const gs = smem + OFF_GS + ((warp >> 2) * 32 + pl) * GS_ROW;
+
+    Blk b;
+    b.blk = warp >> 2;
+    b.leader = (tid & 127) == 0;
+    b.issuer_warp = (__shfl_sync(0xffffffffu, warp, 0) & 3) == 0;
+    {
+      const uint32_t col0 = tmem_base + TCOLS * b.blk;
+      const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
+      b.mAhi = col0; b.mAlo = col0; b.mD = col0;                 // pm3 helpers address columns relative to the block base
+      b.tAhi = col0 + lane_off; b.tAlo = b.tAhi; b.tD = b.tAhi;
+    }
+    b.mma_bar = mma_bars + b.blk;
+    b.wfull = wfull; b.wempty = wempty;
+    b.ring_addr = tc::smem_u32(ring);
+    b.phase = 0;
+    b.wi = 0;
+    b.tk = nullptr;
+    Producer prod;
+    prod.w_tc = pp.w_tc; prod.ring = ring; prod.wfull = wfull; prod.wempty = wempty;
+    prod.next = 0; prod.total = uint32_t(iters) * uint32_t(stages_per_tile);
+    prod.stages_per_tile = stages_per_tile; prod.n_heads = n_heads;
+    b.prod = tid == 0 ? &prod : nullptr;
+    if (tid == 0) prod.feed(0);
+
+#define PM_TICK(id)                                                                          \
+  if (kp.timing != nullptr && blockIdx.x == 0 && b.leader && b.blk < 2 && it < 64) kp.timing[(it * 2 + b.blk) * 32 + (id)] = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const int tile = (it * int(gridDim.x) + int(blockIdx.x)) * NBLK + b.blk;
+      if (tile >= n_tiles) {
+        // nothing to render in this iteration: still take part in the weight-ring accounting
+        for (int s = 0; s < stages_per_tile; ++s) {
+          if (b.leader) {
+            const uint32_t i = b.wi + s;
+            if (b.prod) b.prod->feed(i);
+            tc::mbar_wait(wfull + (i % NBUF), (i / NBUF) & 1);
+            tc::mbar_arrive(wempty + (i % NBUF));
+          }
+        }
+        b.wi += stages_per_tile;
+        continue;
+      }
+      const int n = tile * PB + pl;
+      const bool pt_ok = n < N;
+      const bool row_ok = pt_ok && v < rfn;
+
+      PM_TICK(0)
+      // ---------------- ray geometry of this row's point (every lane of the group computes the same values) ----------------
+      float X = 0.f, Y = 0.f, Z = 0.f, qx = 0.f, qy = 0.f, qz = 0.f, ihp = 0.f, ihc = 0.f;
+      if (pt_ok) {
+        const float* __restrict__ cam = pp.que_cam;
+        const int ray = n / dn, s = n - ray * dn;
+        const float cx = __ldg(pp.coords + 2 * ray), cy = __ldg(pp.coords + 2 * ray + 1);
+        float cm[3], d[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) cm[i] = fmaf(cam[12 + 3 * i + 1], cy, cam[12 + 3 * i] * cx) + cam[12 + 3 * i + 2];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float wld = fmaf(cam[3 * i + 2], cm[2], fmaf(cam[3 * i + 1], cm[1], cam[3 * i] * cm[0])) + cam[9 + i];
+          d[i] = wld - cam[9 + i];   // the reference adds the centre and subtracts it again (render_ops.py:22-23)
+        }
+        const float z = __ldg(pp.que_depth + n);
+        X = fmaf(d[0], z, cam[9]); Y = fmaf(d[1], z, cam[10]); Z = fmaf(d[2], z, cam[11]);
+        const float nrm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        qx = -d[0] / nrm; qy = -d[1] / nrm; qz = -d[2] / nrm;
+        const float a = -1.f / cam[21], bb = -1.f / cam[22];
+        const float tcur = (-1.f / z - a) / (bb - a);
+        float dc = 1e6f;
+        if (s + 1 < dn) dc = (-1.f / __ldg(pp.que_depth + n + 1) - a) / (bb - a) - tcur;
+        float dp = dc;
+        if (s > 0) dp = tcur - (-1.f / __ldg(pp.que_depth + n - 1) - a) / (bb - a);
+        ihc = dc * 0.5f; ihp = dp * 0.5f;
+      }
+
+      // ---------------- projection into this row's view + rgb taps ----------------
+      float mrow = 0.f, zrow = 1.f, dd[4] = {0.f, 0.f, 0.f, 0.f}, fxr = 0.f, fyr = 0.f, rgbin[3] = {0.f, 0.f, 0.f};
+      float dbg_px = 0.f, dbg_py = 0.f, dbg_dir[3] = {0.f, 0.f, 0.f};
+      if (row_ok) {
+        const float* __restrict__ vp = pp.view_params + v * 20;
+        const float xh = fmaf(__ldg(vp + 2), Z, fmaf(__ldg(vp + 1), Y, __ldg(vp + 0) * X)) + __ldg(vp + 3);
+        const float yh = fmaf(__ldg(vp + 6), Z, fmaf(__ldg(vp + 5), Y, __ldg(vp + 4) * X)) + __ldg(vp + 7);
+        float zh = fmaf(__ldg(vp + 10), Z, fmaf(__ldg(vp + 9), Y, __ldg(vp + 8) * X)) + __ldg(vp + 11);
+        const bool degenerate = fabsf(zh) < 1e-4f;
+        if (degenerate) zh = 1e-3f;
+        const float ux = xh / zh, uy = yh / zh;
+        const bool outside = (ux < -0.5f) || (ux >= float(w) - 0.5f) || (uy < -0.5f) || (uy >= float(h) - 0.5f);
+        const bool valid = !degenerate && !outside;
+        mrow = valid ? 1.f : 0.f;
+        zrow = zh;
+        const float dx = X - __ldg(vp + 12), dy = Y - __ldg(vp + 13), dz = Z - __ldg(vp + 14);
+        const float inv = -1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-5f);
+        const float ex = dx * inv, ey = dy * inv, ez = dz * inv;
+        dd[0] = ex - qx; dd[1] = ey - qy; dd[2] = ez - qz; dd[3] = ex * qx + ey * qy + ez * qz;
+        if (DEBUG) { dbg_px = ux; dbg_py = uy; dbg_dir[0] = ex; dbg_dir[1] = ey; dbg_dir[2] = ez; }
+        const float gx = ux / float(w - 1) * 2.f - 1.f, gy = uy / float(h - 1) * 2.f - 1.f;
+        fxr = feat_align ? (gx + 1.f) / 2.f * float(fw - 1) : ((gx + 1.f) * float(fw) - 1.f) / 2.f;
+        fyr = feat_align ? (gy + 1.f) / 2.f * float(fh - 1) : ((gy + 1.f) * float(fh) - 1.f) / 2.f;
+        fxr = fminf(fmaxf(fxr, 0.f), float(fw - 1)); fyr = fminf(fmaxf(fyr, 0.f), float(fh - 1));
+        if (valid) {
+          float ix = (gx + 1.f) / 2.f * float(w - 1), iy = (gy + 1.f) / 2.f * float(h - 1);
+          ix = fminf(fmaxf(ix, 0.f), float(w - 1)); iy = fminf(fmaxf(iy, 0.f), float(h - 1));
+          const float x0f = floorf(ix), y0f = floorf(iy);
+          const int x0 = int(x0f), y0 = int(y0f);
+          const int x1 = min(x0 + 1, w - 1), y1 = min(y0 + 1, h - 1);
+          const float we = ix - x0f, ww = (x0f + 1.f) - ix, ws = iy - y0f, wn = (y0f + 1.f) - iy;
+          const float* __restrict__ base = pp.rgb + size_t(v) * h * w * 4;
+          const float4 t00 = ldg4(base + (size_t(y0) * w + x0) * 4), t01 = ldg4(base + (size_t(y0) * w + x1) * 4);
+          const float4 t10 = ldg4(base + (size_t(y1) * w + x0) * 4), t11 = ldg4(base + (size_t(y1) * w + x1) * 4);
+          const float w00 = ww * wn, w01 = we * wn, w10 = ww * ws, w11 = we * ws;
+          rgbin[0] = t00.x * w00 + t01.x * w01 + t10.x * w10 + t11.x * w11;
+          rgbin[1] = t00.y * w00 + t01.y * w01 + t10.y * w10 + t11.y * w11;
+          rgbin[2] = t00.z * w00 + t01.z * w01 + t10.z * w10 + t11.z * w11;
+        }
+      }
+
+      PM_TICK(1)
+      // ---------------- bilinear gather of this warp's 32 rows, ray_feats (channels 0..31): 8 lanes x float4 per texel ----------------
+      // The gathering quarter-warp and the row owner are different lanes: the row's coordinates come over by shuffle,
+      // the channels go back through the warp-private transposition buffer.
+      auto gather32 = [&](const int ch0) {
+        const int qw = lane >> 3, l = lane & 7;
+        __syncwarp();
+#pragma unroll 1
+        for (int rb = 0; rb < 32; rb += 16) {
+          float4 t[4][4];
+          float wq[4][4];
+          bool on[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = rb + 4 * u + qw;                                   // row (= lane) whose texels this quarter-warp fetches
+            const float mj = __shfl_sync(0xffffffffu, mrow, j);
+            const float ix = __shfl_sync(0xffffffffu, fxr, j), iy = __shfl_sync(0xffffffffu, fyr, j);
+            on[u] = mj != 0.f;
+            if (on[u]) {
+              const int vv = j % G;
+              const float x0f = floorf(ix), y0f = floorf(iy);
+              const int x0 = int(x0f), y0 = int(y0f);
+              const int x1 = min(x0 + 1, fw - 1), y1 = min(y0 + 1, fh - 1);
+              const float we = ix - x0f, ww = (x0f + 1.f) - ix, ws = iy - y0f, wn = (y0f + 1.f) - iy;
+              const float* __restrict__ base = pp.feat + size_t(vv) * fh * fw * 64 + ch0 + 4 * l;
+              t[u][0] = ldg4(base + (size_t(y0) * fw + x0) * 64); t[u][1] = ldg4(base + (size_t(y0) * fw + x1) * 64);
+              t[u][2] = ldg4(base + (size_t(y1) * fw + x0) * 64); t[u][3] = ldg4(base + (size_t(y1) * fw + x1) * 64);
+              wq[u][0] = ww * wn; wq[u][1] = we * wn; wq[u][2] = ww * ws; wq[u][3] = we * ws;
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = rb + 4 * u + qw;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (on[u]) {
+              o.x = t[u][0].x * wq[u][0] + t[u][1].x * wq[u][1] + t[u][2].x * wq[u][2] + t[u][3].x * wq[u][3];
+              o.y = t[u][0].y * wq[u][0] + t[u][1].y * wq[u][1] + t[u][2].y * wq[u][2] + t[u][3].y * wq[u][3];
+              o.z = t[u][0].z * wq[u][0] + t[u][1].z * wq[u][1] + t[u][2].z * wq[u][2] + t[u][3].z * wq[u][3];
+              o.w = t[u][0].w * wq[u][0] + t[u][1].w * wq[u][1] + t[u][2].w * wq[u][2] + t[u][3].w * wq[u][3];
+            }
+            *reinterpret_cast<float4*>(stg + j * STG_ROW + 4 * l) = o;
+          }
+        }
+        __syncwarp();
+      };
+      gather32(0);
+
+      PM_TICK(2)
+      // ---------------- dist decoder on the tensor cores: A[0:32] <- this row's ray_feats ----------------
+      {
+        float x[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 t4 = *reinterpret_cast<const float4*>(stg + lane * STG_ROW + 4 * q);
+          x[4 * q] = t4.x; x[4 * q + 1] = t4.y; x[4 * q + 2] = t4.z; x[4 * q + 3] = t4.w;
+        }
+        st32(b, 0, 64, x);
+        if (DEBUG && kp.dbg != nullptr && row_ok) {
+          float* __restrict__ o = kp.dbg + (size_t(v) * N + n) * 76;
+          for (int k = 0; k < 32; ++k) o[12 + k] = x[k];
+        }
+      }
+      gather32(32);                                                                  // img_feats: stay in the buffer until ray_dir_fc
+      PM_TICK(3)
+      float hv[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll 1
+      for (int hd = 0; hd < n_heads; ++hd) {
+        const float* __restrict__ hw_ = sw + SW_HEAD + hd * SW_HEAD_STRIDE;
+        run_layer<32, 4, 0, 4, 0, 0, 1024 * 4, 0, true, false>(b);              // L0: A[0:32]
+        {
+          float x[32];
+          ld32(b, 128, x);
+          add_bias32(x, hw_);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = elu(x[j]);
+          st32(b, 32, 96, x);
+        }
+        run_layer<32, 4, 32, 4, 0, 2048 * 4, 3072 * 4, 0, false, true>(b);      // L1: A[32:64]
+        float o0 = hw_[128], o1 = hw_[129];
+        {
+          float x[32];
+          ld32(b, 128, x);
+          add_bias32(x, hw_ + 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 wa = *reinterpret_cast<const float4*>(hw_ + 64 + 4 * q);
+            const float4 wb = *reinterpret_cast<const float4*>(hw_ + 96 + 4 * q);
+            const float a0 = elu(x[4 * q]), a1 = elu(x[4 * q + 1]), a2 = elu(x[4 * q + 2]), a3 = elu(x[4 * q + 3]);
+            o0 = fmaf(wa.w, a3, fmaf(wa.z, a2, fmaf(wa.y, a1, fmaf(wa.x, a0, o0))));
+            o1 = fmaf(wb.w, a3, fmaf(wb.z, a2, fmaf(wb.y, a1, fmaf(wb.x, a0, o1))));
+          }
+        }
+        if (hd == 0) { hv[0][0] = o0; hv[0][1] = o1; }
+        else if (hd == 1) { hv[1][0] = o0; hv[1][1] = o1; }
+        else if (hd == 2) { hv[2][0] = o0; hv[2][1] = o1; }
+        else { hv[3][0] = o0; hv[3][1] = o1; }
+      }
+      PM_TICK(4)
+      float hit = 0.f, visib = 0.f;
+      {
+        const float* __restrict__ vp = pp.view_params + (v < rfn ? v : 0) * 20;
+        const float zc = fmaxf(zrow, 1e-5f);
+        const float a = __ldg(vp + 15), bb = __ldg(vp + 16);
+        const float tz = (-1.f / zc - a) / (bb - a);
+        const float lo = tz - ihp, hi = tz + ihc;
+        const float aw = sigmoidf_(hv[2][0]);
+        const float vd = pp.use_vis ? sigmoidf_(hv[3][0]) : 1.f;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float mean = softplusf_(hv[0][i]);
+          const float var = softplusf_(hv[1][i]) + pp.var_bias;
+          const float c0 = logistic_cdf((lo - mean) * var) * vd, c1 = logistic_cdf((hi - mean) * var) * vd;
+          const float mix = i == 0 ? aw : 1.f - aw;
+          visib = fmaf(1.f - c0, mix, visib);
+          hit = fmaf(c1 - c0, mix, hit);
+        }
+        visib *= mrow; hit *= mrow;
+      }
+
+      // ---------------- prob_embed (tensor cores), neuray_fc, ray_dir_fc ----------------
+      {
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = 0.f;
+        x[0] = (hit - 0.5f) * 2.f; x[1] = (visib - 0.5f) * 2.f;
+        st8(b, 32, 96, x);                                                           // A[32:40] = hit', vis', 0... (the heads' hidden layer is dead)
+      }
+      run_layer<32, 5, 0, 4, 32, 0, 2048 * 4, 4096, true, true>(b);                 // prob_embed.0: K = 32 + 8
+      {
+        float x[32];
+        ld32(b, 128, x);
+        add_bias32(x, sw + SW_PE0B);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+        st32(b, 0, 64, x);                                                           // over ray_feats: their last reader has completed
+      }
+      PM_TICK(5)
+      run_layer<32, 4, 0, 4, 0, 0, 1024 * 4, 0, true, true>(b);                     // prob_embed.2
+      float gate;
+      {
+        float h8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h8[j] = sw[SW_NF0B + j];
+        float x[32];
+        ld32(b, 128, x);
+        add_bias32(x, sw + SW_PE1B);                                                 // neuray_feat
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float4 wa = *reinterpret_cast<const float4*>(sw + SW_NF0W + j * 8);
+          const float4 wb = *reinterpret_cast<const float4*>(sw + SW_NF0W + j * 8 + 4);
+          h8[0] = fmaf(wa.x, x[j], h8[0]); h8[1] = fmaf(wa.y, x[j], h8[1]); h8[2] = fmaf(wa.z, x[j], h8[2]); h8[3] = fmaf(wa.w, x[j], h8[3]);
+          h8[4] = fmaf(wb.x, x[j], h8[4]); h8[5] = fmaf(wb.y, x[j], h8[5]); h8[6] = fmaf(wb.z, x[j], h8[6]); h8[7] = fmaf(wb.w, x[j], h8[7]);
+        }
+        st32(b, 0, 64, x);
+        gate = sw[SW_NF1B];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gate = fmaf(sw[SW_NF1W + j], elu(h8[j]), gate);
+      }
+      // base_fc.0, K round A: the neuray_feat inputs (B chunks 5..8), accumulator columns [96,160); completes under ray_dir_fc
+      issue_layer<64, 4, 0, 64, 4, 0, 96, 5, 3, 0, 2048 * 4, 0, true, false, false>(b);
+      float rf[40];                                                                  // rgb_feat (35) + zero padding
+      {
+        float h16[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float* __restrict__ w0 = sw + SW_RD0W;
+          h16[j] = elu(fmaf(w0[48 + j], dd[3], fmaf(w0[32 + j], dd[2], fmaf(w0[16 + j], dd[1], fmaf(w0[j], dd[0], sw[SW_RD0B + j])))));
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < 36; j4 += 4) {
+          float4 acc = *reinterpret_cast<const float4*>(sw + SW_RD1B + j4);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float4 wv = *reinterpret_cast<const float4*>(sw + SW_RD1W + k * 36 + j4);
+            acc.x = fmaf(wv.x, h16[k], acc.x); acc.y = fmaf(wv.y, h16[k], acc.y); acc.z = fmaf(wv.z, h16[k], acc.z); acc.w = fmaf(wv.w, h16[k], acc.w);
+          }
+          rf[j4] = elu(acc.x); rf[j4 + 1] = elu(acc.y); rf[j4 + 2] = elu(acc.z); rf[j4 + 3] = elu(acc.w);
+        }
+        // + [rgb | img_feats] of this row (img_feats come back from the transposition buffer)
+        rf[0] += rgbin[0]; rf[1] += rgbin[1]; rf[2] += rgbin[2];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 t4 = *reinterpret_cast<const float4*>(stg + lane * STG_ROW + 4 * q);
+          rf[3 + 4 * q] += t4.x; rf[4 + 4 * q] += t4.y; rf[5 + 4 * q] += t4.z; rf[6 + 4 * q] += t4.w;
+          if (DEBUG && kp.dbg != nullptr && row_ok) {
+            float* __restrict__ o = kp.dbg + (size_t(v) * N + n) * 76;
+            o[44 + 4 * q] = t4.x; o[45 + 4 * q] = t4.y; o[46 + 4 * q] = t4.z; o[47 + 4 * q] = t4.w;
+          }
+        }
+#pragma unroll
+        for (int j = 35; j < 40; ++j) rf[j] = 0.f;
+        wait_layer(b);                                                               // round A has read neuray_feat: A is free again
+        st32(b, 0, 48, rf);                                                          // rgb_feat: hi [0,40), lo [48,88)
+        st8(b, 32, 80, rf + 32);
+      }
+      if (DEBUG && kp.dbg != nullptr && row_ok) {
+        float* __restrict__ o = kp.dbg + (size_t(v) * N + n) * 76;
+        o[0] = mrow; o[1] = zrow; o[2] = hit; o[3] = visib; o[4] = dbg_px; o[5] = dbg_py;
+        o[6] = dbg_dir[0]; o[7] = dbg_dir[1]; o[8] = dbg_dir[2]; o[9] = rgbin[0]; o[10] = rgbin[1]; o[11] = rgbin[2];
+      }
+
+      PM_TICK(6)
+      // ---------------- view pooling #1 streamed into the hoisted base_fc.0 columns of this lane ----------------
+      const float msum = bsum<G>(mrow);
+      const float w1 = mrow / (msum + 1e-8f);
+      const float w0 = sigmoidf_(gate) * w1;
+      {
+        float g[CPL];
+        ld_cols<G>(sWh + 140 * 64, v, g);                                   // bias
+#pragma unroll
+        for (int f0 = 0; f0 < 35; f0 += 7) {                                         // 7 features x (w0, w1) = 14 butterflies at a time
+          float mm[14];
+#pragma unroll
+          for (int i = 0; i < 7; ++i) { mm[i] = rf[f0 + i] * w0; mm[7 + i] = rf[f0 + i] * w1; }
+          bsum_vec<G, 14>(mm);
+          float vv_[14];
+#pragma unroll
+          for (int i = 0; i < 7; ++i) {
+            const float d0 = rf[f0 + i] - mm[i], d1 = rf[f0 + i] - mm[7 + i];
+            vv_[i] = w0 * d0 * d0; vv_[7 + i] = w1 * d1 * d1;
+          }
+          bsum_vec<G, 14>(vv_);
+#pragma unroll
+          for (int i = 0; i < 7; ++i) {
+            const int f = f0 + i;
+            float wa[CPL], wb[CPL], wc[CPL], wd[CPL];
+            ld_cols<G>(sWh + f * 64, v, wa);
+            ld_cols<G>(sWh + (35 + f) * 64, v, wb);
+            ld_cols<G>(sWh + (70 + f) * 64, v, wc);
+            ld_cols<G>(sWh + (105 + f) * 64, v, wd);
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) g[j] = fmaf(wd[j], vv_[7 + i], fmaf(wc[j], mm[7 + i], fmaf(wb[j], vv_[i], fmaf(wa[j], mm[i], g[j]))));
+          }
+        }
+        __syncwarp();                                                                // previous tile's readers of gs are done
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) gs[own_col<G>(v, j)] = g[j];
+        __syncwarp();
+      }
+
+      PM_TICK(7)
+      // ---------------- base_fc on the tensor cores ----------------
+      issue_layer<64, 5, 0, 48, 5, 0, 96, 0, 3, 0, 2048 * 4, 0, false, true, true>(b);   // base_fc.0, K round B: rgb_feat (B chunks 0..4)
+      wait_layer(b);
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        float x[32];
+        ld32(b, 96 + c0, x);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 g4 = *reinterpret_cast<const float4*>(gs + c0 + 4 * q);
+          x[4 * q] = elu(x[4 * q] + g4.x); x[4 * q + 1] = elu(x[4 * q + 1] + g4.y);
+          x[4 * q + 2] = elu(x[4 * q + 2] + g4.z); x[4 * q + 3] = elu(x[4 * q + 3] + g4.w);
+        }
+        st32(b, c0, 64 + c0, x);                                                     // lo half 1 lands on accumulator columns already consumed
+      }
+      PM_TICK(8)
+      run_layer<32, 8, 0, 8, 0, 0, 2048 * 4, 4096, true, true>(b);                  // base_fc.2: K = 64
+      float xr[32];
+      ld32(b, 128, xr);
+      add_bias32(xr, sw + SW_B1B);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) xr[j] = elu(xr[j]);
+      st32(b, 0, 64, xr);
+
+      PM_TICK(9)
+      // ---------------- vis_fc, vis_fc2, rgb_fc ----------------
+      run_layer<32, 4, 0, 4, 0, 0, 1024 * 4, 0, true, false>(b);                     // vis_fc.0 (row scale folded into the epilogue)
+      float lg = sw[SW_V1LB];
+      {
+        float x[32];
+        ld32(b, 128, x);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 bb = *reinterpret_cast<const float4*>(sw + SW_V0B + 4 * q);
+          const float4 wl = *reinterpret_cast<const float4*>(sw + SW_V1LW + 4 * q);
+          x[4 * q] = elu(fmaf(w1, x[4 * q], bb.x)); x[4 * q + 1] = elu(fmaf(w1, x[4 * q + 1], bb.y));
+          x[4 * q + 2] = elu(fmaf(w1, x[4 * q + 2], bb.z)); x[4 * q + 3] = elu(fmaf(w1, x[4 * q + 3], bb.w));
+          lg = fmaf(wl.w, x[4 * q + 3], fmaf(wl.z, x[4 * q + 2], fmaf(wl.y, x[4 * q + 1], fmaf(wl.x, x[4 * q], lg))));
+        }
+        st32(b, 32, 96, x);
+      }
+      PM_TICK(10)
+      const float visa = sigmoidf_(elu(lg)) * mrow;
+      run_layer<32, 4, 32, 4, 0, 2048 * 4, 3072 * 4, 0, false, true>(b);             // vis_fc.2 outputs 0..31 (residual)
+      {
+        float x[32];
+        ld32(b, 128, x);
+        add_bias32(x, sw + SW_V1B);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xr[j] += elu(x[j]);
+        st32(b, 0, 64, xr);
+      }
+      PM_TICK(11)
+      run_layer<32, 4, 0, 4, 0, 0, 1024 * 4, 0, true, false>(b);                     // vis_fc2.0
+      float vis2;
+      {
+        float l2 = sw[SW_V21B];
+        float x[32];
+        ld32(b, 128, x);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 bb = *reinterpret_cast<const float4*>(sw + SW_V20B + 4 * q);
+          const float4 wl = *reinterpret_cast<const float4*>(sw + SW_V21W + 4 * q);
+          l2 = fmaf(wl.x, elu(fmaf(visa, x[4 * q], bb.x)), l2); l2 = fmaf(wl.y, elu(fmaf(visa, x[4 * q + 1], bb.y)), l2);
+          l2 = fmaf(wl.z, elu(fmaf(visa, x[4 * q + 2], bb.z)), l2); l2 = fmaf(wl.w, elu(fmaf(visa, x[4 * q + 3], bb.w)), l2);
+        }
+        vis2 = sigmoidf_(l2) * mrow;
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = 0.f;
+        y[0] = vis2; y[1] = dd[0]; y[2] = dd[1]; y[3] = dd[2]; y[4] = dd[3];
+        st8(b, 32, 96, y);                                                           // A[32:40] = vis, ray_diff, 0
+      }
+      PM_TICK(12)
+      run_layer<16, 5, 0, 4, 32, 2048 * 4, 3072 * 4, 2048, false, true>(b);          // rgb_fc.0: K = 32 + 8, N = 16
+      float logit;
+      {
+        float x[16];
+        ld16(b, 128, x);
+        float h8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h8[j] = sw[SW_RGB1B + j];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const float a = elu(x[k] + sw[SW_RGB0B + k]);
+          const float4 wa = *reinterpret_cast<const float4*>(sw + SW_RGB1W + k * 8);
+          const float4 wb = *reinterpret_cast<const float4*>(sw + SW_RGB1W + k * 8 + 4);
+          h8[0] = fmaf(wa.x, a, h8[0]); h8[1] = fmaf(wa.y, a, h8[1]); h8[2] = fmaf(wa.z, a, h8[2]); h8[3] = fmaf(wa.w, a, h8[3]);
+          h8[4] = fmaf(wb.x, a, h8[4]); h8[5] = fmaf(wb.y, a, h8[5]); h8[6] = fmaf(wb.z, a, h8[6]); h8[7] = fmaf(wb.w, a, h8[7]);
+        }
+        float l3 = sw[SW_RGB2B];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) l3 = fmaf(sw[SW_RGB2W + j], elu(h8[j]), l3);
+        // masked views get -1e9 like the reference; padding lanes must not take part at all
+        logit = v >= rfn ? -3.0e38f : (mrow == 0.f ? -1e9f : l3);
+      }
+
+      PM_TICK(13)
+      // ---------------- softmax colour blend over the views (ibrnet.py:365-367) ----------------
+      float rgbo[3];
+      {
+        const float mx = bmax<G>(logit);
+        const float e = v >= rfn ? 0.f : expf(logit - mx);
+        float acc[4] = {e, e * rgbin[0], e * rgbin[1], e * rgbin[2]};
+        bsum_vec<G, 4>(acc);
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) rgbo[cc] = acc[1 + cc] / acc[0];
+      }
+
+      PM_TICK(14)
+      // ---------------- view pooling #2 streamed into geometry_fc.0, then geometry_fc.2 across the lanes ----------------
+      {
+        const float vs = bsum<G>(vis2);
+        const float w2 = vis2 / (vs + 1e-8f);
+        float hh[CPL];
+        ld_cols<G>(sWg0 + 65 * 64, v, hh);                                  // bias
+#pragma unroll
+        for (int f0 = 0; f0 < 32; f0 += 8) {
+          float mm[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) mm[i] = xr[f0 + i] * w2;
+          bsum_vec<G, 8>(mm);
+          float vv_[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { const float d0 = xr[f0 + i] - mm[i]; vv_[i] = w2 * d0 * d0; }
+          bsum_vec<G, 8>(vv_);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float wa[CPL], wb[CPL];
+            ld_cols<G>(sWg0 + (f0 + i) * 64, v, wa);
+            ld_cols<G>(sWg0 + (32 + f0 + i) * 64, v, wb);
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) hh[j] = fmaf(wb[j], vv_[i], fmaf(wa[j], mm[i], hh[j]));
+          }
+        }
+        {
+          const float wmean = bsum<G>(w2) / float(rfn);
+          float wa[CPL];
+          ld_cols<G>(sWg0 + 64 * 64, v, wa);
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) hh[j] = elu(fmaf(wa[j], wmean, hh[j]));
+        }
+        float out[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) out[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {                                               // sWg1 is stored output-major: [16][64]
+          float wk[CPL];
+          ld_cols<G>(sWg1 + k * 64, v, wk);
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) out[k] = fmaf(wk[j], hh[j], out[k]);
+        }
+        bsum_vec<G, 16>(out);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) out[k] = elu(out[k] + sWg1[64 * 16 + k]);
+        if (v == 0 && pt_ok) {
+          float4* __restrict__ dst = reinterpret_cast<float4*>(pp.point_rec + size_t(n) * REC);
+          dst[0] = make_float4(out[0], out[1], out[2], out[3]); dst[1] = make_float4(out[4], out[5], out[6], out[7]);
+          dst[2] = make_float4(out[8], out[9], out[10], out[11]); dst[3] = make_float4(out[12], out[13], out[14], out[15]);
+          dst[4] = make_float4(rgbo[0], rgbo[1], rgbo[2], msum);
+        }
+      }
+      PM_TICK(15)
+    }
+  }
+
+  // ---------------- teardown ----------------
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace pm3

@@ -983,6 +983,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
 }
 
 #include "nr_point_kernel_pm.cuh"
+#include "nr_point_kernel_pm3.cuh"
 
 }  // namespace pkt
 
@@ -1017,6 +1018,33 @@ static int launch_pm(const pkt::KParams& kp0, int sms, cudaStream_t stream) {
   return NR_OK;
 }
 
+template <int G>
+static int launch_pm3(const pkt::KParams& kp0, int sms, cudaStream_t stream) {
+  pkt::KParams kp = kp0;
+  constexpr int PB = 128 / G;
+  const long long N = (long long)kp.p.rn * kp.p.dn;
+  kp.P = PB;
+  kp.n_tiles = int((N + PB - 1) / PB);
+  const int groups = (kp.n_tiles + pkt::pm3::NBLK - 1) / pkt::pm3::NBLK;
+  const int grid = groups < sms ? groups : sms;
+  static bool attr_done[2] = {false, false};
+  if (kp.dbg) {
+    if (!attr_done[1]) {
+      cudaFuncSetAttribute(pkt::pm3::point_kernel_pm3<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pkt::pm3::SMEM_BYTES));
+      attr_done[1] = true;
+    }
+    pkt::pm3::point_kernel_pm3<G, true><<<grid, pkt::pm3::NTHR, pkt::pm3::SMEM_BYTES, stream>>>(kp);
+  } else {
+    if (!attr_done[0]) {
+      cudaFuncSetAttribute(pkt::pm3::point_kernel_pm3<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pkt::pm3::SMEM_BYTES));
+      attr_done[0] = true;
+    }
+    pkt::pm3::point_kernel_pm3<G, false><<<grid, pkt::pm3::NTHR, pkt::pm3::SMEM_BYTES, stream>>>(kp);
+  }
+  NR_CHECK_LAUNCH("point_kernel_pm3");
+  return NR_OK;
+}
+
 // point-major kernel (nr_point_kernel_pm.cuh); the row-per-(view,point) kernel above stays selectable for A/B runs
 int launch_point_kernel_pm(const NrPassParams* p, float* dbg, cudaStream_t stream) {
   pkt::KParams kp;
@@ -1027,6 +1055,13 @@ int launch_point_kernel_pm(const NrPassParams* p, float* dbg, cudaStream_t strea
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const char* sel = getenv("NR_POINT_KERNEL");
+  if (sel != nullptr && sel[0] == 'p' && sel[1] == 'm' && sel[2] == '3') {
+    if (p->rfn <= 4) return launch_pm3<4>(kp, sms, stream);
+    if (p->rfn <= 8) return launch_pm3<8>(kp, sms, stream);
+    if (p->rfn <= 16) return launch_pm3<16>(kp, sms, stream);
+    return launch_pm3<32>(kp, sms, stream);
+  }
   if (p->rfn <= 4) return launch_pm<4>(kp, sms, stream);
   if (p->rfn <= 8) return launch_pm<8>(kp, sms, stream);
   if (p->rfn <= 16) return launch_pm<16>(kp, sms, stream);
