@@ -269,7 +269,7 @@ def run_b200(args):
                 "ms_per_step": t_e2e / args.steps * 1e3},
         "gpu_launches": launches,
         "clocks": sampler.summary(),
-        "roofline": {"bound": "tensor", "kernel": "nr::pkt::pm::point_kernel_pm", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+        "roofline": {"bound": "tensor", "kernel": "nr::pkt::pm3::point_kernel_pm3", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": f"{peaks_src} bf16_tflops_sustained",
                      "flops_per_ray_sample": fl, "launches": n_launch, "avg_launch_ms": sum(pk_ms) / max(n_launch, 1),
                      "share_of_step": pk_time / t_res,

@@ -283,6 +283,8 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
       // ---------------- projection into this row's view + rgb taps ----------------
       float mrow = 0.f, zrow = 1.f, dd[4] = {0.f, 0.f, 0.f, 0.f}, fxr = 0.f, fyr = 0.f, rgbin[3] = {0.f, 0.f, 0.f};
       float dbg_px = 0.f, dbg_py = 0.f, dbg_dir[3] = {0.f, 0.f, 0.f};
+      int tcode = -1;
+      float tw[4] = {0.f, 0.f, 0.f, 0.f};
       if (row_ok) {
         const float* __restrict__ vp = pp.view_params + v * 20;
         const float xh = fmaf(__ldg(vp + 2), Z, fmaf(__ldg(vp + 1), Y, __ldg(vp + 0) * X)) + __ldg(vp + 3);
@@ -304,6 +306,15 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
         fxr = feat_align ? (gx + 1.f) / 2.f * float(fw - 1) : ((gx + 1.f) * float(fw) - 1.f) / 2.f;
         fyr = feat_align ? (gy + 1.f) / 2.f * float(fh - 1) : ((gy + 1.f) * float(fh) - 1.f) / 2.f;
         fxr = fminf(fmaxf(fxr, 0.f), float(fw - 1)); fyr = fminf(fmaxf(fyr, 0.f), float(fh - 1));
+        if (valid) {
+          // feature-map taps of this row, worked out once here instead of by each of the gathering lanes: element offset
+          // of the (y0,x0) texel (a multiple of 64) with "x1 > x0" / "y1 > y0" in its two low bits, and the four weights
+          const float x0f = floorf(fxr), y0f = floorf(fyr);
+          const int x0 = int(x0f), y0 = int(y0f);
+          const float we = fxr - x0f, ww = (x0f + 1.f) - fxr, ws = fyr - y0f, wn = (y0f + 1.f) - fyr;
+          tcode = (((v * fh + y0) * fw + x0) << 6) | (x0 + 1 <= fw - 1 ? 1 : 0) | (y0 + 1 <= fh - 1 ? 2 : 0);
+          tw[0] = ww * wn; tw[1] = we * wn; tw[2] = ww * ws; tw[3] = we * ws;
+        }
         if (valid) {
           float ix = (gx + 1.f) / 2.f * float(w - 1), iy = (gy + 1.f) / 2.f * float(h - 1);
           ix = fminf(fmaxf(ix, 0.f), float(w - 1)); iy = fminf(fmaxf(iy, 0.f), float(h - 1));
@@ -336,19 +347,15 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int j = rb + 4 * u + qw;                                   // row (= lane) whose texels this quarter-warp fetches
-            const float mj = __shfl_sync(0xffffffffu, mrow, j);
-            const float ix = __shfl_sync(0xffffffffu, fxr, j), iy = __shfl_sync(0xffffffffu, fyr, j);
-            on[u] = mj != 0.f;
+            const int code = __shfl_sync(0xffffffffu, tcode, j);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) wq[u][k] = __shfl_sync(0xffffffffu, tw[k], j);
+            on[u] = code >= 0;
             if (on[u]) {
-              const int vv = j % G;
-              const float x0f = floorf(ix), y0f = floorf(iy);
-              const int x0 = int(x0f), y0 = int(y0f);
-              const int x1 = min(x0 + 1, fw - 1), y1 = min(y0 + 1, fh - 1);
-              const float we = ix - x0f, ww = (x0f + 1.f) - ix, ws = iy - y0f, wn = (y0f + 1.f) - iy;
-              const float* __restrict__ base = pp.feat + size_t(vv) * fh * fw * 64 + ch0 + 4 * l;
-              t[u][0] = ldg4(base + (size_t(y0) * fw + x0) * 64); t[u][1] = ldg4(base + (size_t(y0) * fw + x1) * 64);
-              t[u][2] = ldg4(base + (size_t(y1) * fw + x0) * 64); t[u][3] = ldg4(base + (size_t(y1) * fw + x1) * 64);
-              wq[u][0] = ww * wn; wq[u][1] = we * wn; wq[u][2] = ww * ws; wq[u][3] = we * ws;
+              const float* __restrict__ base = pp.feat + (code & ~63) + ch0 + 4 * l;
+              const int dx = (code & 1) << 6, dy = (code & 2) ? fw * 64 : 0;
+              t[u][0] = ldg4(base); t[u][1] = ldg4(base + dx);
+              t[u][2] = ldg4(base + dy); t[u][3] = ldg4(base + dy + dx);
             }
           }
 #pragma unroll

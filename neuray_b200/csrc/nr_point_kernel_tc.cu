@@ -1055,8 +1055,9 @@ int launch_point_kernel_pm(const NrPassParams* p, float* dbg, cudaStream_t strea
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // default: three blocks per SM (nr_point_kernel_pm3.cuh); NR_POINT_KERNEL=pm2 keeps the two-block kernel for A/B runs
   const char* sel = getenv("NR_POINT_KERNEL");
-  if (sel != nullptr && sel[0] == 'p' && sel[1] == 'm' && sel[2] == '3') {
+  if (!(sel != nullptr && sel[0] == 'p' && sel[1] == 'm' && sel[2] == '2')) {
     if (p->rfn <= 4) return launch_pm3<4>(kp, sms, stream);
     if (p->rfn <= 8) return launch_pm3<8>(kp, sms, stream);
     if (p->rfn <= 16) return launch_pm3<16>(kp, sms, stream);

@@ -183,3 +183,26 @@ def test_against_oracle_mid_size():
         close(out[k], gold[k], what=k)
         close(out_f[k], gold[k + "_fine"], what=k + "_fine(injected depths)")
     assert torch.equal(out["ray_mask"].cpu(), gold["ray_mask"])
+
+
+@pytest.mark.parametrize("rfn", [1, 2, 5, 10, 16, 20, 32])
+def test_view_counts(rfn):
+    """Every lanes-per-point instantiation of the point kernel (4, 8, 16, 32 lanes; padding lanes when the view count
+    is not a power of two -- cfg4 of SURVEY.md 8d renders with 10 views) against the CPU oracle on a small seeded case."""
+    cfg = {"use_hierarchical_sampling": True, "dist_decoder_cfg": {"use_vis": False}, "render_depth": True}
+    que, ref = synthetic.make_scene(48, 64, rfn, seed=100 + rfn, smooth=2)
+    que = synthetic.slice_rays(que, 1000, 1048)
+    W = synthetic.make_weights(cfg, seed=3)
+    from gen_golden import flat_cfg
+    ocfg = flat_cfg({**renderer.base_cfg, **cfg})
+    gold = orc.render_impl(W, ocfg, que, ref, False)
+    net = renderer.NeuralRayRenderPath(cfg)
+    net.load_state_dict(W, strict=True)
+    net.cuda()
+    out = net.render_impl(dev(que), dev(ref), False)
+    out_f = net.render_by_depth(gold["que_depth_fine"].cuda(), dev(que), dev(ref), False, True)
+    torch.cuda.synchronize()
+    for k in ("pixel_colors_nr", "hit_prob_nr", "render_depth"):
+        close(out[k], gold[k], what=f"{k} rfn={rfn}")
+        close(out_f[k], gold[k + "_fine"], what=f"{k}_fine(injected depths) rfn={rfn}")
+    assert torch.equal(out["ray_mask"].cpu(), gold["ray_mask"])
