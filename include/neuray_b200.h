@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NR_ABI_VERSION 2
+#define NR_ABI_VERSION 3
 
 #define NR_OK 0
 #define NR_E_INVALID (-1)   /* bad argument (null pointer, unsupported shape) */
@@ -64,7 +64,7 @@ int nr_weight_layout(NrWeightLayout* out);
 
 /* Layout of the tensor-core weight buffer (floats; details in csrc/nr_common.cuh namespace tcl). */
 typedef struct NrTcLayout {
-  int32_t total, stage, head0, pe0, pe1, b0, b1, v01, v2r;
+  int32_t total, stage, head0, pe0, pe1, b0, b1, v01, v2r, rd1;
 } NrTcLayout;
 int nr_tc_layout(NrTcLayout* out);
 

@@ -131,11 +131,13 @@ constexpr int STAGE = 4096;
 constexpr int HEAD0 = 0;
 constexpr int PE0 = 4 * STAGE;
 constexpr int PE1 = PE0 + STAGE;
-constexpr int B0 = PE1 + 2048;
+constexpr int B0 = PE1 + STAGE;   // PE1 holds a 48-row tile (prob_embed.2 + neuray_fc.0 behind it): 3072 floats
 constexpr int B1 = B0 + 3 * STAGE;
 constexpr int V01 = B1 + STAGE;
 constexpr int V2R = V01 + STAGE;
-constexpr int TOTAL = V2R + STAGE;
+constexpr int RD1 = V2R + STAGE;    // ray_dir_fc.2 as a 48-row x K16 tile (hi 1536 | lo 1536), resident in shared memory
+constexpr int RD1_SIZE = 3072;
+constexpr int TOTAL = RD1 + RD1_SIZE;
 }  // namespace tcl
 
 // ------------------------------------------------------------------------------------------------------------

@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm(const KParams kp) {
         store_a32(b, 32, x);
       }
       PM_TICK(5)
-      run_layer<32, 4, 32, 4, 0, 1, 0, 1024 * 4, 0, true, true>(b);                 // prob_embed.2
+      run_layer<32, 4, 32, 4, 0, 1, 0, 1536 * 4, 0, true, true>(b);                 // prob_embed.2
       float gate;
       {
         float h8[8];

@@ -27,7 +27,8 @@ constexpr int TCOLS = 160;                                    // tensor-memory c
 
 // ---- shared memory map (floats) ----
 constexpr int OFF_RING = 0;                                   // NBUF x RING_STAGE
-constexpr int OFF_WH = OFF_RING + NBUF * RING_STAGE;          // hoisted base_fc.0: WT[140][64] | bias[64]
+constexpr int OFF_RD1 = OFF_RING + NBUF * RING_STAGE;         // ray_dir_fc.2 tensor-core tile (resident, 1024-byte aligned)
+constexpr int OFF_WH = OFF_RD1 + tcl::RD1_SIZE;               // hoisted base_fc.0: WT[140][64] | bias[64]
 constexpr int WH = 140 * 64 + 64;
 constexpr int OFF_WG0 = OFF_WH + WH;                          // geometry_fc.0: WT[65][64] | bias[64]
 constexpr int WG0 = 65 * 64 + 64;
@@ -44,7 +45,7 @@ constexpr int OFF_BAR = OFF_STG + STG;
 constexpr int SMEM_FLOATS = OFF_BAR + 32;
 constexpr size_t SMEM_BYTES = size_t(SMEM_FLOATS) * 4;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(OFF_WH % 4 == 0 && OFF_WG0 % 4 == 0 && OFF_WG1 % 4 == 0 && OFF_SW % 4 == 0 && OFF_GS % 4 == 0 && OFF_STG % 4 == 0, "alignment");
+static_assert((OFF_RD1 * 4) % 1024 == 0 && OFF_WH % 4 == 0 && OFF_WG0 % 4 == 0 && OFF_WG1 % 4 == 0 && OFF_SW % 4 == 0 && OFF_GS % 4 == 0 && OFF_STG % 4 == 0, "alignment");
 
 // Layer issue, executed by all 128 threads of the block after they wrote their A columns (b.tAhi / b.mAhi = column 0 of
 // the block).  K chunk c (of NCH) reads A columns AHI + 8c (c < NLIN) or TAILHI + 8(c - NLIN), lo parts LOOFF columns
@@ -95,6 +96,31 @@ __device__ __forceinline__ void issue_layer(Blk& b) {
     __syncwarp();
   }
   if (RELEASE) b.wi += NSTG;
+}
+// Same, B operand = a resident shared-memory tile at byte address `base` (one slab, hi part first, lo part OFF_LO bytes
+// further): no ring accounting.
+template <int N, int NCH, int AHI, int LOOFF, int DCOL, uint32_t OFF_LO>
+__device__ __forceinline__ void issue_layer_resident(Blk& b, uint32_t base) {
+  tc::tmem_st_wait();
+  tc::fence_before_thread_sync();
+  tc::named_sync(2 + b.blk, 128);
+  if (b.issuer_warp) {
+    tc::fence_after_thread_sync();
+    if (tc::elect_one()) {
+      constexpr uint32_t idesc = tc::idesc_tf32(N);
+      const uint64_t dhi = tc::smem_desc_sw128(base), dlo = tc::smem_desc_sw128(base + OFF_LO);
+#pragma unroll
+      for (int ps = 0; ps < 3; ++ps) {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int acol = AHI + 8 * c + (ps == 1 ? LOOFF : 0);
+          tc::mma_tf32_ts(b.mAhi + DCOL, b.mAhi + acol, (ps == 2 ? dlo : dhi) + ((c * 32) >> 4), idesc, (ps | c) != 0);
+        }
+      }
+      tc::mma_commit(b.mma_bar);
+    }
+    __syncwarp();
+  }
 }
 __device__ __forceinline__ void wait_layer(Blk& b) {
   tc::mbar_wait(b.mma_bar, b.phase);
@@ -156,6 +182,7 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
   uint64_t* const wempty = bars + NBUF;
   uint64_t* const mma_bars = bars + 2 * NBUF;                 // [NBLK]
   uint32_t* const tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2 * NBUF + NBLK);
+  uint64_t* const res_bar = bars + 2 * NBUF + NBLK + 2;        // resident tensor-core tile has landed
 
   const int rfn = pp.rfn, dn = pp.dn;
   const int N = pp.rn * dn;
@@ -169,7 +196,10 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
   if (tid == 0) {
     for (int i = 0; i < NBUF; ++i) { tc::mbar_init(wfull + i, 1); tc::mbar_init(wempty + i, NBLK); }
     for (int i = 0; i < NBLK; ++i) tc::mbar_init(mma_bars + i, 1);
+    tc::mbar_init(res_bar, 1);
     tc::fence_mbar_init();
+    tc::mbar_arrive_expect_tx(res_bar, tcl::RD1_SIZE * 4);
+    tc::bulk_g2s(smem + OFF_RD1, pp.w_tc + tcl::RD1, tcl::RD1_SIZE * 4, res_bar);
   }
   if (warp == 0) tc::tmem_alloc<512>(tmem_base_s);
   if (tid < NCOMP) {
@@ -197,6 +227,13 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
   __syncthreads();
   tc::fence_after_thread_sync();
   const uint32_t tmem_base = *tmem_base_s;
+  tc::mbar_wait(res_bar, 0);
+  if (tid < 8) {   // neuray_fc.0 rides on prob_embed.2's MMA (8 extra output rows): its bias as seen through that layer
+    float acc = sw[SW_NF0B + tid];
+    for (int j = 0; j < 32; ++j) acc = fmaf(sw[SW_NF0W + j * 8 + tid], sw[SW_PE1B + j], acc);
+    sw[SW_NF0C + tid] = acc;
+  }
+  __syncthreads();
 
   {
     // ---------------- compute warps (thread 0 also feeds the weight ring, see Producer) ----------------
@@ -465,46 +502,48 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
         st32(b, 0, 64, x);                                                           // over ray_feats: their last reader has completed
       }
       PM_TICK(5)
-      run_layer<32, 4, 0, 4, 0, 0, 1024 * 4, 0, true, true>(b);                     // prob_embed.2
+      // prob_embed.2 with neuray_fc.0 behind it: N = 48, accumulator columns [96,144)
+      issue_layer<48, 4, 0, 64, 4, 0, 96, 0, 1, 0, 1536 * 4, 0, true, true, false>(b);
+      wait_layer(b);
       float gate;
       {
-        float h8[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) h8[j] = sw[SW_NF0B + j];
         float x[32];
-        ld32(b, 128, x);
+        ld32(b, 96, x);
         add_bias32(x, sw + SW_PE1B);                                                 // neuray_feat
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float4 wa = *reinterpret_cast<const float4*>(sw + SW_NF0W + j * 8);
-          const float4 wb = *reinterpret_cast<const float4*>(sw + SW_NF0W + j * 8 + 4);
-          h8[0] = fmaf(wa.x, x[j], h8[0]); h8[1] = fmaf(wa.y, x[j], h8[1]); h8[2] = fmaf(wa.z, x[j], h8[2]); h8[3] = fmaf(wa.w, x[j], h8[3]);
-          h8[4] = fmaf(wb.x, x[j], h8[4]); h8[5] = fmaf(wb.y, x[j], h8[5]); h8[6] = fmaf(wb.z, x[j], h8[6]); h8[7] = fmaf(wb.w, x[j], h8[7]);
-        }
         st32(b, 0, 64, x);
+        float h8[16];
+        ld16(b, 128, h8);                                                            // neuray_fc.0 pre-activations (8 used)
         gate = sw[SW_NF1B];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) gate = fmaf(sw[SW_NF1W + j], elu(h8[j]), gate);
+        for (int j = 0; j < 8; ++j) gate = fmaf(sw[SW_NF1W + j], elu(h8[j] + sw[SW_NF0C + j]), gate);
       }
       // base_fc.0, K round A: the neuray_feat inputs (B chunks 5..8), accumulator columns [96,160); completes under ray_dir_fc
       issue_layer<64, 4, 0, 64, 4, 0, 96, 5, 3, 0, 2048 * 4, 0, true, false, false>(b);
       float rf[40];                                                                  // rgb_feat (35) + zero padding
       {
-        float h16[16];
+        {
+          float h16[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float* __restrict__ w0 = sw + SW_RD0W;
-          h16[j] = elu(fmaf(w0[48 + j], dd[3], fmaf(w0[32 + j], dd[2], fmaf(w0[16 + j], dd[1], fmaf(w0[j], dd[0], sw[SW_RD0B + j])))));
+          for (int j = 0; j < 16; ++j) {
+            const float* __restrict__ w0 = sw + SW_RD0W;
+            h16[j] = elu(fmaf(w0[48 + j], dd[3], fmaf(w0[32 + j], dd[2], fmaf(w0[16 + j], dd[1], fmaf(w0[j], dd[0], sw[SW_RD0B + j])))));
+          }
+          wait_layer(b);                                                             // round A has read neuray_feat: A is free again
+          st16(b, 48, 64, h16);                                                      // ray_dir_fc.2 operand: hi [48,64), lo [64,80)
+        }
+        issue_layer_resident<48, 2, 48, 16, 0, 1536 * 4>(b, tc::smem_u32(smem + OFF_RD1));   // ray_dir_fc.2: K = 16, accumulator [0,48)
+        wait_layer(b);
+        ld32(b, 0, rf);
+        {
+          float t16[16];
+          ld16(b, 32, t16);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rf[32 + j] = t16[j];
         }
 #pragma unroll
         for (int j4 = 0; j4 < 36; j4 += 4) {
-          float4 acc = *reinterpret_cast<const float4*>(sw + SW_RD1B + j4);
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const float4 wv = *reinterpret_cast<const float4*>(sw + SW_RD1W + k * 36 + j4);
-            acc.x = fmaf(wv.x, h16[k], acc.x); acc.y = fmaf(wv.y, h16[k], acc.y); acc.z = fmaf(wv.z, h16[k], acc.z); acc.w = fmaf(wv.w, h16[k], acc.w);
-          }
-          rf[j4] = elu(acc.x); rf[j4 + 1] = elu(acc.y); rf[j4 + 2] = elu(acc.z); rf[j4 + 3] = elu(acc.w);
+          const float4 bb = *reinterpret_cast<const float4*>(sw + SW_RD1B + j4);
+          rf[j4] = elu(rf[j4] + bb.x); rf[j4 + 1] = elu(rf[j4 + 1] + bb.y); rf[j4 + 2] = elu(rf[j4 + 2] + bb.z); rf[j4 + 3] = elu(rf[j4 + 3] + bb.w);
         }
         // + [rgb | img_feats] of this row (img_feats come back from the transposition buffer)
         rf[0] += rgbin[0]; rf[1] += rgbin[1]; rf[2] += rgbin[2];
@@ -519,7 +558,6 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
         }
 #pragma unroll
         for (int j = 35; j < 40; ++j) rf[j] = 0.f;
-        wait_layer(b);                                                               // round A has read neuray_feat: A is free again
         st32(b, 0, 48, rf);                                                          // rgb_feat: hi [0,40), lo [48,88)
         st8(b, 32, 80, rf + 32);
       }

@@ -64,8 +64,9 @@ constexpr int SW_HEAD = 0, SW_HEAD_STRIDE = 136;   // per head: L0 bias 32 | L1 
 constexpr int SW_PE0B = 544, SW_PE1B = 576, SW_RD0W = 608, SW_RD0B = 672, SW_RD1W = 688, SW_RD1B = 1264, SW_NF0W = 1300,
               SW_NF0B = 1556, SW_NF1W = 1564, SW_NF1B = 1572, SW_B1B = 1576, SW_V0B = 1608, SW_V1B = 1640, SW_V1LW = 1672,
               SW_V1LB = 1704, SW_V20B = 1708, SW_V21W = 1740, SW_V21B = 1772, SW_RGB0B = 1776, SW_RGB1W = 1792, SW_RGB1B = 1920,
-              SW_RGB2W = 1928, SW_RGB2B = 1936;
-static_assert(SW_RGB2B + 4 <= SW, "small weights overflow");
+              SW_RGB2W = 1928, SW_RGB2B = 1936,
+              SW_NF0C = 1944;   // neuray_fc.0 bias seen through prob_embed.2: W_nf0 @ b_pe2 + b_nf0 (pm3 kernel)
+static_assert(SW_NF0C + 8 <= SW, "small weights overflow");
 
 // ---- TMEM columns per 128-row block (block b starts at column 256*b) ----
 constexpr int T_AHI = 0, T_ALO = 80, T_D = 160;
@@ -105,7 +106,7 @@ struct Producer {
     else {
       const int t = s - n_heads;
       src = t == 0 ? tcl::PE0 : t == 1 ? tcl::PE1 : t <= 4 ? tcl::B0 + (t - 2) * RING_STAGE : t == 5 ? tcl::B1 : t == 6 ? tcl::V01 : tcl::V2R;
-      if (t == 1) bytes = 2048 * 4;
+      if (t == 1) bytes = 3072 * 4;
     }
     const uint32_t buf = next % NBUF;
     tc::mbar_arrive_expect_tx(wfull + buf, bytes);
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
           else {
             const int t = s - n_heads;
             src = t == 0 ? tcl::PE0 : t == 1 ? tcl::PE1 : t <= 4 ? tcl::B0 + (t - 2) * RING_STAGE : t == 5 ? tcl::B1 : t == 6 ? tcl::V01 : tcl::V2R;
-            if (t == 1) bytes = 2048 * 4;
+            if (t == 1) bytes = 3072 * 4;
           }
           const uint32_t buf = i % NBUF;
           if (i >= NBUF) tc::mbar_wait(wempty + buf, ((i / NBUF) - 1) & 1);
@@ -612,7 +613,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) point_kernel_tc(const KParams kp)
         store_a32(b, 32, x);
       }
       NR_TICK(6)
-      run_layer<32, 4, 32, 4, 0, 1, 0, 1024 * 4, 0, true, true>(b);               // prob_embed.2
+      run_layer<32, 4, 32, 4, 0, 1, 0, 1536 * 4, 0, true, true>(b);               // prob_embed.2
       float gate;
       {
         float h8[8];

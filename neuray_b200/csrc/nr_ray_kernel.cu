@@ -12,6 +12,8 @@ namespace nr {
 namespace rk {
 
 constexpr int REC = NR_POINT_REC;
+constexpr int ROW = 20;   // padded stride of the 16-float per-sample rows in shared memory: the lanes' float4 accesses
+                          // (lane = sample) then fall into 8 distinct bank groups instead of 2
 
 struct KParams {
   NrPassParams p;
@@ -28,18 +30,18 @@ __global__ void __launch_bounds__(256) ray_kernel(const KParams kp) {
   const int dn = pp.dn, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // CTA-wide: weights + positional table
   float* const sW = smem;                                   // lay::TOTAL_RAY
-  float* const sPE = sW + lay::TOTAL_RAY;                   // [dn][16]
-  float* const wbase = sPE + dn * 16 + size_t(warp) * kp.per_warp;
-  float* const sX = wbase;                                  // [dn][16] attention input (residual)
-  float* const sK = sX + dn * 16;
-  float* const sV = sK + dn * 16;
-  float* const sHit = sV + dn * 16;                         // [dn]
+  float* const sPE = sW + lay::TOTAL_RAY;                   // [dn][ROW]
+  float* const wbase = sPE + dn * ROW + size_t(warp) * kp.per_warp;
+  float* const sX = wbase;                                  // [dn][ROW] attention input (residual)
+  float* const sK = sX + dn * ROW;
+  float* const sV = sK + dn * ROW;
+  float* const sHit = sV + dn * ROW;                        // [dn]
   float* const sT = sHit + dn;                              // [dn]   normalised inverse depth
   float* const sCdf = sT + dn;                              // [dn+1]
   float* const sSort = sCdf + dn + 4;                       // [sort_n]
 
   for (int i = threadIdx.x; i < lay::TOTAL_RAY; i += blockDim.x) sW[i] = __ldg(pp.w_ray + i);
-  for (int i = threadIdx.x; i < dn * 16; i += blockDim.x) sPE[i] = __ldg(pp.pos_enc + i);
+  for (int i = threadIdx.x; i < dn * 16; i += blockDim.x) sPE[(i >> 4) * ROW + (i & 15)] = __ldg(pp.pos_enc + i);
   __syncthreads();
 
   const int n_chunks = (dn + 31) / 32;
@@ -53,8 +55,8 @@ __global__ void __launch_bounds__(256) ray_kernel(const KParams kp) {
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         const float4 g = __ldg(reinterpret_cast<const float4*>(rec + s * REC) + q4);
-        x[4 * q4 + 0] = g.x + sPE[s * 16 + 4 * q4 + 0]; x[4 * q4 + 1] = g.y + sPE[s * 16 + 4 * q4 + 1];
-        x[4 * q4 + 2] = g.z + sPE[s * 16 + 4 * q4 + 2]; x[4 * q4 + 3] = g.w + sPE[s * 16 + 4 * q4 + 3];
+        const float4 pe = *reinterpret_cast<const float4*>(sPE + s * ROW + 4 * q4);
+        x[4 * q4 + 0] = g.x + pe.x; x[4 * q4 + 1] = g.y + pe.y; x[4 * q4 + 2] = g.z + pe.z; x[4 * q4 + 3] = g.w + pe.w;
       }
       float kk[16], vv[16];
 #pragma unroll
@@ -68,7 +70,11 @@ __global__ void __launch_bounds__(256) ray_kernel(const KParams kp) {
         }
       }
 #pragma unroll
-      for (int j = 0; j < 16; ++j) { sX[s * 16 + j] = x[j]; sK[s * 16 + j] = kk[j]; sV[s * 16 + j] = vv[j]; }
+      for (int q4 = 0; q4 < 4; ++q4) {
+        *reinterpret_cast<float4*>(sX + s * ROW + 4 * q4) = make_float4(x[4 * q4], x[4 * q4 + 1], x[4 * q4 + 2], x[4 * q4 + 3]);
+        *reinterpret_cast<float4*>(sK + s * ROW + 4 * q4) = make_float4(kk[4 * q4], kk[4 * q4 + 1], kk[4 * q4 + 2], kk[4 * q4 + 3]);
+        *reinterpret_cast<float4*>(sV + s * ROW + 4 * q4) = make_float4(vv[4 * q4], vv[4 * q4 + 1], vv[4 * q4 + 2], vv[4 * q4 + 3]);
+      }
     }
     __syncwarp();
 
@@ -77,13 +83,18 @@ __global__ void __launch_bounds__(256) ray_kernel(const KParams kp) {
       {
         float x[16], q[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { x[j] = sX[s * 16 + j]; q[j] = 0.f; }
+        for (int j = 0; j < 16; ++j) q[j] = 0.f;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const float4 t4 = *reinterpret_cast<const float4*>(sX + s * ROW + 4 * q4);
+          x[4 * q4] = t4.x; x[4 * q4 + 1] = t4.y; x[4 * q4 + 2] = t4.z; x[4 * q4 + 3] = t4.w;
+        }
 #pragma unroll
         for (int k = 0; k < 16; ++k)
 #pragma unroll
           for (int j = 0; j < 16; ++j) q[j] = fmaf(sW[lay::WQ + k * 16 + j], x[k], q[j]);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) q[j] = q[j] / 2.f;          // temperature = d_k ** 0.5 = 2
+        for (int j = 0; j < 16; ++j) q[j] = (q[j] / 2.f) * 1.4426950408889634f;   // temperature = d_k ** 0.5 = 2; logits in log2 units (softmax via ex2)
         const float nvalid = __ldg(rec + s * REC + 19);
         float o[16];
 #pragma unroll
@@ -93,7 +104,7 @@ __global__ void __launch_bounds__(256) ray_kernel(const KParams kp) {
           for (int t = 0; t < dn; ++t) {
 #pragma unroll
             for (int hh = 0; hh < 4; ++hh) {
-              const float4 k4 = *reinterpret_cast<const float4*>(sK + t * 16 + 4 * hh);
+              const float4 k4 = *reinterpret_cast<const float4*>(sK + t * ROW + 4 * hh);
               const float l = fmaf(q[4 * hh + 3], k4.w, fmaf(q[4 * hh + 2], k4.z, fmaf(q[4 * hh + 1], k4.y, q[4 * hh] * k4.x)));
               mx[hh] = fmaxf(mx[hh], l);
             }
@@ -102,10 +113,10 @@ __global__ void __launch_bounds__(256) ray_kernel(const KParams kp) {
           for (int t = 0; t < dn; ++t) {
 #pragma unroll
             for (int hh = 0; hh < 4; ++hh) {
-              const float4 k4 = *reinterpret_cast<const float4*>(sK + t * 16 + 4 * hh);
-              const float4 v4 = *reinterpret_cast<const float4*>(sV + t * 16 + 4 * hh);
+              const float4 k4 = *reinterpret_cast<const float4*>(sK + t * ROW + 4 * hh);
+              const float4 v4 = *reinterpret_cast<const float4*>(sV + t * ROW + 4 * hh);
               const float l = fmaf(q[4 * hh + 3], k4.w, fmaf(q[4 * hh + 2], k4.z, fmaf(q[4 * hh + 1], k4.y, q[4 * hh] * k4.x)));
-              const float e = __expf(l - mx[hh]);
+              const float e = ex2_ftz(l - mx[hh]);
               den[hh] += e;
               o[4 * hh + 0] = fmaf(e, v4.x, o[4 * hh + 0]); o[4 * hh + 1] = fmaf(e, v4.y, o[4 * hh + 1]);
               o[4 * hh + 2] = fmaf(e, v4.z, o[4 * hh + 2]); o[4 * hh + 3] = fmaf(e, v4.w, o[4 * hh + 3]);
@@ -118,7 +129,7 @@ __global__ void __launch_bounds__(256) ray_kernel(const KParams kp) {
           for (int t = 0; t < dn; ++t) {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 v4 = *reinterpret_cast<const float4*>(sV + t * 16 + 4 * j4);
+              const float4 v4 = *reinterpret_cast<const float4*>(sV + t * ROW + 4 * j4);
               o[4 * j4 + 0] += v4.x; o[4 * j4 + 1] += v4.y; o[4 * j4 + 2] += v4.z; o[4 * j4 + 3] += v4.w;
             }
           }
@@ -226,9 +237,9 @@ int launch_ray_kernel(const NrPassParams* p, cudaStream_t stream) {
   if (p->fine_dn > 0) {
     kp.sort_n = sort_size_for(p->fine_dn + (p->fine_use_all ? p->dn : 0));
   }
-  kp.per_warp = p->dn * 48 + p->dn * 3 + 8 + kp.sort_n;
+  kp.per_warp = p->dn * 3 * rk::ROW + p->dn * 3 + 8 + kp.sort_n;
   kp.per_warp = (kp.per_warp + 3) & ~3;
-  const int shared_common = lay::TOTAL_RAY + p->dn * 16;
+  const int shared_common = lay::TOTAL_RAY + p->dn * rk::ROW;
   int warps = 8;
   while (warps > 1 && size_t(shared_common + warps * kp.per_warp) * 4 > 200 * 1024) warps >>= 1;
   kp.warps = warps;

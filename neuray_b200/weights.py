@@ -166,7 +166,14 @@ def pack_tc_weights(params, dec, agg, device=None):
         put(base + 2048, g(f"{dec}.{head}.2.weight"), 32, 1024)
     ib = f"{agg}.agg_impl"
     put(T.pe0, g(f"{agg}.prob_embed.0.weight"), 40, 2048)                 # [32, 34] -> K 40
-    put(T.pe1, g(f"{agg}.prob_embed.2.weight"), 32, 1024)
+    # prob_embed.2 carries 8 extra output rows: neuray_fc.0 applied to its (linear) output, so the point kernel gets the
+    # neuray_fc hidden layer out of the same MMA (rows 32..39 = W_nf0 @ W_pe2; its bias is folded in the kernel's setup)
+    wpe1 = g(f"{agg}.prob_embed.2.weight").detach().to(device)
+    wnf0 = g(f"{ib}.neuray_fc.0.weight").detach().to(device)
+    w48 = torch.zeros(48, 32, dtype=torch.float32, device=device)
+    w48[:32] = wpe1.float()
+    w48[32:40] = (wnf0.double() @ wpe1.double()).float()
+    put(T.pe1, w48, 32, 1536)
     w0 = g(f"{ib}.base_fc.0.weight").detach().float().to(device)        # [64, 207]
     b0 = torch.zeros(64, 72, dtype=torch.float32, device=device)          # K order: rgb_feat 35 | 5 zeros | neuray_feat 32
     b0[:, :35] = w0[:, 140:175]
@@ -180,6 +187,9 @@ def pack_tc_weights(params, dec, agg, device=None):
     put(T.v01 + 2048, g(f"{ib}.vis_fc.2.weight")[:32], 32, 1024)
     put(T.v2r, g(f"{ib}.vis_fc2.0.weight"), 32, 1024)
     put(T.v2r + 2048, g(f"{ib}.rgb_fc.0.weight"), 40, 1024)               # [16, 37] -> K 40, two 512-float slabs
+    wrd = torch.zeros(48, 16, dtype=torch.float32, device=device)         # ray_dir_fc.2 [35, 16] -> 48 rows (MMA N % 16 == 0)
+    wrd[:35] = g(f"{ib}.ray_dir_fc.2.weight").detach().float().to(device)
+    put(T.rd1, wrd, 16, 1536)
     return buf
 
 

@@ -84,7 +84,7 @@ def test_tc_weight_pack_roundtrip():
     W = synthetic.make_weights(cfg)
     T = _lib.tc_layout()
     buf = weights.pack_tc_weights(W, "dist_decoder", "agg_net", torch.device("cpu"))
-    assert buf.numel() == T.total == 47104
+    assert buf.numel() == T.total == 52224
 
     def unswz(flat, n):                # [slabs*n*32] -> [n, slabs*32]
         slabs = flat.numel() // (n * 32)
@@ -100,6 +100,14 @@ def test_tc_weight_pack_roundtrip():
                      unswz(buf[T.b0 + s * T.stage + 2048:T.b0 + (s + 1) * T.stage], 64) for s in range(3)], 1)   # [64, 96]
     assert torch.equal(rec[:, :35], w0[:, 140:175]) and torch.equal(rec[:, 40:72], w0[:, 175:207])
     assert float(rec[:, 35:40].abs().sum()) == 0.0 and float(rec[:, 72:].abs().sum()) == 0.0
+    # prob_embed.2 + neuray_fc.0 behind it: 48-row tile, hi 0..1536, lo 1536..3072
+    rec = unswz(buf[T.pe1:T.pe1 + 1536], 48) + unswz(buf[T.pe1 + 1536:T.pe1 + 3072], 48)
+    wpe, wnf = W["agg_net.prob_embed.2.weight"], W["agg_net.agg_impl.neuray_fc.0.weight"]
+    assert torch.equal(rec[:32], wpe) and float(rec[40:].abs().sum()) == 0.0
+    assert torch.allclose(rec[32:40], wnf @ wpe, rtol=1e-5, atol=1e-6)
+    rec = unswz(buf[T.rd1:T.rd1 + 1536], 48) + unswz(buf[T.rd1 + 1536:T.rd1 + 3072], 48)   # ray_dir_fc.2, resident tile
+    wrd = W["agg_net.agg_impl.ray_dir_fc.2.weight"]
+    assert torch.equal(rec[:35, :16], wrd) and float(rec[35:].abs().sum()) == 0.0 and float(rec[:, 16:].abs().sum()) == 0.0
     wr = W["agg_net.agg_impl.rgb_fc.0.weight"]                      # [16, 37] at V2R+2048 (hi, two 512 slabs), lo at +1024
     rec = unswz(buf[T.v2r + 2048:T.v2r + 3072], 16) + unswz(buf[T.v2r + 3072:T.v2r + 4096], 16)
     assert torch.equal(rec[:, :37], wr) and float(rec[:, 37:].abs().sum()) == 0.0
