@@ -137,7 +137,9 @@ constexpr int V01 = B1 + STAGE;
 constexpr int V2R = V01 + STAGE;
 constexpr int RD1 = V2R + STAGE;    // ray_dir_fc.2 as a 48-row x K16 tile (hi 1536 | lo 1536), resident in shared memory
 constexpr int RD1_SIZE = 3072;
-constexpr int TOTAL = RD1 + RD1_SIZE;
+constexpr int HST = RD1 + RD1_SIZE;    // the 140 view-pooled inputs of base_fc.0 as a 64-row x K160 tile: hi 5 slabs | lo 5 slabs; K index
+constexpr int HST_SIZE = 2 * 5 * 2048; //   = 24*round + 6*stat + i  (feature 6*round + i; stat = mean0, var0, mean1, var1), resident in shared memory
+constexpr int TOTAL = HST + HST_SIZE;
 }  // namespace tcl
 
 // ------------------------------------------------------------------------------------------------------------

@@ -27,25 +27,21 @@ constexpr int TCOLS = 160;                                    // tensor-memory c
 
 // ---- shared memory map (floats) ----
 constexpr int OFF_RING = 0;                                   // NBUF x RING_STAGE
-constexpr int OFF_RD1 = OFF_RING + NBUF * RING_STAGE;         // ray_dir_fc.2 tensor-core tile (resident, 1024-byte aligned)
-constexpr int OFF_WH = OFF_RD1 + tcl::RD1_SIZE;               // hoisted base_fc.0: WT[140][64] | bias[64]
-constexpr int WH = 140 * 64 + 64;
-constexpr int OFF_WG0 = OFF_WH + WH;                          // geometry_fc.0: WT[65][64] | bias[64]
+constexpr int OFF_HST = OFF_RING + NBUF * RING_STAGE;         // view-pooled part of base_fc.0, tensor-core tile (resident, 1024-byte aligned)
+constexpr int OFF_RD1 = OFF_HST + tcl::HST_SIZE;              // ray_dir_fc.2 tensor-core tile (resident, 1024-byte aligned)
+constexpr int OFF_WG0 = OFF_RD1 + tcl::RD1_SIZE;              // geometry_fc.0: WT[65][64] | bias[64]
 constexpr int WG0 = 65 * 64 + 64;
 constexpr int OFF_WG1 = OFF_WG0 + WG0;                        // geometry_fc.2: [16][64] (output-major) | bias[16]
 constexpr int WG1 = 64 * 16 + 16;
 constexpr int OFF_SW = OFF_WG1 + WG1;                         // small resident weights (same layout as point_kernel_tc)
-constexpr int GS_ROW = 68;                                    // padded: the points of a warp read their rows conflict-free
-constexpr int OFF_GS = OFF_SW + SW;                           // hoisted partial sums per point: [NBLK][32][GS_ROW]
-constexpr int GS = NBLK * 32 * GS_ROW;
-constexpr int OFF_STG = OFF_GS + GS;                          // gather transposition: per warp [32 rows][36]
+constexpr int OFF_STG = OFF_SW + SW;                          // gather transposition: per warp [32 rows][36]
 constexpr int STG_ROW = 36;
 constexpr int STG = (NCOMP / 32) * 32 * STG_ROW;
 constexpr int OFF_BAR = OFF_STG + STG;
 constexpr int SMEM_FLOATS = OFF_BAR + 32;
 constexpr size_t SMEM_BYTES = size_t(SMEM_FLOATS) * 4;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert((OFF_RD1 * 4) % 1024 == 0 && OFF_WH % 4 == 0 && OFF_WG0 % 4 == 0 && OFF_WG1 % 4 == 0 && OFF_SW % 4 == 0 && OFF_GS % 4 == 0 && OFF_STG % 4 == 0, "alignment");
+static_assert((OFF_HST * 4) % 1024 == 0 && (OFF_RD1 * 4) % 1024 == 0 && OFF_WG0 % 4 == 0 && OFF_WG1 % 4 == 0 && OFF_SW % 4 == 0 && OFF_STG % 4 == 0, "alignment");
 
 // Layer issue, executed by all 128 threads of the block after they wrote their A columns (b.tAhi / b.mAhi = column 0 of
 // the block).  K chunk c (of NCH) reads A columns AHI + 8c (c < NLIN) or TAILHI + 8(c - NLIN), lo parts LOOFF columns
@@ -97,14 +93,15 @@ __device__ __forceinline__ void issue_layer(Blk& b) {
   }
   if (RELEASE) b.wi += NSTG;
 }
-// Same, B operand = a resident shared-memory tile at byte address `base` (one slab, hi part first, lo part OFF_LO bytes
-// further): no ring accounting.
-template <int N, int NCH, int AHI, int LOOFF, int DCOL, uint32_t OFF_LO>
-__device__ __forceinline__ void issue_layer_resident(Blk& b, uint32_t base) {
+// Same, B operand = a resident shared-memory tile at byte address `base` (hi slabs first, SLAB bytes apart; lo parts
+// OFF_LO bytes further): no ring accounting.  `issuer`: warp-uniform, true in the one warp of the block that issues
+// this layer (a completion wait separates consecutive layers, so different layers may be issued by different warps).
+template <int N, int NCH, int AHI, int LOOFF, int DCOL, int CB0, uint32_t OFF_LO, uint32_t SLAB, bool ACC>
+__device__ __forceinline__ void issue_layer_resident(Blk& b, uint32_t base, bool issuer) {
   tc::tmem_st_wait();
   tc::fence_before_thread_sync();
   tc::named_sync(2 + b.blk, 128);
-  if (b.issuer_warp) {
+  if (issuer) {
     tc::fence_after_thread_sync();
     if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::idesc_tf32(N);
@@ -114,7 +111,9 @@ __device__ __forceinline__ void issue_layer_resident(Blk& b, uint32_t base) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           const int acol = AHI + 8 * c + (ps == 1 ? LOOFF : 0);
-          tc::mma_tf32_ts(b.mAhi + DCOL, b.mAhi + acol, (ps == 2 ? dlo : dhi) + ((c * 32) >> 4), idesc, (ps | c) != 0);
+          const int cb = CB0 + c;
+          const uint32_t inc = ((cb >> 2) * SLAB + (cb & 3) * 32) >> 4;
+          tc::mma_tf32_ts(b.mAhi + DCOL, b.mAhi + acol, (ps == 2 ? dlo : dhi) + inc, idesc, ACC || (ps | c) != 0);
         }
       }
       tc::mma_commit(b.mma_bar);
@@ -173,7 +172,6 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   float* const ring = smem + OFF_RING;
-  float* const sWh = smem + OFF_WH;
   float* const sWg0 = smem + OFF_WG0;
   float* const sWg1 = smem + OFF_WG1;
   float* const sw = smem + OFF_SW;
@@ -198,8 +196,9 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
     for (int i = 0; i < NBLK; ++i) tc::mbar_init(mma_bars + i, 1);
     tc::mbar_init(res_bar, 1);
     tc::fence_mbar_init();
-    tc::mbar_arrive_expect_tx(res_bar, tcl::RD1_SIZE * 4);
+    tc::mbar_arrive_expect_tx(res_bar, (tcl::RD1_SIZE + tcl::HST_SIZE) * 4);
     tc::bulk_g2s(smem + OFF_RD1, pp.w_tc + tcl::RD1, tcl::RD1_SIZE * 4, res_bar);
+    for (int i = 0; i < tcl::HST_SIZE; i += 4096) tc::bulk_g2s(smem + OFF_HST + i, pp.w_tc + tcl::HST + i, 4096 * 4, res_bar);
   }
   if (warp == 0) tc::tmem_alloc<512>(tmem_base_s);
   if (tid < NCOMP) {
@@ -218,7 +217,6 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
     cp(sw + SW_V1LB, gd + lay::VIS1L_B, 4); cp(sw + SW_V20B, gd + lay::V20_B, 32); cp(sw + SW_V21W, gd + lay::V21_W, 32);
     cp(sw + SW_V21B, gd + lay::V21_B, 4); cp(sw + SW_RGB0B, gd + lay::RGB0_B, 16); cp(sw + SW_RGB1W, gd + lay::RGB1_W, 128);
     cp(sw + SW_RGB1B, gd + lay::RGB1_B, 8); cp(sw + SW_RGB2W, gd + lay::RGB2_W, 8); cp(sw + SW_RGB2B, gd + lay::RGB2_B, 4);
-    cp(sWh, lay::HOIST_W, WH);                                                    // WT[140][64] | bias[64] are contiguous
     cp(sWg0, lay::GRP_D2 + lay::GEO0_W, WG0);
     for (int i = tid; i < 64 * 16; i += NCOMP) sWg1[(i & 15) * 64 + (i >> 4)] = __ldg(W + lay::GRP_D2 + lay::GEO1_W + i);   // WT[64][16] -> [16][64]
     cp(sWg1 + 64 * 16, lay::GRP_D2 + lay::GEO1_B, 16);
@@ -243,7 +241,6 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
     const int pl = (tid & 127) / G;                 // point inside the block
     const int lane0 = lane - v;                     // first lane of this point's group
     float* const stg = smem + OFF_STG + warp * 32 * STG_ROW;
-    float* const gs = smem + OFF_GS + ((warp >> 2) * 32 + pl) * GS_ROW;
 
     Blk b;
     b.blk = warp >> 2;
@@ -531,7 +528,7 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
           wait_layer(b);                                                             // round A has read neuray_feat: A is free again
           st16(b, 48, 64, h16);                                                      // ray_dir_fc.2 operand: hi [48,64), lo [64,80)
         }
-        issue_layer_resident<48, 2, 48, 16, 0, 1536 * 4>(b, tc::smem_u32(smem + OFF_RD1));   // ray_dir_fc.2: K = 16, accumulator [0,48)
+        issue_layer_resident<48, 2, 48, 16, 0, 0, 1536 * 4, 0, false>(b, tc::smem_u32(smem + OFF_RD1), b.issuer_warp);   // ray_dir_fc.2: K = 16, accumulator [0,48)
         wait_layer(b);
         ld32(b, 0, rf);
         {
@@ -556,11 +553,14 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
             o[44 + 4 * q] = t4.x; o[45 + 4 * q] = t4.y; o[46 + 4 * q] = t4.z; o[47 + 4 * q] = t4.w;
           }
         }
+        rf[35] = 1.f;                                                                // constant input: base_fc.0's bias is column 35 of its tile
 #pragma unroll
-        for (int j = 35; j < 40; ++j) rf[j] = 0.f;
+        for (int j = 36; j < 40; ++j) rf[j] = 0.f;
         st32(b, 0, 48, rf);                                                          // rgb_feat: hi [0,40), lo [48,88)
         st8(b, 32, 80, rf + 32);
       }
+      // base_fc.0, K round B: rgb_feat (B chunks 0..4); completes under the first butterflies of the view pooling
+      issue_layer<64, 5, 0, 48, 5, 0, 96, 0, 3, 0, 2048 * 4, 0, false, true, true>(b);
       if (DEBUG && kp.dbg != nullptr && row_ok) {
         float* __restrict__ o = kp.dbg + (size_t(v) * N + n) * 76;
         o[0] = mrow; o[1] = zrow; o[2] = hit; o[3] = visib; o[4] = dbg_px; o[5] = dbg_py;
@@ -568,58 +568,57 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
       }
 
       PM_TICK(6)
-      // ---------------- view pooling #1 streamed into the hoisted base_fc.0 columns of this lane ----------------
+      // ---------------- view pooling #1 (ibrnet.py:336-339) -> six more K rounds of base_fc.0 ----------------
+      // Every lane of a point ends the butterflies with the point's statistics, which is exactly its row of the
+      // view-invariant operand: 6 features x (mean0, var0, mean1, var1) = K 24 per round go to A[0:24] and are
+      // multiplied into the same accumulator.  The previous round's MMAs finish under this round's butterflies.
       const float msum = bsum<G>(mrow);
       const float w1 = mrow / (msum + 1e-8f);
       const float w0 = sigmoidf_(gate) * w1;
       {
-        float g[CPL];
-        ld_cols<G>(sWh + 140 * 64, v, g);                                   // bias
+        const uint32_t hst = tc::smem_u32(smem + OFF_HST);
+        const int wq = __shfl_sync(0xffffffffu, warp, 0) & 3;
+        auto round = [&](auto rc) {
+          constexpr int R = decltype(rc)::value;
+          float val[6], st[24];
 #pragma unroll
-        for (int f0 = 0; f0 < 35; f0 += 7) {                                         // 7 features x (w0, w1) = 14 butterflies at a time
-          float mm[14];
-#pragma unroll
-          for (int i = 0; i < 7; ++i) { mm[i] = rf[f0 + i] * w0; mm[7 + i] = rf[f0 + i] * w1; }
-          bsum_vec<G, 14>(mm);
-          float vv_[14];
-#pragma unroll
-          for (int i = 0; i < 7; ++i) {
-            const float d0 = rf[f0 + i] - mm[i], d1 = rf[f0 + i] - mm[7 + i];
-            vv_[i] = w0 * d0 * d0; vv_[7 + i] = w1 * d1 * d1;
+          for (int i = 0; i < 6; ++i) {
+            val[i] = (6 * R + i < 35) ? rf[6 * R + i] : 0.f;
+            st[i] = val[i] * w0; st[12 + i] = val[i] * w1;
           }
-          bsum_vec<G, 14>(vv_);
+          {
+            float mm[12];
 #pragma unroll
-          for (int i = 0; i < 7; ++i) {
-            const int f = f0 + i;
-            float wa[CPL], wb[CPL], wc[CPL], wd[CPL];
-            ld_cols<G>(sWh + f * 64, v, wa);
-            ld_cols<G>(sWh + (35 + f) * 64, v, wb);
-            ld_cols<G>(sWh + (70 + f) * 64, v, wc);
-            ld_cols<G>(sWh + (105 + f) * 64, v, wd);
+            for (int i = 0; i < 6; ++i) { mm[i] = st[i]; mm[6 + i] = st[12 + i]; }
+            bsum_vec<G, 12>(mm);
+            float vv_[12];
 #pragma unroll
-            for (int j = 0; j < CPL; ++j) g[j] = fmaf(wd[j], vv_[7 + i], fmaf(wc[j], mm[7 + i], fmaf(wb[j], vv_[i], fmaf(wa[j], mm[i], g[j]))));
+            for (int i = 0; i < 6; ++i) {
+              const float d0 = val[i] - mm[i], d1 = val[i] - mm[6 + i];
+              vv_[i] = w0 * d0 * d0; vv_[6 + i] = w1 * d1 * d1;
+            }
+            bsum_vec<G, 12>(vv_);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { st[i] = mm[i]; st[6 + i] = vv_[i]; st[12 + i] = mm[6 + i]; st[18 + i] = vv_[6 + i]; }
           }
-        }
-        __syncwarp();                                                                // previous tile's readers of gs are done
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) gs[own_col<G>(v, j)] = g[j];
-        __syncwarp();
+          wait_layer(b);                                                             // the MMAs reading A[0:48) have completed
+          st16(b, 0, 24, st);
+          st8(b, 16, 40, st + 16);
+          issue_layer_resident<64, 3, 0, 24, 96, 3 * R, 10240 * 4, 2048 * 4, true>(b, hst, wq == (R & 3));
+        };
+        round(std::integral_constant<int, 0>{}); round(std::integral_constant<int, 1>{}); round(std::integral_constant<int, 2>{});
+        round(std::integral_constant<int, 3>{}); round(std::integral_constant<int, 4>{}); round(std::integral_constant<int, 5>{});
       }
 
       PM_TICK(7)
       // ---------------- base_fc on the tensor cores ----------------
-      issue_layer<64, 5, 0, 48, 5, 0, 96, 0, 3, 0, 2048 * 4, 0, false, true, true>(b);   // base_fc.0, K round B: rgb_feat (B chunks 0..4)
       wait_layer(b);
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 32) {
         float x[32];
         ld32(b, 96 + c0, x);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 g4 = *reinterpret_cast<const float4*>(gs + c0 + 4 * q);
-          x[4 * q] = elu(x[4 * q] + g4.x); x[4 * q + 1] = elu(x[4 * q + 1] + g4.y);
-          x[4 * q + 2] = elu(x[4 * q + 2] + g4.z); x[4 * q + 3] = elu(x[4 * q + 3] + g4.w);
-        }
+        for (int j = 0; j < 32; ++j) x[j] = elu(x[j]);
         st32(b, c0, 64 + c0, x);                                                     // lo half 1 lands on accumulator columns already consumed
       }
       PM_TICK(8)

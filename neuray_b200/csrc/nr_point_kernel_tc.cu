@@ -14,6 +14,7 @@
 //   * gather, projections, per-view scalar heads, the cross-view reductions and the per-point layers (hoisted
 //     base_fc.0, geometry_fc) stay SIMT exactly as in the SIMT kernel
 #include <stdlib.h>
+#include <type_traits>
 
 #include "nr_common.cuh"
 #include "nr_point_common.cuh"

@@ -177,6 +177,7 @@ def pack_tc_weights(params, dec, agg, device=None):
     w0 = g(f"{ib}.base_fc.0.weight").detach().float().to(device)        # [64, 207]
     b0 = torch.zeros(64, 72, dtype=torch.float32, device=device)          # K order: rgb_feat 35 | 5 zeros | neuray_feat 32
     b0[:, :35] = w0[:, 140:175]
+    b0[:, 35] = g(f"{ib}.base_fc.0.bias").detach().float().to(device)     # bias column: the pm3 kernel feeds a constant 1 at K = 35
     b0[:, 40:72] = w0[:, 175:207]
     hi, lo = _tc_tiles(b0, 72)
     for s_ in range(3):
@@ -190,6 +191,15 @@ def pack_tc_weights(params, dec, agg, device=None):
     wrd = torch.zeros(48, 16, dtype=torch.float32, device=device)         # ray_dir_fc.2 [35, 16] -> 48 rows (MMA N % 16 == 0)
     wrd[:35] = g(f"{ib}.ray_dir_fc.2.weight").detach().float().to(device)
     put(T.rd1, wrd, 16, 1536)
+    # view-pooled inputs of base_fc.0 (ibrnet.py:338-342): K = 24*round + 6*stat + i <-> reference column stat*35 + 6*round + i
+    bh = torch.zeros(64, 160, dtype=torch.float32, device=device)
+    for r_ in range(6):
+        for s_ in range(4):
+            n_ = min(6, 35 - 6 * r_)
+            bh[:, 24 * r_ + 6 * s_: 24 * r_ + 6 * s_ + n_] = w0[:, s_ * 35 + 6 * r_: s_ * 35 + 6 * r_ + n_]
+    hi, lo = _tc_tiles(bh, 160)
+    buf[T.hst: T.hst + 10240] = hi
+    buf[T.hst + 10240: T.hst + 20480] = lo
     return buf
 
 

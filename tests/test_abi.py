@@ -84,7 +84,7 @@ def test_tc_weight_pack_roundtrip():
     W = synthetic.make_weights(cfg)
     T = _lib.tc_layout()
     buf = weights.pack_tc_weights(W, "dist_decoder", "agg_net", torch.device("cpu"))
-    assert buf.numel() == T.total == 52224
+    assert buf.numel() == T.total == 72704
 
     def unswz(flat, n):                # [slabs*n*32] -> [n, slabs*32]
         slabs = flat.numel() // (n * 32)
@@ -99,7 +99,12 @@ def test_tc_weight_pack_roundtrip():
     rec = torch.cat([unswz(buf[T.b0 + s * T.stage:T.b0 + s * T.stage + 2048], 64) +
                      unswz(buf[T.b0 + s * T.stage + 2048:T.b0 + (s + 1) * T.stage], 64) for s in range(3)], 1)   # [64, 96]
     assert torch.equal(rec[:, :35], w0[:, 140:175]) and torch.equal(rec[:, 40:72], w0[:, 175:207])
-    assert float(rec[:, 35:40].abs().sum()) == 0.0 and float(rec[:, 72:].abs().sum()) == 0.0
+    assert torch.equal(rec[:, 35], W["agg_net.agg_impl.base_fc.0.bias"])             # bias column (constant-1 input)
+    assert float(rec[:, 36:40].abs().sum()) == 0.0 and float(rec[:, 72:].abs().sum()) == 0.0
+    hst = unswz(buf[T.hst:T.hst + 10240], 64) + unswz(buf[T.hst + 10240:T.hst + 20480], 64)          # [64, 160]
+    for r_, s_, i_ in ((0, 0, 0), (2, 1, 3), (5, 3, 4), (4, 2, 5)):
+        assert torch.equal(hst[:, 24 * r_ + 6 * s_ + i_], w0[:, s_ * 35 + 6 * r_ + i_])
+    assert float(hst[:, 24 * 5 + 5].abs().sum()) == 0.0 and float(hst[:, 144:].abs().sum()) == 0.0    # feature 35 does not exist
     # prob_embed.2 + neuray_fc.0 behind it: 48-row tile, hi 0..1536, lo 1536..3072
     rec = unswz(buf[T.pe1:T.pe1 + 1536], 48) + unswz(buf[T.pe1 + 1536:T.pe1 + 3072], 48)
     wpe, wnf = W["agg_net.prob_embed.2.weight"], W["agg_net.agg_impl.neuray_fc.0.weight"]
