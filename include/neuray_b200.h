@@ -64,7 +64,7 @@ int nr_weight_layout(NrWeightLayout* out);
 
 /* Layout of the tensor-core weight buffer (floats; details in csrc/nr_common.cuh namespace tcl). */
 typedef struct NrTcLayout {
-  int32_t total, stage, head0, pe0, pe1, b0, b1, v01, v2r, rd1, hst;
+  int32_t total, stage, head0, pe0, pe1, b0, b1, v01, v2r, rd1, hst, g0;
 } NrTcLayout;
 int nr_tc_layout(NrTcLayout* out);
 

@@ -43,7 +43,7 @@ class NrPassParams(C.Structure):
 
 
 class NrTcLayout(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in "total stage head0 pe0 pe1 b0 b1 v01 v2r rd1 hst".split()]
+    _fields_ = [(n, C.c_int32) for n in "total stage head0 pe0 pe1 b0 b1 v01 v2r rd1 hst g0".split()]
 
 
 # name -> (restype, argtypes); mirrors include/neuray_b200.h one to one (tests/test_abi.py checks the header against this)

@@ -248,7 +248,7 @@ int nr_weight_layout(NrWeightLayout* o) {
 int nr_tc_layout(NrTcLayout* o) {
   NR_CHECK_ARG(o != nullptr, "out");
   o->total = tcl::TOTAL; o->stage = tcl::STAGE; o->head0 = tcl::HEAD0; o->pe0 = tcl::PE0; o->pe1 = tcl::PE1; o->b0 = tcl::B0;
-  o->b1 = tcl::B1; o->v01 = tcl::V01; o->v2r = tcl::V2R; o->rd1 = tcl::RD1; o->hst = tcl::HST;
+  o->b1 = tcl::B1; o->v01 = tcl::V01; o->v2r = tcl::V2R; o->rd1 = tcl::RD1; o->hst = tcl::HST; o->g0 = tcl::G0;
   return NR_OK;
 }
 

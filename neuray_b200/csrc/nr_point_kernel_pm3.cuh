@@ -29,9 +29,7 @@ constexpr int TCOLS = 160;                                    // tensor-memory c
 constexpr int OFF_RING = 0;                                   // NBUF x RING_STAGE
 constexpr int OFF_HST = OFF_RING + NBUF * RING_STAGE;         // view-pooled part of base_fc.0, tensor-core tile (resident, 1024-byte aligned)
 constexpr int OFF_RD1 = OFF_HST + tcl::HST_SIZE;              // ray_dir_fc.2 tensor-core tile (resident, 1024-byte aligned)
-constexpr int OFF_WG0 = OFF_RD1 + tcl::RD1_SIZE;              // geometry_fc.0: WT[65][64] | bias[64]
-constexpr int WG0 = 65 * 64 + 64;
-constexpr int OFF_WG1 = OFF_WG0 + WG0;                        // geometry_fc.2: [16][64] (output-major) | bias[16]
+constexpr int OFF_WG1 = OFF_RD1 + tcl::RD1_SIZE;              // geometry_fc.2: [16][64] (output-major, columns in own_col order) | bias[16]
 constexpr int WG1 = 64 * 16 + 16;
 constexpr int OFF_SW = OFF_WG1 + WG1;                         // small resident weights (same layout as point_kernel_tc)
 constexpr int OFF_STG = OFF_SW + SW;                          // gather transposition: per warp [32 rows][36]
@@ -41,7 +39,7 @@ constexpr int OFF_BAR = OFF_STG + STG;
 constexpr int SMEM_FLOATS = OFF_BAR + 32;
 constexpr size_t SMEM_BYTES = size_t(SMEM_FLOATS) * 4;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert((OFF_HST * 4) % 1024 == 0 && (OFF_RD1 * 4) % 1024 == 0 && OFF_WG0 % 4 == 0 && OFF_WG1 % 4 == 0 && OFF_SW % 4 == 0 && OFF_STG % 4 == 0, "alignment");
+static_assert((OFF_HST * 4) % 1024 == 0 && (OFF_RD1 * 4) % 1024 == 0 && OFF_WG1 % 4 == 0 && OFF_SW % 4 == 0 && OFF_STG % 4 == 0, "alignment");
 
 // Layer issue, executed by all 128 threads of the block after they wrote their A columns (b.tAhi / b.mAhi = column 0 of
 // the block).  K chunk c (of NCH) reads A columns AHI + 8c (c < NLIN) or TAILHI + 8(c - NLIN), lo parts LOOFF columns
@@ -172,7 +170,6 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   float* const ring = smem + OFF_RING;
-  float* const sWg0 = smem + OFF_WG0;
   float* const sWg1 = smem + OFF_WG1;
   float* const sw = smem + OFF_SW;
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -185,7 +182,7 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
   const int rfn = pp.rfn, dn = pp.dn;
   const int N = pp.rn * dn;
   const int n_heads = kp.n_heads;
-  const int stages_per_tile = n_heads + 8;
+  const int stages_per_tile = n_heads + 11;                    // heads, prob_embed x2, base_fc.0 x3, base_fc.2, vis, vis2+rgb, geometry_fc.0 x3
   const int n_tiles = kp.n_tiles;                              // tiles of PB points
   const int iters = (n_tiles + int(gridDim.x) * NBLK - 1) / (int(gridDim.x) * NBLK);
   const float* __restrict__ W = pp.w_point;
@@ -217,8 +214,9 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
     cp(sw + SW_V1LB, gd + lay::VIS1L_B, 4); cp(sw + SW_V20B, gd + lay::V20_B, 32); cp(sw + SW_V21W, gd + lay::V21_W, 32);
     cp(sw + SW_V21B, gd + lay::V21_B, 4); cp(sw + SW_RGB0B, gd + lay::RGB0_B, 16); cp(sw + SW_RGB1W, gd + lay::RGB1_W, 128);
     cp(sw + SW_RGB1B, gd + lay::RGB1_B, 8); cp(sw + SW_RGB2W, gd + lay::RGB2_W, 8); cp(sw + SW_RGB2B, gd + lay::RGB2_B, 4);
-    cp(sWg0, lay::GRP_D2 + lay::GEO0_W, WG0);
-    for (int i = tid; i < 64 * 16; i += NCOMP) sWg1[(i & 15) * 64 + (i >> 4)] = __ldg(W + lay::GRP_D2 + lay::GEO1_W + i);   // WT[64][16] -> [16][64]
+    // WT[64][16] -> [16][64]; hidden unit c = v*CPL + j sits where lane v's j-th own column is (conflict-free ld_cols)
+    for (int i = tid; i < 64 * 16; i += NCOMP)
+      sWg1[(i & 15) * 64 + own_col<G>((i >> 4) / CPL, (i >> 4) % CPL)] = __ldg(W + lay::GRP_D2 + lay::GEO1_W + i);
     cp(sWg1 + 64 * 16, lay::GRP_D2 + lay::GEO1_B, 16);
   }
   tc::fence_before_thread_sync();
@@ -716,37 +714,52 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
       }
 
       PM_TICK(14)
-      // ---------------- view pooling #2 streamed into geometry_fc.0, then geometry_fc.2 across the lanes ----------------
+      // ---------------- view pooling #2 (ibrnet.py:352-353) -> geometry_fc.0 on the tensor cores, geometry_fc.2 across the lanes ----------------
       {
         const float vs = bsum<G>(vis2);
         const float w2 = vis2 / (vs + 1e-8f);
-        float hh[CPL];
-        ld_cols<G>(sWg0 + 65 * 64, v, hh);                                  // bias
+        const float wmean = bsum<G>(w2) / float(rfn);
+        // three K rounds of 12 features x (mean, var), one ring stage each; the last one also carries the mean weight
+        // and the constant that multiplies the bias column
+        auto ground = [&](auto rc) {
+          constexpr int R = decltype(rc)::value;
+          constexpr int NF = R == 2 ? 8 : 12;
+          float st[24];
 #pragma unroll
-        for (int f0 = 0; f0 < 32; f0 += 8) {
-          float mm[8];
+          for (int i = 0; i < 24; ++i) st[i] = 0.f;
+          {
+            float mm[NF];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) mm[i] = xr[f0 + i] * w2;
-          bsum_vec<G, 8>(mm);
-          float vv_[8];
+            for (int i = 0; i < NF; ++i) mm[i] = xr[12 * R + i] * w2;
+            bsum_vec<G, NF>(mm);
+            float vv_[NF];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { const float d0 = xr[f0 + i] - mm[i]; vv_[i] = w2 * d0 * d0; }
-          bsum_vec<G, 8>(vv_);
+            for (int i = 0; i < NF; ++i) { const float d0 = xr[12 * R + i] - mm[i]; vv_[i] = w2 * d0 * d0; }
+            bsum_vec<G, NF>(vv_);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float wa[CPL], wb[CPL];
-            ld_cols<G>(sWg0 + (f0 + i) * 64, v, wa);
-            ld_cols<G>(sWg0 + (32 + f0 + i) * 64, v, wb);
-#pragma unroll
-            for (int j = 0; j < CPL; ++j) hh[j] = fmaf(wb[j], vv_[i], fmaf(wa[j], mm[i], hh[j]));
+            for (int i = 0; i < NF; ++i) { st[i] = mm[i]; st[12 + i] = vv_[i]; }
+            if (R == 2) { st[8] = wmean; st[9] = 1.f; }
           }
-        }
+          if (R > 0) wait_layer(b);                                                  // the previous round has read A[0:48)
+          st16(b, 0, 24, st);
+          st8(b, 16, 40, st + 16);
+          issue_layer<64, 3, 0, 24, 3, 0, 96, 0, 1, 0, 2048 * 4, 0, true, true, (R > 0)>(b);
+        };
+        ground(std::integral_constant<int, 0>{}); ground(std::integral_constant<int, 1>{}); ground(std::integral_constant<int, 2>{});
+        wait_layer(b);
+        // all G rows of a point hold the same 64 hidden pre-activations; lane v keeps columns [v*CPL, (v+1)*CPL)
+        float hh[CPL];
         {
-          const float wmean = bsum<G>(w2) / float(rfn);
-          float wa[CPL];
-          ld_cols<G>(sWg0 + 64 * 64, v, wa);
+          float d[64];
+          ld32(b, 96, d);
+          ld32(b, 128, d + 32);
 #pragma unroll
-          for (int j = 0; j < CPL; ++j) hh[j] = elu(fmaf(wa[j], wmean, hh[j]));
+          for (int m = G >> 1, len = 32; m >= 1; m >>= 1, len >>= 1) {
+#pragma unroll
+            for (int k = 0; k < len; ++k) d[k] = (v & m) ? d[len + k] : d[k];
+          }
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) hh[j] = elu(d[j]);
         }
         float out[16];
 #pragma unroll

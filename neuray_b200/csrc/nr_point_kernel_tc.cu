@@ -106,7 +106,8 @@ struct Producer {
     if (s < n_heads) src = tcl::HEAD0 + s * RING_STAGE;
     else {
       const int t = s - n_heads;
-      src = t == 0 ? tcl::PE0 : t == 1 ? tcl::PE1 : t <= 4 ? tcl::B0 + (t - 2) * RING_STAGE : t == 5 ? tcl::B1 : t == 6 ? tcl::V01 : tcl::V2R;
+      src = t == 0 ? tcl::PE0 : t == 1 ? tcl::PE1 : t <= 4 ? tcl::B0 + (t - 2) * RING_STAGE : t == 5 ? tcl::B1 : t == 6 ? tcl::V01 : t == 7 ? tcl::V2R
+                                                                                                                       : tcl::G0 + (t - 8) * RING_STAGE;   // pm3 only
       if (t == 1) bytes = 3072 * 4;
     }
     const uint32_t buf = next % NBUF;

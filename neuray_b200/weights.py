@@ -200,6 +200,19 @@ def pack_tc_weights(params, dec, agg, device=None):
     hi, lo = _tc_tiles(bh, 160)
     buf[T.hst: T.hst + 10240] = hi
     buf[T.hst + 10240: T.hst + 20480] = lo
+    # geometry_fc.0 on the second view pooling (ibrnet.py:352-354): K = 32*round + 12*stat + i <-> reference column stat*32 + 12*round + i
+    wg = g(f"{ib}.geometry_fc.0.weight").detach().float().to(device)     # [64, 65]: mean 32 | var 32 | mean weight
+    bg = torch.zeros(64, 96, dtype=torch.float32, device=device)
+    for r_ in range(3):
+        n_ = min(12, 32 - 12 * r_)
+        for s_ in range(2):
+            bg[:, 32 * r_ + 12 * s_: 32 * r_ + 12 * s_ + n_] = wg[:, s_ * 32 + 12 * r_: s_ * 32 + 12 * r_ + n_]
+    bg[:, 72] = wg[:, 64]
+    bg[:, 73] = g(f"{ib}.geometry_fc.0.bias").detach().float().to(device)
+    hi, lo = _tc_tiles(bg, 96)
+    for s_ in range(3):
+        buf[T.g0 + s_ * T.stage: T.g0 + s_ * T.stage + 2048] = hi[s_ * 2048:(s_ + 1) * 2048]
+        buf[T.g0 + s_ * T.stage + 2048: T.g0 + (s_ + 1) * T.stage] = lo[s_ * 2048:(s_ + 1) * 2048]
     return buf
 
 

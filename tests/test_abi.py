@@ -84,7 +84,7 @@ def test_tc_weight_pack_roundtrip():
     W = synthetic.make_weights(cfg)
     T = _lib.tc_layout()
     buf = weights.pack_tc_weights(W, "dist_decoder", "agg_net", torch.device("cpu"))
-    assert buf.numel() == T.total == 72704
+    assert buf.numel() == T.total == 84992
 
     def unswz(flat, n):                # [slabs*n*32] -> [n, slabs*32]
         slabs = flat.numel() // (n * 32)
@@ -105,6 +105,13 @@ def test_tc_weight_pack_roundtrip():
     for r_, s_, i_ in ((0, 0, 0), (2, 1, 3), (5, 3, 4), (4, 2, 5)):
         assert torch.equal(hst[:, 24 * r_ + 6 * s_ + i_], w0[:, s_ * 35 + 6 * r_ + i_])
     assert float(hst[:, 24 * 5 + 5].abs().sum()) == 0.0 and float(hst[:, 144:].abs().sum()) == 0.0    # feature 35 does not exist
+    wg = W["agg_net.agg_impl.geometry_fc.0.weight"]
+    geo = torch.cat([unswz(buf[T.g0 + s * T.stage:T.g0 + s * T.stage + 2048], 64) +
+                     unswz(buf[T.g0 + s * T.stage + 2048:T.g0 + (s + 1) * T.stage], 64) for s in range(3)], 1)      # [64, 96]
+    for r_, s_, i_ in ((0, 0, 0), (1, 1, 11), (2, 0, 7), (2, 1, 7)):
+        assert torch.equal(geo[:, 32 * r_ + 12 * s_ + i_], wg[:, s_ * 32 + 12 * r_ + i_])
+    assert torch.equal(geo[:, 72], wg[:, 64]) and torch.equal(geo[:, 73], W["agg_net.agg_impl.geometry_fc.0.bias"])
+    assert float(geo[:, 24:32].abs().sum()) == 0.0 and float(geo[:, 74:76].abs().sum()) == 0.0 and float(geo[:, 84:].abs().sum()) == 0.0
     # prob_embed.2 + neuray_fc.0 behind it: 48-row tile, hi 0..1536, lo 1536..3072
     rec = unswz(buf[T.pe1:T.pe1 + 1536], 48) + unswz(buf[T.pe1 + 1536:T.pe1 + 3072], 48)
     wpe, wnf = W["agg_net.prob_embed.2.weight"], W["agg_net.agg_impl.neuray_fc.0.weight"]
