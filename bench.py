@@ -167,6 +167,7 @@ def run_b200(args):
     host_out = {}
     gathered = [torch.empty(1, rays, 3, device=dev) for _ in range(world)] if world > 1 else None
 
+    @torch.no_grad()                      # inference, like the reference's render.py (renderer(data) under torch.no_grad())
     def step_device(dq, dr):
         out = net.render(dq, dr, False)
         if world > 1:   # the rendered tiles of all ranks are gathered (north_star: all-gather of the final tiles)

@@ -41,8 +41,37 @@ base_cfg = {
 }
 
 
+# Grow-only device workspaces, reused across passes, chunks and frames.  The C-ABI never allocates (the caller owns
+# the workspace); taking 335 MB of point records per pass and 246 MB of repacked maps per frame from torch's caching
+# allocator every time fragmented it (small long-lived outputs land in the freed big blocks) and cost cudaMalloc calls
+# in steady state (tools/e2e_breakdown.py).  Everything is stream-ordered on the caller's current stream; rendering
+# with one network object from several streams at once is not supported.
+_WORKSPACES = {}
+
+
+def _workspace(key, numel, dev):
+    buf = _WORKSPACES.get((key, str(dev)))
+    if buf is None or buf.numel() < numel:
+        buf = None
+        _WORKSPACES.pop((key, str(dev)), None)
+        buf = torch.empty(numel, dtype=torch.float32, device=dev)
+        _WORKSPACES[(key, str(dev))] = buf
+    return buf[:numel]
+
+
+_PACK_POOL = {}      # (device, feat shape, rgb shape) -> [(feat, rgb)] of dropped FramePacks, at most two kept
+
+
 class FramePack:
     """Per-frame device data shared by every chunk and both passes: channel-last maps + per-view parameters."""
+
+    def __del__(self):
+        try:
+            pool = _PACK_POOL.setdefault(self._pool_key, [])
+            if len(pool) < 2:
+                pool.append((self.feat, self.rgb))
+        except Exception:      # interpreter shutdown
+            pass
 
     def __init__(self, ref_imgs_info):
         imgs = ref_imgs_info["imgs"]
@@ -57,8 +86,13 @@ class FramePack:
         fh, fw = rf.shape[-2:]
         dev = imgs.device
         self.rfn, self.h, self.w, self.fh, self.fw = rfn, h, w, fh, fw
-        self.feat = torch.empty(rfn, fh, fw, 64, dtype=torch.float32, device=dev)
-        self.rgb = torch.empty(rfn, h, w, 4, dtype=torch.float32, device=dev)
+        self._pool_key = (str(dev), (rfn, fh, fw, 64), (rfn, h, w, 4))
+        spare = _PACK_POOL.get(self._pool_key)
+        if spare:
+            self.feat, self.rgb = spare.pop()
+        else:
+            self.feat = torch.empty(rfn, fh, fw, 64, dtype=torch.float32, device=dev)
+            self.rgb = torch.empty(rfn, h, w, 4, dtype=torch.float32, device=dev)
         _lib.check(_lib.lib().nr_pack_feature_maps(
             _lib.ptr(rf.detach().contiguous().float()), _lib.ptr(imf.detach().contiguous().float()),
             _lib.ptr(imgs.detach().contiguous().float()), rfn, h, w, fh, fw, _lib.ptr(self.feat), _lib.ptr(self.rgb),
@@ -136,7 +170,7 @@ def _launch_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine, 
         "render_depth": torch.empty(1, rn, dtype=torch.float32, device=dev),
         "ray_mask_u8": torch.empty(1, rn, dtype=torch.uint8, device=dev),
     }
-    rec = torch.empty(rn * dn * _lib.NR_POINT_REC, dtype=torch.float32, device=dev)
+    rec = _workspace("point_rec", rn * dn * _lib.NR_POINT_REC, dev)
     p = _lib.NrPassParams()
     p.coords, p.que_depth, p.que_cam = _lib.ptr(coords_c), _lib.ptr(que_depth), _lib.ptr(cam)
     p.rn, p.dn = rn, dn

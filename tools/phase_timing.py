@@ -5,6 +5,8 @@ import sys
 
 import torch
 
+torch.set_grad_enabled(False)      # inference
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
