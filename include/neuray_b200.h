@@ -160,6 +160,29 @@ int nr_interpolate_feats(const float* feats, const float* pts, const float* mask
 int nr_sample_fine_depth(const float* depth, const float* hit_prob, float near, float far, int rn, int dn, int fine_dn,
                          const float* u, int u_stride, int use_all, int do_sort, float* out, void* stream);
 
+/* ---- training: backward of one pass -------------------------------------------------------------------------- */
+
+/* Backward of nr_render_pass_fwd for the same NrPassParams (reference: loss.backward() through renderer.py:168-203;
+ * SURVEY.md 8b nr_render_pass_bwd).  The call recomputes the pass in fp32, keeps every Linear layer's input on a
+ * "tape" and writes every Linear layer's pre-activation gradient next to it; the caller forms the weight gradients as
+ * plain GEMMs dW = dz * x^T over all rows (bias = row sums).  Tapes are slot-major: element (slot, i) of a tape with
+ * S slots over M rows is tape[slot * M + i]; row i of the row tapes is view * (rn*dn) + point.  Slot numbers come from
+ * nr_bwd_slot("R_RF"), ... (names: csrc/nr_train_math.cuh; "R_SLOTS", "G_SLOTS", "P_SLOTS", "GP_SLOTS" = sizes).
+ * d_feat [rfn,fh,fw,64] must be zero-initialised (or hold a running sum): gradients of the gathered ray_feats
+ * (channels 0..31) and img_feats (32..63) are atomically added to it.  Any upstream gradient may be NULL (= zero). */
+typedef struct NrBwdParams {
+  const float* d_pixel_colors;   /* [rn,3]  */
+  const float* d_hit_prob;       /* [rn,dn] */
+  const float* d_render_depth;   /* [rn]    */
+  float* tape_row;               /* [R_SLOTS,  rfn*rn*dn] */
+  float* grad_row;               /* [G_SLOTS,  rfn*rn*dn] */
+  float* tape_point;             /* [P_SLOTS,  rn*dn]     */
+  float* grad_point;             /* [GP_SLOTS, rn*dn]     */
+  float* d_feat;                 /* [rfn,fh,fw,64] accumulated; NULL: feature-map gradients not wanted */
+} NrBwdParams;
+int nr_render_pass_bwd(const NrPassParams* p, const NrBwdParams* b, void* stream);
+int nr_bwd_slot(const char* name);   /* -1: unknown name */
+
 /* ---- diagnostics ------------------------------------------------------------------------------------------- */
 
 /* Self-test of the tcgen05 layer primitive the point kernel uses: D[128,n] = A[128,k] * W[n,k]^T with A staged in

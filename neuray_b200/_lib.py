@@ -69,7 +69,26 @@ SIGNATURES = {
     "nr_interpolate_feats": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _i, _i, _vp, _vp]),
     "nr_sample_fine_depth": (C.c_int, [_vp, _vp, _f, _f, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
     "nr_tc_selftest": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "nr_render_pass_bwd": (C.c_int, [_vp, _vp, _vp]),
+    "nr_bwd_slot": (C.c_int, [C.c_char_p]),
 }
+
+
+class NrBwdParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in "d_pixel_colors d_hit_prob d_render_depth tape_row grad_row tape_point grad_point d_feat".split()]
+
+
+_slot_cache = {}
+
+
+def bwd_slot(name):
+    """Slot number on the backward tapes (csrc/nr_train_math.cuh)."""
+    if name not in _slot_cache:
+        v = lib().nr_bwd_slot(name.encode())
+        if v < 0:
+            raise NeurayB200Error(f"unknown tape slot {name}")
+        _slot_cache[name] = v
+    return _slot_cache[name]
 
 _lib = None
 _layout = None

@@ -7,6 +7,8 @@ w.r.t. the reference feature maps and every parameter of the pass.  This keeps `
 `neuray_b200.patch`, at PyTorch-eager speed for the backward half; DESIGN.md section 7 lists the native backward as the
 next step.  Nothing here is used at inference time, and nothing here touches the CPU or oracle/.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -178,6 +180,7 @@ class RenderPassFn(torch.autograd.Function):
         with torch.no_grad():
             res = runner()
         ctx.meta = meta
+        ctx.bwd = res.pop("_bwd", None)
         ctx.save_for_backward(ray_feats, img_feats, *params)
         ctx.mark_non_differentiable(res["ray_mask_u8"])
         fine = res.get("fine_depth")
@@ -191,6 +194,15 @@ class RenderPassFn(torch.autograd.Function):
     def backward(ctx, g_pix, g_hit, g_depth, *unused):
         meta = ctx.meta
         ray_feats, img_feats, *params = ctx.saved_tensors
+        if ctx.bwd is not None and os.environ.get("NR_BACKWARD", "native") != "torch":
+            # native backward: nr_render_pass_bwd fills the tapes, the weight gradients are GEMMs over them (backward.py)
+            from . import backward as nb
+            p, _keep, feat_shape, stream = ctx.bwd
+            want_feat = ray_feats.requires_grad or img_feats.requires_grad
+            grads, drf, dimf = nb.render_pass_backward(p, meta["names"], meta["dec"], meta["agg"], g_pix, g_hit, g_depth, want_feat,
+                                                       feat_shape, stream)
+            gp = [grads[n] if t.requires_grad else None for n, t in zip(meta["names"], params)]
+            return (None, None, drf if ray_feats.requires_grad else None, dimf if img_feats.requires_grad else None, *gp)
         with torch.enable_grad():
             leaves = [t.detach().requires_grad_(t.requires_grad) for t in (ray_feats, img_feats, *params)]
             P = dict(zip(meta["names"], leaves[2:]))

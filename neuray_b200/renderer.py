@@ -205,6 +205,8 @@ def _launch_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine, 
     else:
         _lib.check(_lib.lib().nr_render_pass_fwd(C.byref(p), stream), "nr_render_pass_fwd")
     _lib.count_launches(2)
+    # what nr_render_pass_bwd needs to run on the same inputs (kept alive by the autograd node, dropped otherwise)
+    out["_bwd"] = (p, (coords_c, que_depth, cam, pack, w_point, w_ray, pos_enc, w_tc), (pack.rfn, pack.fh, pack.fw, 64), stream)
     return out
 
 
@@ -230,6 +232,7 @@ def run_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine=None,
     launch = lambda: _launch_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine, want_hit)
     if not needs_grad:
         out = launch()
+        out.pop("_bwd", None)
     else:
         from .autograd_path import RenderPassFn
         meta = {

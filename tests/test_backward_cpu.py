@@ -1,0 +1,121 @@
+"""CPU: the hand-written backward of a render pass (csrc/nr_train_math.cuh, the code the CUDA kernels run per point /
+sample / ray) compiled as HOST code and checked against PyTorch autograd over the same pass.  No GPU needed: nvcc
+compiles the __host__ __device__ routines for the CPU (tests/cpu_harness/train_cpu_harness.cu)."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import pytest
+import torch
+
+from neuray_b200 import _lib, autograd_path, backward, renderer, synthetic, weights
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "tests", "_build")
+
+
+@pytest.fixture(scope="module")
+def harness():
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not available")
+    os.makedirs(BUILD, exist_ok=True)
+    so = os.path.join(BUILD, "libnr_train_cpu.so")
+    src = os.path.join(ROOT, "tests", "cpu_harness", "train_cpu_harness.cu")
+    deps = [src, os.path.join(ROOT, "neuray_b200", "csrc", "nr_train_math.cuh"), os.path.join(ROOT, "neuray_b200", "csrc", "nr_common.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.run(["nvcc", "-shared", "-Xcompiler", "-fPIC", "-O1", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
+                        "-o", so, src], check=True, capture_output=True)
+    lib = C.CDLL(so)
+    lib.nr_train_cpu.restype = C.c_int
+    lib.nr_train_cpu.argtypes = [C.c_void_p, C.c_void_p]
+    return lib
+
+
+def run_case(harness, rfn, use_vis, dn=8, rays=5, seed=0, with_hit=True):
+    torch.manual_seed(seed)
+    cfg = {"depth_sample_num": dn, "agg_net_cfg": {"sample_num": dn}, "dist_decoder_cfg": {"use_vis": use_vis}, "render_depth": True}
+    que, ref = synthetic.make_scene(40, 48, rfn, seed=20 + seed, smooth=2)
+    n = que["coords"].shape[1]
+    idx = torch.randperm(n)[:rays]
+    # push one ray outside most views so that masks / padding paths are exercised
+    coords = que["coords"][:, idx].clone()
+    W = synthetic.make_weights(cfg, seed=seed)
+    dec, agg = "dist_decoder", "agg_net"
+    names = [k for k in W if k.startswith(dec + ".") or k.startswith(agg + ".")]
+    depth = renderer.render_ops.sample_depth if False else None
+    import neuray_oracle as orc
+    que_depth, _ = orc.sample_depth(que["depth_range"], coords, dn, False)            # [1,rays,dn]
+    pos_enc = weights.posenc_table(dn)
+    g_pix, g_hit, g_dep = torch.randn(1, rays, 3), torch.randn(1, rays, dn) * 0.5, torch.randn(1, rays) * 0.3
+
+    # ---- autograd reference ----
+    P = {k: W[k].clone().requires_grad_(True) for k in names}
+    rref = {k: ref[k] for k in ("poses", "Ks", "depth_range", "imgs")}
+    rref["ray_feats"] = ref["ray_feats"].clone().requires_grad_(True)
+    rref["img_feats"] = ref["img_feats"].clone().requires_grad_(True)
+    cfgv = {"use_vis_prob": use_vis, "var_bias": 0.05}
+    pix, hit, dep = autograd_path.render_pass_torch(P, dec, agg, cfgv, que_depth, coords, que["poses"], que["Ks"], que["depth_range"],
+                                                    rref, pos_enc)
+    loss = (pix * g_pix).sum() + (dep * g_dep).sum() + ((hit * g_hit).sum() if with_hit else 0.0)
+    loss.backward()
+
+    # ---- hand-written backward on the host ----
+    wp, wr = weights.pack_pass_weights({k: W[k] for k in names}, dec, agg, torch.device("cpu"))
+    feat = torch.cat([ref["ray_feats"], ref["img_feats"]], 1).permute(0, 2, 3, 1).contiguous()
+    rgb = torch.cat([ref["imgs"], torch.zeros_like(ref["imgs"][:, :1])], 1).permute(0, 2, 3, 1).contiguous()
+    vp = weights.view_param_block(ref["poses"], ref["Ks"], ref["depth_range"])
+    cam = weights.camera_block(que["poses"][0], que["Ks"][0], que["depth_range"][0])
+    cc, qd = coords[0].contiguous(), que_depth[0].contiguous()
+    p = _lib.NrPassParams()
+    p.coords, p.que_depth, p.que_cam, p.rn, p.dn = cc.data_ptr(), qd.data_ptr(), cam.data_ptr(), rays, dn
+    p.feat, p.rgb, p.view_params = feat.data_ptr(), rgb.data_ptr(), vp.data_ptr()
+    p.rfn, p.h, p.w, p.fh, p.fw = rfn, ref["imgs"].shape[2], ref["imgs"].shape[3], ref["ray_feats"].shape[2], ref["ray_feats"].shape[3]
+    p.w_point, p.w_ray, p.pos_enc = wp.data_ptr(), wr.data_ptr(), pos_enc.data_ptr()
+    p.use_vis, p.var_bias = int(use_vis), 0.05
+    shapes = backward.tape_shapes(rfn, rays * dn)
+    bufs = {k: torch.full(sh, float("nan")) for k, sh in shapes.items()}
+    d_feat = torch.zeros_like(feat)
+    b = _lib.NrBwdParams()
+    gp_, gh_, gd_ = g_pix[0].contiguous(), g_hit[0].contiguous(), g_dep[0].contiguous()
+    b.d_pixel_colors, b.d_render_depth = gp_.data_ptr(), gd_.data_ptr()
+    b.d_hit_prob = gh_.data_ptr() if with_hit else None
+    b.tape_row, b.grad_row = bufs["tape_row"].data_ptr(), bufs["grad_row"].data_ptr()
+    b.tape_point, b.grad_point = bufs["tape_point"].data_ptr(), bufs["grad_point"].data_ptr()
+    b.d_feat = d_feat.data_ptr()
+    assert harness.nr_train_cpu(C.addressof(p), C.addressof(b)) == 0
+    s = _lib.bwd_slot
+    # recomputed forward agrees with the reference pass
+    tp = bufs["tape_point"]
+    alpha = tp[s("P_ALPHA")].reshape(rays, dn)
+    T = torch.cumprod(torch.cat([torch.ones(rays, 1), 1 - alpha + 1e-10], 1), 1)[:, :-1]
+    assert torch.allclose(alpha * T, hit[0].detach(), atol=2e-5), (alpha * T - hit[0].detach()).abs().max()
+    grads = backward.assemble_param_grads(names, dec, agg, 4 if use_vis else 3, bufs["tape_row"], bufs["grad_row"], bufs["tape_point"],
+                                          bufs["grad_point"])
+    worst = {}
+    for k in names:
+        ga, gn = P[k].grad, grads[k]
+        if ga is None:
+            assert gn is None or float(gn.abs().max()) == 0.0, k
+            continue
+        assert gn is not None, k
+        assert gn.shape == ga.shape, (k, gn.shape, ga.shape)
+        err = (gn - ga).abs().max().item()
+        scale = ga.abs().max().item()
+        worst[k] = (err, scale)
+        assert err <= 2e-4 * max(scale, 1e-3) + 2e-6, (k, err, scale)
+    drf, dimf = backward.feat_grads_to_nchw(d_feat)
+    for name, gn, ga in (("ray_feats", drf, rref["ray_feats"].grad), ("img_feats", dimf, rref["img_feats"].grad)):
+        err, scale = (gn - ga).abs().max().item(), ga.abs().max().item()
+        assert err <= 2e-4 * max(scale, 1e-3) + 2e-6, (name, err, scale)
+    return worst
+
+
+@pytest.mark.parametrize("rfn,use_vis", [(3, False), (5, True), (8, False)])
+def test_hand_written_backward_matches_autograd(harness, rfn, use_vis):
+    worst = run_case(harness, rfn, use_vis, seed=rfn)
+    assert len(worst) > 60
+
+
+def test_backward_without_hit_prob_gradient(harness):
+    run_case(harness, 4, True, dn=6, rays=3, seed=9, with_hit=False)

@@ -58,9 +58,20 @@ def timeit(fn, k):
     return (time.perf_counter() - t0) / k * 1e3, r
 
 
+if os.environ.get("NR_TRAIN_PROFILE"):
+    from torch.profiler import ProfilerActivity, profile
+    for _ in range(3):
+        train_step()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        for _ in range(3):
+            train_step()
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
+    sys.exit(0)
 ms_f, _ = timeit(fwd_only, steps)
 ms_t, loss = timeit(train_step, steps)
 samples = rays * 128
 print(f"cfg5 shape, {rays} rays x (64+64) samples, 8 views 304x400")
 print(f"forward only (kernels, is_train=True): {ms_f:.2f} ms/step  ({samples / ms_f / 1e3:.2f} M ray-samples/s)")
-print(f"training step (kernel forward + PyTorch-recompute backward + Adam): {ms_t:.2f} ms/step  ({samples / ms_t / 1e3:.3f} M ray-samples/s), loss {float(loss):.5f}")
+print(f"training step (kernel forward + backward [NR_BACKWARD=native|torch] + Adam): {ms_t:.2f} ms/step  ({samples / ms_t / 1e3:.3f} M ray-samples/s), loss {float(loss):.5f}")
