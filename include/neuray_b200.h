@@ -183,6 +183,16 @@ typedef struct NrBwdParams {
 int nr_render_pass_bwd(const NrPassParams* p, const NrBwdParams* b, void* stream);
 int nr_bwd_slot(const char* name);   /* -1: unknown name */
 
+/* All weight gradients of a pass in one launch.  Layer i: dz = n_out slots starting at g_slot of tape g_tape, x = n_in
+ * slots starting at x_slot of tape x_tape (tapes: 0 = tape_row, 1 = grad_row, 2 = tape_point, 3 = grad_point; the two
+ * tapes of a layer must have the same row count).  out + out_off receives [n_out][n_in + 1], ADDED to what is there:
+ * columns 0..n_in-1 = dW, column n_in = the bias gradient.  `descs` is a host array of at most 48 entries. */
+typedef struct NrGemmDesc {
+  int32_t g_tape, g_slot, n_out, x_tape, x_slot, n_in, out_off, reserved;
+} NrGemmDesc;
+int nr_tape_gemms(const NrGemmDesc* descs, int n_desc, const float* tape_row, const float* grad_row, long long rows,
+                  const float* tape_point, const float* grad_point, long long points, float* out, void* stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------------------------- */
 
 /* Self-test of the tcgen05 layer primitive the point kernel uses: D[128,n] = A[128,k] * W[n,k]^T with A staged in

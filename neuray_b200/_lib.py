@@ -71,7 +71,12 @@ SIGNATURES = {
     "nr_tc_selftest": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "nr_render_pass_bwd": (C.c_int, [_vp, _vp, _vp]),
     "nr_bwd_slot": (C.c_int, [C.c_char_p]),
+    "nr_tape_gemms": (C.c_int, [_vp, _i, _vp, _vp, C.c_longlong, _vp, _vp, C.c_longlong, _vp, _vp]),
 }
+
+
+class NrGemmDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in "g_tape g_slot n_out x_tape x_slot n_in out_off reserved".split()]
 
 
 class NrBwdParams(C.Structure):

@@ -29,60 +29,113 @@ def tape_shapes(rfn, n_points):
             "grad_point": (s("GP_SLOTS"), n_points)}
 
 
-def assemble_param_grads(names, dec, agg, n_heads, tape_row, grad_row, tape_point, grad_point):
-    """dW = dz @ x^T for every Linear of the pass (bias = row sums of dz), from the tapes of nr_render_pass_bwd.
-    names: parameter names of the pass (state-dict names).  Returns {name: grad or None}."""
+ROW, GROW, POINT, GPOINT = 0, 1, 2, 3      # tape numbers of nr_tape_gemms
+
+
+def layer_table(names, dec, agg, n_heads):
+    """Every Linear of the pass as (g_tape, g_slot, n_out, x_tape, x_slot, n_in, weight name, bias name, kind)."""
     s = _lib.bwd_slot
-    TR, GR, TP, GP = tape_row, grad_row, tape_point, grad_point
+    T = []
 
-    def lin(out, g_tape, g_slot, n_out, x_tape, x_slot, n_in, w, b):
-        dz = g_tape[g_slot:g_slot + n_out]
-        out[w] = dz @ x_tape[x_slot:x_slot + n_in].t()
-        if b is not None:
-            out[b] = dz.sum(1)
+    def add(gt, g_slot, n_out, xt, x_slot, n_in, w, b, kind="plain"):
+        T.append((gt, g_slot, n_out, xt, x_slot, n_in, w, b, kind))
 
-    out = {}
     for hd, head in enumerate(HEADS):
-        if f"{dec}.{head}.0.weight" not in names:
+        # a head the pass does not evaluate (the fine decoder's vis head under a coarse use_vis=False) gets no gradient
+        if f"{dec}.{head}.0.weight" not in names or hd >= n_heads:
             continue
-        if hd >= n_heads:        # a head the pass does not evaluate (fine decoder's vis head under a coarse use_vis=False)
-            continue
-        n_out = 2 if hd < 2 else 1
-        lin(out, GR, s("G_DD0") + 32 * hd, 32, TR, s("R_RF"), 32, f"{dec}.{head}.0.weight", f"{dec}.{head}.0.bias")
-        lin(out, GR, s("G_DD1") + 32 * hd, 32, TR, s("R_H1") + 32 * hd, 32, f"{dec}.{head}.2.weight", f"{dec}.{head}.2.bias")
-        lin(out, GR, s("G_DD2") + 2 * hd, n_out, TR, s("R_H2") + 32 * hd, 32, f"{dec}.{head}.4.weight", f"{dec}.{head}.4.bias")
+        add(GROW, s("G_DD0") + 32 * hd, 32, ROW, s("R_RF"), 32, f"{dec}.{head}.0.weight", f"{dec}.{head}.0.bias")
+        add(GROW, s("G_DD1") + 32 * hd, 32, ROW, s("R_H1") + 32 * hd, 32, f"{dec}.{head}.2.weight", f"{dec}.{head}.2.bias")
+        add(GROW, s("G_DD2") + 2 * hd, 2 if hd < 2 else 1, ROW, s("R_H2") + 32 * hd, 32, f"{dec}.{head}.4.weight", f"{dec}.{head}.4.bias")
     ib = f"{agg}.agg_impl"
-    lin(out, GR, s("G_PE0"), 32, TR, s("R_RF"), 34, f"{agg}.prob_embed.0.weight", f"{agg}.prob_embed.0.bias")
-    lin(out, GR, s("G_PE1"), 32, TR, s("R_P1"), 32, f"{agg}.prob_embed.2.weight", f"{agg}.prob_embed.2.bias")
-    lin(out, GR, s("G_RD0"), 16, TR, s("R_DD"), 4, f"{ib}.ray_dir_fc.0.weight", f"{ib}.ray_dir_fc.0.bias")
-    lin(out, GR, s("G_RD1"), 35, TR, s("R_R16"), 16, f"{ib}.ray_dir_fc.2.weight", f"{ib}.ray_dir_fc.2.bias")
-    lin(out, GR, s("G_NF0"), 8, TR, s("R_NF"), 32, f"{ib}.neuray_fc.0.weight", f"{ib}.neuray_fc.0.bias")
-    lin(out, GR, s("G_NF1"), 1, TR, s("R_Q8"), 8, f"{ib}.neuray_fc.2.weight", f"{ib}.neuray_fc.2.bias")
-    dz0 = GR[s("G_B0"):s("G_B0") + 64]
-    out[f"{ib}.base_fc.0.weight"] = torch.cat([GP[s("GP_B0SUM"):s("GP_B0SUM") + 64] @ TP[s("P_GLOB"):s("P_GLOB") + 140].t(),
-                                               dz0 @ TR[s("R_RGBF"):s("R_RGBF") + 67].t()], 1)
-    out[f"{ib}.base_fc.0.bias"] = dz0.sum(1)
-    lin(out, GR, s("G_B1"), 32, TR, s("R_B1"), 64, f"{ib}.base_fc.2.weight", f"{ib}.base_fc.2.bias")
-    lin(out, GR, s("G_V0"), 32, TR, s("R_U"), 32, f"{ib}.vis_fc.0.weight", f"{ib}.vis_fc.0.bias")
-    lin(out, GR, s("G_V1"), 33, TR, s("R_VH"), 32, f"{ib}.vis_fc.2.weight", f"{ib}.vis_fc.2.bias")
-    lin(out, GR, s("G_V20"), 32, TR, s("R_U2"), 32, f"{ib}.vis_fc2.0.weight", f"{ib}.vis_fc2.0.bias")
-    lin(out, GR, s("G_V21"), 1, TR, s("R_WH"), 32, f"{ib}.vis_fc2.2.weight", f"{ib}.vis_fc2.2.bias")
-    lin(out, GR, s("G_C0"), 16, TR, s("R_X2"), 37, f"{ib}.rgb_fc.0.weight", f"{ib}.rgb_fc.0.bias")
-    lin(out, GR, s("G_C1"), 8, TR, s("R_CH1"), 16, f"{ib}.rgb_fc.2.weight", f"{ib}.rgb_fc.2.bias")
-    lin(out, GR, s("G_C2"), 1, TR, s("R_CH2"), 8, f"{ib}.rgb_fc.4.weight", f"{ib}.rgb_fc.4.bias")
-    lin(out, GP, s("GP_GEO0"), 64, TP, s("P_GIN"), 65, f"{ib}.geometry_fc.0.weight", f"{ib}.geometry_fc.0.bias")
-    lin(out, GP, s("GP_GEO1"), 16, TP, s("P_GH"), 64, f"{ib}.geometry_fc.2.weight", f"{ib}.geometry_fc.2.bias")
     at = f"{ib}.ray_attention"
-    lin(out, GP, s("GP_DQ"), 16, TP, s("P_AX"), 16, f"{at}.w_qs.weight", None)
-    lin(out, GP, s("GP_DK"), 16, TP, s("P_AX"), 16, f"{at}.w_ks.weight", None)
-    lin(out, GP, s("GP_DV"), 16, TP, s("P_AX"), 16, f"{at}.w_vs.weight", None)
-    lin(out, GP, s("GP_DFC"), 16, TP, s("P_O"), 16, f"{at}.fc.weight", None)
-    dy = GP[s("GP_DLNY"):s("GP_DLNY") + 16]
-    out[f"{at}.layer_norm.weight"] = (dy * TP[s("P_XH"):s("P_XH") + 16]).sum(1)
-    out[f"{at}.layer_norm.bias"] = dy.sum(1)
-    lin(out, GP, s("GP_OG0"), 16, TP, s("P_Y"), 16, f"{ib}.out_geometry_fc.0.weight", f"{ib}.out_geometry_fc.0.bias")
-    lin(out, GP, s("GP_OG1"), 1, TP, s("P_T16"), 16, f"{ib}.out_geometry_fc.2.weight", f"{ib}.out_geometry_fc.2.bias")
+    add(GROW, s("G_PE0"), 32, ROW, s("R_RF"), 34, f"{agg}.prob_embed.0.weight", f"{agg}.prob_embed.0.bias")
+    add(GROW, s("G_PE1"), 32, ROW, s("R_P1"), 32, f"{agg}.prob_embed.2.weight", f"{agg}.prob_embed.2.bias")
+    add(GROW, s("G_RD0"), 16, ROW, s("R_DD"), 4, f"{ib}.ray_dir_fc.0.weight", f"{ib}.ray_dir_fc.0.bias")
+    add(GROW, s("G_RD1"), 35, ROW, s("R_R16"), 16, f"{ib}.ray_dir_fc.2.weight", f"{ib}.ray_dir_fc.2.bias")
+    add(GROW, s("G_NF0"), 8, ROW, s("R_NF"), 32, f"{ib}.neuray_fc.0.weight", f"{ib}.neuray_fc.0.bias")
+    add(GROW, s("G_NF1"), 1, ROW, s("R_Q8"), 8, f"{ib}.neuray_fc.2.weight", f"{ib}.neuray_fc.2.bias")
+    add(GPOINT, s("GP_B0SUM"), 64, POINT, s("P_GLOB"), 140, f"{ib}.base_fc.0.weight", None, "base_glob")
+    add(GROW, s("G_B0"), 64, ROW, s("R_RGBF"), 67, f"{ib}.base_fc.0.weight", f"{ib}.base_fc.0.bias", "base_row")
+    add(GROW, s("G_B1"), 32, ROW, s("R_B1"), 64, f"{ib}.base_fc.2.weight", f"{ib}.base_fc.2.bias")
+    add(GROW, s("G_V0"), 32, ROW, s("R_U"), 32, f"{ib}.vis_fc.0.weight", f"{ib}.vis_fc.0.bias")
+    add(GROW, s("G_V1"), 33, ROW, s("R_VH"), 32, f"{ib}.vis_fc.2.weight", f"{ib}.vis_fc.2.bias")
+    add(GROW, s("G_V20"), 32, ROW, s("R_U2"), 32, f"{ib}.vis_fc2.0.weight", f"{ib}.vis_fc2.0.bias")
+    add(GROW, s("G_V21"), 1, ROW, s("R_WH"), 32, f"{ib}.vis_fc2.2.weight", f"{ib}.vis_fc2.2.bias")
+    add(GROW, s("G_C0"), 16, ROW, s("R_X2"), 37, f"{ib}.rgb_fc.0.weight", f"{ib}.rgb_fc.0.bias")
+    add(GROW, s("G_C1"), 8, ROW, s("R_CH1"), 16, f"{ib}.rgb_fc.2.weight", f"{ib}.rgb_fc.2.bias")
+    add(GROW, s("G_C2"), 1, ROW, s("R_CH2"), 8, f"{ib}.rgb_fc.4.weight", f"{ib}.rgb_fc.4.bias")
+    add(GPOINT, s("GP_GEO0"), 64, POINT, s("P_GIN"), 65, f"{ib}.geometry_fc.0.weight", f"{ib}.geometry_fc.0.bias")
+    add(GPOINT, s("GP_GEO1"), 16, POINT, s("P_GH"), 64, f"{ib}.geometry_fc.2.weight", f"{ib}.geometry_fc.2.bias")
+    add(GPOINT, s("GP_DQ"), 16, POINT, s("P_AX"), 16, f"{at}.w_qs.weight", None)
+    add(GPOINT, s("GP_DK"), 16, POINT, s("P_AX"), 16, f"{at}.w_ks.weight", None)
+    add(GPOINT, s("GP_DV"), 16, POINT, s("P_AX"), 16, f"{at}.w_vs.weight", None)
+    add(GPOINT, s("GP_DFC"), 16, POINT, s("P_O"), 16, f"{at}.fc.weight", None)
+    add(GPOINT, s("GP_DLNY"), 16, POINT, s("P_XH"), 16, f"{at}.layer_norm.weight", f"{at}.layer_norm.bias", "ln")
+    add(GPOINT, s("GP_OG0"), 16, POINT, s("P_Y"), 16, f"{ib}.out_geometry_fc.0.weight", f"{ib}.out_geometry_fc.0.bias")
+    add(GPOINT, s("GP_OG1"), 1, POINT, s("P_T16"), 16, f"{ib}.out_geometry_fc.2.weight", f"{ib}.out_geometry_fc.2.bias")
+    return T
+
+
+def _finish(names, table, blocks):
+    """blocks[i] = [n_out, n_in + 1] (dW | db) of table[i] -> {name: grad or None}."""
+    out, base = {}, {}
+    for (gt, g_slot, n_out, xt, x_slot, n_in, w, b, kind), blk in zip(table, blocks):
+        if kind == "ln":
+            out[w] = torch.diagonal(blk[:, :n_in]).clone()
+            out[b] = blk[:, n_in].clone()
+            continue
+        if kind in ("base_glob", "base_row"):
+            base[kind] = blk[:, :n_in]
+            if b is not None:
+                out[b] = blk[:, n_in].clone()
+            continue
+        out[w] = blk[:, :n_in].clone()
+        if b is not None:
+            out[b] = blk[:, n_in].clone()
+    wname = next(w for (*_, w, _b, kind) in table if kind == "base_glob")
+    out[wname] = torch.cat([base["base_glob"], base["base_row"]], 1)
     return {n: out.get(n) for n in names}
+
+
+def assemble_param_grads(names, dec, agg, n_heads, tape_row, grad_row, tape_point, grad_point):
+    """dW = dz @ x^T for every Linear of the pass (bias = row sums of dz) with torch GEMMs over the tapes (any device;
+    the CUDA path uses one fused launch instead, `assemble_param_grads_fused`).  Returns {name: grad or None}."""
+    tapes = (tape_row, grad_row, tape_point, grad_point)
+    table = layer_table(names, dec, agg, n_heads)
+    blocks = []
+    for gt, g_slot, n_out, xt, x_slot, n_in, *_ in table:
+        dz = tapes[gt][g_slot:g_slot + n_out]
+        blocks.append(torch.cat([dz @ tapes[xt][x_slot:x_slot + n_in].t(), dz.sum(1, keepdim=True)], 1))
+    return _finish(names, table, blocks)
+
+
+_DESC_CACHE = {}
+
+
+def assemble_param_grads_fused(names, dec, agg, n_heads, tape_row, grad_row, tape_point, grad_point, stream):
+    """Same result through nr_tape_gemms: all layers in one launch."""
+    key = (tuple(names), dec, agg, n_heads)
+    hit = _DESC_CACHE.get(key)
+    if hit is None:
+        table = layer_table(names, dec, agg, n_heads)
+        descs = (_lib.NrGemmDesc * len(table))()
+        off = 0
+        offs = []
+        for i, (gt, g_slot, n_out, xt, x_slot, n_in, *_rest) in enumerate(table):
+            descs[i].g_tape, descs[i].g_slot, descs[i].n_out = gt, g_slot, n_out
+            descs[i].x_tape, descs[i].x_slot, descs[i].n_in, descs[i].out_off = xt, x_slot, n_in, off
+            offs.append(off)
+            off += n_out * (n_in + 1)
+        hit = (table, descs, offs, off)
+        _DESC_CACHE[key] = hit
+    table, descs, offs, total = hit
+    out = torch.zeros(total, dtype=torch.float32, device=tape_row.device)
+    _lib.check(_lib.lib().nr_tape_gemms(descs, len(table), _lib.ptr(tape_row), _lib.ptr(grad_row), tape_row.shape[1], _lib.ptr(tape_point),
+                                        _lib.ptr(grad_point), tape_point.shape[1], _lib.ptr(out), stream), "nr_tape_gemms")
+    _lib.count_launches(1)
+    blocks = [out[o:o + t[2] * (t[5] + 1)].view(t[2], t[5] + 1) for o, t in zip(offs, table)]
+    return _finish(names, table, blocks)
 
 
 def feat_grads_to_nchw(d_feat):
@@ -105,9 +158,9 @@ def render_pass_backward(p, names, dec, agg, g_pix, g_hit, g_depth, want_feat_gr
     b.tape_point, b.grad_point = _lib.ptr(bufs["tape_point"]), _lib.ptr(bufs["grad_point"])
     b.d_feat = _lib.ptr(d_feat)
     _lib.check(_lib.lib().nr_render_pass_bwd(C.byref(p), C.byref(b), stream), "nr_render_pass_bwd")
-    _lib.count_launches(5)
-    grads = assemble_param_grads(names, dec, agg, 4 if p.use_vis else 3, bufs["tape_row"], bufs["grad_row"], bufs["tape_point"],
-                                 bufs["grad_point"])
+    _lib.count_launches(11)
+    grads = assemble_param_grads_fused(names, dec, agg, 4 if p.use_vis else 3, bufs["tape_row"], bufs["grad_row"], bufs["tape_point"],
+                                       bufs["grad_point"], stream)
     if d_feat is None:
         return grads, None, None
     drf, dimf = feat_grads_to_nchw(d_feat)

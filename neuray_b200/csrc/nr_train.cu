@@ -14,11 +14,17 @@ namespace tr {
 template <int WHICH>
 __global__ void __launch_bounds__(128) train_kernel(const Ctx c, long long count) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
-    if (WHICH == 0) point_forward(c, i);
-    else if (WHICH == 1) sample_forward(c, i);
-    else if (WHICH == 2) ray_backward(c, i);
-    else if (WHICH == 3) sample_backward_q(c, i);
-    else { sample_backward_kv(c, i); point_backward(c, i); }
+    if (WHICH == 0) row_forward_a(c, i);
+    else if (WHICH == 1) point_forward_b(c, i);
+    else if (WHICH == 2) row_forward_c(c, i);
+    else if (WHICH == 3) { point_forward_d(c, i); }
+    else if (WHICH == 4) sample_forward(c, i);
+    else if (WHICH == 5) ray_backward(c, i);
+    else if (WHICH == 6) sample_backward_q(c, i);
+    else if (WHICH == 7) { sample_backward_kv(c, i); point_backward_a(c, i); }
+    else if (WHICH == 8) row_backward_b(c, i);
+    else if (WHICH == 9) point_backward_c(c, i);
+    else row_backward_d(c, i);
   }
 }
 
@@ -72,12 +78,18 @@ int nr_render_pass_bwd(const NrPassParams* p, const NrBwdParams* b, void* stream
   c.d_hit = b->d_hit_prob;
   c.d_depth = b->d_render_depth;
   cudaStream_t s = (cudaStream_t)stream;
-  auto blocks = [](long long n) { long long g = (n + 127) / 128; return int(g < 148 * 16 ? g : 148 * 16); };
-  tr::train_kernel<0><<<blocks(N), 128, 0, s>>>(c, N);
-  tr::train_kernel<1><<<blocks(N), 128, 0, s>>>(c, N);
-  tr::train_kernel<2><<<blocks(p->rn), 128, 0, s>>>(c, (long long)p->rn);
-  tr::train_kernel<3><<<blocks(N), 128, 0, s>>>(c, N);
-  tr::train_kernel<4><<<blocks(N), 128, 0, s>>>(c, N);
+  auto blocks = [](long long n) { long long g = (n + 127) / 128; return int(g < 148 * 32 ? g : 148 * 32); };
+  tr::train_kernel<0><<<blocks(R), 128, 0, s>>>(c, R);      // rows:   gather .. ray_dir_fc
+  tr::train_kernel<1><<<blocks(N), 128, 0, s>>>(c, N);      // points: view pooling #1
+  tr::train_kernel<2><<<blocks(R), 128, 0, s>>>(c, R);      // rows:   base_fc .. rgb_fc
+  tr::train_kernel<3><<<blocks(N), 128, 0, s>>>(c, N);      // points: view pooling #2, geometry_fc, blend, q/k/v
+  tr::train_kernel<4><<<blocks(N), 128, 0, s>>>(c, N);      // samples: attention .. alpha
+  tr::train_kernel<5><<<blocks(p->rn), 128, 0, s>>>(c, (long long)p->rn);   // rays: compositing forward + backward
+  tr::train_kernel<6><<<blocks(N), 128, 0, s>>>(c, N);      // samples: out_geometry_fc, LayerNorm, attention wrt q
+  tr::train_kernel<7><<<blocks(N), 128, 0, s>>>(c, N);      // samples/points: attention wrt k, v; geometry_fc; pooling #2
+  tr::train_kernel<8><<<blocks(R), 128, 0, s>>>(c, R);      // rows:   rgb_fc .. base_fc
+  tr::train_kernel<9><<<blocks(N), 128, 0, s>>>(c, N);      // points: pooling #1
+  tr::train_kernel<10><<<blocks(R), 128, 0, s>>>(c, R);     // rows:   neuray_fc .. dist decoder, scatter
   NR_CHECK_LAUNCH("render_pass_bwd");
   return NR_OK;
 }

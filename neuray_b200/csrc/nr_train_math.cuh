@@ -82,7 +82,8 @@ enum PointSlot {
   P_SIG = 419, P_ALPHA = 420,
   P_AM = 421,      // 4 softmax max per head
   P_AD = 425,      // 4 softmax denominators
-  P_SLOTS = 429
+  P_HZ = 429,      // 64 view-invariant part of base_fc.0's pre-activation (incl. bias)
+  P_SLOTS = 493
 };
 enum PointGrad {
   GP_B0SUM = 0,    // 64  sum over views of base_fc.0's dz (pairs with P_GLOB)
@@ -94,7 +95,13 @@ enum PointGrad {
   GP_DRGB = 257,   // 3
   GP_DELTA = 260,  // 4
   GP_DO = 264,     // 16
-  GP_SLOTS = 280
+  GP_DGIN = 280,   // 65 gradient of geometry_fc.0's input
+  GP_DMT = 345,    // 32 total gradient of the pooled means (#2)
+  GP_DW2SUM = 377, GP_BSUM = 378,
+  GP_DGLOB = 379,  // 140 gradient of the pooled statistics (#1)
+  GP_DM0 = 519,    // 35 total gradient of mean0
+  GP_DM1 = 554,    // 35 total gradient of mean1
+  GP_SLOTS = 589
 };
 
 struct Tape {
@@ -190,19 +197,17 @@ NR_HD PointGeo point_geometry(const NrPassParams& pp, long long n) {
   return g;
 }
 
-// ---- forward of one point -----------------------------------------------------------------------------------------
-NR_HD void point_forward(const Ctx& c, long long n) {
+// ---- forward, phase a, one (point, view) row: gather, dist decoder, probabilities, prob_embed, neuray_fc, ray_dir_fc ----
+NR_HD void row_forward_a(const Ctx& c, long long r) {
   const NrPassParams& pp = c.p;
   const float* __restrict__ W = c.W;
-  const int rfn = pp.rfn, h = pp.h, w = pp.w, fh = pp.fh, fw = pp.fw;
+  const int h = pp.h, w = pp.w, fh = pp.fh, fw = pp.fw;
   const long long N = (long long)pp.rn * pp.dn;
+  const int v = int(r / N);
+  const long long n = r - (long long)v * N;
   const bool feat_align = (fh == h && fw == w);
   const PointGeo g = point_geometry(pp, n);
-
-  // pass 1 over the views: gather, dist decoder, probabilities, prob_embed, neuray_fc, ray_dir_fc
-  float msum = 0.f;
-  for (int v = 0; v < rfn; ++v) {
-    const long long r = (long long)v * N + n;
+  {
     const float* vp = pp.view_params + v * 20;
     const float xh = fmaf(vp[2], g.Z, fmaf(vp[1], g.Y, vp[0] * g.X)) + vp[3];
     const float yh = fmaf(vp[6], g.Z, fmaf(vp[5], g.Y, vp[4] * g.X)) + vp[7];
@@ -213,7 +218,6 @@ NR_HD void point_forward(const Ctx& c, long long n) {
     const bool outside = (ux < -0.5f) || (ux >= float(w) - 0.5f) || (uy < -0.5f) || (uy >= float(h) - 0.5f);
     const bool valid = !degenerate && !outside;
     const float mask = valid ? 1.f : 0.f;
-    msum += mask;
     const float dx = g.X - vp[12], dy = g.Y - vp[13], dz = g.Z - vp[14];
     const float inv = -1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-5f);
     const float ex = dx * inv, ey = dy * inv, ez = dz * inv;
@@ -331,8 +335,16 @@ NR_HD void point_forward(const Ctx& c, long long n) {
     stv<35>(c.tr, R_DF, r, df);
     stv<35>(c.tr, R_RGBF, r, rgbf);
   }
+}
 
-  // view pooling #1 (ibrnet.py:324-339)
+// ---- forward, phase b, one point: view pooling #1 (ibrnet.py:324-339) and the view-invariant part of base_fc.0 ----------
+NR_HD void point_forward_b(const Ctx& c, long long n) {
+  const NrPassParams& pp = c.p;
+  const float* __restrict__ W = c.W;
+  const int rfn = pp.rfn;
+  const long long N = (long long)pp.rn * pp.dn;
+  float msum = 0.f;
+  for (int v = 0; v < rfn; ++v) msum += c.tr.at(R_MASK, (long long)v * N + n);
   float glob[140];
   for (int k = 0; k < 140; ++k) glob[k] = 0.f;
   for (int v = 0; v < rfn; ++v) {
@@ -355,12 +367,19 @@ NR_HD void point_forward(const Ctx& c, long long n) {
   c.tp.at(P_MSUM, n) = msum;
   float hz[64];
   lin<140, 64>(W + lay::HOIST_W, W + lay::HOIST_B, glob, hz);
+  stv<64>(c.tp, P_HZ, n, hz);
+}
 
-  // pass 2: base_fc, vis_fc, vis_fc2 (ibrnet.py:341-350)
+// ---- forward, phase c, one row: base_fc, vis_fc, vis_fc2, rgb_fc logit (ibrnet.py:341-350, 362-365) --------------------
+NR_HD void row_forward_c(const Ctx& c, long long r) {
+  const NrPassParams& pp = c.p;
+  const float* __restrict__ W = c.W;
+  const long long N = (long long)pp.rn * pp.dn;
+  const long long n = r % N;
   const float* Wd = W + lay::GRP_D1;
-  float vsum = 0.f;
-  for (int v = 0; v < rfn; ++v) {
-    const long long r = (long long)v * N + n;
+  float hz[64];
+  ldv<64>(c.tp, P_HZ, n, hz);
+  {
     const float mask = c.tr.at(R_MASK, r), w1 = c.tr.at(R_W1, r);
     float in67[67], b1[64], x[32];
     ldv<67>(c.tr, R_RGBF, r, in67);
@@ -390,9 +409,30 @@ NR_HD void point_forward(const Ctx& c, long long n) {
     const float vis2 = sigm(l2) * mask;
     stv<32>(c.tr, R_U2, r, u2); stv<32>(c.tr, R_WH, r, wh);
     c.tr.at(R_VIS2, r) = vis2;
-    vsum += vis2;
+    // rgb_fc (the softmax over the views happens in phase d)
+    float cin[37], c1[16], c2[8];
+    for (int k = 0; k < 32; ++k) cin[k] = x2[k];
+    cin[32] = vis2;
+    ldv<4>(c.tr, R_DDC, r, cin + 33);
+    lin<37, 16>(Wd + lay::RGB0_W, Wd + lay::RGB0_B, cin, c1);
+    for (int k = 0; k < 16; ++k) c1[k] = elu_f(c1[k]);
+    lin<16, 8>(Wd + lay::RGB1_W, Wd + lay::RGB1_B, c1, c2);
+    float lg = Wd[lay::RGB2_B];
+    for (int k = 0; k < 8; ++k) { c2[k] = elu_f(c2[k]); lg = fmaf(Wd[lay::RGB2_W + k], c2[k], lg); }
+    if (mask == 0.f) lg = -1e9f;
+    stv<16>(c.tr, R_CH1, r, c1); stv<8>(c.tr, R_CH2, r, c2);
+    c.tr.at(R_BLEND, r) = lg;
   }
+}
 
+// ---- forward, phase d, one point: view pooling #2, geometry_fc, colour blend, attention inputs ------------------------
+NR_HD void point_forward_d(const Ctx& c, long long n) {
+  const NrPassParams& pp = c.p;
+  const float* __restrict__ W = c.W;
+  const int rfn = pp.rfn;
+  const long long N = (long long)pp.rn * pp.dn;
+  float vsum = 0.f;
+  for (int v = 0; v < rfn; ++v) vsum += c.tr.at(R_VIS2, (long long)v * N + n);
   // view pooling #2 + geometry_fc (ibrnet.py:351-354)
   float gin[65];
   for (int k = 0; k < 65; ++k) gin[k] = 0.f;
@@ -420,22 +460,9 @@ NR_HD void point_forward(const Ctx& c, long long n) {
   stv<64>(c.tp, P_GH, n, gh);
   stv<16>(c.tp, P_G16, n, g16);
 
-  // rgb_fc + softmax blend (ibrnet.py:362-367)
+  // softmax blend over the views (ibrnet.py:365-367)
   float mx = -3.0e38f;
-  for (int v = 0; v < rfn; ++v) {
-    const long long r = (long long)v * N + n;
-    float cin[37], c1[16], c2[8];
-    ldv<37>(c.tr, R_X2, r, cin);
-    lin<37, 16>(Wd + lay::RGB0_W, Wd + lay::RGB0_B, cin, c1);
-    for (int k = 0; k < 16; ++k) c1[k] = elu_f(c1[k]);
-    lin<16, 8>(Wd + lay::RGB1_W, Wd + lay::RGB1_B, c1, c2);
-    float lg = Wd[lay::RGB2_B];
-    for (int k = 0; k < 8; ++k) { c2[k] = elu_f(c2[k]); lg = fmaf(Wd[lay::RGB2_W + k], c2[k], lg); }
-    if (c.tr.at(R_MASK, r) == 0.f) lg = -1e9f;
-    stv<16>(c.tr, R_CH1, r, c1); stv<8>(c.tr, R_CH2, r, c2);
-    c.tr.at(R_BLEND, r) = lg;
-    mx = fmaxf(mx, lg);
-  }
+  for (int v = 0; v < rfn; ++v) mx = fmaxf(mx, c.tr.at(R_BLEND, (long long)v * N + n));
   float den = 0.f, rgbo[3] = {0.f, 0.f, 0.f};
   for (int v = 0; v < rfn; ++v) {
     const long long r = (long long)v * N + n;
@@ -651,15 +678,13 @@ NR_HD void sample_backward_kv(const Ctx& c, long long n) {
   stv<16>(c.gp, GP_DG16, n, dax);
 }
 
-// ---- backward of one point ------------------------------------------------------------------------------------------
-NR_HD void point_backward(const Ctx& c, long long n) {
+// ---- backward, phase a, one point: geometry_fc, what view pooling #2 and the colour blend hand to their rows --------------
+NR_HD void point_backward_a(const Ctx& c, long long n) {
   const NrPassParams& pp = c.p;
   const float* __restrict__ W = c.W;
-  const int rfn = pp.rfn, fw = pp.fw;
+  const int rfn = pp.rfn;
   const long long N = (long long)pp.rn * pp.dn;
-  const float* Wd = W + lay::GRP_D1;
   const float* We = W + lay::GRP_D2;
-  const float* Wb = W + lay::GRP_B;
 
   // geometry_fc
   float dgin[65];
@@ -702,12 +727,25 @@ NR_HD void point_backward(const Ctx& c, long long n) {
     for (int k = 0; k < 3; ++k) db += drgbo[k] * c.tr.at(R_RGB + k, r);
     bsum += c.tr.at(R_BLEND, r) * db;
   }
+  stv<65>(c.gp, GP_DGIN, n, dgin);
+  stv<32>(c.gp, GP_DMT, n, dmt);
+  c.gp.at(GP_DW2SUM, n) = dw2sum;
+  c.gp.at(GP_BSUM, n) = bsum;
+}
 
-  // per view: rgb_fc, vis_fc2, vis_fc, base_fc (down to the gradient of the per-view base_fc.0 inputs)
-  float dzsum[64];
-  for (int k = 0; k < 64; ++k) dzsum[k] = 0.f;
-  for (int v = 0; v < rfn; ++v) {
-    const long long r = (long long)v * N + n;
+// ---- backward, phase b, one row: rgb_fc, vis_fc2, vis_fc, base_fc (down to base_fc.0's pre-activation gradient) ---------
+NR_HD void row_backward_b(const Ctx& c, long long r) {
+  const NrPassParams& pp = c.p;
+  const float* __restrict__ W = c.W;
+  const int rfn = pp.rfn;
+  const long long N = (long long)pp.rn * pp.dn;
+  const long long n = r % N;
+  const float* Wd = W + lay::GRP_D1;
+  float dgin[65], gin[65], dmt[32], drgbo[3];
+  ldv<65>(c.gp, GP_DGIN, n, dgin); ldv<65>(c.tp, P_GIN, n, gin); ldv<32>(c.gp, GP_DMT, n, dmt); ldv<3>(c.gp, GP_DRGB, n, drgbo);
+  const float dw2sum = c.gp.at(GP_DW2SUM, n), bsum = c.gp.at(GP_BSUM, n);
+  const float vden = c.tp.at(P_VSUM, n) + 1e-8f;
+  {
     const float mask = c.tr.at(R_MASK, r), w1 = c.tr.at(R_W1, r);
     const float vis2 = c.tr.at(R_VIS2, r), w2 = vis2 / vden;
     float dx2[32];
@@ -776,10 +814,22 @@ NR_HD void point_backward(const Ctx& c, long long n) {
       stv<32>(c.gr, G_B1, r, dx);
       lin_t<64, 32>(W + lay::BASE1_W, dx, db1);
       ldv<64>(c.tr, R_B1, r, b1);
-      for (int k = 0; k < 64; ++k) { db1[k] *= elu_g(b1[k]); dzsum[k] += db1[k]; }
+      for (int k = 0; k < 64; ++k) db1[k] *= elu_g(b1[k]);
       stv<64>(c.gr, G_B0, r, db1);
     }
   }
+}
+
+// ---- backward, phase c, one point: gradient of the pooled statistics #1 --------------------------------------------------
+NR_HD void point_backward_c(const Ctx& c, long long n) {
+  const NrPassParams& pp = c.p;
+  const float* __restrict__ W = c.W;
+  const int rfn = pp.rfn;
+  const long long N = (long long)pp.rn * pp.dn;
+  float dzsum[64];
+  for (int k = 0; k < 64; ++k) dzsum[k] = 0.f;
+  for (int v = 0; v < rfn; ++v)
+    for (int k = 0; k < 64; ++k) dzsum[k] += c.gr.at(G_B0 + k, (long long)v * N + n);
   stv<64>(c.gp, GP_B0SUM, n, dzsum);
   float dglob[140], glob[140];
   lin_t<140, 64>(W + lay::HOIST_W, dzsum, dglob);
@@ -796,9 +846,22 @@ NR_HD void point_backward(const Ctx& c, long long n) {
     }
   }
   for (int f = 0; f < 35; ++f) { dm0[f] = dglob[f] - 2.f * dglob[35 + f] * dm0[f]; dm1[f] = dglob[70 + f] - 2.f * dglob[105 + f] * dm1[f]; }
+  stv<140>(c.gp, GP_DGLOB, n, dglob);
+  stv<35>(c.gp, GP_DM0, n, dm0);
+  stv<35>(c.gp, GP_DM1, n, dm1);
+}
 
-  for (int v = 0; v < rfn; ++v) {
-    const long long r = (long long)v * N + n;
+// ---- backward, phase d, one row: view pooling #1, neuray_fc, ray_dir_fc, prob_embed, compute_prob, heads, scatter ----------
+NR_HD void row_backward_d(const Ctx& c, long long r) {
+  const NrPassParams& pp = c.p;
+  const float* __restrict__ W = c.W;
+  const int fw = pp.fw;
+  const long long N = (long long)pp.rn * pp.dn;
+  const long long n = r % N;
+  const float* Wb = W + lay::GRP_B;
+  float dglob[140], glob[140], dm0[35], dm1[35];
+  ldv<140>(c.gp, GP_DGLOB, n, dglob); ldv<140>(c.tp, P_GLOB, n, glob); ldv<35>(c.gp, GP_DM0, n, dm0); ldv<35>(c.gp, GP_DM1, n, dm1);
+  {
     const float mask = c.tr.at(R_MASK, r), w1 = c.tr.at(R_W1, r), sg = c.tr.at(R_SG, r), w0 = sg * w1;
     float dz0[64], din[67];
     ldv<64>(c.gr, G_B0, r, dz0);

@@ -24,7 +24,7 @@ import torch.nn as nn
 
 from . import _lib, modules
 from .render_ops import fine_sample_u, interpolate_feats, sample_depth
-from .weights import camera_block, pack_pass_weights, pack_tc_weights, posenc_table, view_param_block
+from .weights import PackPlan, camera_block, posenc_table, view_param_block
 
 PACK_KEY = "_nr_frame_pack"
 
@@ -130,9 +130,13 @@ def pass_weights(owner, is_fine, dn, device):
     cache = owner.__dict__.setdefault("_nr_wcache", {})
     hit = cache.get(is_fine)
     if hit is None or hit[0] != stamp:
-        wp, wr = pack_pass_weights(params, dec_name, agg_name, device)
-        wt = pack_tc_weights(params, dec_name, agg_name, device)
-        hit = (stamp, wp, wr, {}, wt)
+        plans = owner.__dict__.setdefault("_nr_plans", {})
+        plan = plans.get((is_fine, str(device)))
+        if plan is None or not plan.matches(params, dec_name, agg_name):
+            plan = PackPlan(params, dec_name, agg_name, device)
+            plans[(is_fine, str(device))] = plan
+        wp, wr, wt = plan.pack(params)
+        hit = (stamp, wp, wr, hit[3] if hit is not None else {}, wt)
         cache[is_fine] = hit
     pe = hit[3].get(dn)
     if pe is None:

@@ -134,8 +134,11 @@ def _tc_tiles(wmat, k_cols):
     slabs = (k_cols + 31) // 32
     full = torch.zeros(n, slabs * 32, dtype=torch.float32, device=wmat.device)
     full[:, :k] = wmat.detach().float()
-    hi = (full.view(torch.int32) & -8192).view(torch.float32)          # 0xffffe000
-    lo = full - hi
+    if _RAW:      # PackPlan derivation: keep the (coded) values, mark the lo positions with the sign
+        hi, lo = full, -full
+    else:
+        hi = (full.view(torch.int32) & -8192).view(torch.float32)      # 0xffffe000
+        lo = full - hi
     perm = _sw128_perm(n, wmat.device)
     out = []
     for part in (hi, lo):
@@ -146,7 +149,10 @@ def _tc_tiles(wmat, k_cols):
     return out
 
 
-def pack_tc_weights(params, dec, agg, device=None):
+_RAW = False
+
+
+def pack_tc_weights(params, dec, agg, device=None, _comp=None):
     """Tensor-core weight buffer of one pass (layout: csrc/nr_common.cuh namespace tcl / NrTcLayout)."""
     T = _lib.tc_layout()
     g = lambda name: params[name]
@@ -172,7 +178,7 @@ def pack_tc_weights(params, dec, agg, device=None):
     wnf0 = g(f"{ib}.neuray_fc.0.weight").detach().to(device)
     w48 = torch.zeros(48, 32, dtype=torch.float32, device=device)
     w48[:32] = wpe1.float()
-    w48[32:40] = (wnf0.double() @ wpe1.double()).float()
+    w48[32:40] = (wnf0.double() @ wpe1.double()).float() if _comp is None else _comp.to(device)
     put(T.pe1, w48, 32, 1536)
     w0 = g(f"{ib}.base_fc.0.weight").detach().float().to(device)        # [64, 207]
     b0 = torch.zeros(64, 72, dtype=torch.float32, device=device)          # K order: rgb_feat 35 | 5 zeros | neuray_feat 32
@@ -237,3 +243,45 @@ def view_param_block(poses, Ks, depth_range=None):
         inv = -1 / depth_range
     pad = torch.zeros(rfn, 3, dtype=torch.float32, device=poses.device)
     return torch.cat([KRt.reshape(rfn, 12), centre.reshape(rfn, 3), inv, pad], 1).contiguous()
+
+
+class PackPlan:
+    """The three packed weight buffers of a pass as gathers from the flattened parameters.
+
+    `pack_pass_weights` / `pack_tc_weights` place every parameter element with a few hundred small tensor ops — fine once
+    per checkpoint, but training re-packs after every optimizer step (14 ms of host time per step).  The placement does
+    not depend on the values, so it is derived once by packing parameters whose elements are their own (1-based) flat
+    index; afterwards a pack is one `cat`, three gathers and the hi/lo split."""
+
+    def __init__(self, params, dec, agg, device):
+        global _RAW
+        self.names = list(params)
+        self.dec, self.agg = dec, agg
+        cpu = torch.device("cpu")
+        coded, off = {}, 1
+        for k in self.names:
+            n = params[k].numel()
+            coded[k] = torch.arange(off, off + n, dtype=torch.float32).reshape(params[k].shape)
+            off += n
+        self.nf0, self.pe1 = f"{agg}.agg_impl.neuray_fc.0.weight", f"{agg}.prob_embed.2.weight"
+        comp = torch.arange(off, off + 8 * 32, dtype=torch.float32).reshape(8, 32)     # neuray_fc.0 @ prob_embed.2 rows
+        assert off + 8 * 32 < 2 ** 24
+        wp, wr = pack_pass_weights(coded, dec, agg, cpu)
+        _RAW = True
+        try:
+            wt = pack_tc_weights(coded, dec, agg, cpu, _comp=comp)
+        finally:
+            _RAW = False
+        self.i_point, self.i_ray = wp.long().to(device), wr.long().to(device)
+        self.i_tc, self.lo = wt.abs().long().to(device), (wt < 0).to(device)
+        self.zero = torch.zeros(1, dtype=torch.float32, device=device)
+
+    def matches(self, params, dec, agg):
+        return self.names == list(params) and (self.dec, self.agg) == (dec, agg)
+
+    def pack(self, params):
+        comp = (params[self.nf0].detach().double() @ params[self.pe1].detach().double()).float()
+        flat = torch.cat([self.zero] + [params[k].detach().reshape(-1).float() for k in self.names] + [comp.reshape(-1)])
+        full = flat[self.i_tc]
+        hi = (full.view(torch.int32) & -8192).view(torch.float32)
+        return flat[self.i_point], flat[self.i_ray], torch.where(self.lo, full - hi, hi)

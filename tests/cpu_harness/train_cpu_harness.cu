@@ -19,10 +19,17 @@ extern "C" int nr_train_cpu(const NrPassParams* p, const NrBwdParams* b) {
   c.d_pix = b->d_pixel_colors;
   c.d_hit = b->d_hit_prob;
   c.d_depth = b->d_render_depth;
-  for (long long n = 0; n < N; ++n) point_forward(c, n);
+  // the same phase order as nr_render_pass_bwd's kernel launches (csrc/nr_train.cu)
+  for (long long r = 0; r < R; ++r) row_forward_a(c, r);
+  for (long long n = 0; n < N; ++n) point_forward_b(c, n);
+  for (long long r = 0; r < R; ++r) row_forward_c(c, r);
+  for (long long n = 0; n < N; ++n) point_forward_d(c, n);
   for (long long n = 0; n < N; ++n) sample_forward(c, n);
   for (long long r = 0; r < p->rn; ++r) ray_backward(c, r);
   for (long long n = 0; n < N; ++n) sample_backward_q(c, n);
-  for (long long n = 0; n < N; ++n) { sample_backward_kv(c, n); point_backward(c, n); }
+  for (long long n = 0; n < N; ++n) { sample_backward_kv(c, n); point_backward_a(c, n); }
+  for (long long r = 0; r < R; ++r) row_backward_b(c, r);
+  for (long long n = 0; n < N; ++n) point_backward_c(c, n);
+  for (long long r = 0; r < R; ++r) row_backward_d(c, r);
   return 0;
 }

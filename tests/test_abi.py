@@ -123,3 +123,21 @@ def test_tc_weight_pack_roundtrip():
     wr = W["agg_net.agg_impl.rgb_fc.0.weight"]                      # [16, 37] at V2R+2048 (hi, two 512 slabs), lo at +1024
     rec = unswz(buf[T.v2r + 2048:T.v2r + 3072], 16) + unswz(buf[T.v2r + 3072:T.v2r + 4096], 16)
     assert torch.equal(rec[:, :37], wr) and float(rec[:, 37:].abs().sum()) == 0.0
+
+
+def test_pack_plan_equals_the_reference_packers():
+    """PackPlan (gather-based re-pack used after every optimizer step) reproduces pack_pass_weights / pack_tc_weights
+    bit for bit, for both passes' module sets."""
+    cfg = {"use_hierarchical_sampling": True, "dist_decoder_cfg": {"use_vis": False}}
+    W = synthetic.make_weights(cfg, seed=2)
+    for dec, agg in (("dist_decoder", "agg_net"), ("fine_dist_decoder", "fine_agg_net")):
+        params = {k: v for k, v in W.items() if k.startswith(dec + ".") or k.startswith(agg + ".")}
+        plan = weights.PackPlan(params, dec, agg, torch.device("cpu"))
+        wp, wr, wt = plan.pack(params)
+        rp, rr = weights.pack_pass_weights(params, dec, agg, torch.device("cpu"))
+        rt = weights.pack_tc_weights(params, dec, agg, torch.device("cpu"))
+        assert torch.equal(wp, rp) and torch.equal(wr, rr) and torch.equal(wt, rt)
+        params2 = {k: v * 1.5 + 0.01 for k, v in params.items()}                     # same plan, new values
+        wp, wr, wt = plan.pack(params2)
+        assert torch.equal(wt, weights.pack_tc_weights(params2, dec, agg, torch.device("cpu")))
+        assert torch.equal(wp, weights.pack_pass_weights(params2, dec, agg, torch.device("cpu"))[0])
