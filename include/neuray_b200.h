@@ -165,8 +165,10 @@ int nr_sample_fine_depth(const float* depth, const float* hit_prob, float near, 
 /* Backward of nr_render_pass_fwd for the same NrPassParams (reference: loss.backward() through renderer.py:168-203;
  * SURVEY.md 8b nr_render_pass_bwd).  The call recomputes the pass in fp32, keeps every Linear layer's input on a
  * "tape" and writes every Linear layer's pre-activation gradient next to it; the caller forms the weight gradients as
- * plain GEMMs dW = dz * x^T over all rows (bias = row sums).  Tapes are slot-major: element (slot, i) of a tape with
- * S slots over M rows is tape[slot * M + i]; row i of the row tapes is view * (rn*dn) + point.  Slot numbers come from
+ * plain GEMMs dW = dz * x^T over all rows (bias = row sums; nr_tape_gemms below does all of them in one launch).
+ * Tape layout: tiles of 128 rows, slot-major inside a tile: element (slot, i) of a tape with S slots is
+ * tape[((i / 128) * S + slot) * 128 + i % 128], so a tape over M rows holds S * 128 * ceil(M / 128) floats; row i of
+ * the row tapes is view * (rn*dn) + point.  Slot numbers come from
  * nr_bwd_slot("R_RF"), ... (names: csrc/nr_train_math.cuh; "R_SLOTS", "G_SLOTS", "P_SLOTS", "GP_SLOTS" = sizes).
  * d_feat [rfn,fh,fw,64] must be zero-initialised (or hold a running sum): gradients of the gathered ray_feats
  * (channels 0..31) and img_feats (32..63) are atomically added to it.  Any upstream gradient may be NULL (= zero). */
@@ -174,10 +176,10 @@ typedef struct NrBwdParams {
   const float* d_pixel_colors;   /* [rn,3]  */
   const float* d_hit_prob;       /* [rn,dn] */
   const float* d_render_depth;   /* [rn]    */
-  float* tape_row;               /* [R_SLOTS,  rfn*rn*dn] */
-  float* grad_row;               /* [G_SLOTS,  rfn*rn*dn] */
-  float* tape_point;             /* [P_SLOTS,  rn*dn]     */
-  float* grad_point;             /* [GP_SLOTS, rn*dn]     */
+  float* tape_row;               /* R_SLOTS  slots over rfn*rn*dn rows */
+  float* grad_row;               /* G_SLOTS  slots over rfn*rn*dn rows */
+  float* tape_point;             /* P_SLOTS  slots over rn*dn rows     */
+  float* grad_point;             /* GP_SLOTS slots over rn*dn rows     */
   float* d_feat;                 /* [rfn,fh,fw,64] accumulated; NULL: feature-map gradients not wanted */
 } NrBwdParams;
 int nr_render_pass_bwd(const NrPassParams* p, const NrBwdParams* b, void* stream);

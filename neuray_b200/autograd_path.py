@@ -1,11 +1,11 @@
-"""Gradients for the rendering path (training): INTERIM, not native yet.
+"""Autograd hook of the rendering path (training).
 
-Forward values always come from the CUDA kernels.  For backward, round 1 has no hand-written kernels; instead
-`RenderPassFn.backward` recomputes the pass with differentiable PyTorch ops ON THE GPU (the restatement below, same
-arithmetic as reference network/renderer.py:168-203 and the modules it calls) and lets autograd produce the gradients
-w.r.t. the reference feature maps and every parameter of the pass.  This keeps `run_training.py` working through
-`neuray_b200.patch`, at PyTorch-eager speed for the backward half; DESIGN.md section 7 lists the native backward as the
-next step.  Nothing here is used at inference time, and nothing here touches the CPU or oracle/.
+Forward values always come from the CUDA kernels.  `RenderPassFn.backward` calls the native backward
+(`neuray_b200/backward.py` -> `nr_render_pass_bwd` + `nr_tape_gemms`).  The PyTorch restatement of the pass below
+(`render_pass_torch`, same arithmetic as reference network/renderer.py:168-203 and the modules it calls) is kept as the
+A/B reference for that backward (`NR_BACKWARD=torch` runs autograd over it ON THE GPU instead; tests compare the two) and
+for `predict_self_hit_prob` (fine-tuning only).  Nothing here is used at inference time, and nothing here touches the CPU
+or oracle/.
 """
 import os
 
@@ -173,7 +173,7 @@ def self_hit_prob_torch(P, dec, use_vis_prob, var_bias, que_ray_feats, coords, h
 
 
 class RenderPassFn(torch.autograd.Function):
-    """forward = the fused CUDA pass (values), backward = autograd over `render_pass_torch` (gradients)."""
+    """forward = the fused CUDA pass (values), backward = the native backward (NR_BACKWARD=torch: autograd over `render_pass_torch`)."""
 
     @staticmethod
     def forward(ctx, runner, meta, ray_feats, img_feats, *params):

@@ -22,11 +22,21 @@ def _ws(key, numel, dev):
     return buf[:numel]
 
 
+TILE = 128
+
+
 def tape_shapes(rfn, n_points):
+    """Tape buffers as [tiles, slots, 128] (layout: include/neuray_b200.h, NrBwdParams)."""
     s = _lib.bwd_slot
     rows = rfn * n_points
-    return {"tape_row": (s("R_SLOTS"), rows), "grad_row": (s("G_SLOTS"), rows), "tape_point": (s("P_SLOTS"), n_points),
-            "grad_point": (s("GP_SLOTS"), n_points)}
+    t = lambda m: (m + TILE - 1) // TILE
+    return {"tape_row": (t(rows), s("R_SLOTS"), TILE), "grad_row": (t(rows), s("G_SLOTS"), TILE),
+            "tape_point": (t(n_points), s("P_SLOTS"), TILE), "grad_point": (t(n_points), s("GP_SLOTS"), TILE)}
+
+
+def _slots(tape, slot, n, rows):
+    """[n, rows] view-copy of n consecutive slots of a tiled tape."""
+    return tape[:, slot:slot + n, :].permute(1, 0, 2).reshape(n, -1)[:, :rows]
 
 
 ROW, GROW, POINT, GPOINT = 0, 1, 2, 3      # tape numbers of nr_tape_gemms
@@ -98,22 +108,23 @@ def _finish(names, table, blocks):
     return {n: out.get(n) for n in names}
 
 
-def assemble_param_grads(names, dec, agg, n_heads, tape_row, grad_row, tape_point, grad_point):
+def assemble_param_grads(names, dec, agg, n_heads, tape_row, grad_row, tape_point, grad_point, rows, points):
     """dW = dz @ x^T for every Linear of the pass (bias = row sums of dz) with torch GEMMs over the tapes (any device;
     the CUDA path uses one fused launch instead, `assemble_param_grads_fused`).  Returns {name: grad or None}."""
     tapes = (tape_row, grad_row, tape_point, grad_point)
+    count = (rows, rows, points, points)
     table = layer_table(names, dec, agg, n_heads)
     blocks = []
     for gt, g_slot, n_out, xt, x_slot, n_in, *_ in table:
-        dz = tapes[gt][g_slot:g_slot + n_out]
-        blocks.append(torch.cat([dz @ tapes[xt][x_slot:x_slot + n_in].t(), dz.sum(1, keepdim=True)], 1))
+        dz = _slots(tapes[gt], g_slot, n_out, count[gt])
+        blocks.append(torch.cat([dz @ _slots(tapes[xt], x_slot, n_in, count[xt]).t(), dz.sum(1, keepdim=True)], 1))
     return _finish(names, table, blocks)
 
 
 _DESC_CACHE = {}
 
 
-def assemble_param_grads_fused(names, dec, agg, n_heads, tape_row, grad_row, tape_point, grad_point, stream):
+def assemble_param_grads_fused(names, dec, agg, n_heads, tape_row, grad_row, tape_point, grad_point, rows, points, stream):
     """Same result through nr_tape_gemms: all layers in one launch."""
     key = (tuple(names), dec, agg, n_heads)
     hit = _DESC_CACHE.get(key)
@@ -131,8 +142,8 @@ def assemble_param_grads_fused(names, dec, agg, n_heads, tape_row, grad_row, tap
         _DESC_CACHE[key] = hit
     table, descs, offs, total = hit
     out = torch.zeros(total, dtype=torch.float32, device=tape_row.device)
-    _lib.check(_lib.lib().nr_tape_gemms(descs, len(table), _lib.ptr(tape_row), _lib.ptr(grad_row), tape_row.shape[1], _lib.ptr(tape_point),
-                                        _lib.ptr(grad_point), tape_point.shape[1], _lib.ptr(out), stream), "nr_tape_gemms")
+    _lib.check(_lib.lib().nr_tape_gemms(descs, len(table), _lib.ptr(tape_row), _lib.ptr(grad_row), rows, _lib.ptr(tape_point),
+                                        _lib.ptr(grad_point), points, _lib.ptr(out), stream), "nr_tape_gemms")
     _lib.count_launches(1)
     blocks = [out[o:o + t[2] * (t[5] + 1)].view(t[2], t[5] + 1) for o, t in zip(offs, table)]
     return _finish(names, table, blocks)
@@ -149,7 +160,7 @@ def render_pass_backward(p, names, dec, agg, g_pix, g_hit, g_depth, want_feat_gr
     dev = torch.device("cuda", torch.cuda.current_device())
     n_points = p.rn * p.dn
     shapes = tape_shapes(p.rfn, n_points)
-    bufs = {k: _ws(k, sh[0] * sh[1], dev).view(sh) for k, sh in shapes.items()}
+    bufs = {k: _ws(k, sh[0] * sh[1] * sh[2], dev).view(sh) for k, sh in shapes.items()}
     d_feat = torch.zeros(feat_shape, dtype=torch.float32, device=dev) if want_feat_grads else None
     b = _lib.NrBwdParams()
     keep = [t.contiguous().float() if t is not None else None for t in (g_pix, g_hit, g_depth)]
@@ -160,7 +171,7 @@ def render_pass_backward(p, names, dec, agg, g_pix, g_hit, g_depth, want_feat_gr
     _lib.check(_lib.lib().nr_render_pass_bwd(C.byref(p), C.byref(b), stream), "nr_render_pass_bwd")
     _lib.count_launches(11)
     grads = assemble_param_grads_fused(names, dec, agg, 4 if p.use_vis else 3, bufs["tape_row"], bufs["grad_row"], bufs["tape_point"],
-                                       bufs["grad_point"], stream)
+                                       bufs["grad_point"], p.rfn * n_points, n_points, stream)
     if d_feat is None:
         return grads, None, None
     drf, dimf = feat_grads_to_nchw(d_feat)

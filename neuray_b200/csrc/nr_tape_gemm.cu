@@ -6,19 +6,20 @@
 // shared memory (row stride 65 floats: no bank conflicts between the operand rows a warp touches), each thread
 // accumulates up to three 4x4 output tiles in registers over all its chunks and adds them to the result once.
 // cuBLAS runs these shapes (M, N <= 64, K = 262 144) as sgemm_largek at ~320 us each, 26 per pass.
-#include "nr_common.cuh"
+#include "nr_train_math.cuh"
 
 namespace nr {
 namespace tg {
 
 constexpr int MAXD = 48;
-constexpr int KC = 64, LDK = KC + 1;
+constexpr int KC = tr::TILE, LDK = KC + 1;   // one tape tile per K chunk
 constexpr int MAXT = 3;      // 4x4 tiles per thread: 16 x 36 tiles at most (64 outputs, 140 + 1 inputs)
 
 struct Args {
   NrGemmDesc d[MAXD];
   const float* tape[4];      // 0 row tape, 1 row gradients, 2 point tape, 3 point gradients
   long long rows[4];
+  int slots[4];
   float* out;
 };
 
@@ -26,8 +27,9 @@ __global__ void __launch_bounds__(256) tape_gemm_kernel(const __grid_constant__ 
   extern __shared__ float sm[];
   const NrGemmDesc& d = a.d[blockIdx.x];
   const int n_in = d.n_in + 1, n_out = d.n_out;                  // + the constant-1 input (bias)
-  const float* __restrict__ X = a.tape[d.x_tape] + (long long)d.x_slot * a.rows[d.x_tape];
-  const float* __restrict__ Z = a.tape[d.g_tape] + (long long)d.g_slot * a.rows[d.g_tape];
+  const float* __restrict__ X = a.tape[d.x_tape] + (long long)d.x_slot * KC;      // + tile * slots * KC
+  const float* __restrict__ Z = a.tape[d.g_tape] + (long long)d.g_slot * KC;
+  const long long xt = (long long)a.slots[d.x_tape] * KC, zt = (long long)a.slots[d.g_tape] * KC;   // floats per tape tile
   const long long M = a.rows[d.x_tape];
   float* xs = sm;                       // [n_in][LDK]
   float* zs = sm + n_in * LDK;          // [n_out][LDK]
@@ -43,8 +45,12 @@ __global__ void __launch_bounds__(256) tape_gemm_kernel(const __grid_constant__ 
   for (int t = 0; t < MAXT; ++t)
 #pragma unroll
     for (int e = 0; e < 16; ++e) acc[t][e] = 0.f;
+  // a CTA walks a CONTIGUOUS range of chunks: every operand slot is then one sequential stream per CTA (chunks strided
+  // over the CTAs made each 256-byte piece come from a different DRAM page: 4.1 ms per call instead of ~1)
   const long long chunks = (M + KC - 1) / KC;
-  for (long long ch = blockIdx.y; ch < chunks; ch += gridDim.y) {
+  const long long per = (chunks + gridDim.y - 1) / gridDim.y;
+  const long long ch_end = min(chunks, (long long)(blockIdx.y + 1) * per);
+  for (long long ch = (long long)blockIdx.y * per; ch < ch_end; ++ch) {
     const long long k0 = ch * KC;
     const int kn = int(M - k0 < KC ? M - k0 : KC);
     __syncthreads();
@@ -52,9 +58,9 @@ __global__ void __launch_bounds__(256) tape_gemm_kernel(const __grid_constant__ 
       const int row = idx / KC, k = idx - row * KC;
       float v = 0.f;
       if (k < kn) {
-        if (row < n_in - 1) v = X[(long long)row * M + k0 + k];
+        if (row < n_in - 1) v = X[ch * xt + row * KC + k];          // the chunk's operand rows are contiguous in the tile
         else if (row == n_in - 1) v = 1.f;
-        else v = Z[(long long)(row - n_in) * M + k0 + k];
+        else v = Z[ch * zt + (row - n_in) * KC + k];
       }
       sm[row * LDK + k] = v;
     }
@@ -122,6 +128,7 @@ extern "C" int nr_tape_gemms(const NrGemmDesc* descs, int n_desc, const float* t
   }
   a.tape[0] = tape_row; a.tape[1] = grad_row; a.tape[2] = tape_point; a.tape[3] = grad_point;
   a.rows[0] = rows; a.rows[1] = rows; a.rows[2] = points; a.rows[3] = points;
+  a.slots[0] = tr::R_SLOTS; a.slots[1] = tr::G_SLOTS; a.slots[2] = tr::P_SLOTS; a.slots[3] = tr::GP_SLOTS;
   a.out = out;
   const size_t smem = size_t(max_rows) * tg::LDK * sizeof(float);
   static size_t smem_set = 0;

@@ -69,10 +69,10 @@ int nr_render_pass_bwd(const NrPassParams* p, const NrBwdParams* b, void* stream
   c.n_heads = p->use_vis ? 4 : 3;
   c.W = p->w_point;
   c.Wr = p->w_ray;
-  c.tr = {b->tape_row, R};
-  c.gr = {b->grad_row, R};
-  c.tp = {b->tape_point, N};
-  c.gp = {b->grad_point, N};
+  c.tr = {b->tape_row, R, tr::R_SLOTS};
+  c.gr = {b->grad_row, R, tr::G_SLOTS};
+  c.tp = {b->tape_point, N, tr::P_SLOTS};
+  c.gp = {b->grad_point, N, tr::GP_SLOTS};
   c.d_feat = b->d_feat;
   c.d_pix = b->d_pixel_colors;
   c.d_hit = b->d_hit_prob;

@@ -104,10 +104,17 @@ enum PointGrad {
   GP_SLOTS = 589
 };
 
+// Tape layout: rows are grouped in tiles of 128; a tile holds all slots of its 128 rows, slot-major:
+//   element (slot, i) = p[((i >> 7) * slots + slot) * 128 + (i & 127)].
+// A CTA of 128 threads (consecutive rows) therefore works on ONE contiguous piece of memory (slots x 512 bytes) and a
+// K-chunk of 128 rows of a Linear's input is one contiguous n_in x 512-byte block for the weight-gradient GEMMs; with a
+// plain slot-major layout every slot of a row was a megabyte apart (one DRAM page per 512 bytes).
+constexpr int TILE = 128;
 struct Tape {
   float* p;
-  long long stride;   // elements per slot
-  NR_HD float& at(int slot, long long i) const { return p[(long long)slot * stride + i]; }
+  long long rows;     // logical rows (the buffer holds ceil(rows / 128) * 128)
+  int slots;
+  NR_HD float& at(int slot, long long i) const { return p[((i >> 7) * slots + slot) * TILE + (i & (TILE - 1))]; }
 };
 template <int K>
 NR_HD void ldv(const Tape& t, int slot, long long i, float* o) {

@@ -11,10 +11,10 @@ extern "C" int nr_train_cpu(const NrPassParams* p, const NrBwdParams* b) {
   c.n_heads = p->use_vis ? 4 : 3;
   c.W = p->w_point;
   c.Wr = p->w_ray;
-  c.tr = {b->tape_row, R};
-  c.gr = {b->grad_row, R};
-  c.tp = {b->tape_point, N};
-  c.gp = {b->grad_point, N};
+  c.tr = {b->tape_row, R, R_SLOTS};
+  c.gr = {b->grad_row, R, G_SLOTS};
+  c.tp = {b->tape_point, N, P_SLOTS};
+  c.gp = {b->grad_point, N, GP_SLOTS};
   c.d_feat = b->d_feat;
   c.d_pix = b->d_pixel_colors;
   c.d_hit = b->d_hit_prob;

@@ -86,12 +86,11 @@ def run_case(harness, rfn, use_vis, dn=8, rays=5, seed=0, with_hit=True):
     assert harness.nr_train_cpu(C.addressof(p), C.addressof(b)) == 0
     s = _lib.bwd_slot
     # recomputed forward agrees with the reference pass
-    tp = bufs["tape_point"]
-    alpha = tp[s("P_ALPHA")].reshape(rays, dn)
+    alpha = backward._slots(bufs["tape_point"], s("P_ALPHA"), 1, rays * dn).reshape(rays, dn)
     T = torch.cumprod(torch.cat([torch.ones(rays, 1), 1 - alpha + 1e-10], 1), 1)[:, :-1]
     assert torch.allclose(alpha * T, hit[0].detach(), atol=2e-5), (alpha * T - hit[0].detach()).abs().max()
     grads = backward.assemble_param_grads(names, dec, agg, 4 if use_vis else 3, bufs["tape_row"], bufs["grad_row"], bufs["tape_point"],
-                                          bufs["grad_point"])
+                                          bufs["grad_point"], rfn * rays * dn, rays * dn)
     worst = {}
     for k in names:
         ga, gn = P[k].grad, grads[k]
