@@ -82,6 +82,47 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def training_step(dev, rays=512, steps=8):
+    """Auxiliary number (not the headline metric): one optimisation step on the DTU-train shape of SURVEY.md 8d cfg5
+    (8 reference views 304x400, 512 rays, 64+64 samples): kernel forward + native backward + Adam, inputs resident."""
+    from neuray_b200 import renderer, synthetic
+    cfg = {"use_hierarchical_sampling": True, "fine_dist_decoder_cfg": {"use_vis": True}, "dist_decoder_cfg": {"use_vis": False},
+           "render_depth": True, "ray_batch_num": rays}
+    que, ref = synthetic.make_scene(304, 400, 8, seed=5, smooth=2)
+    net = renderer.NeuralRayRenderPath(cfg)
+    net.load_state_dict(synthetic.make_weights(cfg, seed=1), strict=True)
+    net.to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+    dr = synthetic.to_device(ref, dev)
+    gen = torch.Generator().manual_seed(0)
+    n = que["coords"].shape[1]
+    batches = []
+    for _ in range(4):
+        idx = torch.randperm(n, generator=gen)[:rays]
+        q = dict(que)
+        q["coords"] = que["coords"][:, idx]
+        batches.append(synthetic.to_device(q, dev))
+
+    def step(i):
+        out = net.render(batches[i % 4], dr, True)
+        loss = ((out["pixel_colors_nr"] - out["pixel_colors_gt"]) ** 2).mean() + ((out["pixel_colors_nr_fine"] - out["pixel_colors_gt_fine"]) ** 2).mean()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / steps * 1e3
+    return {"ms_per_step": ms, "ray_samples_per_s": rays * 128 / ms * 1e3, "rays": rays, "samples_per_ray": 128, "ref_views": 8,
+            "backward": os.environ.get("NR_BACKWARD", "native"),
+            "note": "wall clock incl. host work; kernel forward + nr_render_pass_bwd + nr_tape_gemms + Adam"}
+
+
 def cpu_threads():
     """Threads for the CPU arm: the measured optimum on the GPU box's 128-core host is 16 (8: 61 k, 16: 67 k, 32: 63 k,
     64: 22 k, 128: 1.6 k ray-samples/s on the same rays, profiles/README.md): beyond that torch's intra-op pool only adds
@@ -297,6 +338,8 @@ def run_b200(args):
                             "note": "gather runs inside the point kernel; algorithmic bytes / point-kernel time"},
         "cpu_baseline": cpu,
     }
+    if world == 1 and not args.no_train_step:
+        line["training_step"] = training_step(dev)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -313,6 +356,7 @@ def main():
     ap.add_argument("--cpu-rays", type=int, default=512, help="rays of the workload timed on the CPU oracle (cpu_baseline)")
     ap.add_argument("--ref-rays", type=int, default=512, help="rays per step for --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the auxiliary training-step timing")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

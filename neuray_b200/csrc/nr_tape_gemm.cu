@@ -54,15 +54,36 @@ __global__ void __launch_bounds__(256) tape_gemm_kernel(const __grid_constant__ 
     const long long k0 = ch * KC;
     const int kn = int(M - k0 < KC ? M - k0 : KC);
     __syncthreads();
-    for (int idx = threadIdx.x; idx < (n_in + n_out) * KC; idx += blockDim.x) {
-      const int row = idx / KC, k = idx - row * KC;
-      float v = 0.f;
-      if (k < kn) {
-        if (row < n_in - 1) v = X[ch * xt + row * KC + k];          // the chunk's operand rows are contiguous in the tile
-        else if (row == n_in - 1) v = 1.f;
-        else v = Z[ch * zt + (row - n_in) * KC + k];
+    // stage the chunk: (n_in - 1 + n_out) operand rows of 128 floats, as 128-bit loads, four in flight per thread (one
+    // scalar load per loop trip left a single load in flight per thread: 20 us per chunk of pure latency)
+    {
+      const int nvec = (n_in - 1 + n_out) * (KC / 4);
+      const float* __restrict__ xsrc = X + ch * xt;
+      const float* __restrict__ zsrc = Z + ch * zt;
+      for (int base = 0; base < nvec; base += 4 * 256) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + u * 256 + int(threadIdx.x);
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (idx < nvec) {
+            const int row = idx / (KC / 4), q = idx - row * (KC / 4);
+            const float* src = row < n_in - 1 ? xsrc + row * KC : zsrc + (row - (n_in - 1)) * KC;
+            v[u] = __ldg(reinterpret_cast<const float4*>(src) + q);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + u * 256 + int(threadIdx.x);
+          if (idx < nvec) {
+            const int row = idx / (KC / 4), q = idx - row * (KC / 4);
+            float* dst = sm + (row < n_in - 1 ? row : row + 1) * LDK + 4 * q;      // row n_in - 1 is the constant input
+            dst[0] = 4 * q + 0 < kn ? v[u].x : 0.f; dst[1] = 4 * q + 1 < kn ? v[u].y : 0.f;
+            dst[2] = 4 * q + 2 < kn ? v[u].z : 0.f; dst[3] = 4 * q + 3 < kn ? v[u].w : 0.f;
+          }
+        }
       }
-      sm[row * LDK + k] = v;
+      if (threadIdx.x < KC) sm[(n_in - 1) * LDK + threadIdx.x] = int(threadIdx.x) < kn ? 1.f : 0.f;
     }
     __syncthreads();
     if (active) {

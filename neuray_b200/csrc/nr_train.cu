@@ -12,7 +12,7 @@ namespace nr {
 namespace tr {
 
 template <int WHICH>
-__global__ void __launch_bounds__(128) train_kernel(const Ctx c, long long count) {
+__global__ void __launch_bounds__(128, 4) train_kernel(const Ctx c, long long count) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
     if (WHICH == 0) row_forward_a(c, i);
     else if (WHICH == 1) point_forward_b(c, i);
