@@ -284,16 +284,17 @@ int nr_render_pass_fwd(const NrPassParams* p, void* stream) {
 }
 
 int nr_sample_depth(float near, float far, int rn, int dn, const float* jitter, float* depth, float* dists, void* stream) {
-  NR_CHECK_ARG(depth != nullptr && dn > 2 && rn >= 0, "sample_depth arguments (dn must be > 2, render_ops.py:157)");
-  if (rn == 0) return NR_OK;
+  if (rn == 0) return NR_OK;   // empty input: nothing to do (pointers of empty tensors are null)
+  NR_CHECK_ARG(dn > 2 && rn >= 0, "sample_depth arguments (dn must be > 2, render_ops.py:157)");
+  NR_CHECK_ARG(depth != nullptr, "sample_depth: null output");
   sample_depth_kernel<<<blocks_for((long long)rn * dn), TPB, 0, (cudaStream_t)stream>>>(near, far, rn, dn, jitter, depth, dists);
   NR_CHECK_LAUNCH("sample_depth");
   return NR_OK;
 }
 
 int nr_coords2rays(const float* coords, const float* cam, int rn, float* centers, float* directions, void* stream) {
+  if (rn == 0) return NR_OK;   // empty input: nothing to do (pointers of empty tensors are null)
   NR_CHECK_ARG(coords && cam && centers && directions && rn >= 0, "coords2rays arguments");
-  if (rn == 0) return NR_OK;
   coords2rays_kernel<<<blocks_for(rn), TPB, 0, (cudaStream_t)stream>>>(coords, cam, rn, centers, directions);
   NR_CHECK_LAUNCH("coords2rays");
   return NR_OK;
@@ -301,24 +302,24 @@ int nr_coords2rays(const float* coords, const float* cam, int rn, float* centers
 
 int nr_depth2points(const float* coords, const float* cam, const float* depth, int rn, int dn, float* pts, float* dirs,
                     void* stream) {
+  if (rn == 0) return NR_OK;   // empty input: nothing to do (pointers of empty tensors are null)
   NR_CHECK_ARG(coords && cam && depth && pts && dirs && rn >= 0 && dn > 0, "depth2points arguments");
-  if (rn == 0) return NR_OK;
   depth2points_kernel<<<blocks_for((long long)rn * dn), TPB, 0, (cudaStream_t)stream>>>(coords, cam, depth, rn, dn, pts, dirs);
   NR_CHECK_LAUNCH("depth2points");
   return NR_OK;
 }
 
 int nr_depth2dists(const float* depth, int rows, int dn, float* dists, void* stream) {
+  if (rows == 0) return NR_OK;   // empty input: nothing to do (pointers of empty tensors are null)
   NR_CHECK_ARG(depth && dists && rows >= 0 && dn > 0, "depth2dists arguments");
-  if (rows == 0) return NR_OK;
   depth2dists_kernel<<<blocks_for((long long)rows * dn), TPB, 0, (cudaStream_t)stream>>>(depth, rows, dn, 0, 0.f, 0.f, dists);
   NR_CHECK_LAUNCH("depth2dists");
   return NR_OK;
 }
 
 int nr_depth2inv_dists(const float* depth, float near, float far, int rows, int dn, float* dists, void* stream) {
+  if (rows == 0) return NR_OK;   // empty input: nothing to do (pointers of empty tensors are null)
   NR_CHECK_ARG(depth && dists && rows >= 0 && dn > 0, "depth2inv_dists arguments");
-  if (rows == 0) return NR_OK;
   depth2dists_kernel<<<blocks_for((long long)rows * dn), TPB, 0, (cudaStream_t)stream>>>(depth, rows, dn, 1, -1.f / near,
                                                                                          -1.f / far, dists);
   NR_CHECK_LAUNCH("depth2inv_dists");
@@ -326,8 +327,8 @@ int nr_depth2inv_dists(const float* depth, float near, float far, int rows, int 
 }
 
 int nr_alpha_values2hit_prob(const float* alpha, int rows, int dn, float* hit, void* stream) {
+  if (rows == 0) return NR_OK;   // empty input: nothing to do (pointers of empty tensors are null)
   NR_CHECK_ARG(alpha && hit && rows >= 0 && dn > 0, "alpha_values2hit_prob arguments");
-  if (rows == 0) return NR_OK;
   alpha2hit_kernel<<<blocks_for(rows), TPB, 0, (cudaStream_t)stream>>>(alpha, rows, dn, hit);
   NR_CHECK_LAUNCH("alpha_values2hit_prob");
   return NR_OK;
@@ -335,8 +336,8 @@ int nr_alpha_values2hit_prob(const float* alpha, int rows, int dn, float* hit, v
 
 int nr_project_points(const float* pts, int pn, const float* view_params, int rfn, int h, int w, float* dir, float* pix,
                       float* depth, float* mask, float* valid_z, void* stream) {
+  if (pn == 0) return NR_OK;   // empty input: nothing to do (pointers of empty tensors are null)
   NR_CHECK_ARG(pts && view_params && pn >= 0 && rfn >= 1, "project_points arguments");
-  if (pn == 0) return NR_OK;
   project_kernel<<<min(blocks_for((long long)pn * rfn), 148 * 32), TPB, 0, (cudaStream_t)stream>>>(pts, pn, view_params, rfn, h, w,
                                                                                                   dir, pix, depth, mask, valid_z);
   NR_CHECK_LAUNCH("project_points");
@@ -345,8 +346,8 @@ int nr_project_points(const float* pts, int pn, const float* view_params, int rf
 
 int nr_interpolate_feats(const float* feats, const float* pts, const float* mask, int b, int c, int fh, int fw, int n, float h,
                          float w, int border, int align_corners, float* out, void* stream) {
+  if (n == 0) return NR_OK;   // empty input: nothing to do (pointers of empty tensors are null)
   NR_CHECK_ARG(feats && pts && out && b >= 1 && c >= 1 && fh >= 1 && fw >= 1 && n >= 0, "interpolate_feats arguments");
-  if (n == 0) return NR_OK;
   interp_kernel<<<min(blocks_for((long long)b * n), 148 * 32), TPB, 0, (cudaStream_t)stream>>>(feats, pts, mask, b, c, fh, fw, n, h, w,
                                                                                               border, align_corners, out);
   NR_CHECK_LAUNCH("interpolate_feats");
@@ -355,9 +356,9 @@ int nr_interpolate_feats(const float* feats, const float* pts, const float* mask
 
 int nr_sample_fine_depth(const float* depth, const float* hit_prob, float near, float far, int rn, int dn, int fine_dn,
                          const float* u, int u_stride, int use_all, int do_sort, float* out, void* stream) {
+  if (rn == 0) return NR_OK;   // empty input: nothing to do (pointers of empty tensors are null)
   NR_CHECK_ARG(depth && hit_prob && u && out && rn >= 0 && dn >= 2 && fine_dn >= 1, "sample_fine_depth arguments");
   NR_CHECK_ARG(dn <= 4096 && fine_dn <= 4096, "sample_fine_depth: dn / fine_dn too large");
-  if (rn == 0) return NR_OK;
   const int M = fine_dn + (use_all ? dn : 0);
   const int sort_n = sort_size_for(M);
   const int per_warp = (2 * dn + 8 + sort_n + 3) & ~3;

@@ -198,6 +198,9 @@ def _launch_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine, 
         p.fine_dn, p.fine_use_all = int(fine["dn"]), 1 if fine["use_all"] else 0
         p.fine_u, p.fine_u_stride, p.fine_depth = _lib.ptr(fine["u"]), int(fine["u_stride"]), _lib.ptr(out["fine_depth"])
     stream = _lib.stream_of(coords)
+    if rn == 0:          # nothing to render: the (empty) outputs are already in place
+        out["_bwd"] = None
+        return out
     if _lib.PROFILE is not None:
         # bench.py: time the dominant kernel alone, with CUDA events on the launching stream
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

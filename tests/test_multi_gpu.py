@@ -46,3 +46,51 @@ def test_sharded_render_equals_single_gpu():
         ret = m.dict()
         mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
         assert dict(ret) == {0: True, 1: True}
+
+
+def _train_worker(rank, world, port, ret):
+    """Data-parallel step: every rank renders its own ray batch in training mode, backward through the
+    native path, one flat-bucket all-reduce; the result must equal the mean of the per-batch gradients."""
+    from neuray_b200 import dist as nrd
+    from neuray_b200 import renderer, synthetic
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    que, ref = synthetic.make_scene(64, 80, 6, seed=12, smooth=2)
+    dr = synthetic.to_device(ref, f"cuda:{rank}")
+    W = synthetic.make_weights(CFG, seed=2)
+    torch.manual_seed(0)                      # same fine-sampling quantiles on every rank: batches differ only in the rays
+
+    def grads_of(batch_rank):
+        net = renderer.NeuralRayRenderPath(CFG)
+        net.load_state_dict(W, strict=True)
+        net.cuda()
+        q = synthetic.to_device(synthetic.slice_rays(que, 300 * batch_rank + 100, 300 * batch_rank + 164), f"cuda:{rank}")
+        torch.manual_seed(7)
+        out = net.render(q, dr, True)
+        loss = (out["pixel_colors_nr"] ** 2).mean() + (out["pixel_colors_nr_fine"] ** 2).mean() + out["hit_prob_nr"].pow(2).sum() * 0.01
+        loss.backward()
+        return net
+
+    net = grads_of(rank)
+    nrd.allreduce_gradients(net.parameters())
+    torch.cuda.synchronize()
+    ok = True
+    if rank == 0:
+        singles = [grads_of(r) for r in range(world)]
+        for (k, p), *others in zip(net.named_parameters(), *[s.parameters() for s in singles]):
+            if p.grad is None:
+                continue
+            mean = sum(o.grad for o in others) / world
+            ok = ok and bool(torch.allclose(p.grad, mean, rtol=1e-4, atol=1e-7))
+    ret[rank] = ok
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_data_parallel_gradients_equal_the_mean_of_single_rank_gradients():
+    world = 2
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_train_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+        assert dict(ret) == {0: True, 1: True}

@@ -206,3 +206,58 @@ def test_view_counts(rfn):
         close(out[k], gold[k], what=f"{k} rfn={rfn}")
         close(out_f[k], gold[k + "_fine"], what=f"{k}_fine(injected depths) rfn={rfn}")
     assert torch.equal(out["ray_mask"].cpu(), gold["ray_mask"])
+
+
+def _edge_case(rn, dn, rfn, look_away=False, seed=0):
+    cfg = {"use_hierarchical_sampling": True, "depth_sample_num": dn, "fine_depth_sample_num": dn, "agg_net_cfg": {"sample_num": dn},
+           "fine_agg_net_cfg": {"sample_num": dn}, "dist_decoder_cfg": {"use_vis": False}, "render_depth": True}
+    que, ref = synthetic.make_scene(48, 64, rfn, seed=40 + seed, smooth=2)
+    que = synthetic.slice_rays(que, 700, 700 + rn)
+    if look_away:   # turn the query camera around: every sample projects behind / outside every reference view
+        que["poses"] = que["poses"].clone()
+        que["poses"][:, :, :3] = que["poses"][:, :, :3] * torch.tensor([1.0, 1.0, -1.0])[None, :, None]
+    W = synthetic.make_weights(cfg, seed=seed)
+    from gen_golden import flat_cfg
+    gold = orc.render_impl(W, flat_cfg({**renderer.base_cfg, **cfg}), que, ref, False)
+    net = renderer.NeuralRayRenderPath(cfg)
+    net.load_state_dict(W, strict=True)
+    net.cuda()
+    with torch.no_grad():
+        out = net.render_impl(dev(que), dev(ref), False)
+        out_f = net.render_by_depth(gold["que_depth_fine"].cuda(), dev(que), dev(ref), False, True)
+    torch.cuda.synchronize()
+    for k in ("pixel_colors_nr", "hit_prob_nr", "render_depth"):
+        close(out[k], gold[k], what=f"{k} rn={rn} dn={dn}")
+        close(out_f[k], gold[k + "_fine"], what=f"{k}_fine rn={rn} dn={dn}")
+    assert torch.equal(out["ray_mask"].cpu(), gold["ray_mask"])
+    return out, gold
+
+
+@pytest.mark.parametrize("rn,dn", [(1, 3), (7, 5), (130, 16), (3, 200)])
+def test_ragged_and_extreme_sizes(rn, dn):
+    """One ray, ray counts that are not a multiple of any tile, the minimum of 3 samples (sample_depth asserts dn > 2,
+    render_ops.py:147) and 200 samples per ray (limit 256), against the oracle."""
+    _edge_case(rn, dn, 3, seed=rn)
+
+
+def test_rays_looking_away_from_the_scene():
+    """Query camera turned around: most (point, view) pairs are masked or project from behind the reference cameras
+    (negative depth stays valid in the reference, render_ops.py:97-103); no ray passes the ray_mask test
+    (renderer.py:195-200).  Parity with the oracle and no NaN from nearly empty pools / masked softmax rows."""
+    out, gold = _edge_case(24, 8, 4, look_away=True, seed=5)
+    assert not bool(gold["ray_mask"].any())
+    for v in out.values():
+        assert bool(torch.isfinite(v.float()).all())
+
+
+def test_empty_chunk():
+    """Zero rays: every entry point returns empty outputs instead of launching."""
+    cfg = {"use_hierarchical_sampling": True, "render_depth": True}
+    que, ref = synthetic.make_scene(48, 64, 3, seed=2, smooth=2)
+    que = synthetic.slice_rays(que, 10, 10)
+    net = renderer.NeuralRayRenderPath(cfg)
+    net.load_state_dict(synthetic.make_weights(cfg, seed=0), strict=True)
+    net.cuda()
+    with torch.no_grad():
+        out = net.render_impl(dev(que), dev(ref), False)
+    assert out["pixel_colors_nr"].shape == (1, 0, 3) and out["pixel_colors_nr_fine"].shape == (1, 0, 3)
