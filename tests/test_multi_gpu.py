@@ -75,14 +75,19 @@ def _train_worker(rank, world, port, ret):
     net = grads_of(rank)
     nrd.allreduce_gradients(net.parameters())
     torch.cuda.synchronize()
-    ok = True
+    ok, bad = True, []
     if rank == 0:
         singles = [grads_of(r) for r in range(world)]
         for (k, p), *others in zip(net.named_parameters(), *[s.parameters() for s in singles]):
             if p.grad is None:
                 continue
             mean = sum(o.grad for o in others) / world
-            ok = ok and bool(torch.allclose(p.grad, mean, rtol=1e-4, atol=1e-7))
+            err, scale = float((p.grad - mean).abs().max()), float(mean.abs().max())
+            # fp32 atomics: the summation order differs from run to run; rgb_fc.4.bias has a zero true gradient (softmax
+            # is shift invariant), so it only ever holds rounding noise -> absolute floor
+            if err > 1e-4 * scale + 1e-7:
+                bad.append(f"{k}: err {err:.3e} scale {scale:.3e}")
+        ok = True if not bad else "; ".join(bad)
     ret[rank] = ok
     dist.destroy_process_group()
 
