@@ -195,6 +195,24 @@ typedef struct NrGemmDesc {
 int nr_tape_gemms(const NrGemmDesc* descs, int n_desc, const float* tape_row, const float* grad_row, long long rows,
                   const float* tape_point, const float* grad_point, long long points, float* out, void* stream);
 
+/* predict_self_hit_prob (reference renderer.py:137-155, fine-tuning configs): the query view's own ray_feats sampled at
+ * each ray's pixel, decoded by the pass' dist decoder, hit probability per sample (compute_prob, is_ref=False).
+ * d_hit == NULL: forward only (writes hit).  Otherwise also the backward: weight gradients are ADDED to d_w_point in the
+ * packed w_point layout (NrWeightLayout), the map gradient to d_map (may be NULL). */
+typedef struct NrSelfParams {
+  const float* map;          /* [32,fh,fw] query ray_feats */
+  const float* coords;       /* [rn,2] */
+  const float* que_depth;    /* [rn,dn] */
+  const float* w_point;
+  int32_t rn, dn, h, w, fh, fw, use_vis;
+  float near, far, var_bias;
+  float* hit;                /* [rn,dn] */
+  const float* d_hit;        /* [rn,dn] or NULL */
+  float* d_w_point;          /* [NrWeightLayout.total_point] accumulated */
+  float* d_map;              /* [32,fh,fw] accumulated, or NULL */
+} NrSelfParams;
+int nr_self_hit_prob(const NrSelfParams* p, void* stream);
+
 /* ---- diagnostics ------------------------------------------------------------------------------------------- */
 
 /* Self-test of the tcgen05 layer primitive the point kernel uses: D[128,n] = A[128,k] * W[n,k]^T with A staged in

@@ -72,7 +72,15 @@ SIGNATURES = {
     "nr_render_pass_bwd": (C.c_int, [_vp, _vp, _vp]),
     "nr_bwd_slot": (C.c_int, [C.c_char_p]),
     "nr_tape_gemms": (C.c_int, [_vp, _i, _vp, _vp, C.c_longlong, _vp, _vp, C.c_longlong, _vp, _vp]),
+    "nr_self_hit_prob": (C.c_int, [_vp, _vp]),
 }
+
+
+class NrSelfParams(C.Structure):
+    _fields_ = [("map", C.c_void_p), ("coords", C.c_void_p), ("que_depth", C.c_void_p), ("w_point", C.c_void_p),
+                ("rn", C.c_int32), ("dn", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("fh", C.c_int32), ("fw", C.c_int32),
+                ("use_vis", C.c_int32), ("near", C.c_float), ("far", C.c_float), ("var_bias", C.c_float),
+                ("hit", C.c_void_p), ("d_hit", C.c_void_p), ("d_w_point", C.c_void_p), ("d_map", C.c_void_p)]
 
 
 class NrGemmDesc(C.Structure):

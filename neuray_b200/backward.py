@@ -176,3 +176,48 @@ def render_pass_backward(p, names, dec, agg, g_pix, g_hit, g_depth, want_feat_gr
         return grads, None, None
     drf, dimf = feat_grads_to_nchw(d_feat)
     return grads, drf, dimf
+
+
+def unpack_point_grads(plan, d_w_point):
+    """Gradient in the packed w_point layout -> {name: grad}: every parameter element sits at exactly one packed
+    position (PackPlan.i_point maps position -> 1 + flat parameter index, 0 = padding)."""
+    sizes = plan.sizes
+    flat = torch.zeros(1 + sum(sizes), dtype=torch.float32, device=d_w_point.device).index_add_(0, plan.i_point, d_w_point)
+    out, off = {}, 1
+    for name, n, shape in zip(plan.names, sizes, plan.shapes):
+        out[name] = flat[off:off + n].view(shape)
+        off += n
+    return out
+
+
+class SelfHitProbFn(torch.autograd.Function):
+    """predict_self_hit_prob (reference renderer.py:137-155) through nr_self_hit_prob, forward and backward."""
+
+    @staticmethod
+    def forward(ctx, meta, que_ray_feats, *dec_params):
+        p = meta["params"]()
+        hit = torch.empty(p.rn, p.dn, dtype=torch.float32, device=que_ray_feats.device)
+        p.hit = _lib.ptr(hit)
+        _lib.check(_lib.lib().nr_self_hit_prob(C.byref(p), meta["stream"]), "nr_self_hit_prob")
+        _lib.count_launches(1)
+        ctx.meta = meta
+        ctx.feats_need = que_ray_feats.requires_grad
+        ctx.need = [t.requires_grad for t in dec_params]
+        return hit[None]
+
+    @staticmethod
+    def backward(ctx, g_hit):
+        meta = ctx.meta
+        plan = meta["plan"]
+        p = meta["params"]()
+        dev = g_hit.device
+        g = g_hit[0].contiguous().float()
+        hit = torch.empty(p.rn, p.dn, dtype=torch.float32, device=dev)
+        d_w = torch.zeros(plan.i_point.numel(), dtype=torch.float32, device=dev)
+        d_map = torch.zeros(meta["map_shape"], dtype=torch.float32, device=dev) if ctx.feats_need else None
+        p.hit, p.d_hit, p.d_w_point, p.d_map = _lib.ptr(hit), _lib.ptr(g), _lib.ptr(d_w), _lib.ptr(d_map)
+        _lib.check(_lib.lib().nr_self_hit_prob(C.byref(p), meta["stream"]), "nr_self_hit_prob (backward)")
+        _lib.count_launches(1)
+        grads = unpack_point_grads(plan, d_w)
+        gp = [grads[n] if need else None for n, need in zip(meta["dec_names"], ctx.need)]
+        return (None, d_map[None] if d_map is not None else None, *gp)

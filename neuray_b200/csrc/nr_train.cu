@@ -28,6 +28,10 @@ __global__ void __launch_bounds__(128, 4) train_kernel(const Ctx c, long long co
   }
 }
 
+__global__ void __launch_bounds__(64) self_kernel(const NrSelfParams c) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < c.rn; i += (long long)gridDim.x * blockDim.x) self_hit_prob_ray(c, i);
+}
+
 struct SlotName { const char* name; int value; };
 static const SlotName kSlots[] = {
     {"R_SLOTS", R_SLOTS}, {"G_SLOTS", G_SLOTS}, {"P_SLOTS", P_SLOTS}, {"GP_SLOTS", GP_SLOTS},
@@ -53,6 +57,18 @@ int nr_bwd_slot(const char* name) {
   for (const auto& s : nr::tr::kSlots)
     if (strcmp(s.name, name) == 0) return s.value;
   return -1;
+}
+
+int nr_self_hit_prob(const NrSelfParams* p, void* stream) {
+  using namespace nr;
+  NR_CHECK_ARG(p != nullptr, "params");
+  if (p->rn == 0) return NR_OK;
+  NR_CHECK_ARG(p->map && p->coords && p->que_depth && p->w_point && p->hit, "null device pointer");
+  NR_CHECK_ARG(p->dn >= 2 && p->fh >= 1 && p->fw >= 1 && p->h > 1 && p->w > 1, "shape");
+  NR_CHECK_ARG(p->d_hit == nullptr || p->d_w_point != nullptr, "d_w_point required for the backward");
+  tr::self_kernel<<<(p->rn + 63) / 64, 64, 0, (cudaStream_t)stream>>>(*p);
+  NR_CHECK_LAUNCH("self_hit_prob");
+  return NR_OK;
 }
 
 int nr_render_pass_bwd(const NrPassParams* p, const NrBwdParams* b, void* stream) {

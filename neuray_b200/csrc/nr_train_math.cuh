@@ -977,5 +977,120 @@ NR_HD void row_backward_d(const Ctx& c, long long r) {
   }
 }
 
+
+// ---- predict_self_hit_prob (reference renderer.py:137-155; dist_decoder.py compute_prob with is_ref=False) ---------------
+// The query view's own ray_feats (NCHW [32,fh,fw]) sampled at the ray's pixel, decoded by the pass' dist decoder, and
+// turned into per-sample hit probabilities along the ray.  One routine does forward and (optionally) backward for one
+// ray: d_hit == nullptr -> forward only.  Weight gradients are added to dW in the packed w_point layout (512 rays only:
+// plain atomics), the feature-map gradient to d_map (NCHW).
+typedef NrSelfParams SelfCtx;   // include/neuray_b200.h
+
+NR_HD void self_hit_prob_ray(const SelfCtx& c, long long ray) {
+  const int dn = c.dn, fh = c.fh, fw = c.fw, n_heads = c.use_vis ? 4 : 3;
+  const float* __restrict__ W = c.w_point;
+  // bilinear sample, border clamp (interpolate_feats, ops.py:14-34; align_corners when the map is full resolution)
+  const float x = c.coords[2 * ray], y = c.coords[2 * ray + 1];
+  const bool al = (fh == c.h && fw == c.w);
+  const float gx = x / float(c.w - 1) * 2.f - 1.f, gy = y / float(c.h - 1) * 2.f - 1.f;
+  float fx = al ? (gx + 1.f) / 2.f * float(fw - 1) : ((gx + 1.f) * float(fw) - 1.f) / 2.f;
+  float fy = al ? (gy + 1.f) / 2.f * float(fh - 1) : ((gy + 1.f) * float(fh) - 1.f) / 2.f;
+  fx = fminf(fmaxf(fx, 0.f), float(fw - 1)); fy = fminf(fmaxf(fy, 0.f), float(fh - 1));
+  const float x0f = floorf(fx), y0f = floorf(fy);
+  const int x0 = int(x0f), y0 = int(y0f);
+  const int x1 = x0 + 1 < fw ? x0 + 1 : fw - 1, y1 = y0 + 1 < fh ? y0 + 1 : fh - 1;
+  const float we = fx - x0f, ww = (x0f + 1.f) - fx, ws = fy - y0f, wn = (y0f + 1.f) - fy;
+  const float tw[4] = {ww * wn, we * wn, ww * ws, we * ws};
+  const int to[4] = {y0 * fw + x0, y0 * fw + x1, y1 * fw + x0, y1 * fw + x1};
+  float rf[32];
+  for (int k = 0; k < 32; ++k) {
+    const float* m = c.map + (size_t)k * fh * fw;
+    rf[k] = m[to[0]] * tw[0] + m[to[1]] * tw[1] + m[to[2]] * tw[2] + m[to[3]] * tw[3];
+  }
+  float h1[4][32], h2[4][32], ho[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  for (int hd = 0; hd < n_heads; ++hd) {
+    const float* Wh = W + lay::DD_HEAD + hd * lay::DD_HEAD_STRIDE;
+    lin<32, 32>(Wh + lay::DD_L0_W, Wh + lay::DD_L0_B, rf, h1[hd]);
+    for (int k = 0; k < 32; ++k) h1[hd][k] = elu_f(h1[hd][k]);
+    lin<32, 32>(Wh + lay::DD_L1_W, Wh + lay::DD_L1_B, h1[hd], h2[hd]);
+    for (int k = 0; k < 32; ++k) h2[hd][k] = elu_f(h2[hd][k]);
+    for (int o = 0; o < 2; ++o) {
+      float a = Wh[lay::DD_L2_B + o];
+      for (int k = 0; k < 32; ++k) a = fmaf(Wh[lay::DD_L2_W + o * 32 + k], h2[hd][k], a);
+      ho[hd][o] = a;
+    }
+  }
+  float mean[2], var[2];
+  for (int i = 0; i < 2; ++i) { mean[i] = softplus_f(ho[0][i]); var[i] = softplus_f(ho[1][i]) + c.var_bias; }
+  const float aw = sigm(ho[2][0]);
+  const float visd = c.use_vis ? sigm(ho[3][0]) : 1.f;
+  // bin edges in normalised inverse depth (get_near_far_points, is_ref=False: midpoints, half intervals at the ends)
+  const float a = -1.f / c.near, b = -1.f / c.far;
+  const float* qd = c.que_depth + ray * dn;
+  auto tn = [&](int s) { return (-1.f / fmaxf(qd[s], 1e-5f) - a) / (b - a); };
+  float dmean[2] = {0.f, 0.f}, dvar[2] = {0.f, 0.f}, dmix[2] = {0.f, 0.f}, dvisd = 0.f;
+  for (int s = 0; s < dn; ++s) {
+    const float t = tn(s);
+    const float lo = s == 0 ? t - (tn(1) - t) * 0.5f : (tn(s - 1) + t) * 0.5f;
+    const float hi = s == dn - 1 ? t + 1e6f * 0.5f : (t + tn(s + 1)) * 0.5f;
+    float hit = 0.f, c0[2], c1[2];
+    for (int i = 0; i < 2; ++i) {
+      c0[i] = sigm(2.f * (lo - mean[i]) * var[i]);
+      c1[i] = sigm(2.f * (hi - mean[i]) * var[i]);
+      hit += (c1[i] - c0[i]) * visd * (i == 0 ? aw : 1.f - aw);
+    }
+    c.hit[ray * dn + s] = hit;
+    if (c.d_hit != nullptr) {
+      const float dh = c.d_hit[ray * dn + s];
+      for (int i = 0; i < 2; ++i) {
+        const float mix = i == 0 ? aw : 1.f - aw;
+        const float dc = dh * mix;                                  // wrt c1*visd; -dc wrt c0*visd
+        dmix[i] += dh * (c1[i] - c0[i]) * visd;
+        dvisd += dc * (c1[i] - c0[i]);
+        const float dx1 = dc * visd * 2.f * c1[i] * (1.f - c1[i]), dx0 = -dc * visd * 2.f * c0[i] * (1.f - c0[i]);
+        dmean[i] -= (dx1 + dx0) * var[i];
+        dvar[i] += dx1 * (hi - mean[i]) + dx0 * (lo - mean[i]);
+      }
+    }
+  }
+  if (c.d_hit == nullptr) return;
+  float dho[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+  for (int i = 0; i < 2; ++i) {
+    dho[0][i] = dmean[i] * (1.f - expf(-mean[i]));
+    dho[1][i] = dvar[i] * (1.f - expf(-(var[i] - c.var_bias)));
+  }
+  dho[2][0] = (dmix[0] - dmix[1]) * aw * (1.f - aw);
+  if (c.use_vis) dho[3][0] = dvisd * visd * (1.f - visd);
+  float drf[32];
+  for (int k = 0; k < 32; ++k) drf[k] = 0.f;
+  for (int hd = 0; hd < n_heads; ++hd) {
+    const int base = lay::DD_HEAD + hd * lay::DD_HEAD_STRIDE;
+    const float* Wh = W + base;
+    float* dWh = c.d_w_point + base;
+    float dz1[32], dz0[32], t[32];
+    for (int o = 0; o < 2; ++o) {
+      atomic_add(dWh + lay::DD_L2_B + o, dho[hd][o]);
+      for (int k = 0; k < 32; ++k) atomic_add(dWh + lay::DD_L2_W + o * 32 + k, dho[hd][o] * h2[hd][k]);
+    }
+    for (int k = 0; k < 32; ++k) dz1[k] = (Wh[lay::DD_L2_W + k] * dho[hd][0] + Wh[lay::DD_L2_W + 32 + k] * dho[hd][1]) * elu_g(h2[hd][k]);
+    lin_t<32, 32>(Wh + lay::DD_L1_W, dz1, dz0);
+    for (int k = 0; k < 32; ++k) dz0[k] *= elu_g(h1[hd][k]);
+    for (int j = 0; j < 32; ++j) {
+      atomic_add(dWh + lay::DD_L1_B + j, dz1[j]);
+      atomic_add(dWh + lay::DD_L0_B + j, dz0[j]);
+      for (int i = 0; i < 32; ++i) {                                  // WT[in][out]
+        atomic_add(dWh + lay::DD_L1_W + i * 32 + j, h1[hd][i] * dz1[j]);
+        atomic_add(dWh + lay::DD_L0_W + i * 32 + j, rf[i] * dz0[j]);
+      }
+    }
+    lin_t<32, 32>(Wh + lay::DD_L0_W, dz0, t);
+    for (int k = 0; k < 32; ++k) drf[k] += t[k];
+  }
+  if (c.d_map != nullptr)
+    for (int k = 0; k < 32; ++k) {
+      float* m = c.d_map + (size_t)k * fh * fw;
+      for (int q = 0; q < 4; ++q) atomic_add(m + to[q], drf[k] * tw[q]);
+    }
+}
+
 }  // namespace tr
 }  // namespace nr

@@ -271,13 +271,38 @@ def _finish_outputs(owner, res, que_depth, que_imgs_info):
 
 
 def _self_hit_prob(self, que_depth, que_imgs_info, is_fine):
-    """a17 predict_self_hit_prob (reference renderer.py:137-155): fine-tuning only; interim PyTorch (autograd_path.py)."""
-    from .autograd_path import self_hit_prob_torch
+    """a17 predict_self_hit_prob (reference renderer.py:137-155): the query view's own ray_feats decoded along its rays
+    (fine-tuning configs).  nr_self_hit_prob, forward and backward; NR_BACKWARD=torch keeps the PyTorch restatement."""
     dec, _, dec_name, _ = _pass_modules(self, is_fine)
-    P = {f"{dec_name}.{k}": v for k, v in dec.named_parameters()}
+    feats = que_imgs_info["ray_feats"]
+    coords = que_imgs_info["coords"]
     h, w = que_imgs_info["imgs"].shape[-2:]
-    return self_hit_prob_torch(P, dec_name, bool(dec.cfg["use_vis"]), float(dec.cfg["bias_val"]), que_imgs_info["ray_feats"],
-                               que_imgs_info["coords"], h, w, que_depth, que_imgs_info["depth_range"])
+    if os.environ.get("NR_BACKWARD", "native") == "torch" or feats.shape[0] != 1:
+        from .autograd_path import self_hit_prob_torch
+        P = {f"{dec_name}.{k}": v for k, v in dec.named_parameters()}
+        return self_hit_prob_torch(P, dec_name, bool(dec.cfg["use_vis"]), float(dec.cfg["bias_val"]), feats, coords, h, w, que_depth,
+                                   que_imgs_info["depth_range"])
+    from .backward import SelfHitProbFn
+    dev = coords.device
+    _, rn, dn = que_depth.shape
+    w_point = pass_weights(self, is_fine, dn, dev)[0]
+    plan = self.__dict__["_nr_plans"][(is_fine, str(dev))]
+    fmap = feats[0].detach().contiguous().float()
+    cc, qd = coords[0].detach().contiguous().float(), que_depth[0].detach().contiguous().float()
+    rng = que_imgs_info["depth_range"][0].detach().float().cpu()
+    use_vis, var_bias = 1 if dec.cfg["use_vis"] else 0, float(dec.cfg["bias_val"])
+
+    def params():
+        p = _lib.NrSelfParams()
+        p.map, p.coords, p.que_depth, p.w_point = _lib.ptr(fmap), _lib.ptr(cc), _lib.ptr(qd), _lib.ptr(w_point)
+        p.rn, p.dn, p.h, p.w, p.fh, p.fw, p.use_vis = rn, dn, int(h), int(w), fmap.shape[1], fmap.shape[2], use_vis
+        p.near, p.far, p.var_bias = float(rng[0]), float(rng[1]), var_bias
+        return p
+
+    named = [(f"{dec_name}.{k}", v) for k, v in dec.named_parameters()]
+    meta = {"params": params, "plan": plan, "stream": _lib.stream_of(coords), "map_shape": tuple(fmap.shape),
+            "dec_names": [n for n, _ in named], "keep": (fmap, cc, qd, w_point)}
+    return SelfHitProbFn.apply(meta, feats, *[v for _, v in named])
 
 
 def render_by_depth(self, que_depth, que_imgs_info, ref_imgs_info, is_train, is_fine):

@@ -256,6 +256,8 @@ class PackPlan:
     def __init__(self, params, dec, agg, device):
         global _RAW
         self.names = list(params)
+        self.sizes = [params[k].numel() for k in self.names]
+        self.shapes = [tuple(params[k].shape) for k in self.names]
         self.dec, self.agg = dec, agg
         cpu = torch.device("cpu")
         coded, off = {}, 1

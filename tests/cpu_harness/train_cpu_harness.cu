@@ -3,6 +3,11 @@
 // backward against PyTorch autograd without a GPU.  Not part of the product library.
 #include "../../neuray_b200/csrc/nr_train_math.cuh"
 
+extern "C" int nr_self_cpu(const NrSelfParams* p) {
+  for (long long r = 0; r < p->rn; ++r) nr::tr::self_hit_prob_ray(*p, r);
+  return 0;
+}
+
 extern "C" int nr_train_cpu(const NrPassParams* p, const NrBwdParams* b) {
   using namespace nr::tr;
   const long long N = (long long)p->rn * p->dn, R = N * p->rfn;

@@ -118,3 +118,53 @@ def test_hand_written_backward_matches_autograd(harness, rfn, use_vis):
 
 def test_backward_without_hit_prob_gradient(harness):
     run_case(harness, 4, True, dn=6, rays=3, seed=9, with_hit=False)
+
+
+@pytest.mark.parametrize("use_vis", [False, True])
+def test_self_hit_prob_forward_and_backward(harness, use_vis):
+    """nr_self_hit_prob's routine (host build) against the PyTorch restatement of predict_self_hit_prob
+    (reference renderer.py:137-155) and autograd over it: values, every decoder parameter gradient (through the packed
+    layout and PackPlan's inverse map) and the gradient of the query feature map."""
+    torch.manual_seed(3)
+    dn, rays = 12, 9
+    cfg = {"depth_sample_num": dn, "agg_net_cfg": {"sample_num": dn}, "dist_decoder_cfg": {"use_vis": use_vis}}
+    que, ref = synthetic.make_scene(40, 48, 3, seed=31, smooth=2)
+    coords = que["coords"][:, torch.randperm(que["coords"].shape[1])[:rays]].clone()
+    fmap = torch.randn(1, 32, 10, 12)
+    W = synthetic.make_weights(cfg, seed=5)
+    dec, agg = "dist_decoder", "agg_net"
+    names = [k for k in W if k.startswith(dec + ".") or k.startswith(agg + ".")]
+    import neuray_oracle as orc
+    que_depth, _ = orc.sample_depth(que["depth_range"], coords, dn, False)
+    g_hit = torch.randn(1, rays, dn)
+    P = {k: W[k].clone().requires_grad_(True) for k in names}
+    fm = fmap.clone().requires_grad_(True)
+    ref_hit = autograd_path.self_hit_prob_torch(P, dec, use_vis, 0.05, fm, coords, 40, 48, que_depth, que["depth_range"])
+    (ref_hit * g_hit).sum().backward()
+
+    params = {k: W[k] for k in names}
+    plan = weights.PackPlan(params, dec, agg, torch.device("cpu"))
+    wp = plan.pack(params)[0]
+    cc, qd, m0, gh = coords[0].contiguous(), que_depth[0].contiguous(), fmap[0].contiguous(), g_hit[0].contiguous()
+    hit, d_w, d_map = torch.empty(rays, dn), torch.zeros_like(wp), torch.zeros_like(m0)
+    p = _lib.NrSelfParams()
+    p.map, p.coords, p.que_depth, p.w_point = m0.data_ptr(), cc.data_ptr(), qd.data_ptr(), wp.data_ptr()
+    p.rn, p.dn, p.h, p.w, p.fh, p.fw, p.use_vis = rays, dn, 40, 48, 10, 12, int(use_vis)
+    p.near, p.far, p.var_bias = float(que["depth_range"][0, 0]), float(que["depth_range"][0, 1]), 0.05
+    p.hit, p.d_hit, p.d_w_point, p.d_map = hit.data_ptr(), gh.data_ptr(), d_w.data_ptr(), d_map.data_ptr()
+    harness.nr_self_cpu.restype = C.c_int
+    harness.nr_self_cpu.argtypes = [C.c_void_p]
+    assert harness.nr_self_cpu(C.addressof(p)) == 0
+    assert torch.allclose(hit, ref_hit[0].detach(), atol=2e-6), (hit - ref_hit[0].detach()).abs().max()
+    grads = backward.unpack_point_grads(plan, d_w)
+    checked = 0
+    for k in names:
+        ga = P[k].grad
+        if ga is None or not k.startswith(dec + "."):
+            assert float(grads[k].abs().max()) == 0.0, k
+            continue
+        err, scale = float((grads[k] - ga).abs().max()), float(ga.abs().max())
+        assert err <= 2e-4 * max(scale, 1e-3) + 2e-6, (k, err, scale)
+        checked += 1
+    assert checked == (24 if use_vis else 18)
+    assert float((d_map - fm.grad[0]).abs().max()) <= 2e-4 * float(fm.grad.abs().max()) + 2e-6

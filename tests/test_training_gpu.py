@@ -122,3 +122,40 @@ def test_native_backward_matches_torch_recompute(monkeypatch):
     assert checked > 120
     for a, b in ((gn[1], gt[1]), (gn[2], gt[2])):
         assert float((a - b).abs().max()) <= 1e-3 * float(b.abs().max()) + 1e-6
+
+
+def test_self_hit_prob_native_matches_torch(monkeypatch):
+    """use_self_hit_prob (fine-tuning configs, reference renderer.py:137-155, 188-189): nr_self_hit_prob against the PyTorch
+    restatement on the GPU -- values of hit_prob_self and the gradients it sends into the decoder and the query map."""
+    cfg = dict(CFG, use_self_hit_prob=True, dist_decoder_cfg={"use_vis": True})
+    que, ref = synthetic.make_scene(64, 80, 4, seed=21, smooth=2)
+    que = synthetic.slice_rays(que, 500, 564)
+    W = synthetic.make_weights(cfg, seed=6)
+    gw = torch.randn(1, 64, 24, device="cuda")
+    torch.manual_seed(1)
+    fmap = torch.randn(1, 32, 16, 20)
+    res = {}
+    for mode in ("native", "torch"):
+        monkeypatch.setenv("NR_BACKWARD", mode)
+        net = renderer.NeuralRayRenderPath(cfg)
+        net.load_state_dict(W, strict=True)
+        net.cuda()
+        dq, dr = synthetic.to_device(que, "cuda"), synthetic.to_device(ref, "cuda")
+        dq["ray_feats"] = fmap.cuda().requires_grad_(True)
+        depth = renderer.sample_depth(dq["depth_range"], dq["coords"], 24, False)[0]
+        out = net.render_by_depth(depth, dq, dr, True, False)
+        (out["hit_prob_self"] * gw).sum().backward()
+        torch.cuda.synchronize()
+        res[mode] = (out["hit_prob_self"].detach().clone(), dq["ray_feats"].grad.clone(),
+                     {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None})
+    a, b = res["native"], res["torch"]
+    assert torch.allclose(a[0], b[0], atol=5e-6)
+    assert float((a[1] - b[1]).abs().max()) <= 1e-3 * float(b[1].abs().max()) + 1e-7
+    checked = 0
+    for k, g in b[2].items():
+        if float(g.abs().max()) == 0.0:
+            continue
+        assert k in a[2], k
+        assert float((a[2][k] - g).abs().max()) <= 1e-3 * float(g.abs().max()) + 1e-7, k
+        checked += 1
+    assert checked >= 24
