@@ -43,7 +43,6 @@ def run_case(harness, rfn, use_vis, dn=8, rays=5, seed=0, with_hit=True):
     W = synthetic.make_weights(cfg, seed=seed)
     dec, agg = "dist_decoder", "agg_net"
     names = [k for k in W if k.startswith(dec + ".") or k.startswith(agg + ".")]
-    depth = renderer.render_ops.sample_depth if False else None
     import neuray_oracle as orc
     que_depth, _ = orc.sample_depth(que["depth_range"], coords, dn, False)            # [1,rays,dn]
     pos_enc = weights.posenc_table(dn)
