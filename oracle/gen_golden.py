@@ -42,6 +42,14 @@ CASES = {
              "fine_depth_use_all": True, "agg_net_cfg": {"sample_num": 24}, "fine_agg_net_cfg": {"sample_num": 40},
              "render_depth": True, "ray_batch_num": 1024},
         is_train=True, stage_rays=32, seed=5),
+    # SURVEY.md 8d cfg4 in miniature: 10 reference views (not a power of two: padding lanes in the point kernel), wide
+    # COLMAP-like depth range, non-square images
+    "views10": dict(
+        scene=dict(h=48, w=64, rfn=10, que_h=20, que_w=24, seed=7, smooth=2, depth_range=(1.2, 12.0), arc_deg=100.0),
+        cfg={"use_hierarchical_sampling": True, "dist_decoder_cfg": {"use_vis": False}, "depth_sample_num": 16,
+             "fine_depth_sample_num": 16, "agg_net_cfg": {"sample_num": 16}, "fine_agg_net_cfg": {"sample_num": 16},
+             "render_depth": True, "ray_batch_num": 512},
+        is_train=False, stage_rays=24, seed=11),
 }
 
 

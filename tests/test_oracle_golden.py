@@ -6,7 +6,7 @@ import torch
 import neuray_oracle as orc
 from golden_io import GoldenCase
 
-CASES = ["cfg1", "train8"]
+CASES = ["cfg1", "train8", "views10"]
 ATOL, RTOL = 1e-4, 1e-3      # BASELINE.json north_star: 1e-4 abs / 1e-3 rel fp32
 
 

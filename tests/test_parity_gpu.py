@@ -12,7 +12,7 @@ from neuray_b200 import _lib, renderer, render_ops, synthetic
 
 pytestmark = pytest.mark.gpu
 ATOL, RTOL = 1e-4, 1e-3
-CASES = ["cfg1", "train8"]
+CASES = ["cfg1", "train8", "views10"]
 
 
 FAILS = []
