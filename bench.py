@@ -316,6 +316,10 @@ def run_b200(args):
         cpu = {"value": v, "unit": "ray-samples/s", "cores": threads, "kind": "port",
                "sample": f"{args.cpu_rays} rays x ({dn_c}+{dn_f}) samples of the same workload, 1 warm-up + 1 timed pass, {t:.1f} s"}
 
+    # DRAM bytes of one point-kernel launch from the ncu --set full capture of this kernel at this launch size
+    # (profiles/r1_point_kernel_pm3_v1_ncu.md: dram__bytes_read 57.7 MB + dram__bytes_write 385.1 MB per 65 536-ray launch;
+    # the algorithmic gather of that launch is 36 GB -- the maps stay L2 resident -- and the record written is 335 MB)
+    traffic = 57697280 + 385050624 if (args.workload == "black_800" and args.ray_batch == 65536) else None
     line = {
         "metric": METRIC, "value": value, "unit": "ray-samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -329,7 +333,7 @@ def run_b200(args):
         "gpu_launches": launches,
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "kernel": "nr::pkt::pm3::point_kernel_pm3", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": f"{peaks_src} bf16_tflops_sustained",
+                     "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/r1_point_kernel_pm3_v1_ncu.md)", "peak_source": f"{peaks_src} bf16_tflops_sustained",
                      "flops_per_ray_sample": fl, "launches": n_launch, "avg_launch_ms": sum(pk_ms) / max(n_launch, 1),
                      "share_of_step": pk_time / t_res,
                      "note": "dense layers on tcgen05 with 3xTF32 (3 MMAs per algorithmic one); the kernel is epilogue/latency bound, not tensor-pipe bound (profiles/README.md)"},
