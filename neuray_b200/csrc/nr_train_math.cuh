@@ -145,15 +145,27 @@ NR_HD float elu_g(float a) { return a > 0.f ? 1.f : a + 1.f; }           // deri
 NR_HD float sigm(float x) { return 1.f / (1.f + expf(-x)); }
 NR_HD float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 
-// z[OUT] = b + W^T x with W stored [IN][LD]
+// z[OUT] = b + W^T x with W stored [IN][LD].  Weight rows are read with 128-bit loads when the shapes allow (all
+// weight blocks start on 16-byte boundaries, nr_common.cuh lay::): every thread reads the same addresses, so the load
+// instruction count, not the bandwidth, is what these row loops pay for.
 template <int IN, int OUT, int LD = OUT>
 NR_HD void lin(const float* __restrict__ W, const float* __restrict__ b, const float* x, float* z) {
 #pragma unroll
   for (int j = 0; j < OUT; ++j) z[j] = b ? b[j] : 0.f;
   for (int i = 0; i < IN; ++i) {
     const float xi = x[i];
+    if constexpr (OUT % 4 == 0 && LD % 4 == 0) {
+      const float4* __restrict__ w4 = reinterpret_cast<const float4*>(W + i * LD);
 #pragma unroll
-    for (int j = 0; j < OUT; ++j) z[j] = fmaf(W[i * LD + j], xi, z[j]);
+      for (int j = 0; j < OUT / 4; ++j) {
+        const float4 w = w4[j];
+        z[4 * j] = fmaf(w.x, xi, z[4 * j]); z[4 * j + 1] = fmaf(w.y, xi, z[4 * j + 1]);
+        z[4 * j + 2] = fmaf(w.z, xi, z[4 * j + 2]); z[4 * j + 3] = fmaf(w.w, xi, z[4 * j + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < OUT; ++j) z[j] = fmaf(W[i * LD + j], xi, z[j]);
+    }
   }
 }
 // dx[IN] = W dz
@@ -161,8 +173,17 @@ template <int IN, int OUT, int LD = OUT>
 NR_HD void lin_t(const float* __restrict__ W, const float* dz, float* dx) {
   for (int i = 0; i < IN; ++i) {
     float a = 0.f;
+    if constexpr (OUT % 4 == 0 && LD % 4 == 0) {
+      const float4* __restrict__ w4 = reinterpret_cast<const float4*>(W + i * LD);
 #pragma unroll
-    for (int j = 0; j < OUT; ++j) a = fmaf(W[i * LD + j], dz[j], a);
+      for (int j = 0; j < OUT / 4; ++j) {
+        const float4 w = w4[j];
+        a = fmaf(w.x, dz[4 * j], a); a = fmaf(w.y, dz[4 * j + 1], a); a = fmaf(w.z, dz[4 * j + 2], a); a = fmaf(w.w, dz[4 * j + 3], a);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < OUT; ++j) a = fmaf(W[i * LD + j], dz[j], a);
+    }
     dx[i] = a;
   }
 }
