@@ -12,7 +12,7 @@ namespace nr {
 namespace tg {
 
 constexpr int MAXD = 48;
-constexpr int KC = tr::TILE, LDK = KC + 1;   // one tape tile per K chunk
+constexpr int KC = 64, LDK = KC + 1;   // half a tape tile per K chunk; odd row stride: the operand rows a warp touches fall into distinct banks
 constexpr int MAXT = 3;      // 4x4 tiles per thread: 16 x 36 tiles at most (64 outputs, 140 + 1 inputs)
 
 struct Args {
@@ -23,16 +23,24 @@ struct Args {
   float* out;
 };
 
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int n = valid ? 4 : 0;                                   // src-size 0: the destination is zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(256) tape_gemm_kernel(const __grid_constant__ Args a) {
   extern __shared__ float sm[];
   const NrGemmDesc& d = a.d[blockIdx.x];
   const int n_in = d.n_in + 1, n_out = d.n_out;                  // + the constant-1 input (bias)
-  const float* __restrict__ X = a.tape[d.x_tape] + (long long)d.x_slot * KC;      // + tile * slots * KC
-  const float* __restrict__ Z = a.tape[d.g_tape] + (long long)d.g_slot * KC;
-  const long long xt = (long long)a.slots[d.x_tape] * KC, zt = (long long)a.slots[d.g_tape] * KC;   // floats per tape tile
+  const float* __restrict__ X = a.tape[d.x_tape] + (long long)d.x_slot * tr::TILE;      // + tile * slots * 128
+  const float* __restrict__ Z = a.tape[d.g_tape] + (long long)d.g_slot * tr::TILE;
+  const long long xt = (long long)a.slots[d.x_tape] * tr::TILE, zt = (long long)a.slots[d.g_tape] * tr::TILE;   // floats per tape tile
   const long long M = a.rows[d.x_tape];
-  float* xs = sm;                       // [n_in][LDK]
-  float* zs = sm + n_in * LDK;          // [n_out][LDK]
+  const int buf_floats = (n_in + n_out) * LDK;
   const int ti_n = (n_in + 3) >> 2, to_n = (n_out + 3) >> 2, tiles = ti_n * to_n;
   // thread -> (tile, k group): a layer with few output tiles splits the chunk's rows over the spare threads instead of
   // leaving them idle (a 32x33 layer has 72 tiles: three k groups); the partial sums meet in the final atomic adds
@@ -45,47 +53,37 @@ __global__ void __launch_bounds__(256) tape_gemm_kernel(const __grid_constant__ 
   for (int t = 0; t < MAXT; ++t)
 #pragma unroll
     for (int e = 0; e < 16; ++e) acc[t][e] = 0.f;
-  // a CTA walks a CONTIGUOUS range of chunks: every operand slot is then one sequential stream per CTA (chunks strided
-  // over the CTAs made each 256-byte piece come from a different DRAM page: 4.1 ms per call instead of ~1)
+  // a CTA walks a contiguous range of 64-row chunks (sequential streams per operand slot), double buffered: the
+  // cp.async copies of chunk c+1 are in flight while chunk c is multiplied (a plain load-then-compute loop spent most of
+  // its time waiting for the loads: one chunk is only ~17 KB)
   const long long chunks = (M + KC - 1) / KC;
   const long long per = (chunks + gridDim.y - 1) / gridDim.y;
-  const long long ch_end = min(chunks, (long long)(blockIdx.y + 1) * per);
-  for (long long ch = (long long)blockIdx.y * per; ch < ch_end; ++ch) {
+  const long long ch0 = (long long)blockIdx.y * per, ch_end = min(chunks, ch0 + per);
+  auto stage = [&](long long ch, float* buf) {
+    const long long tile = ch >> 1;
+    const int half = int(ch & 1) * KC;
     const long long k0 = ch * KC;
     const int kn = int(M - k0 < KC ? M - k0 : KC);
-    __syncthreads();
-    // stage the chunk: (n_in - 1 + n_out) operand rows of 128 floats, as 128-bit loads, four in flight per thread (one
-    // scalar load per loop trip left a single load in flight per thread: 20 us per chunk of pure latency)
-    {
-      const int nvec = (n_in - 1 + n_out) * (KC / 4);
-      const float* __restrict__ xsrc = X + ch * xt;
-      const float* __restrict__ zsrc = Z + ch * zt;
-      for (int base = 0; base < nvec; base += 4 * 256) {
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int idx = base + u * 256 + int(threadIdx.x);
-          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (idx < nvec) {
-            const int row = idx / (KC / 4), q = idx - row * (KC / 4);
-            const float* src = row < n_in - 1 ? xsrc + row * KC : zsrc + (row - (n_in - 1)) * KC;
-            v[u] = __ldg(reinterpret_cast<const float4*>(src) + q);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int idx = base + u * 256 + int(threadIdx.x);
-          if (idx < nvec) {
-            const int row = idx / (KC / 4), q = idx - row * (KC / 4);
-            float* dst = sm + (row < n_in - 1 ? row : row + 1) * LDK + 4 * q;      // row n_in - 1 is the constant input
-            dst[0] = 4 * q + 0 < kn ? v[u].x : 0.f; dst[1] = 4 * q + 1 < kn ? v[u].y : 0.f;
-            dst[2] = 4 * q + 2 < kn ? v[u].z : 0.f; dst[3] = 4 * q + 3 < kn ? v[u].w : 0.f;
-          }
-        }
-      }
-      if (threadIdx.x < KC) sm[(n_in - 1) * LDK + threadIdx.x] = int(threadIdx.x) < kn ? 1.f : 0.f;
+    const float* __restrict__ xsrc = X + tile * xt + half;
+    const float* __restrict__ zsrc = Z + tile * zt + half;
+    const int n = (n_in - 1 + n_out) * KC;
+    for (int idx = threadIdx.x; idx < n; idx += 256) {
+      const int row = idx / KC, k = idx - row * KC;
+      const float* src = row < n_in - 1 ? xsrc + row * tr::TILE + k : zsrc + (row - (n_in - 1)) * tr::TILE + k;
+      cp_async4(buf + (row < n_in - 1 ? row : row + 1) * LDK + k, src, k < kn);       // row n_in - 1 is the constant input
     }
+  };
+  for (int i = threadIdx.x; i < 2 * KC; i += 256) sm[(i / KC) * buf_floats + (n_in - 1) * LDK + (i % KC)] = 1.f;
+  if (ch0 < ch_end) stage(ch0, sm);
+  cp_async_commit();
+  for (long long ch = ch0; ch < ch_end; ++ch) {
+    float* buf = sm + int((ch - ch0) & 1) * buf_floats;
+    if (ch + 1 < ch_end) stage(ch + 1, sm + int((ch - ch0 + 1) & 1) * buf_floats);
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
+    const float* xs = buf;                       // [n_in][LDK]
+    const float* zs = buf + n_in * LDK;          // [n_out][LDK]
     if (active) {
 #pragma unroll
       for (int t = 0; t < MAXT; ++t) {
@@ -111,6 +109,7 @@ __global__ void __launch_bounds__(256) tape_gemm_kernel(const __grid_constant__ 
         }
       }
     }
+    __syncthreads();                             // the buffer is refilled by the prefetch of the iteration after next
   }
   float* out = a.out + d.out_off;
   if (active) {
@@ -151,7 +150,7 @@ extern "C" int nr_tape_gemms(const NrGemmDesc* descs, int n_desc, const float* t
   a.rows[0] = rows; a.rows[1] = rows; a.rows[2] = points; a.rows[3] = points;
   a.slots[0] = tr::R_SLOTS; a.slots[1] = tr::G_SLOTS; a.slots[2] = tr::P_SLOTS; a.slots[3] = tr::GP_SLOTS;
   a.out = out;
-  const size_t smem = size_t(max_rows) * tg::LDK * sizeof(float);
+  const size_t smem = 2 * size_t(max_rows) * tg::LDK * sizeof(float);     // two chunk buffers
   static size_t smem_set = 0;
   if (smem > smem_set) {
     cudaFuncSetAttribute(tg::tape_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));

@@ -107,8 +107,8 @@ enum PointGrad {
 // Tape layout: rows are grouped in tiles of 128; a tile holds all slots of its 128 rows, slot-major:
 //   element (slot, i) = p[((i >> 7) * slots + slot) * 128 + (i & 127)].
 // A CTA of 128 threads (consecutive rows) therefore works on ONE contiguous piece of memory (slots x 512 bytes) and a
-// K-chunk of 128 rows of a Linear's input is one contiguous n_in x 512-byte block for the weight-gradient GEMMs; with a
-// plain slot-major layout every slot of a row was a megabyte apart (one DRAM page per 512 bytes).
+// K-chunk of a Linear's input is one contiguous block of n_in x 512 bytes for the weight-gradient GEMMs (with a plain
+// slot-major layout every slot of a row is a megabyte apart).
 constexpr int TILE = 128;
 struct Tape {
   float* p;
