@@ -81,7 +81,11 @@ def _train_worker(rank, world, port, ret):
         for (k, p), *others in zip(net.named_parameters(), *[s.parameters() for s in singles]):
             if p.grad is None:
                 continue
-            mean = sum(o.grad for o in others) / world
+            if all(o.grad is None for o in others):          # e.g. a head no pass evaluates: the collective filled in zeros
+                if float(p.grad.abs().max()) != 0.0:
+                    bad.append(f"{k}: expected a zero gradient")
+                continue
+            mean = sum((o.grad if o.grad is not None else torch.zeros_like(o)) for o in others) / world
             err, scale = float((p.grad - mean).abs().max()), float(mean.abs().max())
             # fp32 atomics: the summation order differs from run to run; rgb_fc.4.bias has a zero true gradient (softmax
             # is shift invariant), so it only ever holds rounding noise -> absolute floor
