@@ -32,10 +32,13 @@ def harness():
     return lib
 
 
-def run_case(harness, rfn, use_vis, dn=8, rays=5, seed=0, with_hit=True):
+def run_case(harness, rfn, use_vis, dn=8, rays=5, seed=0, with_hit=True, full_res=False):
     torch.manual_seed(seed)
     cfg = {"depth_sample_num": dn, "agg_net_cfg": {"sample_num": dn}, "dist_decoder_cfg": {"use_vis": use_vis}, "render_depth": True}
     que, ref = synthetic.make_scene(40, 48, rfn, seed=20 + seed, smooth=2)
+    if full_res:      # feature maps at image resolution: the align_corners sampling path (ops.py:14-34)
+        ph, pw = ref["imgs"].shape[-2:]
+        ref["ray_feats"], ref["img_feats"] = torch.randn(rfn, 32, ph, pw), torch.randn(rfn, 32, ph, pw)
     n = que["coords"].shape[1]
     idx = torch.randperm(n)[:rays]
     # push one ray outside most views so that masks / padding paths are exercised
@@ -167,3 +170,9 @@ def test_self_hit_prob_forward_and_backward(harness, use_vis):
         checked += 1
     assert checked == (24 if use_vis else 18)
     assert float((d_map - fm.grad[0]).abs().max()) <= 2e-4 * float(fm.grad.abs().max()) + 2e-6
+
+
+def test_backward_single_view_and_full_resolution_maps(harness):
+    """One reference view (every pool degenerates to its single element) and feature maps at image resolution."""
+    run_case(harness, 1, False, dn=5, rays=4, seed=2)
+    run_case(harness, 4, True, dn=6, rays=4, seed=4, full_res=True)
