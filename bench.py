@@ -343,7 +343,10 @@ def run_b200(args):
         "cpu_baseline": cpu,
     }
     if world == 1 and not args.no_train_step:
-        line["training_step"] = training_step(dev)
+        try:          # auxiliary number: never let it cost the headline line
+            line["training_step"] = training_step(dev)
+        except Exception as e:
+            line["training_step"] = {"error": f"{type(e).__name__}: {e}"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
