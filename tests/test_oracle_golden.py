@@ -64,3 +64,34 @@ def test_render_impl_matches_reference(name):
         else:
             close(out[k], v[:, :n], what=f"{name}/{k}")
     assert set(g.out) <= set(out), set(g.out) - set(out)
+
+
+@pytest.mark.parametrize("name", ["train8", "views10"])
+def test_oracle_autograd_matches_the_reference_gradients(name):
+    """Gradients of a fixed linear loss over both passes, produced by the unmodified reference's autograd
+    (tests/golden/grads_*.npz, oracle/gen_golden_grads.py), against autograd over the oracle restatement."""
+    import os
+
+    import numpy as np
+
+    import neuray_oracle as orc
+    from golden_io import GOLDEN_DIR, GoldenCase
+    g = GoldenCase(name)
+    z = np.load(os.path.join(GOLDEN_DIR, f"grads_{name}.npz"))
+    lw = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("lw_")}
+    gold = {k[5:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad_")}
+    W = {k: v.clone().requires_grad_(True) for k, v in g.W.items()}
+    ref = dict(g.ref)
+    ref["ray_feats"] = g.ref["ray_feats"].clone().requires_grad_(True)
+    ref["img_feats"] = g.ref["img_feats"].clone().requires_grad_(True)
+    q, sel, cfg = g.stage_que(), g.stage_sel, g.flat_cfg()
+    oc = orc.render_by_depth(W, cfg, g.que_depth[:, sel], q, ref, True, False)
+    of = orc.render_by_depth(W, cfg, g.que_depth_fine[:, sel], q, ref, True, True)
+    loss = (oc["pixel_colors_nr"] * lw["gw_c"]).sum() + (oc["hit_prob_nr"] * lw["gh_c"]).sum() \
+        + (of["pixel_colors_nr"] * lw["gw_f"]).sum() + (of["render_depth"] * lw["gd_f"]).sum()
+    loss.backward()
+    for k, gref in gold.items():
+        got = ref[k[4:]].grad if k.startswith("ref_") else W[k].grad
+        assert got is not None, k
+        err, scale = float((got - gref).abs().max()), float(gref.abs().max())
+        assert err <= 2e-4 * max(scale, 1e-3) + 2e-6, (k, err, scale)
