@@ -59,6 +59,21 @@ def run(name, mod):
             n += 1
     blob["grad_ref_ray_feats"] = r["ray_feats"].grad.numpy()
     blob["grad_ref_img_feats"] = r["img_feats"].grad.numpy()
+    # predict_self_hit_prob (renderer.py:137-155) on the same rays with a seeded query feature map
+    gen = torch.Generator().manual_seed(91)
+    qh, qw = q["imgs"].shape[-2:]
+    qmap = torch.randn(1, 32, (qh + 3) // 4, (qw + 3) // 4, generator=gen).requires_grad_(True)
+    gs = torch.randn(1, len(sel), dc.shape[-1], generator=gen)
+    net.zero_grad()
+    qq = dict(q, ray_feats=qmap)
+    hit_self = net.predict_self_hit_prob(qq, dc, mod.depth2inv_dists(dc, q["depth_range"]), False)
+    (hit_self * gs).sum().backward()
+    blob["self_map"], blob["self_gs"] = qmap.detach().numpy(), gs.numpy()
+    blob["self_hit"] = hit_self.detach().numpy()
+    blob["self_grad_map"] = qmap.grad.numpy()
+    for k, p in net.named_parameters():
+        if k.startswith("dist_decoder.") and p.grad is not None and float(p.grad.abs().max()) > 0:
+            blob["selfgrad_" + k] = p.grad.numpy()
     blob["out_c_pixel_colors_nr"] = out_c["pixel_colors_nr"].detach().numpy()
     blob["out_f_pixel_colors_nr"] = out_f["pixel_colors_nr"].detach().numpy()
     path = os.path.join(ROOT, "tests", "golden", f"grads_{name}.npz")

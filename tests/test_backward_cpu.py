@@ -223,3 +223,51 @@ def test_hand_written_backward_matches_the_reference_gradients(harness, name):
     drf, dimf = backward.feat_grads_to_nchw(total_feat)
     for got, ref_g in ((drf, gold["ref_ray_feats"]), (dimf, gold["ref_img_feats"])):
         assert float((got - ref_g).abs().max()) <= 3e-4 * float(ref_g.abs().max()) + 3e-6
+
+
+@pytest.mark.parametrize("name", ["train8", "views10"])
+def test_self_hit_prob_matches_the_reference(harness, name):
+    """predict_self_hit_prob as the unmodified reference computes it (values and autograd gradients stored in
+    tests/golden/grads_*.npz) against nr_self_hit_prob's routine (host build) and against the oracle."""
+    import numpy as np
+    import neuray_oracle as orc
+    from golden_io import GOLDEN_DIR, GoldenCase
+    g = GoldenCase(name)
+    z = np.load(os.path.join(GOLDEN_DIR, f"grads_{name}.npz"))
+    t = lambda k: torch.from_numpy(z[k])
+    sel = g.stage_sel
+    coords, depth = g.que["coords"][:, sel].contiguous(), g.que_depth[:, sel].contiguous()
+    use_vis = g.cfg.get("dist_decoder_cfg", {}).get("use_vis", True)
+    # oracle
+    q = dict(g.stage_que(), ray_feats=t("self_map"))
+    o = orc.predict_self_hit_prob(g.W, g.flat_cfg(), q, depth, orc.depth2inv_dists(depth, g.que["depth_range"]), False)
+    assert torch.allclose(o, t("self_hit"), atol=2e-6)
+    # hand-written routine
+    dec, agg = "dist_decoder", "agg_net"
+    params = {k: v for k, v in g.W.items() if k.startswith(dec + ".") or k.startswith(agg + ".")}
+    plan = weights.PackPlan(params, dec, agg, torch.device("cpu"))
+    wp = plan.pack(params)[0]
+    rays, dn = depth.shape[1:]
+    m0, cc, qd, gh = t("self_map")[0].contiguous(), coords[0].contiguous(), depth[0].contiguous(), t("self_gs")[0].contiguous()
+    hit, d_w, d_map = torch.empty(rays, dn), torch.zeros_like(wp), torch.zeros_like(m0)
+    p = _lib.NrSelfParams()
+    p.map, p.coords, p.que_depth, p.w_point = m0.data_ptr(), cc.data_ptr(), qd.data_ptr(), wp.data_ptr()
+    p.rn, p.dn, p.h, p.w, p.fh, p.fw, p.use_vis = rays, dn, g.que["imgs"].shape[2], g.que["imgs"].shape[3], m0.shape[1], m0.shape[2], int(use_vis)
+    p.near, p.far, p.var_bias = float(g.que["depth_range"][0, 0]), float(g.que["depth_range"][0, 1]), 0.05
+    p.hit, p.d_hit, p.d_w_point, p.d_map = hit.data_ptr(), gh.data_ptr(), d_w.data_ptr(), d_map.data_ptr()
+    harness.nr_self_cpu.restype = C.c_int
+    harness.nr_self_cpu.argtypes = [C.c_void_p]
+    assert harness.nr_self_cpu(C.addressof(p)) == 0
+    assert torch.allclose(hit, t("self_hit")[0], atol=2e-6), (hit - t("self_hit")[0]).abs().max()
+    grads = backward.unpack_point_grads(plan, d_w)
+    checked = 0
+    for k in z.files:
+        if not k.startswith("selfgrad_"):
+            continue
+        ga = t(k)
+        err, scale = float((grads[k[9:]] - ga).abs().max()), float(ga.abs().max())
+        assert err <= 3e-4 * max(scale, 1e-3) + 3e-6, (k, err, scale)
+        checked += 1
+    assert checked >= 18
+    gm = t("self_grad_map")[0]
+    assert float((d_map - gm).abs().max()) <= 3e-4 * float(gm.abs().max()) + 3e-6
