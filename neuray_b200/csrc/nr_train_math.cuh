@@ -583,8 +583,8 @@ NR_HD void ray_backward(const Ctx& c, long long ray) {
   float dpix[3] = {0.f, 0.f, 0.f};
   if (c.d_pix) for (int k = 0; k < 3; ++k) dpix[k] = c.d_pix[ray * 3 + k];
   const float ddep = c.d_depth ? c.d_depth[ray] : 0.f;
-  // backward sweep needs T_i: first pass computes the total transmittance, second walks back dividing it out would be
-  // unstable, so keep T_i in the (otherwise unused at this point) GP_DRGB slot 0.. no: recompute forward, store T in GP_DELTA[0]
+  // forward sweep: transmittance T_i in front of every sample, parked in the GP_DELTA slot (free until
+  // sample_backward_q writes the attention deltas there); dividing the total transmittance back out would be unstable
   float T = 1.f;
   for (int i = 0; i < dn; ++i) {
     c.gp.at(GP_DELTA, n0 + i) = T;
