@@ -123,6 +123,40 @@ def training_step(dev, rays=512, steps=8):
             "note": "wall clock incl. host work; kernel forward + nr_render_pass_bwd + nr_tape_gemms + Adam"}
 
 
+def eager_gpu_baseline(net, dq, dr, dn, dev, rays=4096, reps=3):
+    """Auxiliary GPU-vs-GPU number: the same pass as plain PyTorch-eager tensor ops on the same GPU
+    (neuray_b200/autograd_path.render_pass_torch, the restatement of reference renderer.py:168-203 that the tests use as
+    the A/B reference of the backward), coarse pass only, forward only, on a slice of the workload's rays."""
+    from neuray_b200 import render_ops
+    from neuray_b200.autograd_path import render_pass_torch
+    from neuray_b200.weights import posenc_table
+    n = dq["coords"].shape[1]
+    start = max(0, n // 2 - rays // 2)                 # a stretch of rays through the middle of the image
+    coords = dq["coords"][:, start:start + rays].contiguous()
+    depth = render_ops.sample_depth(dq["depth_range"], coords, dn, False)[0]
+    P = {f"dist_decoder.{k}": v for k, v in net.dist_decoder.named_parameters()}
+    P.update({f"agg_net.{k}": v for k, v in net.agg_net.named_parameters()})
+    cfgv = {"use_vis_prob": bool(net.dist_decoder.cfg["use_vis"]), "var_bias": float(net.dist_decoder.cfg["bias_val"])}
+    ref = {k: dr[k] for k in ("poses", "Ks", "depth_range", "imgs", "ray_feats", "img_feats")}
+    pe = posenc_table(dn).to(dev)
+
+    def run():
+        with torch.no_grad():
+            return render_pass_torch(P, "dist_decoder", "agg_net", cfgv, depth, coords, dq["poses"], dq["Ks"], dq["depth_range"], ref, pe)
+
+    run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"value": rays * dn / ms * 1e3, "unit": "ray-samples/s", "ms_per_pass": ms, "rays": rays, "samples_per_ray": dn,
+            "what": "one coarse pass as PyTorch-eager ops on the same GPU (autograd_path.render_pass_torch), forward only"}
+
+
 def cpu_threads():
     """Threads for the CPU arm: the measured optimum on the GPU box's 128-core host is 16 (8: 61 k, 16: 67 k, 32: 63 k,
     64: 22 k, 128: 1.6 k ray-samples/s on the same rays, profiles/README.md): beyond that torch's intra-op pool only adds
@@ -343,7 +377,12 @@ def run_b200(args):
         "cpu_baseline": cpu,
     }
     if world == 1 and not args.no_train_step:
-        try:          # auxiliary number: never let it cost the headline line
+        try:          # auxiliary numbers: never let them cost the headline line
+            line["eager_gpu_baseline"] = eager_gpu_baseline(net, dq, dr, dn_c, dev)
+        except Exception as e:
+            line["eager_gpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
+        try:
             line["training_step"] = training_step(dev)
         except Exception as e:
             line["training_step"] = {"error": f"{type(e).__name__}: {e}"}
