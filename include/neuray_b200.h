@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NR_ABI_VERSION 3
+#define NR_ABI_VERSION 4
 
 #define NR_OK 0
 #define NR_E_INVALID (-1)   /* bad argument (null pointer, unsupported shape) */
@@ -68,7 +68,40 @@ typedef struct NrTcLayout {
 } NrTcLayout;
 int nr_tc_layout(NrTcLayout* out);
 
+/* ---- weight packing ------------------------------------------------------------------------------------- */
+
+/* One nn.Linear of the reference: weight [out][in] row-major (PyTorch layout), bias [out]; device pointers. */
+typedef struct NrLinear {
+  const float* w;
+  const float* b;
+} NrLinear;
+
+/* The parameters of ONE pass (coarse: dist_decoder + agg_net; fine: fine_dist_decoder + fine_agg_net), by the reference's
+ * module structure (dist_decoder.py:64-97, aggregate_net.py:28-32, ibrnet.py:246-290, 52-102):
+ *   dist_decoder[h][l]  head h = mean, var, aw, vis (all-NULL vis head when the decoder has none); l = layers .0 .2 .4
+ *   prob_embed[l]       agg_net.prob_embed.{0,2}
+ *   the rest            agg_net.agg_impl.<name>.{0,2(,4)}; ray attention: w_qs / w_ks / w_vs / fc weights (no bias),
+ *                       layer_norm weight + bias */
+typedef struct NrPassWeights {
+  NrLinear dist_decoder[4][3];
+  NrLinear prob_embed[2];
+  NrLinear ray_dir_fc[2], neuray_fc[2], base_fc[2], vis_fc[2], vis_fc2[2], rgb_fc[3], geometry_fc[2], out_geometry_fc[2];
+  const float *w_qs, *w_ks, *w_vs, *attn_fc, *layer_norm_w, *layer_norm_b;
+} NrPassWeights;
+
+/* Packs the three weight buffers of a pass (once per checkpoint load; in training once per optimizer step):
+ * w_point [NrWeightLayout.total_point], w_ray [NrWeightLayout.total_ray], w_tc [NrTcLayout.total].  One memset + one
+ * kernel per buffer set on `stream`; `w` is a HOST struct of device pointers. */
+int nr_pack_weights(const NrPassWeights* w, float* w_point, float* w_ray, float* w_tc, void* stream);
+
 /* ---- per-frame packing ---------------------------------------------------------------------------------- */
+
+/* que_cam [24] (NrPassParams.que_cam) and view_params [rfn,20] (NrPassParams.view_params) from the reference's camera
+ * tensors (device pointers): que_pose [3,4] world->camera, que_K [3,3], que_range [2]; ref_poses [rfn,3,4], ref_Ks
+ * [rfn,3,3], ref_range [rfn,2] (NULL: the -1/near, -1/far entries are zero).  Replaces the torch expressions of
+ * render_ops.py:14-20, 95, 112 (K^-1, K@Rt, -R^T t), evaluated in fp64 and rounded once.  Either output may be NULL. */
+int nr_camera_blocks(const float* que_pose, const float* que_K, const float* que_range, const float* ref_poses,
+                     const float* ref_Ks, const float* ref_range, int rfn, float* que_cam, float* view_params, void* stream);
 
 /* NCHW -> channel-last repack of the reference views' maps, once per frame.
  *   ray_feats, img_feats : [rfn,32,fh,fw]   (reference: ref_imgs_info['ray_feats'|'img_feats'], renderer.py:229-231)
@@ -112,8 +145,7 @@ typedef struct NrPassParams {
   const float* fine_u;       /* quantiles: [fine_dn] if fine_u_stride == 0, else [rn,fine_dn] with that row stride */
   int32_t fine_u_stride;
   float* fine_depth;         /* [rn, fine_dn (+dn)] sorted */
-  /* tensor-core weights of this pass (NrTcLayout.total floats: hi/lo tf32 parts, pre-swizzled).  NULL selects the
-   * fp32 SIMT point kernel; non-NULL the tcgen05 point kernel. */
+  /* tensor-core weights of this pass (NrTcLayout.total floats: hi/lo tf32 parts, pre-swizzled; nr_pack_weights) */
   const float* w_tc;
 } NrPassParams;
 
@@ -136,8 +168,10 @@ int nr_point_kernel_timing(const NrPassParams* p, long long* timing, void* strea
 
 /* ---- stand-alone render_ops (reference network/render_ops.py; same names in neuray_b200/render_ops.py) ------- */
 
-/* sample_depth (render_ops.py:146-170).  jitter: NULL or [rn,dn-2] uniforms in [0,1). */
-int nr_sample_depth(float near, float far, int rn, int dn, const float* jitter, float* depth, float* dists, void* stream);
+/* Depth ranges are DEVICE pointers to [near, far] (one query view): the reference keeps depth_range on the device and no
+ * entry point forces a device->host read of it.
+ * sample_depth (render_ops.py:146-170).  jitter: NULL or [rn,dn-2] uniforms in [0,1). */
+int nr_sample_depth(const float* depth_range, int rn, int dn, const float* jitter, float* depth, float* dists, void* stream);
 /* coords2rays (render_ops.py:4-25), one camera.  cam as NrPassParams.que_cam. */
 int nr_coords2rays(const float* coords, const float* cam, int rn, float* centers, float* directions, void* stream);
 /* depth2points (render_ops.py:27-39) */
@@ -145,7 +179,7 @@ int nr_depth2points(const float* coords, const float* cam, const float* depth, i
 /* depth2dists (render_ops.py:41-44) over rows of length dn */
 int nr_depth2dists(const float* depth, int rows, int dn, float* dists, void* stream);
 /* depth2inv_dists (render_ops.py:46-52) */
-int nr_depth2inv_dists(const float* depth, float near, float far, int rows, int dn, float* dists, void* stream);
+int nr_depth2inv_dists(const float* depth, const float* depth_range, int rows, int dn, float* dists, void* stream);
 /* alpha_values2hit_prob (render_ops.py:72-80) */
 int nr_alpha_values2hit_prob(const float* alpha, int rows, int dn, float* hit, void* stream);
 /* project_points_ref_views (render_ops.py:82-130): pts [pn,3] -> dir [rfn,pn,3], pix [rfn,pn,2], depth [rfn,pn],
@@ -156,8 +190,14 @@ int nr_project_points(const float* pts, int pn, const float* view_params, int rf
  * border: 1 = 'border', 0 = 'zeros'; mask (may be NULL) [b,n] multiplies the result (interpolate_feature_map). */
 int nr_interpolate_feats(const float* feats, const float* pts, const float* mask, int b, int c, int fh, int fw, int n,
                          float h, float w, int border, int align_corners, float* out, void* stream);
-/* sample_fine_depth (render_ops.py:172-229, inv_mode) followed by the caller-visible sort (renderer.py:210-213). */
-int nr_sample_fine_depth(const float* depth, const float* hit_prob, float near, float far, int rn, int dn, int fine_dn,
+/* Gradient of nr_interpolate_feats with respect to the map: d_feats [b,c,fh,fw] += bilinear taps * mask * d_out [b,n,c]
+ * (reference: autograd through interpolate_feature_map in predict_mean_for_depth_loss, renderer.py:293, and
+ * predict_self_hit_prob, renderer.py:151).  d_feats must be zero-initialised or hold a running sum. */
+int nr_interpolate_feats_bwd(const float* d_out, const float* pts, const float* mask, int b, int c, int fh, int fw, int n,
+                             float h, float w, int border, int align_corners, float* d_feats, void* stream);
+/* sample_fine_depth (render_ops.py:172-229) followed by the caller-visible sort (renderer.py:210-213).  depth_range
+ * non-NULL: inv_mode=True (resampling in normalised inverse depth, the renderer's mode); NULL: inv_mode=False. */
+int nr_sample_fine_depth(const float* depth, const float* hit_prob, const float* depth_range, int rn, int dn, int fine_dn,
                          const float* u, int u_stride, int use_all, int do_sort, float* out, void* stream);
 
 /* ---- training: backward of one pass -------------------------------------------------------------------------- */
@@ -205,7 +245,8 @@ typedef struct NrSelfParams {
   const float* que_depth;    /* [rn,dn] */
   const float* w_point;
   int32_t rn, dn, h, w, fh, fw, use_vis;
-  float near, far, var_bias;
+  const float* depth_range;  /* device [2]: near, far of the query view */
+  float var_bias;
   float* hit;                /* [rn,dn] */
   const float* d_hit;        /* [rn,dn] or NULL */
   float* d_w_point;          /* [NrWeightLayout.total_point] accumulated */

@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libneuray_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 NR_POINT_REC = 20
 NR_MAX_VIEWS = 32
 NR_MAX_SAMPLES = 256
@@ -42,6 +42,18 @@ class NrPassParams(C.Structure):
     ]
 
 
+class NrLinear(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("b", C.c_void_p)]
+
+
+class NrPassWeights(C.Structure):
+    _fields_ = [("dist_decoder", NrLinear * 3 * 4), ("prob_embed", NrLinear * 2), ("ray_dir_fc", NrLinear * 2),
+                ("neuray_fc", NrLinear * 2), ("base_fc", NrLinear * 2), ("vis_fc", NrLinear * 2), ("vis_fc2", NrLinear * 2),
+                ("rgb_fc", NrLinear * 3), ("geometry_fc", NrLinear * 2), ("out_geometry_fc", NrLinear * 2),
+                ("w_qs", C.c_void_p), ("w_ks", C.c_void_p), ("w_vs", C.c_void_p), ("attn_fc", C.c_void_p),
+                ("layer_norm_w", C.c_void_p), ("layer_norm_b", C.c_void_p)]
+
+
 class NrTcLayout(C.Structure):
     _fields_ = [(n, C.c_int32) for n in "total stage head0 pe0 pe1 b0 b1 v01 v2r rd1 hst g0".split()]
 
@@ -53,21 +65,24 @@ SIGNATURES = {
     "nr_last_error": (C.c_char_p, []),
     "nr_weight_layout": (C.c_int, [C.POINTER(NrWeightLayout)]),
     "nr_tc_layout": (C.c_int, [C.POINTER(NrTcLayout)]),
+    "nr_pack_weights": (C.c_int, [C.POINTER(NrPassWeights), _vp, _vp, _vp, _vp]),
+    "nr_camera_blocks": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "nr_pack_feature_maps": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "nr_render_pass_fwd": (C.c_int, [C.POINTER(NrPassParams), _vp]),
     "nr_point_kernel": (C.c_int, [C.POINTER(NrPassParams), _vp]),
     "nr_ray_kernel": (C.c_int, [C.POINTER(NrPassParams), _vp]),
     "nr_point_kernel_debug": (C.c_int, [C.POINTER(NrPassParams), _vp, _vp]),
     "nr_point_kernel_timing": (C.c_int, [C.POINTER(NrPassParams), _vp, _vp]),
-    "nr_sample_depth": (C.c_int, [_f, _f, _i, _i, _vp, _vp, _vp, _vp]),
+    "nr_sample_depth": (C.c_int, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "nr_coords2rays": (C.c_int, [_vp, _vp, _i, _vp, _vp, _vp]),
     "nr_depth2points": (C.c_int, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "nr_depth2dists": (C.c_int, [_vp, _i, _i, _vp, _vp]),
-    "nr_depth2inv_dists": (C.c_int, [_vp, _f, _f, _i, _i, _vp, _vp]),
+    "nr_depth2inv_dists": (C.c_int, [_vp, _vp, _i, _i, _vp, _vp]),
     "nr_alpha_values2hit_prob": (C.c_int, [_vp, _i, _i, _vp, _vp]),
     "nr_project_points": (C.c_int, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nr_interpolate_feats": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _i, _i, _vp, _vp]),
-    "nr_sample_fine_depth": (C.c_int, [_vp, _vp, _f, _f, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "nr_interpolate_feats_bwd": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _i, _i, _vp, _vp]),
+    "nr_sample_fine_depth": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
     "nr_tc_selftest": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "nr_render_pass_bwd": (C.c_int, [_vp, _vp, _vp]),
     "nr_bwd_slot": (C.c_int, [C.c_char_p]),
@@ -79,7 +94,7 @@ SIGNATURES = {
 class NrSelfParams(C.Structure):
     _fields_ = [("map", C.c_void_p), ("coords", C.c_void_p), ("que_depth", C.c_void_p), ("w_point", C.c_void_p),
                 ("rn", C.c_int32), ("dn", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("fh", C.c_int32), ("fw", C.c_int32),
-                ("use_vis", C.c_int32), ("near", C.c_float), ("far", C.c_float), ("var_bias", C.c_float),
+                ("use_vis", C.c_int32), ("depth_range", C.c_void_p), ("var_bias", C.c_float),
                 ("hit", C.c_void_p), ("d_hit", C.c_void_p), ("d_w_point", C.c_void_p), ("d_map", C.c_void_p)]
 
 
@@ -175,3 +190,12 @@ def ptr(t):
 def stream_of(t):
     import torch
     return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def on_device(t):
+    """Context that makes t's device the current CUDA device: the library launches on the current device of the calling
+    thread, so every entry point of the package wraps its launches in this."""
+    import torch
+    if not t.is_cuda:
+        raise NeurayB200Error("neuray_b200 ops need CUDA tensors (no CPU fallback)")
+    return torch.cuda.device(t.device)

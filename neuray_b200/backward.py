@@ -157,7 +157,7 @@ def feat_grads_to_nchw(d_feat):
 
 def render_pass_backward(p, names, dec, agg, g_pix, g_hit, g_depth, want_feat_grads, feat_shape, stream):
     """p: the NrPassParams of the forward launch (CUDA).  Returns ({name: grad}, d_ray_feats, d_img_feats)."""
-    dev = torch.device("cuda", torch.cuda.current_device())
+    dev = (g_pix if g_pix is not None else g_hit if g_hit is not None else g_depth).device
     n_points = p.rn * p.dn
     shapes = tape_shapes(p.rfn, n_points)
     bufs = {k: _ws(k, sh[0] * sh[1] * sh[2], dev).view(sh) for k, sh in shapes.items()}
@@ -178,16 +178,49 @@ def render_pass_backward(p, names, dec, agg, g_pix, g_hit, g_depth, want_feat_gr
     return grads, drf, dimf
 
 
-def unpack_point_grads(plan, d_w_point):
+def unpack_point_grads(index_map, d_w_point):
     """Gradient in the packed w_point layout -> {name: grad}: every parameter element sits at exactly one packed
-    position (PackPlan.i_point maps position -> 1 + flat parameter index, 0 = padding)."""
-    sizes = plan.sizes
-    flat = torch.zeros(1 + sum(sizes), dtype=torch.float32, device=d_w_point.device).index_add_(0, plan.i_point, d_w_point)
+    position (weights.point_index_map: position -> 1 + flat parameter index, 0 = padding)."""
+    i_point, names, sizes, shapes = index_map
+    flat = torch.zeros(1 + sum(sizes), dtype=torch.float32, device=d_w_point.device).index_add_(0, i_point, d_w_point)
     out, off = {}, 1
-    for name, n, shape in zip(plan.names, sizes, plan.shapes):
+    for name, n, shape in zip(names, sizes, shapes):
         out[name] = flat[off:off + n].view(shape)
         off += n
     return out
+
+
+class RenderPassFn(torch.autograd.Function):
+    """forward = the fused CUDA pass (values), backward = nr_render_pass_bwd + nr_tape_gemms."""
+
+    @staticmethod
+    def forward(ctx, runner, meta, ray_feats, img_feats, *params):
+        with torch.no_grad():
+            res = runner()
+        ctx.meta = meta
+        ctx.bwd = res.pop("_bwd", None)
+        ctx.save_for_backward(ray_feats, img_feats, *params)
+        ctx.mark_non_differentiable(res["ray_mask_u8"])
+        fine = res.get("fine_depth")
+        outs = (res["pixel_colors"], res["hit_prob"], res["render_depth"], res["ray_mask_u8"])
+        if fine is not None:
+            ctx.mark_non_differentiable(fine)
+            return outs + (fine,)
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_pix, g_hit, g_depth, *unused):
+        meta = ctx.meta
+        ray_feats, img_feats, *params = ctx.saved_tensors
+        if ctx.bwd is None:          # an empty chunk: nothing was launched, nothing flows back
+            return (None, None, None, None, *[None] * len(params))
+        p, _keep, feat_shape, stream = ctx.bwd
+        want_feat = ray_feats.requires_grad or img_feats.requires_grad
+        with _lib.on_device(ray_feats):
+            grads, drf, dimf = render_pass_backward(p, meta["names"], meta["dec"], meta["agg"], g_pix, g_hit, g_depth, want_feat,
+                                                    feat_shape, stream)
+        gp = [grads[n] if t.requires_grad else None for n, t in zip(meta["names"], params)]
+        return (None, None, drf if ray_feats.requires_grad else None, dimf if img_feats.requires_grad else None, *gp)
 
 
 class SelfHitProbFn(torch.autograd.Function):
@@ -198,7 +231,8 @@ class SelfHitProbFn(torch.autograd.Function):
         p = meta["params"]()
         hit = torch.empty(p.rn, p.dn, dtype=torch.float32, device=que_ray_feats.device)
         p.hit = _lib.ptr(hit)
-        _lib.check(_lib.lib().nr_self_hit_prob(C.byref(p), meta["stream"]), "nr_self_hit_prob")
+        with _lib.on_device(que_ray_feats):
+            _lib.check(_lib.lib().nr_self_hit_prob(C.byref(p), meta["stream"]), "nr_self_hit_prob")
         _lib.count_launches(1)
         ctx.meta = meta
         ctx.feats_need = que_ray_feats.requires_grad
@@ -208,16 +242,17 @@ class SelfHitProbFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_hit):
         meta = ctx.meta
-        plan = meta["plan"]
+        index_map = meta["index_map"]
         p = meta["params"]()
         dev = g_hit.device
         g = g_hit[0].contiguous().float()
         hit = torch.empty(p.rn, p.dn, dtype=torch.float32, device=dev)
-        d_w = torch.zeros(plan.i_point.numel(), dtype=torch.float32, device=dev)
+        d_w = torch.zeros(index_map[0].numel(), dtype=torch.float32, device=dev)
         d_map = torch.zeros(meta["map_shape"], dtype=torch.float32, device=dev) if ctx.feats_need else None
         p.hit, p.d_hit, p.d_w_point, p.d_map = _lib.ptr(hit), _lib.ptr(g), _lib.ptr(d_w), _lib.ptr(d_map)
-        _lib.check(_lib.lib().nr_self_hit_prob(C.byref(p), meta["stream"]), "nr_self_hit_prob (backward)")
+        with _lib.on_device(g_hit):
+            _lib.check(_lib.lib().nr_self_hit_prob(C.byref(p), meta["stream"]), "nr_self_hit_prob (backward)")
         _lib.count_launches(1)
-        grads = unpack_point_grads(plan, d_w)
+        grads = unpack_point_grads(index_map, d_w)
         gp = [grads[n] if need else None for n, need in zip(meta["dec_names"], ctx.need)]
         return (None, d_map[None] if d_map is not None else None, *gp)

@@ -40,9 +40,10 @@ __global__ void pack_rgb_kernel(const float* __restrict__ imgs, int rfn, int h, 
 }
 
 // ---- sampling / ray geometry -------------------------------------------------------------------------------
-__global__ void sample_depth_kernel(float near, float far, int rn, int dn, const float* __restrict__ jitter,
+__global__ void sample_depth_kernel(const float* __restrict__ range, int rn, int dn, const float* __restrict__ jitter,
                                     float* __restrict__ depth, float* __restrict__ dists) {
   const long long total = (long long)rn * dn;
+  const float near = __ldg(range), far = __ldg(range + 1);
   const float span = 1.f / far - 1.f / near;
   const float step = span / float(dn - 1);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -97,9 +98,11 @@ __global__ void depth2points_kernel(const float* __restrict__ coords, const floa
   }
 }
 
-__global__ void depth2dists_kernel(const float* __restrict__ depth, long long rows, int dn, int inv, float a, float b,
+__global__ void depth2dists_kernel(const float* __restrict__ depth, long long rows, int dn, const float* __restrict__ range,
                                    float* __restrict__ dists) {
   const long long total = rows * dn;
+  const bool inv = range != nullptr;
+  const float a = inv ? -1.f / __ldg(range) : 0.f, b = inv ? -1.f / __ldg(range + 1) : 1.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int s = int(i % dn);
     auto val = [&](long long j) -> float { return inv ? (-1.f / depth[j] - a) / (b - a) : depth[j]; };
@@ -182,8 +185,46 @@ __global__ void interp_kernel(const float* __restrict__ feats, const float* __re
   }
 }
 
+// gradient of interp_kernel with respect to the map (the points carry no gradient on any path of the reference that
+// reaches this function: coordinates come from projections of detached geometry): d_feats[b,c,fh,fw] += taps * d_out
+__global__ void interp_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ pts, const float* __restrict__ mask,
+                                  int b, int c, int fh, int fw, long long n, float h, float w, int border, int align,
+                                  float* __restrict__ d_feats) {
+  const long long total = (long long)b * n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long bi = i / n;
+    const float gx = pts[2 * i] / (w - 1.f) * 2.f - 1.f, gy = pts[2 * i + 1] / (h - 1.f) * 2.f - 1.f;
+    float ix = align ? (gx + 1.f) / 2.f * float(fw - 1) : ((gx + 1.f) * float(fw) - 1.f) / 2.f;
+    float iy = align ? (gy + 1.f) / 2.f * float(fh - 1) : ((gy + 1.f) * float(fh) - 1.f) / 2.f;
+    if (border) {
+      ix = fminf(fmaxf(ix, 0.f), float(fw - 1));
+      iy = fminf(fmaxf(iy, 0.f), float(fh - 1));
+    }
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    const float we = ix - x0f, ww = (x0f + 1.f) - ix, ws = iy - y0f, wn = (y0f + 1.f) - iy;
+    const bool finite = fabsf(x0f) < 1e9f && fabsf(y0f) < 1e9f;
+    const int x0 = finite ? int(x0f) : -10, y0 = finite ? int(y0f) : -10;
+    const bool vx0 = x0 >= 0 && x0 < fw, vx1 = x0 + 1 >= 0 && x0 + 1 < fw;
+    const bool vy0 = y0 >= 0 && y0 < fh, vy1 = y0 + 1 >= 0 && y0 + 1 < fh;
+    const float m = mask ? mask[i] : 1.f;
+    const float w00 = (vx0 && vy0) ? ww * wn * m : 0.f, w01 = (vx1 && vy0) ? we * wn * m : 0.f;
+    const float w10 = (vx0 && vy1) ? ww * ws * m : 0.f, w11 = (vx1 && vy1) ? we * ws * m : 0.f;
+    const int xa = min(max(x0, 0), fw - 1), xb = min(max(x0 + 1, 0), fw - 1);
+    const int ya = min(max(y0, 0), fh - 1), yb = min(max(y0 + 1, 0), fh - 1);
+    float* __restrict__ base = d_feats + bi * c * fh * fw;
+    for (int ch = 0; ch < c; ++ch) {
+      float* __restrict__ pl = base + (long long)ch * fh * fw;
+      const float g = d_out[i * c + ch];
+      if (w00 != 0.f) atomicAdd(pl + ya * fw + xa, g * w00);
+      if (w01 != 0.f) atomicAdd(pl + ya * fw + xb, g * w01);
+      if (w10 != 0.f) atomicAdd(pl + yb * fw + xa, g * w10);
+      if (w11 != 0.f) atomicAdd(pl + yb * fw + xb, g * w11);
+    }
+  }
+}
+
 // ---- stand-alone sample_fine_depth: one warp per ray ------------------------------------------------------------
-__global__ void fine_depth_kernel(const float* __restrict__ depth, const float* __restrict__ hit, float near, float far, int rn,
+__global__ void fine_depth_kernel(const float* __restrict__ depth, const float* __restrict__ hit, const float* __restrict__ range, int rn,
                                   int dn, int fdn, const float* __restrict__ u, int u_stride, int use_all, int do_sort, int sort_n,
                                   int per_warp, float* __restrict__ out) {
   extern __shared__ __align__(16) float fsm[];
@@ -192,8 +233,10 @@ __global__ void fine_depth_kernel(const float* __restrict__ depth, const float* 
   float* sCdf = sT + dn;
   float* sSort = sCdf + dn + 4;
   const int M = fdn + (use_all ? dn : 0);
+  const bool inv = range != nullptr;
+  const float near = inv ? __ldg(range) : 1.f, far = inv ? __ldg(range + 1) : 2.f;
   for (int ray = blockIdx.x * warps + warp; ray < rn; ray += gridDim.x * warps) {
-    resample_ray(hit + size_t(ray) * dn, depth + size_t(ray) * dn, dn, near, far, u + size_t(ray) * u_stride, fdn, use_all,
+    resample_ray(hit + size_t(ray) * dn, depth + size_t(ray) * dn, dn, inv, near, far, u + size_t(ray) * u_stride, fdn, use_all,
                  do_sort, sort_n, sT, sCdf, sSort, out + size_t(ray) * M, lane);
     __syncwarp();
   }
@@ -202,9 +245,8 @@ __global__ void fine_depth_kernel(const float* __restrict__ depth, const float* 
 }  // namespace ops
 
 // implemented in nr_point_kernel.cu / nr_ray_kernel.cu
-int launch_point_kernel(const NrPassParams* p, float* dbg, cudaStream_t stream);
+int launch_point_kernel(const NrPassParams* p, float* dbg, long long* timing, cudaStream_t stream);
 int launch_ray_kernel(const NrPassParams* p, cudaStream_t stream);
-void set_point_kernel_timing(long long* buf);
 
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
@@ -264,30 +306,27 @@ int nr_pack_feature_maps(const float* ray_feats, const float* img_feats, const f
   return NR_OK;
 }
 
-int nr_point_kernel(const NrPassParams* p, void* stream) { return launch_point_kernel(p, nullptr, (cudaStream_t)stream); }
+int nr_point_kernel(const NrPassParams* p, void* stream) { return launch_point_kernel(p, nullptr, nullptr, (cudaStream_t)stream); }
 int nr_point_kernel_debug(const NrPassParams* p, float* dbg, void* stream) {
   NR_CHECK_ARG(dbg != nullptr, "dbg");
-  return launch_point_kernel(p, dbg, (cudaStream_t)stream);
+  return launch_point_kernel(p, dbg, nullptr, (cudaStream_t)stream);
 }
 int nr_point_kernel_timing(const NrPassParams* p, long long* timing, void* stream) {
   NR_CHECK_ARG(timing != nullptr && p != nullptr && p->w_tc != nullptr, "timing buffer / tensor-core weights required");
-  set_point_kernel_timing(timing);
-  const int rc = launch_point_kernel(p, nullptr, (cudaStream_t)stream);
-  set_point_kernel_timing(nullptr);
-  return rc;
+  return launch_point_kernel(p, nullptr, timing, (cudaStream_t)stream);
 }
 int nr_ray_kernel(const NrPassParams* p, void* stream) { return launch_ray_kernel(p, (cudaStream_t)stream); }
 int nr_render_pass_fwd(const NrPassParams* p, void* stream) {
-  const int rc = launch_point_kernel(p, nullptr, (cudaStream_t)stream);
+  const int rc = launch_point_kernel(p, nullptr, nullptr, (cudaStream_t)stream);
   if (rc != NR_OK) return rc;
   return launch_ray_kernel(p, (cudaStream_t)stream);
 }
 
-int nr_sample_depth(float near, float far, int rn, int dn, const float* jitter, float* depth, float* dists, void* stream) {
+int nr_sample_depth(const float* depth_range, int rn, int dn, const float* jitter, float* depth, float* dists, void* stream) {
   if (rn == 0) return NR_OK;   // empty input: nothing to do (pointers of empty tensors are null)
   NR_CHECK_ARG(dn > 2 && rn >= 0, "sample_depth arguments (dn must be > 2, render_ops.py:157)");
-  NR_CHECK_ARG(depth != nullptr, "sample_depth: null output");
-  sample_depth_kernel<<<blocks_for((long long)rn * dn), TPB, 0, (cudaStream_t)stream>>>(near, far, rn, dn, jitter, depth, dists);
+  NR_CHECK_ARG(depth != nullptr && depth_range != nullptr, "sample_depth: null pointer");
+  sample_depth_kernel<<<blocks_for((long long)rn * dn), TPB, 0, (cudaStream_t)stream>>>(depth_range, rn, dn, jitter, depth, dists);
   NR_CHECK_LAUNCH("sample_depth");
   return NR_OK;
 }
@@ -312,16 +351,15 @@ int nr_depth2points(const float* coords, const float* cam, const float* depth, i
 int nr_depth2dists(const float* depth, int rows, int dn, float* dists, void* stream) {
   if (rows == 0) return NR_OK;   // empty input: nothing to do (pointers of empty tensors are null)
   NR_CHECK_ARG(depth && dists && rows >= 0 && dn > 0, "depth2dists arguments");
-  depth2dists_kernel<<<blocks_for((long long)rows * dn), TPB, 0, (cudaStream_t)stream>>>(depth, rows, dn, 0, 0.f, 0.f, dists);
+  depth2dists_kernel<<<blocks_for((long long)rows * dn), TPB, 0, (cudaStream_t)stream>>>(depth, rows, dn, nullptr, dists);
   NR_CHECK_LAUNCH("depth2dists");
   return NR_OK;
 }
 
-int nr_depth2inv_dists(const float* depth, float near, float far, int rows, int dn, float* dists, void* stream) {
+int nr_depth2inv_dists(const float* depth, const float* depth_range, int rows, int dn, float* dists, void* stream) {
   if (rows == 0) return NR_OK;   // empty input: nothing to do (pointers of empty tensors are null)
-  NR_CHECK_ARG(depth && dists && rows >= 0 && dn > 0, "depth2inv_dists arguments");
-  depth2dists_kernel<<<blocks_for((long long)rows * dn), TPB, 0, (cudaStream_t)stream>>>(depth, rows, dn, 1, -1.f / near,
-                                                                                         -1.f / far, dists);
+  NR_CHECK_ARG(depth && dists && depth_range && rows >= 0 && dn > 0, "depth2inv_dists arguments");
+  depth2dists_kernel<<<blocks_for((long long)rows * dn), TPB, 0, (cudaStream_t)stream>>>(depth, rows, dn, depth_range, dists);
   NR_CHECK_LAUNCH("depth2inv_dists");
   return NR_OK;
 }
@@ -354,7 +392,17 @@ int nr_interpolate_feats(const float* feats, const float* pts, const float* mask
   return NR_OK;
 }
 
-int nr_sample_fine_depth(const float* depth, const float* hit_prob, float near, float far, int rn, int dn, int fine_dn,
+int nr_interpolate_feats_bwd(const float* d_out, const float* pts, const float* mask, int b, int c, int fh, int fw, int n, float h,
+                             float w, int border, int align_corners, float* d_feats, void* stream) {
+  if (n == 0) return NR_OK;
+  NR_CHECK_ARG(d_out && pts && d_feats && b >= 1 && c >= 1 && fh >= 1 && fw >= 1 && n >= 0, "interpolate_feats_bwd arguments");
+  interp_bwd_kernel<<<min(blocks_for((long long)b * n), 148 * 32), TPB, 0, (cudaStream_t)stream>>>(d_out, pts, mask, b, c, fh, fw, n, h,
+                                                                                                  w, border, align_corners, d_feats);
+  NR_CHECK_LAUNCH("interpolate_feats_bwd");
+  return NR_OK;
+}
+
+int nr_sample_fine_depth(const float* depth, const float* hit_prob, const float* depth_range, int rn, int dn, int fine_dn,
                          const float* u, int u_stride, int use_all, int do_sort, float* out, void* stream) {
   if (rn == 0) return NR_OK;   // empty input: nothing to do (pointers of empty tensors are null)
   NR_CHECK_ARG(depth && hit_prob && u && out && rn >= 0 && dn >= 2 && fine_dn >= 1, "sample_fine_depth arguments");
@@ -366,13 +414,10 @@ int nr_sample_fine_depth(const float* depth, const float* hit_prob, float near, 
   while (warps > 1 && size_t(warps) * per_warp * 4 > 160 * 1024) warps >>= 1;
   const size_t smem = size_t(warps) * per_warp * 4;
   NR_CHECK_ARG(smem <= 200 * 1024, "sample_fine_depth shared memory");
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
+  if (smem > 48 * 1024)   // per-device attribute, set per launch: no per-process state (see nr_point_kernel.cu)
     cudaFuncSetAttribute(fine_depth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    smem_set = smem;
-  }
   const int grid = min((rn + warps - 1) / warps, 148 * 8);
-  fine_depth_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(depth, hit_prob, near, far, rn, dn, fine_dn, u, u_stride,
+  fine_depth_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(depth, hit_prob, depth_range, rn, dn, fine_dn, u, u_stride,
                                                                       use_all, do_sort, sort_n, per_warp, out);
   NR_CHECK_LAUNCH("sample_fine_depth");
   return NR_OK;

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256) ray_kernel(const KParams kp) {
     // ---- D: inverse-CDF resampling of the next pass' depths ----
     if (pp.fine_dn > 0) {
       const int M = pp.fine_dn + (pp.fine_use_all ? dn : 0);
-      resample_ray(sHit, qd, dn, pp.que_cam[21], pp.que_cam[22], pp.fine_u + size_t(ray) * pp.fine_u_stride, pp.fine_dn,
+      resample_ray(sHit, qd, dn, true, pp.que_cam[21], pp.que_cam[22], pp.fine_u + size_t(ray) * pp.fine_u_stride, pp.fine_dn,
                    pp.fine_use_all, 1, kp.sort_n, sT, sCdf, sSort, pp.fine_depth + size_t(ray) * M, lane);
     }
     __syncwarp();
@@ -245,11 +245,8 @@ int launch_ray_kernel(const NrPassParams* p, cudaStream_t stream) {
   kp.warps = warps;
   const size_t smem = size_t(shared_common + warps * kp.per_warp) * 4;
   NR_CHECK_ARG(smem <= 227 * 1024, "ray kernel shared memory");
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
+  if (smem > 48 * 1024)   // per-device attribute, set per launch: no per-process state
     cudaFuncSetAttribute(rk::ray_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    smem_set = smem;
-  }
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

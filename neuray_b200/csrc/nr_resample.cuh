@@ -13,13 +13,14 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 
 // hit: [dn] hit probabilities (shared or global); qd: [dn] depths of the current samples (global)
 // sT [dn], sCdf [dn+1], sSort [sort_n] are per-warp shared scratch.  out: [fine_dn (+dn)] global.
-__device__ __forceinline__ void resample_ray(const float* hit, const float* __restrict__ qd, int dn, float near, float far,
+// inv: resample in normalised inverse depth (inv_mode=True, the renderer's mode); otherwise directly in depth.
+__device__ __forceinline__ void resample_ray(const float* hit, const float* __restrict__ qd, int dn, bool inv, float near, float far,
                                              const float* __restrict__ u_row, int fdn, int use_all, int do_sort, int sort_n,
                                              float* sT, float* sCdf, float* sSort, float* __restrict__ out, int lane) {
   const float a = -1.f / near, b = -1.f / far;
   float psum = 0.f;
   for (int s = lane; s < dn; s += 32) {
-    sT[s] = (-1.f / __ldg(qd + s) - a) / (b - a);
+    sT[s] = inv ? (-1.f / __ldg(qd + s) - a) / (b - a) : __ldg(qd + s);
     psum += hit[s] + 1e-5f;
   }
   psum = warp_sum_f(psum);
@@ -51,7 +52,7 @@ __device__ __forceinline__ void resample_ray(const float* hit, const float* __re
     if (den < 1e-5f) den = 1.f;
     const float tt = (u - c0) / den;
     const float fd = e0 + tt * (e1 - e0);
-    sSort[base + k] = -1.f / (fd * (b - a) + a);
+    sSort[base + k] = inv ? -1.f / (fd * (b - a) + a) : fd;
   }
   if (use_all)
     for (int s = lane; s < dn; s += 32) sSort[s] = __ldg(qd + s);

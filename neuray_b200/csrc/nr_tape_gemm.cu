@@ -151,11 +151,8 @@ extern "C" int nr_tape_gemms(const NrGemmDesc* descs, int n_desc, const float* t
   a.slots[0] = tr::R_SLOTS; a.slots[1] = tr::G_SLOTS; a.slots[2] = tr::P_SLOTS; a.slots[3] = tr::GP_SLOTS;
   a.out = out;
   const size_t smem = 2 * size_t(max_rows) * tg::LDK * sizeof(float);     // two chunk buffers
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
+  if (smem > 48 * 1024)   // per-device attribute, set per launch: no per-process state
     cudaFuncSetAttribute(tg::tape_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    smem_set = smem;
-  }
   const long long chunks = (rows + tg::KC - 1) / tg::KC;
   int gy = int(chunks < 48 ? chunks : 48);
   if (gy < 1) gy = 1;

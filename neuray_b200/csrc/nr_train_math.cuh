@@ -1045,7 +1045,7 @@ NR_HD void self_hit_prob_ray(const SelfCtx& c, long long ray) {
   const float aw = sigm(ho[2][0]);
   const float visd = c.use_vis ? sigm(ho[3][0]) : 1.f;
   // bin edges in normalised inverse depth (get_near_far_points, is_ref=False: midpoints, half intervals at the ends)
-  const float a = -1.f / c.near, b = -1.f / c.far;
+  const float a = -1.f / c.depth_range[0], b = -1.f / c.depth_range[1];
   const float* qd = c.que_depth + ray * dn;
   auto tn = [&](int s) { return (-1.f / fmaxf(qd[s], 1e-5f) - a) / (b - a); };
   float dmean[2] = {0.f, 0.f}, dvar[2] = {0.f, 0.f}, dmix[2] = {0.f, 0.f}, dvisd = 0.f;

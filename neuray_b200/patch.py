@@ -17,8 +17,21 @@ import importlib
 
 from . import render_ops, renderer
 
+_ORIGINALS = []          # (object, attribute name, original value) of everything install() rebound
+
+
+def _rebind(obj, name, value):
+    _ORIGINALS.append((obj, name, getattr(obj, name)))
+    setattr(obj, name, value)
+
 
 def install():
+    """Idempotent.  Autograd: the renderer methods attach their outputs to the graph (backward.RenderPassFn /
+    SelfHitProbFn); of the render_ops drop-ins only interpolate_feats / interpolate_feature_map are differentiated by the
+    reference (with respect to the map: predict_mean_for_depth_loss, predict_self_hit_prob) and carry a native backward;
+    the others raise if handed an input that requires grad instead of silently cutting the graph."""
+    if _ORIGINALS:
+        return importlib.import_module("network.renderer").NeuralRayBaseRenderer
     ref_ops = importlib.import_module("network.render_ops")
     ref_renderer = importlib.import_module("network.renderer")
     targets = [ref_ops, ref_renderer]
@@ -30,10 +43,17 @@ def install():
         fn = getattr(render_ops, name)
         for mod in targets:
             if hasattr(mod, name):
-                setattr(mod, name, fn)
+                _rebind(mod, name, fn)
     base = ref_renderer.NeuralRayBaseRenderer
-    base.render_by_depth = renderer.render_by_depth
-    base.fine_render_impl = renderer.fine_render_impl
-    base.render_impl = renderer.render_impl
-    base.render = renderer.render
+    _rebind(base, "render_by_depth", renderer.render_by_depth)
+    _rebind(base, "fine_render_impl", renderer.fine_render_impl)
+    _rebind(base, "render_impl", renderer.render_impl)
+    _rebind(base, "render", renderer.render)
     return base
+
+
+def uninstall():
+    """Puts the reference's own functions back (tests compare patched and unpatched runs in one process)."""
+    while _ORIGINALS:
+        obj, name, value = _ORIGINALS.pop()
+        setattr(obj, name, value)

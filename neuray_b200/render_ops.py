@@ -5,13 +5,19 @@ fused point/ray kernels; these keep stand-alone callers working (e.g. reference 
 project_points_ref_views).
 
 All tensors are contiguous fp32 CUDA tensors; there is no CPU path (calling with CPU tensors raises).
+
+Autograd: the reference differentiates through exactly one of these functions -- `interpolate_feats` /
+`interpolate_feature_map` with respect to the MAP (predict_mean_for_depth_loss, renderer.py:293; predict_self_hit_prob,
+renderer.py:151) -- and that gradient is implemented (nr_interpolate_feats_bwd).  Every other input reaches these functions
+detached in the reference (coordinates, poses, depths); if one of them requires grad while gradients are being recorded
+the call raises instead of silently cutting the graph.
 """
 import ctypes as C
 
 import torch
 
 from . import _lib
-from .weights import camera_block, view_param_block
+from .weights import camera_blocks
 
 __all__ = [
     "coords2rays", "depth2points", "depth2dists", "depth2inv_dists", "interpolate_feats", "interpolate_feature_map",
@@ -29,111 +35,155 @@ def _ck(rc, what):
     _lib.count_launches(1)
 
 
+def _no_grad_inputs(what, **tensors):
+    """These launchers have no backward: refuse inputs that would need one (see the module docstring)."""
+    if torch.is_grad_enabled():
+        for name, t in tensors.items():
+            if torch.is_tensor(t) and t.requires_grad:
+                raise _lib.NeurayB200Error(
+                    f"{what}: `{name}` requires grad but this CUDA drop-in has no backward for it (the reference never "
+                    "differentiates this input); detach it or run under torch.no_grad()")
+
+
+def _cam_of(poses, Ks, i):
+    return camera_blocks({"poses": poses[i:i + 1], "Ks": Ks[i:i + 1]}, None)[0]
+
+
 def coords2rays(coords, poses, Ks):
     """reference render_ops.py:4-25.  coords [n,rn,2], poses [n,3,4], Ks [n,3,3] -> centers, directions [n,rn,3]."""
+    _no_grad_inputs("coords2rays", coords=coords, poses=poses, Ks=Ks)
     n, rn, _ = coords.shape
     coords = _c(coords)
     centers = torch.empty(n, rn, 3, dtype=torch.float32, device=coords.device)
     dirs = torch.empty_like(centers)
-    zero_range = torch.zeros(2, dtype=torch.float32, device=coords.device)
-    for i in range(n):
-        cam = camera_block(poses[i].float(), Ks[i].float(), zero_range)
-        _ck(_lib.lib().nr_coords2rays(_lib.ptr(coords[i]), _lib.ptr(cam), rn, _lib.ptr(centers[i]), _lib.ptr(dirs[i]),
-                                             _lib.stream_of(coords)), "nr_coords2rays")
+    with _lib.on_device(coords):
+        for i in range(n):
+            cam = _cam_of(poses, Ks, i)
+            _ck(_lib.lib().nr_coords2rays(_lib.ptr(coords[i]), _lib.ptr(cam), rn, _lib.ptr(centers[i]), _lib.ptr(dirs[i]),
+                                          _lib.stream_of(coords)), "nr_coords2rays")
     return centers, dirs
 
 
 def depth2points(que_imgs_info, que_depth):
     """reference render_ops.py:27-39 -> que_pts, que_dir [qn,rn,dn,3]."""
+    _no_grad_inputs("depth2points", coords=que_imgs_info["coords"], que_depth=que_depth, poses=que_imgs_info["poses"])
     coords = _c(que_imgs_info["coords"])
     que_depth = _c(que_depth)
     qn, rn, dn = que_depth.shape
     pts = torch.empty(qn, rn, dn, 3, dtype=torch.float32, device=coords.device)
     dirs = torch.empty_like(pts)
-    zero_range = torch.zeros(2, dtype=torch.float32, device=coords.device)
-    for i in range(qn):
-        cam = camera_block(que_imgs_info["poses"][i].float(), que_imgs_info["Ks"][i].float(), zero_range)
-        _ck(_lib.lib().nr_depth2points(_lib.ptr(coords[i]), _lib.ptr(cam), _lib.ptr(que_depth[i]), rn, dn,
-                                              _lib.ptr(pts[i]), _lib.ptr(dirs[i]), _lib.stream_of(coords)), "nr_depth2points")
+    with _lib.on_device(coords):
+        for i in range(qn):
+            cam = _cam_of(que_imgs_info["poses"], que_imgs_info["Ks"], i)
+            _ck(_lib.lib().nr_depth2points(_lib.ptr(coords[i]), _lib.ptr(cam), _lib.ptr(que_depth[i]), rn, dn,
+                                           _lib.ptr(pts[i]), _lib.ptr(dirs[i]), _lib.stream_of(coords)), "nr_depth2points")
     return pts, dirs
 
 
 def depth2dists(depth):
     """reference render_ops.py:41-44."""
+    _no_grad_inputs("depth2dists", depth=depth)
     depth = _c(depth)
     out = torch.empty_like(depth)
     dn = depth.shape[-1]
-    _ck(_lib.lib().nr_depth2dists(_lib.ptr(depth), depth.numel() // dn, dn, _lib.ptr(out), _lib.stream_of(depth)),
-               "nr_depth2dists")
+    with _lib.on_device(depth):
+        _ck(_lib.lib().nr_depth2dists(_lib.ptr(depth), depth.numel() // dn, dn, _lib.ptr(out), _lib.stream_of(depth)), "nr_depth2dists")
     return out
 
 
 def depth2inv_dists(depth, depth_range):
     """reference render_ops.py:46-52.  depth [qn,rn,dn], depth_range [qn,2]."""
+    _no_grad_inputs("depth2inv_dists", depth=depth)
     depth = _c(depth)
     out = torch.empty_like(depth)
     qn, rn, dn = depth.shape
-    dr = depth_range.detach().float().cpu()
-    for i in range(qn):
-        _ck(_lib.lib().nr_depth2inv_dists(_lib.ptr(depth[i]), float(dr[i, 0]), float(dr[i, 1]), rn, dn, _lib.ptr(out[i]),
-                                                 _lib.stream_of(depth)), "nr_depth2inv_dists")
+    dr = _c(depth_range.detach())
+    with _lib.on_device(depth):
+        for i in range(qn):
+            _ck(_lib.lib().nr_depth2inv_dists(_lib.ptr(depth[i]), _lib.ptr(dr[i]), rn, dn, _lib.ptr(out[i]), _lib.stream_of(depth)),
+                "nr_depth2inv_dists")
     return out
+
+
+class _InterpFn(torch.autograd.Function):
+    """Bilinear sampling of an NCHW map with the gradient with respect to the map (atomic scatter of the taps)."""
+
+    @staticmethod
+    def forward(ctx, feats, points, mask, h, w, border, align):
+        f, pts = _c(feats.detach()), _c(points.detach())
+        m = _c(mask.detach()) if mask is not None else None
+        b, c, ch, cw = f.shape
+        n = pts.shape[1]
+        out = torch.empty(b, n, c, dtype=torch.float32, device=f.device)
+        with _lib.on_device(f):
+            _ck(_lib.lib().nr_interpolate_feats(_lib.ptr(f), _lib.ptr(pts), _lib.ptr(m), b, c, ch, cw, n, float(h), float(w), border, align,
+                                                _lib.ptr(out), _lib.stream_of(f)), "nr_interpolate_feats")
+        ctx.save_for_backward(pts, m)
+        ctx.geom = (b, c, ch, cw, n, float(h), float(w), border, align)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pts, m = ctx.saved_tensors
+        b, c, ch, cw, n, h, w, border, align = ctx.geom
+        g = _c(g)
+        d_feats = torch.zeros(b, c, ch, cw, dtype=torch.float32, device=g.device)
+        with _lib.on_device(g):
+            _ck(_lib.lib().nr_interpolate_feats_bwd(_lib.ptr(g), _lib.ptr(pts), _lib.ptr(m), b, c, ch, cw, n, h, w, border, align,
+                                                    _lib.ptr(d_feats), _lib.stream_of(g)), "nr_interpolate_feats_bwd")
+        return d_feats, None, None, None, None, None, None
+
+
+def _interp(feats, points, mask, h, w, border, align, what):
+    _no_grad_inputs(what, points=points, mask=mask)
+    return _InterpFn.apply(feats, points, mask, h, w, border, align)
 
 
 def interpolate_feats(feats, points, h=None, w=None, padding_mode="zeros", align_corners=False, inter_mode="bilinear"):
-    """reference network/ops.py:14-34 (bilinear only).  feats [b,f,ch,cw], points [b,n,2] -> [b,n,f]."""
+    """reference network/ops.py:14-34.  feats [b,f,ch,cw], points [b,n,2] -> [b,n,f].  Bilinear is the only mode any
+    caller in the reference uses; 'nearest' / 'bicubic' would need their own kernels and raise."""
     if inter_mode != "bilinear":
-        raise NotImplementedError("only bilinear interpolation is used on the rendering path")
-    feats, points = _c(feats), _c(points)
+        raise NotImplementedError(f"interpolate_feats: inter_mode={inter_mode!r} (every caller of the reference uses 'bilinear')")
     b, f, ch, cw = feats.shape
     if h is None and w is None:
         h, w = ch, cw
-    n = points.shape[1]
-    out = torch.empty(b, n, f, dtype=torch.float32, device=feats.device)
-    _ck(_lib.lib().nr_interpolate_feats(_lib.ptr(feats), _lib.ptr(points), None, b, f, ch, cw, n, float(h), float(w),
-                                               1 if padding_mode == "border" else 0, 1 if align_corners else 0,
-                                               _lib.ptr(out), _lib.stream_of(feats)), "nr_interpolate_feats")
-    return out
+    return _interp(feats, points, None, h, w, 1 if padding_mode == "border" else 0, 1 if align_corners else 0, "interpolate_feats")
 
 
 def interpolate_feature_map(ray_feats, coords, mask, h, w, border_type="border"):
     """reference render_ops.py:54-70.  ray_feats [rfn,f,fh,fw], coords [rfn,pn,2], mask [rfn,pn] -> [rfn,pn,f]."""
-    ray_feats, coords = _c(ray_feats), _c(coords)
-    maskf = _c(mask)
     rfn, f, fh, fw = ray_feats.shape
-    n = coords.shape[1]
-    out = torch.empty(rfn, n, f, dtype=torch.float32, device=ray_feats.device)
     align = 1 if (fh == h and fw == w) else 0
-    _ck(_lib.lib().nr_interpolate_feats(_lib.ptr(ray_feats), _lib.ptr(coords), _lib.ptr(maskf), rfn, f, fh, fw, n,
-                                               float(h), float(w), 1 if border_type == "border" else 0, align,
-                                               _lib.ptr(out), _lib.stream_of(ray_feats)), "nr_interpolate_feats")
-    return out
+    return _interp(ray_feats, coords, mask.float(), h, w, 1 if border_type == "border" else 0, align, "interpolate_feature_map")
 
 
 def alpha_values2hit_prob(alpha_values):
     """reference render_ops.py:72-80."""
+    _no_grad_inputs("alpha_values2hit_prob", alpha_values=alpha_values)
     a = _c(alpha_values)
     out = torch.empty_like(a)
     dn = a.shape[-1]
-    _ck(_lib.lib().nr_alpha_values2hit_prob(_lib.ptr(a), a.numel() // dn, dn, _lib.ptr(out), _lib.stream_of(a)),
-               "nr_alpha_values2hit_prob")
+    with _lib.on_device(a):
+        _ck(_lib.lib().nr_alpha_values2hit_prob(_lib.ptr(a), a.numel() // dn, dn, _lib.ptr(out), _lib.stream_of(a)),
+            "nr_alpha_values2hit_prob")
     return out
 
 
 def _project(pts, poses, Ks, h, w, want_dir):
+    _no_grad_inputs("project_points", pts=pts, poses=poses, Ks=Ks)
     pts = _c(pts)
     pn = pts.shape[0]
     rfn = poses.shape[0]
-    vp = view_param_block(poses.float(), Ks.float())
+    _, vp = camera_blocks(None, {"poses": poses, "Ks": Ks})
     dev = pts.device
     pix = torch.empty(rfn, pn, 2, dtype=torch.float32, device=dev)
     depth = torch.empty(rfn, pn, 1, dtype=torch.float32, device=dev)
     mask = torch.empty(rfn, pn, dtype=torch.float32, device=dev)
     valid = torch.empty(rfn, pn, dtype=torch.float32, device=dev)
     d = torch.empty(rfn, pn, 3, dtype=torch.float32, device=dev) if want_dir else None
-    _ck(_lib.lib().nr_project_points(_lib.ptr(pts), pn, _lib.ptr(vp), rfn, int(h), int(w), _lib.ptr(d), _lib.ptr(pix),
-                                            _lib.ptr(depth), _lib.ptr(mask), _lib.ptr(valid), _lib.stream_of(pts)),
-               "nr_project_points")
+    with _lib.on_device(pts):
+        _ck(_lib.lib().nr_project_points(_lib.ptr(pts), pn, _lib.ptr(vp), rfn, int(h), int(w), _lib.ptr(d), _lib.ptr(pix),
+                                         _lib.ptr(depth), _lib.ptr(mask), _lib.ptr(valid), _lib.stream_of(pts)), "nr_project_points")
     return d, pix, depth, mask, valid
 
 
@@ -177,13 +227,13 @@ def sample_depth(depth_range, coords, sample_num, random_sample):
     dev = coords.device
     depth = torch.empty(qn, rn, dn, dtype=torch.float32, device=dev)
     dists = torch.empty_like(depth)
-    dr = depth_range.detach().float().cpu()
+    dr = _c(depth_range.detach())
     # the uniforms come from torch's generator exactly like the reference's torch.rand(..., device=device)
     jitter = torch.rand(qn, rn, dn - 2, dtype=torch.float32, device=dev) if random_sample else None
-    for i in range(qn):
-        _ck(_lib.lib().nr_sample_depth(float(dr[i, 0]), float(dr[i, 1]), rn, dn,
-                                              _lib.ptr(jitter[i]) if jitter is not None else None,
-                                              _lib.ptr(depth[i]), _lib.ptr(dists[i]), _lib.stream_of(coords)), "nr_sample_depth")
+    with _lib.on_device(coords):
+        for i in range(qn):
+            _ck(_lib.lib().nr_sample_depth(_lib.ptr(dr[i]), rn, dn, _lib.ptr(jitter[i]) if jitter is not None else None,
+                                           _lib.ptr(depth[i]), _lib.ptr(dists[i]), _lib.stream_of(coords)), "nr_sample_depth")
     return depth, dists
 
 
@@ -194,25 +244,24 @@ def fine_sample_u(fdn, device):
 
 
 def sample_fine_depth(depth, hit_prob, depth_range, sample_num, random_sample, inv_mode=True):
-    """reference render_ops.py:172-229 (inv_mode only, as used by the renderer) -> [qn,rn,sample_num] (unsorted)."""
-    if not inv_mode:
-        raise NotImplementedError("sample_fine_depth: only inv_mode=True is used by the renderer")
+    """reference render_ops.py:172-229 -> [qn,rn,sample_num] (unsorted)."""
+    _no_grad_inputs("sample_fine_depth", depth=depth, hit_prob=hit_prob)
     depth, hit_prob = _c(depth), _c(hit_prob)
     qn, rn, dn = depth.shape
     fdn = int(sample_num)
     dev = depth.device
     out = torch.empty(qn, rn, fdn, dtype=torch.float32, device=dev)
-    dr = depth_range.detach().float().cpu()
-    near, far = float(dr[0, 0]), float(dr[0, 1])      # the reference uses depth_range[0] for every query (render_ops.py:183)
+    # the reference uses depth_range[0] for every query (render_ops.py:183)
+    dr = _c(depth_range.detach()[0]) if inv_mode else None
     if random_sample:
         u = torch.rand([qn, rn, fdn]).to(dev).contiguous()      # CPU generator, like render_ops.py:205
         stride = fdn
     else:
         u = fine_sample_u(fdn, dev)
         stride = 0
-    for i in range(qn):
-        ui = u[i] if random_sample else u
-        _ck(_lib.lib().nr_sample_fine_depth(_lib.ptr(depth[i]), _lib.ptr(hit_prob[i]), near, far, rn, dn, fdn,
-                                                   _lib.ptr(ui), stride, 0, 0, _lib.ptr(out[i]), _lib.stream_of(depth)),
-                   "nr_sample_fine_depth")
+    with _lib.on_device(depth):
+        for i in range(qn):
+            ui = u[i] if random_sample else u
+            _ck(_lib.lib().nr_sample_fine_depth(_lib.ptr(depth[i]), _lib.ptr(hit_prob[i]), _lib.ptr(dr), rn, dn, fdn, _lib.ptr(ui), stride,
+                                                0, 0, _lib.ptr(out[i]), _lib.stream_of(depth)), "nr_sample_fine_depth")
     return out

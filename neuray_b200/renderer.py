@@ -17,16 +17,16 @@ The functions below are written against "owner": any nn.Module that has `.cfg` (
 sub-modules dist_decoder / agg_net (/ fine_dist_decoder / fine_agg_net) with the reference's parameter names.
 """
 import ctypes as C
-import os
 
 import torch
 import torch.nn as nn
 
 from . import _lib, modules
 from .render_ops import fine_sample_u, interpolate_feats, sample_depth
-from .weights import PackPlan, camera_block, posenc_table, view_param_block
+from .weights import camera_blocks, pack_pass, point_index_map, posenc_table
 
-PACK_KEY = "_nr_frame_pack"
+PACK_KEY = "_nr_frame_pack"        # ref_imgs_info: the FramePack of the frame being rendered (lives for one render() call)
+CAM_KEY = "_nr_que_cam"            # que_imgs_info: que_cam block of the frame being rendered (same lifetime)
 
 base_cfg = {
     "vis_encoder_type": "default", "vis_encoder_cfg": {},
@@ -62,8 +62,15 @@ def _workspace(key, numel, dev):
 _PACK_POOL = {}      # (device, feat shape, rgb shape) -> [(feat, rgb)] of dropped FramePacks, at most two kept
 
 
+_PACK_SOURCES = ("ray_feats", "img_feats", "imgs", "poses", "Ks", "depth_range")
+
+
 class FramePack:
-    """Per-frame device data shared by every chunk and both passes: channel-last maps + per-view parameters."""
+    """Per-frame device data shared by every chunk and both passes: channel-last maps + per-view parameters.
+
+    A pack keeps strong references to the tensors it was built from and is valid only for exactly those tensor objects
+    at exactly those versions (`matches`): a fresh encoder output that happens to get a recycled address is a different
+    object, and an in-place edit bumps `_version`."""
 
     def __del__(self):
         try:
@@ -93,25 +100,25 @@ class FramePack:
         else:
             self.feat = torch.empty(rfn, fh, fw, 64, dtype=torch.float32, device=dev)
             self.rgb = torch.empty(rfn, h, w, 4, dtype=torch.float32, device=dev)
-        _lib.check(_lib.lib().nr_pack_feature_maps(
-            _lib.ptr(rf.detach().contiguous().float()), _lib.ptr(imf.detach().contiguous().float()),
-            _lib.ptr(imgs.detach().contiguous().float()), rfn, h, w, fh, fw, _lib.ptr(self.feat), _lib.ptr(self.rgb),
-            _lib.stream_of(imgs)), "nr_pack_feature_maps")
+        with _lib.on_device(imgs):
+            _lib.check(_lib.lib().nr_pack_feature_maps(
+                _lib.ptr(rf.detach().contiguous().float()), _lib.ptr(imf.detach().contiguous().float()),
+                _lib.ptr(imgs.detach().contiguous().float()), rfn, h, w, fh, fw, _lib.ptr(self.feat), _lib.ptr(self.rgb),
+                _lib.stream_of(imgs)), "nr_pack_feature_maps")
         _lib.count_launches(2)
-        self.view_params = view_param_block(ref_imgs_info["poses"].float(), ref_imgs_info["Ks"].float(),
-                                            ref_imgs_info["depth_range"].float())
-        self.src = (rf.data_ptr(), imf.data_ptr(), imgs.data_ptr(), rf._version, imf._version)
+        _, self.view_params = camera_blocks(None, ref_imgs_info)
+        self.src = tuple((ref_imgs_info[k], ref_imgs_info[k]._version) for k in _PACK_SOURCES)
 
     def matches(self, ref_imgs_info):
-        rf, imf, imgs = ref_imgs_info["ray_feats"], ref_imgs_info["img_feats"], ref_imgs_info["imgs"]
-        return self.src == (rf.data_ptr(), imf.data_ptr(), imgs.data_ptr(), rf._version, imf._version)
+        return all(ref_imgs_info.get(k) is t and t._version == ver for k, (t, ver) in zip(_PACK_SOURCES, self.src))
 
 
 def frame_pack(ref_imgs_info):
+    """The pack of the frame in flight (installed by render_chunks for the duration of one render() call), or a fresh one
+    for a direct render_by_depth / render_impl call.  A fresh pack is NOT left in the caller's dict."""
     pack = ref_imgs_info.get(PACK_KEY)
     if pack is None or not pack.matches(ref_imgs_info):
         pack = FramePack(ref_imgs_info)
-        ref_imgs_info[PACK_KEY] = pack
     return pack
 
 
@@ -121,8 +128,9 @@ def _pass_modules(owner, is_fine):
 
 
 def pass_weights(owner, is_fine, dn, device):
-    """Packed weights of one pass, cached on the owner and re-packed when any parameter changed (optimizer steps
-    bump tensor._version)."""
+    """Packed weights of one pass (nr_pack_weights), cached on the owner and re-packed when any parameter changed
+    (optimizer steps bump tensor._version).  Every re-pack gets fresh buffers: an autograd graph recorded before the
+    parameter update keeps reading the buffers it was recorded with."""
     dec, agg, dec_name, agg_name = _pass_modules(owner, is_fine)
     params = {f"{dec_name}.{k}": v for k, v in dec.named_parameters()}
     params.update({f"{agg_name}.{k}": v for k, v in agg.named_parameters()})
@@ -130,12 +138,10 @@ def pass_weights(owner, is_fine, dn, device):
     cache = owner.__dict__.setdefault("_nr_wcache", {})
     hit = cache.get(is_fine)
     if hit is None or hit[0] != stamp:
-        plans = owner.__dict__.setdefault("_nr_plans", {})
-        plan = plans.get((is_fine, str(device)))
-        if plan is None or not plan.matches(params, dec_name, agg_name):
-            plan = PackPlan(params, dec_name, agg_name, device)
-            plans[(is_fine, str(device))] = plan
-        wp, wr, wt = plan.pack(params)
+        first = next(iter(params.values()))
+        if first.device != torch.device(device):
+            raise _lib.NeurayB200Error(f"parameters live on {first.device} but the rays are on {device}")
+        wp, wr, wt = pack_pass(params, dec_name, agg_name)
         hit = (stamp, wp, wr, hit[3] if hit is not None else {}, wt)
         cache[is_fine] = hit
     pe = hit[3].get(dn)
@@ -165,7 +171,9 @@ def _launch_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine, 
     _, rn, dn = que_depth.shape
     dec, agg, _, _ = _pass_modules(owner, is_fine)
     w_point, w_ray, pos_enc, w_tc = pass_weights(owner, is_fine, dn, dev)
-    cam = camera_block(que_imgs_info["poses"][0].float(), que_imgs_info["Ks"][0].float(), que_imgs_info["depth_range"][0].float())
+    cam = que_imgs_info.get(CAM_KEY)
+    if cam is None:
+        cam, _ = camera_blocks(que_imgs_info, None)
     coords_c = coords[0].detach().contiguous().float()
 
     out = {
@@ -181,8 +189,7 @@ def _launch_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine, 
     p.feat, p.rgb, p.view_params = _lib.ptr(pack.feat), _lib.ptr(pack.rgb), _lib.ptr(pack.view_params)
     p.rfn, p.h, p.w, p.fh, p.fw = pack.rfn, pack.h, pack.w, pack.fh, pack.fw
     p.w_point, p.w_ray, p.pos_enc = _lib.ptr(w_point), _lib.ptr(w_ray), _lib.ptr(pos_enc)
-    # NR_POINT_KERNEL=simt selects the fp32 SIMT point kernel (development A/B switch); default: tcgen05 point kernel
-    p.w_tc = None if os.environ.get("NR_POINT_KERNEL", "") == "simt" else _lib.ptr(w_tc)
+    p.w_tc = _lib.ptr(w_tc)
     # compute_prob is always the COARSE decoder's method (reference renderer.py:75): its use_vis decides
     p.use_vis = 1 if owner.dist_decoder.cfg["use_vis"] else 0
     if p.use_vis and not dec.cfg["use_vis"]:
@@ -201,16 +208,18 @@ def _launch_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine, 
     if rn == 0:          # nothing to render: the (empty) outputs are already in place
         out["_bwd"] = None
         return out
-    if _lib.PROFILE is not None:
-        # bench.py: time the dominant kernel alone, with CUDA events on the launching stream
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        _lib.check(_lib.lib().nr_point_kernel(C.byref(p), stream), "nr_point_kernel")
-        e1.record()
-        _lib.check(_lib.lib().nr_ray_kernel(C.byref(p), stream), "nr_ray_kernel")
-        _lib.PROFILE.append((e0, e1, rn * dn))
-    else:
-        _lib.check(_lib.lib().nr_render_pass_fwd(C.byref(p), stream), "nr_render_pass_fwd")
+    with _lib.on_device(coords):
+        if _lib.PROFILE is not None:
+            # bench.py: time the dominant kernel alone, with CUDA events on the launching stream
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            _lib.check(_lib.lib().nr_point_kernel(C.byref(p), stream), "nr_point_kernel")
+            e1.record()
+            _lib.check(_lib.lib().nr_ray_kernel(C.byref(p), stream), "nr_ray_kernel")
+            e2.record()
+            _lib.PROFILE.append((e0, e1, rn * dn, e2))
+        else:
+            _lib.check(_lib.lib().nr_render_pass_fwd(C.byref(p), stream), "nr_render_pass_fwd")
     _lib.count_launches(2)
     # what nr_render_pass_bwd needs to run on the same inputs (kept alive by the autograd node, dropped otherwise)
     out["_bwd"] = (p, (coords_c, que_depth, cam, pack, w_point, w_ray, pos_enc, w_tc), (pack.rfn, pack.fh, pack.fw, 64), stream)
@@ -223,7 +232,7 @@ def run_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine=None,
     ray_mask [1,rn] (bool) and optionally fine_depth [1,rn,M].
 
     When gradients are being recorded and the reference feature maps or any parameter of the pass require them, the
-    outputs are attached to autograd through autograd_path.RenderPassFn (forward values still come from the kernels)."""
+    outputs are attached to autograd through backward.RenderPassFn (forward values still come from the kernels)."""
     _check_supported(owner)
     coords = que_imgs_info["coords"]
     if coords.shape[0] != 1:
@@ -241,15 +250,8 @@ def run_pass(owner, que_depth, que_imgs_info, ref_imgs_info, is_fine, fine=None,
         out = launch()
         out.pop("_bwd", None)
     else:
-        from .autograd_path import RenderPassFn
-        meta = {
-            "names": [n for n, _ in named], "dec": dec_name, "agg": agg_name,
-            "cfgv": {"use_vis_prob": bool(owner.dist_decoder.cfg["use_vis"]), "var_bias": float(dec.cfg["bias_val"])},
-            "que_depth": que_depth, "coords": coords.detach().float(), "que_pose": que_imgs_info["poses"].detach().float(),
-            "que_K": que_imgs_info["Ks"].detach().float(), "que_range": que_imgs_info["depth_range"].detach().float(),
-            "ref": {k: ref_imgs_info[k].detach().float() for k in ("poses", "Ks", "depth_range", "imgs")},
-            "pos_enc": posenc_table(dn).to(coords.device),
-        }
+        from .backward import RenderPassFn
+        meta = {"names": [n for n, _ in named], "dec": dec_name, "agg": agg_name}
         res = RenderPassFn.apply(launch, meta, rf, imf, *[v for _, v in named])
         out = {"pixel_colors": res[0], "hit_prob": res[1], "render_depth": res[2], "ray_mask_u8": res[3]}
         if fine:
@@ -272,36 +274,40 @@ def _finish_outputs(owner, res, que_depth, que_imgs_info):
 
 def _self_hit_prob(self, que_depth, que_imgs_info, is_fine):
     """a17 predict_self_hit_prob (reference renderer.py:137-155): the query view's own ray_feats decoded along its rays
-    (fine-tuning configs).  nr_self_hit_prob, forward and backward; NR_BACKWARD=torch keeps the PyTorch restatement."""
+    (fine-tuning configs).  nr_self_hit_prob, forward and backward."""
     dec, _, dec_name, _ = _pass_modules(self, is_fine)
     feats = que_imgs_info["ray_feats"]
     coords = que_imgs_info["coords"]
     h, w = que_imgs_info["imgs"].shape[-2:]
-    if os.environ.get("NR_BACKWARD", "native") == "torch" or feats.shape[0] != 1:
-        from .autograd_path import self_hit_prob_torch
-        P = {f"{dec_name}.{k}": v for k, v in dec.named_parameters()}
-        return self_hit_prob_torch(P, dec_name, bool(dec.cfg["use_vis"]), float(dec.cfg["bias_val"]), feats, coords, h, w, que_depth,
-                                   que_imgs_info["depth_range"])
+    if feats.shape[0] != 1 or coords.shape[0] != 1:
+        raise _lib.NeurayB200Error("one query view per call (qn == 1), like every call site of the reference")
     from .backward import SelfHitProbFn
     dev = coords.device
     _, rn, dn = que_depth.shape
     w_point = pass_weights(self, is_fine, dn, dev)[0]
-    plan = self.__dict__["_nr_plans"][(is_fine, str(dev))]
+    dec_params = {f"{dec_name}.{k}": v for k, v in dec.named_parameters()}
+    maps = self.__dict__.setdefault("_nr_index_maps", {})
+    key = (is_fine, str(dev), tuple(dec_params))
+    if key not in maps:
+        _, agg, _, agg_name = _pass_modules(self, is_fine)
+        allp = dict(dec_params)
+        allp.update({f"{agg_name}.{k}": v for k, v in agg.named_parameters()})
+        maps[key] = point_index_map(allp, dec_name, agg_name)
     fmap = feats[0].detach().contiguous().float()
     cc, qd = coords[0].detach().contiguous().float(), que_depth[0].detach().contiguous().float()
-    rng = que_imgs_info["depth_range"][0].detach().float().cpu()
+    rng = que_imgs_info["depth_range"][0].detach().float().contiguous()
     use_vis, var_bias = 1 if dec.cfg["use_vis"] else 0, float(dec.cfg["bias_val"])
 
     def params():
         p = _lib.NrSelfParams()
         p.map, p.coords, p.que_depth, p.w_point = _lib.ptr(fmap), _lib.ptr(cc), _lib.ptr(qd), _lib.ptr(w_point)
         p.rn, p.dn, p.h, p.w, p.fh, p.fw, p.use_vis = rn, dn, int(h), int(w), fmap.shape[1], fmap.shape[2], use_vis
-        p.near, p.far, p.var_bias = float(rng[0]), float(rng[1]), var_bias
+        p.depth_range, p.var_bias = _lib.ptr(rng), var_bias
         return p
 
-    named = [(f"{dec_name}.{k}", v) for k, v in dec.named_parameters()]
-    meta = {"params": params, "plan": plan, "stream": _lib.stream_of(coords), "map_shape": tuple(fmap.shape),
-            "dec_names": [n for n, _ in named], "keep": (fmap, cc, qd, w_point)}
+    named = list(dec_params.items())
+    meta = {"params": params, "index_map": maps[key], "stream": _lib.stream_of(coords), "map_shape": tuple(fmap.shape),
+            "dec_names": [n for n, _ in named], "keep": (fmap, cc, qd, w_point, rng)}
     return SelfHitProbFn.apply(meta, feats, *[v for _, v in named])
 
 
@@ -356,19 +362,26 @@ def render_impl(self, que_imgs_info, ref_imgs_info, is_train):
 
 
 def render_chunks(self, que_imgs_info, ref_imgs_info, is_train):
-    """The chunk loop of reference renderer.py:236-254 (everything after the encoders)."""
-    frame_pack(ref_imgs_info)
+    """The chunk loop of reference renderer.py:236-254 (everything after the encoders).  The per-frame pack (channel-last
+    maps, per-view parameters) and the query camera block are built once here and live exactly as long as this call: they
+    are handed to the per-chunk functions through the two info dicts and removed again before returning."""
     ray_batch_num = self.cfg["ray_batch_num"]
     coords = que_imgs_info["coords"]
     ray_num = coords.shape[1]
     render_info_all = {}
-    for ray_id in range(0, ray_num, ray_batch_num):
-        que_imgs_info["coords"] = coords[:, ray_id:ray_id + ray_batch_num]
-        render_info = render_impl(self, que_imgs_info, ref_imgs_info, is_train)
-        for k, v in render_info.items():
-            if is_train or (not k.startswith("hit_prob")):
-                render_info_all.setdefault(k, []).append(v)
-    que_imgs_info["coords"] = coords
+    ref_imgs_info[PACK_KEY] = FramePack(ref_imgs_info)
+    que_imgs_info[CAM_KEY] = camera_blocks(que_imgs_info, None)[0]
+    try:
+        for ray_id in range(0, ray_num, ray_batch_num):
+            que_imgs_info["coords"] = coords[:, ray_id:ray_id + ray_batch_num]
+            render_info = render_impl(self, que_imgs_info, ref_imgs_info, is_train)
+            for k, v in render_info.items():
+                if is_train or (not k.startswith("hit_prob")):
+                    render_info_all.setdefault(k, []).append(v)
+    finally:
+        que_imgs_info["coords"] = coords
+        ref_imgs_info.pop(PACK_KEY, None)
+        que_imgs_info.pop(CAM_KEY, None)
     return {k: (v[0] if len(v) == 1 else torch.cat(v, 1)) for k, v in render_info_all.items()}
 
 

@@ -9,7 +9,9 @@ import subprocess
 import pytest
 import torch
 
-from neuray_b200 import _lib, autograd_path, backward, renderer, synthetic, weights
+import ref_packers as weights
+import torch_restatement as autograd_path
+from neuray_b200 import _lib, backward, renderer, synthetic
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "tests", "_build")
@@ -138,7 +140,7 @@ def test_backward_without_hit_prob_gradient(harness):
 def test_self_hit_prob_forward_and_backward(harness, use_vis):
     """nr_self_hit_prob's routine (host build) against the PyTorch restatement of predict_self_hit_prob
     (reference renderer.py:137-155) and autograd over it: values, every decoder parameter gradient (through the packed
-    layout and PackPlan's inverse map) and the gradient of the query feature map."""
+    layout and the position -> parameter index map) and the gradient of the query feature map."""
     torch.manual_seed(3)
     dn, rays = 12, 9
     cfg = {"depth_sample_num": dn, "agg_net_cfg": {"sample_num": dn}, "dist_decoder_cfg": {"use_vis": use_vis}}
@@ -157,14 +159,15 @@ def test_self_hit_prob_forward_and_backward(harness, use_vis):
     (ref_hit * g_hit).sum().backward()
 
     params = {k: W[k] for k in names}
-    plan = weights.PackPlan(params, dec, agg, torch.device("cpu"))
-    wp = plan.pack(params)[0]
+    plan = weights.point_index_map_cpu(params, dec, agg)
+    wp = weights.pack_pass_weights(params, dec, agg, torch.device("cpu"))[0]
     cc, qd, m0, gh = coords[0].contiguous(), que_depth[0].contiguous(), fmap[0].contiguous(), g_hit[0].contiguous()
     hit, d_w, d_map = torch.empty(rays, dn), torch.zeros_like(wp), torch.zeros_like(m0)
     p = _lib.NrSelfParams()
     p.map, p.coords, p.que_depth, p.w_point = m0.data_ptr(), cc.data_ptr(), qd.data_ptr(), wp.data_ptr()
     p.rn, p.dn, p.h, p.w, p.fh, p.fw, p.use_vis = rays, dn, 40, 48, 10, 12, int(use_vis)
-    p.near, p.far, p.var_bias = float(que["depth_range"][0, 0]), float(que["depth_range"][0, 1]), 0.05
+    rng = que["depth_range"][0].contiguous().float()
+    p.depth_range, p.var_bias = rng.data_ptr(), 0.05
     p.hit, p.d_hit, p.d_w_point, p.d_map = hit.data_ptr(), gh.data_ptr(), d_w.data_ptr(), d_map.data_ptr()
     harness.nr_self_cpu.restype = C.c_int
     harness.nr_self_cpu.argtypes = [C.c_void_p]
@@ -245,15 +248,16 @@ def test_self_hit_prob_matches_the_reference(harness, name):
     # hand-written routine
     dec, agg = "dist_decoder", "agg_net"
     params = {k: v for k, v in g.W.items() if k.startswith(dec + ".") or k.startswith(agg + ".")}
-    plan = weights.PackPlan(params, dec, agg, torch.device("cpu"))
-    wp = plan.pack(params)[0]
+    plan = weights.point_index_map_cpu(params, dec, agg)
+    wp = weights.pack_pass_weights(params, dec, agg, torch.device("cpu"))[0]
     rays, dn = depth.shape[1:]
     m0, cc, qd, gh = t("self_map")[0].contiguous(), coords[0].contiguous(), depth[0].contiguous(), t("self_gs")[0].contiguous()
     hit, d_w, d_map = torch.empty(rays, dn), torch.zeros_like(wp), torch.zeros_like(m0)
     p = _lib.NrSelfParams()
     p.map, p.coords, p.que_depth, p.w_point = m0.data_ptr(), cc.data_ptr(), qd.data_ptr(), wp.data_ptr()
     p.rn, p.dn, p.h, p.w, p.fh, p.fw, p.use_vis = rays, dn, g.que["imgs"].shape[2], g.que["imgs"].shape[3], m0.shape[1], m0.shape[2], int(use_vis)
-    p.near, p.far, p.var_bias = float(g.que["depth_range"][0, 0]), float(g.que["depth_range"][0, 1]), 0.05
+    rng = g.que["depth_range"][0].contiguous().float()
+    p.depth_range, p.var_bias = rng.data_ptr(), 0.05
     p.hit, p.d_hit, p.d_w_point, p.d_map = hit.data_ptr(), gh.data_ptr(), d_w.data_ptr(), d_map.data_ptr()
     harness.nr_self_cpu.restype = C.c_int
     harness.nr_self_cpu.argtypes = [C.c_void_p]

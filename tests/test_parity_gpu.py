@@ -12,6 +12,9 @@ from neuray_b200 import _lib, renderer, render_ops, synthetic
 
 pytestmark = pytest.mark.gpu
 ATOL, RTOL = 1e-4, 1e-3
+# Projected pixel coordinates are O(100) values computed through x/z in fp32 on both sides: 1e-4 abs on a coordinate of
+# 50 px is 2e-6 relative, i.e. a handful of ulps; measured max difference 4e-5 px (cfg1), 3x that is the gate.
+PTS_ATOL = 1.2e-4
 CASES = ["cfg1", "train8", "views10"]
 
 
@@ -62,8 +65,8 @@ def test_point_kernel_stage_tap(name):
         _, rn, dn = depth.shape
         pack = renderer.frame_pack(ref)
         wp, wr, pe, wt = renderer.pass_weights(net, is_fine, dn, depth.device)
-        from neuray_b200.weights import camera_block
-        cam = camera_block(que["poses"][0], que["Ks"][0], que["depth_range"][0])
+        from neuray_b200.weights import camera_blocks
+        cam, _ = camera_blocks(que, None)
         rec = torch.empty(rn * dn * 20, device="cuda")
         dbg = torch.zeros(pack.rfn, rn * dn, 76, device="cuda")
         p = _lib.NrPassParams()
@@ -76,20 +79,20 @@ def test_point_kernel_stage_tap(name):
         p.use_vis = 1 if net.dist_decoder.cfg["use_vis"] else 0
         p.var_bias = dec.cfg["bias_val"]
         p.point_rec = rec.data_ptr()
-        p.w_tc = None if os.environ.get("NR_POINT_KERNEL", "") == "simt" else wt.data_ptr()
+        p.w_tc = wt.data_ptr()
         _lib.check(_lib.lib().nr_point_kernel_debug(C.byref(p), dbg.data_ptr(), None), "debug")
         torch.cuda.synchronize()
         d = dbg.reshape(pack.rfn, 1, rn, dn, 76)
         gold = g.stage[tag]
         close(d[..., 0:1], gold["prj_mask"], what=f"{name}/{tag}/mask", atol=0, rtol=0, defer=True)
         close(d[..., 1:2], gold["prj_depth"], what=f"{name}/{tag}/depth", defer=True)
-        close(d[..., 4:6], gold["prj_pts"], what=f"{name}/{tag}/pts", atol=2e-3, rtol=1e-4, defer=True)   # pixel units
+        close(d[..., 4:6], gold["prj_pts"], what=f"{name}/{tag}/pts", atol=PTS_ATOL, rtol=2e-6, defer=True)   # pixel units
         close(d[..., 6:9], gold["prj_dir"], what=f"{name}/{tag}/dir", defer=True)
-        close(d[..., 9:12], gold["prj_rgb"], what=f"{name}/{tag}/rgb", atol=3e-4, defer=True)
-        close(d[..., 12:44], gold["prj_ray_feats"], what=f"{name}/{tag}/ray_feats", atol=1e-3, defer=True)
-        close(d[..., 44:76], gold["prj_img_feats"], what=f"{name}/{tag}/img_feats", atol=1e-3, defer=True)
-        close(d[..., 2:3], gold["prj_hit_prob"], what=f"{name}/{tag}/hit_prob", atol=2e-4, defer=True)
-        close(d[..., 3:4], gold["prj_vis"], what=f"{name}/{tag}/vis", atol=2e-4, defer=True)
+        close(d[..., 9:12], gold["prj_rgb"], what=f"{name}/{tag}/rgb", defer=True)
+        close(d[..., 12:44], gold["prj_ray_feats"], what=f"{name}/{tag}/ray_feats", defer=True)
+        close(d[..., 44:76], gold["prj_img_feats"], what=f"{name}/{tag}/img_feats", defer=True)
+        close(d[..., 2:3], gold["prj_hit_prob"], what=f"{name}/{tag}/hit_prob", defer=True)
+        close(d[..., 3:4], gold["prj_vis"], what=f"{name}/{tag}/vis", defer=True)
     flush_fails()
 
 
@@ -127,8 +130,8 @@ def test_fused_resampling(name):
         u, stride = render_ops.fine_sample_u(fdn, "cuda"), 0
     out = torch.empty(rn, m, device="cuda")
     depth, hit = g.que_depth[0].cuda().contiguous(), g.out["hit_prob_nr"][0].cuda().contiguous()
-    dr = g.que["depth_range"]
-    _lib.check(_lib.lib().nr_sample_fine_depth(depth.data_ptr(), hit.data_ptr(), float(dr[0, 0]), float(dr[0, 1]), rn,
+    dr = g.que["depth_range"][0].cuda().contiguous()
+    _lib.check(_lib.lib().nr_sample_fine_depth(depth.data_ptr(), hit.data_ptr(), dr.data_ptr(), rn,
                                                depth.shape[1], fdn, u.data_ptr(), stride, int(use_all), 1, out.data_ptr(), None), "fine")
     torch.cuda.synchronize()
     close(out[None], g.que_depth_fine, atol=2e-5, rtol=2e-5, what="standalone resample", max_bad_frac=2e-3)
@@ -159,6 +162,11 @@ def test_render_end_to_end(name):
     fine, gold = out["pixel_colors_nr_fine"].cpu(), g.out["pixel_colors_nr_fine"]
     assert psnr(fine, gold) > 60.0, psnr(fine, gold)
     close(fine, gold, what="fine colours", max_bad_frac=0.01)
+    # how far the <= 1 % of pixels may be off where a quantile crossed a CDF knot: one resampled depth moves by at most one
+    # coarse bin, i.e. one of the 16..64 fine samples of the ray changes its colour contribution
+    err = (fine - gold).abs().flatten()
+    q999 = torch.quantile(err, 0.999).item()
+    assert q999 < 2e-3 and err.max().item() < 2e-2, (q999, err.max().item())
     expect = set(g.out) if g.is_train else {k for k in g.out if not k.startswith("hit_prob")}
     assert set(out) == expect, (set(out) ^ expect)
 

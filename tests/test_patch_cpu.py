@@ -26,9 +26,10 @@ def test_install_rebinds_reference_api():
         with pytest.raises(_lib.NeurayB200Error):
             net.render_impl(que, dict(ref), False)
     finally:
-        for k, v in orig.items():
-            setattr(ref_renderer.NeuralRayBaseRenderer, k, v)
-        for n, v in orig_ops.items():
-            setattr(ref_ops, n, v)
-        for n, v in orig_ren.items():
-            setattr(ref_renderer, n, v)
+        patch.uninstall()
+    for k, v in orig.items():
+        assert getattr(ref_renderer.NeuralRayBaseRenderer, k) is v, k
+    for n, v in orig_ops.items():
+        assert getattr(ref_ops, n) is v, n
+    for n, v in orig_ren.items():
+        assert getattr(ref_renderer, n) is v, n

@@ -1,0 +1,159 @@
+"""GPU: the drop-in proof.  The UNMODIFIED reference (baseline/_ref, the verbatim copy made by baseline/install_ref.py; or
+/root/reference in the build container) is imported, its own NeuralRayGenRenderer is built and run under CUDA twice -- as
+is, and after neuray_b200.patch.install() -- on the same seeded inputs, and everything the reference's callers read is
+compared: every output key of forward() in eval and training mode, and after backward() of the reference's kind of loss
+(render + depth terms, self-hit-prob term) the gradient of EVERY parameter of the network (hot-path modules, image
+encoder, vis encoder, init net) -- i.e. also what flows out of the CUDA path into the PyTorch encoders in front of it.
+
+This is the test of SURVEY.md section 8b: `render.py` / `run_training.py` construct the network by name, call
+`network(data)` and `loss.backward()`; nothing else touches the renderer.
+"""
+import numpy as np
+import pytest
+import torch
+
+import ref_import
+from neuray_b200 import patch, synthetic
+
+pytestmark = pytest.mark.gpu
+
+DN = 24
+CFG = {"init_net_type": "depth", "use_hierarchical_sampling": True, "use_depth_loss": True, "dist_decoder_cfg": {"use_vis": False},
+       "depth_sample_num": DN, "fine_depth_sample_num": DN, "agg_net_cfg": {"sample_num": DN}, "fine_agg_net_cfg": {"sample_num": DN},
+       "ray_batch_num": 192, "render_depth": True, "depth_loss_coords_num": 256}
+
+
+@pytest.fixture(scope="module")
+def ref_mod():
+    if not ref_import.available():
+        pytest.fail("the reference tree is missing: run `python baseline/install_ref.py` before gpurun (baseline/_ref travels to the box)")
+    mod = ref_import.load_reference()
+    yield mod
+    patch.uninstall()
+
+
+def make_data(rfn=6, rays=384, self_feats=False, seed=3):
+    que, ref = synthetic.make_scene(64, 80, rfn, seed=seed, smooth=2)
+    ref = dict(ref)
+    ref.pop("ray_feats"), ref.pop("img_feats")
+    rs = np.random.RandomState(seed)
+    ref["depth"] = torch.from_numpy(rs.uniform(2.5, 5.0, (rfn, 1, 64, 80)).astype(np.float32))
+    ref["true_depth"] = ref["depth"]
+    n = que["coords"].shape[1]
+    idx = torch.from_numpy(rs.permutation(n)[:rays])
+    que = dict(que, coords=que["coords"][:, idx].contiguous())
+    if self_feats:
+        que["ray_feats"] = torch.from_numpy(rs.standard_normal((1, 32, 16, 20)).astype(np.float32))
+    return que, ref
+
+
+def build(ref_mod, cfg, seed=0):
+    torch.manual_seed(seed)
+    net = ref_mod.NeuralRayGenRenderer(cfg)
+    W = synthetic.make_weights(cfg, seed=seed)            # hot-path modules: random init with a density head that terminates rays
+    missing, unexpected = net.load_state_dict(W, strict=False)
+    assert not unexpected
+    return net.cuda()
+
+
+def run(net, que, ref, is_train, seed=77):
+    data = {"que_imgs_info": synthetic.to_device(que, "cuda"), "ref_imgs_info": synthetic.to_device(ref, "cuda")}
+    if not is_train:
+        data["eval"] = True
+    torch.manual_seed(seed)            # randperm of the depth-loss coordinates, torch.rand of the fine quantiles
+    return net(data)
+
+
+def loss_of(out):
+    """The shape of the reference's training loss (network/loss.py:46-132): render terms on both passes + a depth term on
+    the decoder means + the self-hit-prob consistency term when present."""
+    loss = ((out["pixel_colors_nr"] - out["pixel_colors_gt"]) ** 2).mean() + ((out["pixel_colors_nr_fine"] - out["pixel_colors_gt_fine"]) ** 2).mean()
+    loss = loss + 0.1 * out["depth_mean"].abs().mean() + 0.1 * out["depth_mean_fine"].abs().mean()
+    if "hit_prob_self" in out:
+        loss = loss + ((out["hit_prob_self"] - out["hit_prob_nr"].detach()) ** 2).mean() + ((out["hit_prob_self_fine"] - out["hit_prob_nr_fine"].detach()) ** 2).mean()
+    return loss
+
+
+def compare_outputs(a, b, fine_bad_frac):
+    assert set(a) == set(b), set(a) ^ set(b)
+    for k in a:
+        x, y = a[k].detach().float().cpu(), b[k].detach().float().cpu()
+        assert x.shape == y.shape, k
+        if a[k].dtype == torch.bool:
+            assert (x != y).float().mean().item() <= (fine_bad_frac if k.endswith("_fine") else 0.0), k
+            continue
+        bad = ((x - y).abs() > 1e-4 + 1e-3 * y.abs()).float().mean().item()
+        # fine-pass quantities sit behind searchsorted: isolated samples may move by a bin
+        allowed = fine_bad_frac if ("fine" in k) else 0.0
+        assert bad <= allowed, (k, bad, float((x - y).abs().max()))
+
+
+def test_eval_forward_patched_equals_unpatched(ref_mod):
+    que, ref = make_data()
+    net = build(ref_mod, CFG).eval()
+    with torch.no_grad():
+        want = run(net, que, ref, False)
+        patch.install()
+        try:
+            got = run(net, que, ref, False)
+        finally:
+            patch.uninstall()
+    torch.cuda.synchronize()
+    assert "hit_prob_nr" not in got and "depth_mean_fine" in got
+    compare_outputs(got, want, fine_bad_frac=0.01)
+
+
+@pytest.mark.parametrize("self_hit", [False, True])
+def test_training_forward_and_every_gradient(ref_mod, self_hit):
+    cfg = dict(CFG, use_self_hit_prob=self_hit)
+    que, ref = make_data(self_feats=self_hit)
+    net = build(ref_mod, cfg).train()
+    grads = {}
+    outs = {}
+    for mode in ("reference", "patched"):
+        if mode == "patched":
+            patch.install()
+        try:
+            net.zero_grad(set_to_none=True)
+            out = run(net, que, ref, True)
+            loss_of(out).backward()
+            torch.cuda.synchronize()
+        finally:
+            patch.uninstall()
+        outs[mode] = {k: v.detach().clone() for k, v in out.items()}
+        grads[mode] = {k: (p.grad.detach().clone() if p.grad is not None else None) for k, p in net.named_parameters()}
+    compare_outputs(outs["patched"], outs["reference"], fine_bad_frac=0.01)
+    checked, flows_upstream = 0, 0
+    for k, g_ref in grads["reference"].items():
+        g = grads["patched"][k]
+        if g_ref is None or float(g_ref.abs().max()) == 0.0:
+            assert g is None or float(g.abs().max()) < 1e-7, k
+            continue
+        assert g is not None, f"{k}: the patched network sends no gradient here"
+        scale = float(g_ref.abs().max())
+        err = float((g - g_ref).abs().max())
+        assert err <= 2e-3 * scale + 1e-7, (k, err, scale)
+        checked += 1
+        if k.split(".")[0] in ("image_encoder", "vis_encoder", "init_net"):
+            flows_upstream += 1
+    assert checked > 250 and flows_upstream > 100, (checked, flows_upstream)
+
+
+def test_render_ops_refuse_to_cut_a_graph(ref_mod):
+    """A drop-in without a backward raises when handed an input that requires grad (instead of silently detaching)."""
+    from neuray_b200 import _lib, render_ops
+    d = torch.rand(1, 8, 16, device="cuda", requires_grad=True)
+    with pytest.raises(_lib.NeurayB200Error):
+        render_ops.depth2dists(d)
+    with torch.no_grad():
+        render_ops.depth2dists(d)
+    fm = torch.randn(2, 32, 12, 16, device="cuda", requires_grad=True)
+    pts = torch.rand(2, 50, 2, device="cuda") * torch.tensor([60.0, 44.0], device="cuda")
+    mask = (torch.rand(2, 50, device="cuda") > 0.2).float()
+    out = render_ops.interpolate_feature_map(fm, pts, mask, 48, 64)
+    out.square().sum().backward()
+    import network.render_ops as ref_ops          # the reference's own torch implementation
+    fm2 = fm.detach().clone().requires_grad_(True)
+    want = ref_ops.interpolate_feature_map(fm2, pts, mask, 48, 64)
+    want.square().sum().backward()
+    assert torch.allclose(out, want, atol=1e-5) and torch.allclose(fm.grad, fm2.grad, atol=1e-4, rtol=1e-4)

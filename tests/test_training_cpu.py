@@ -1,10 +1,11 @@
-"""CPU: the interim PyTorch restatement used for gradients (neuray_b200/autograd_path.py) equals the oracle, in value and
+"""CPU: the interim PyTorch restatement used for gradients (tests/torch_restatement.py, the A/B reference of the native backward) equals the oracle, in value and
 in gradient, so that the GPU training tests only have to check the plumbing."""
 import torch
 
 import neuray_oracle as orc
 from gen_golden import flat_cfg
-from neuray_b200 import autograd_path, renderer, synthetic
+import torch_restatement as autograd_path
+from neuray_b200 import renderer, synthetic
 from neuray_b200.weights import posenc_table
 
 CFG = {"use_hierarchical_sampling": True, "depth_sample_num": 16, "fine_depth_sample_num": 16, "agg_net_cfg": {"sample_num": 16},

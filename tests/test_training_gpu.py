@@ -5,7 +5,9 @@ import torch
 
 import neuray_oracle as orc
 from gen_golden import flat_cfg
+import torch_restatement as tr
 from neuray_b200 import render_ops, renderer, synthetic
+from neuray_b200.weights import posenc_table
 
 pytestmark = pytest.mark.gpu
 CFG = {"use_hierarchical_sampling": True, "depth_sample_num": 24, "fine_depth_sample_num": 24, "agg_net_cfg": {"sample_num": 24},
@@ -80,7 +82,17 @@ def test_training_step_runs_and_updates():
     assert all(torch.isfinite(p.grad).all() for p in net.parameters() if p.grad is not None)
 
 
-def test_native_backward_matches_torch_recompute(monkeypatch):
+def _torch_pass(net, dec, agg, use_vis_prob, depth, dq, dr_leaf):
+    """One pass through the PyTorch restatement (tests/torch_restatement.py) on the GPU, differentiable."""
+    P = {k: v for k, v in net.named_parameters() if k.startswith(dec + ".") or k.startswith(agg + ".")}
+    decm = getattr(net, dec)
+    cfgv = {"use_vis_prob": use_vis_prob, "var_bias": float(decm.cfg["bias_val"])}
+    ref = {k: dr_leaf[k] for k in ("poses", "Ks", "depth_range", "imgs", "ray_feats", "img_feats")}
+    return tr.render_pass_torch(P, dec, agg, cfgv, depth, dq["coords"], dq["poses"], dq["Ks"], dq["depth_range"], ref,
+                                posenc_table(depth.shape[-1]).to(depth.device))
+
+
+def test_native_backward_matches_torch_recompute():
     """nr_render_pass_bwd (hand-written kernels + GEMMs over the tapes) against autograd over the PyTorch restatement of
     the same pass, on the GPU, at a size with thousands of rows per weight gradient (8 views, 48 rays x 24 samples, both
     passes, gradients into pixel colours, hit probabilities and depth)."""
@@ -91,7 +103,6 @@ def test_native_backward_matches_torch_recompute(monkeypatch):
     gw, gh = torch.randn(1, 48, 3, device="cuda"), torch.randn(1, 48, 24, device="cuda") * 0.3
     results = {}
     for mode in ("native", "torch"):
-        monkeypatch.setenv("NR_BACKWARD", mode)
         net = renderer.NeuralRayRenderPath(cfg)
         net.load_state_dict(W, strict=True)
         net.cuda()
@@ -99,11 +110,18 @@ def test_native_backward_matches_torch_recompute(monkeypatch):
         dr["ray_feats"].requires_grad_(True)
         dr["img_feats"].requires_grad_(True)
         depth = renderer.sample_depth(dq["depth_range"], dq["coords"], 24, False)[0]
-        pc = net.render_by_depth(depth, dq, dr, True, False)
-        fd = torch.sort(render_ops.sample_fine_depth(depth, pc["hit_prob_nr"].detach(), dq["depth_range"], 24, False), -1)[0]
-        pf = net.render_by_depth(fd, dq, dr, True, True)
-        loss = (pc["pixel_colors_nr"] * gw).sum() + (pf["pixel_colors_nr"] * gw).sum() * 0.5 + (pc["hit_prob_nr"] * gh).sum() \
-            + pf["render_depth"].sum() * 0.2
+        if mode == "native":
+            pc = net.render_by_depth(depth, dq, dr, True, False)
+            pix_c, hit_c = pc["pixel_colors_nr"], pc["hit_prob_nr"]
+        else:
+            pix_c, hit_c, _ = _torch_pass(net, "dist_decoder", "agg_net", True, depth, dq, dr)
+        fd = torch.sort(render_ops.sample_fine_depth(depth, hit_c.detach(), dq["depth_range"], 24, False), -1)[0]
+        if mode == "native":
+            pf = net.render_by_depth(fd, dq, dr, True, True)
+            pix_f, dep_f = pf["pixel_colors_nr"], pf["render_depth"]
+        else:
+            pix_f, _, dep_f = _torch_pass(net, "fine_dist_decoder", "fine_agg_net", True, fd, dq, dr)
+        loss = (pix_c * gw).sum() + (pix_f * gw).sum() * 0.5 + (hit_c * gh).sum() + dep_f.sum() * 0.2
         loss.backward()
         torch.cuda.synchronize()
         results[mode] = ({k: (p.grad.clone() if p.grad is not None else None) for k, p in net.named_parameters()},
@@ -124,38 +142,44 @@ def test_native_backward_matches_torch_recompute(monkeypatch):
         assert float((a - b).abs().max()) <= 1e-3 * float(b.abs().max()) + 1e-6
 
 
-def test_self_hit_prob_native_matches_torch(monkeypatch):
-    """use_self_hit_prob (fine-tuning configs, reference renderer.py:137-155, 188-189): nr_self_hit_prob against the PyTorch
-    restatement on the GPU -- values of hit_prob_self and the gradients it sends into the decoder and the query map."""
-    cfg = dict(CFG, use_self_hit_prob=True, dist_decoder_cfg={"use_vis": True})
+@pytest.mark.parametrize("use_vis", [True, False])
+def test_self_hit_prob_matches_the_oracle(use_vis):
+    """use_self_hit_prob (fine-tuning configs, reference renderer.py:137-155, 188-189): nr_self_hit_prob on the GPU against
+    the CPU ORACLE (oracle/neuray_oracle.py predict_self_hit_prob, itself pinned to the unmodified reference's values and
+    gradients in tests/test_backward_cpu.py) -- values of hit_prob_self and the gradients its autograd sends into every
+    decoder parameter and into the query view's feature map."""
+    cfg = dict(CFG, use_self_hit_prob=True, dist_decoder_cfg={"use_vis": use_vis})
     que, ref = synthetic.make_scene(64, 80, 4, seed=21, smooth=2)
     que = synthetic.slice_rays(que, 500, 564)
     W = synthetic.make_weights(cfg, seed=6)
-    gw = torch.randn(1, 64, 24, device="cuda")
     torch.manual_seed(1)
+    gw = torch.randn(1, 64, 24)
     fmap = torch.randn(1, 32, 16, 20)
-    res = {}
-    for mode in ("native", "torch"):
-        monkeypatch.setenv("NR_BACKWARD", mode)
-        net = renderer.NeuralRayRenderPath(cfg)
-        net.load_state_dict(W, strict=True)
-        net.cuda()
-        dq, dr = synthetic.to_device(que, "cuda"), synthetic.to_device(ref, "cuda")
-        dq["ray_feats"] = fmap.cuda().requires_grad_(True)
-        depth = renderer.sample_depth(dq["depth_range"], dq["coords"], 24, False)[0]
-        out = net.render_by_depth(depth, dq, dr, True, False)
-        (out["hit_prob_self"] * gw).sum().backward()
-        torch.cuda.synchronize()
-        res[mode] = (out["hit_prob_self"].detach().clone(), dq["ray_feats"].grad.clone(),
-                     {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None})
-    a, b = res["native"], res["torch"]
-    assert torch.allclose(a[0], b[0], atol=5e-6)
-    assert float((a[1] - b[1]).abs().max()) <= 1e-3 * float(b[1].abs().max()) + 1e-7
+    # oracle, CPU autograd
+    Wo = {k: v.clone().requires_grad_(True) for k, v in W.items()}
+    fo = fmap.clone().requires_grad_(True)
+    depth = orc.sample_depth(que["depth_range"], que["coords"], 24, False)[0]
+    qo = dict(que, ray_feats=fo)
+    ho = orc.predict_self_hit_prob(Wo, flat_cfg({**renderer.base_cfg, **cfg}), qo, depth, orc.depth2inv_dists(depth, que["depth_range"]), False)
+    (ho * gw).sum().backward()
+    # CUDA
+    net = renderer.NeuralRayRenderPath(cfg)
+    net.load_state_dict(W, strict=True)
+    net.cuda()
+    dq, dr = synthetic.to_device(que, "cuda"), synthetic.to_device(ref, "cuda")
+    dq["ray_feats"] = fmap.cuda().requires_grad_(True)
+    out = net.render_by_depth(depth.cuda(), dq, dr, True, False)
+    (out["hit_prob_self"] * gw.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    assert torch.allclose(out["hit_prob_self"].detach().cpu(), ho.detach(), atol=5e-6)
+    gm = fo.grad
+    assert float((dq["ray_feats"].grad.cpu() - gm).abs().max()) <= 1e-3 * float(gm.abs().max()) + 1e-7
     checked = 0
-    for k, g in b[2].items():
-        if float(g.abs().max()) == 0.0:
+    for k, p in net.named_parameters():
+        g = Wo[k].grad
+        if g is None or float(g.abs().max()) == 0.0:
             continue
-        assert k in a[2], k
-        assert float((a[2][k] - g).abs().max()) <= 1e-3 * float(g.abs().max()) + 1e-7, k
+        assert p.grad is not None, k
+        assert float((p.grad.cpu() - g).abs().max()) <= 1e-3 * float(g.abs().max()) + 1e-7, k
         checked += 1
-    assert checked >= 24
+    assert checked == (24 if use_vis else 18)

@@ -1,11 +1,7 @@
-"""Autograd hook of the rendering path (training).
-
-Forward values always come from the CUDA kernels.  `RenderPassFn.backward` calls the native backward
-(`neuray_b200/backward.py` -> `nr_render_pass_bwd` + `nr_tape_gemms`).  The PyTorch restatement of the pass below
-(`render_pass_torch`, same arithmetic as reference network/renderer.py:168-203 and the modules it calls) is kept as the
-A/B reference for that backward (`NR_BACKWARD=torch` runs autograd over it ON THE GPU instead; tests compare the two) and
-for `predict_self_hit_prob` (fine-tuning only).  Nothing here is used at inference time, and nothing here touches the CPU
-or oracle/.
+"""TEST INFRASTRUCTURE: PyTorch restatement of one render pass (same arithmetic as reference network/renderer.py:168-203 and
+the modules it calls) and of predict_self_hit_prob, as differentiable torch ops that run on any device.  Used by the tests
+as the GPU-side A/B reference of the native backward (autograd over these functions).  Nothing under neuray_b200/ imports
+this file.
 """
 import os
 
@@ -171,52 +167,3 @@ def self_hit_prob_torch(P, dec, use_vis_prob, var_bias, que_ray_feats, coords, h
         c0, c1 = c0 * visd, c1 * visd
     mix = torch.cat([aw, 1 - aw], -1)
     return ((c1 - c0) * mix).sum(-1)
-
-
-class RenderPassFn(torch.autograd.Function):
-    """forward = the fused CUDA pass (values), backward = the native backward (NR_BACKWARD=torch: autograd over `render_pass_torch`)."""
-
-    @staticmethod
-    def forward(ctx, runner, meta, ray_feats, img_feats, *params):
-        with torch.no_grad():
-            res = runner()
-        ctx.meta = meta
-        ctx.bwd = res.pop("_bwd", None)
-        ctx.save_for_backward(ray_feats, img_feats, *params)
-        ctx.mark_non_differentiable(res["ray_mask_u8"])
-        fine = res.get("fine_depth")
-        outs = (res["pixel_colors"], res["hit_prob"], res["render_depth"], res["ray_mask_u8"])
-        if fine is not None:
-            ctx.mark_non_differentiable(fine)
-            return outs + (fine,)
-        return outs
-
-    @staticmethod
-    def backward(ctx, g_pix, g_hit, g_depth, *unused):
-        meta = ctx.meta
-        ray_feats, img_feats, *params = ctx.saved_tensors
-        if ctx.bwd is not None and os.environ.get("NR_BACKWARD", "native") != "torch":
-            # native backward: nr_render_pass_bwd fills the tapes, the weight gradients are GEMMs over them (backward.py)
-            from . import backward as nb
-            p, _keep, feat_shape, stream = ctx.bwd
-            want_feat = ray_feats.requires_grad or img_feats.requires_grad
-            grads, drf, dimf = nb.render_pass_backward(p, meta["names"], meta["dec"], meta["agg"], g_pix, g_hit, g_depth, want_feat,
-                                                       feat_shape, stream)
-            gp = [grads[n] if t.requires_grad else None for n, t in zip(meta["names"], params)]
-            return (None, None, drf if ray_feats.requires_grad else None, dimf if img_feats.requires_grad else None, *gp)
-        with torch.enable_grad():
-            leaves = [t.detach().requires_grad_(t.requires_grad) for t in (ray_feats, img_feats, *params)]
-            P = dict(zip(meta["names"], leaves[2:]))
-            ref = dict(meta["ref"], ray_feats=leaves[0], img_feats=leaves[1])
-            pix, hit, dep = render_pass_torch(P, meta["dec"], meta["agg"], meta["cfgv"], meta["que_depth"], meta["coords"],
-                                              meta["que_pose"], meta["que_K"], meta["que_range"], ref, meta["pos_enc"])
-            outs, gouts = [], []
-            for o, g in ((pix, g_pix), (hit, g_hit), (dep, g_depth)):
-                if g is not None:
-                    outs.append(o)
-                    gouts.append(g)
-            wanted = [t for t in leaves if t.requires_grad]
-            grads = torch.autograd.grad(outs, wanted, gouts, allow_unused=True) if wanted and outs else []
-        it = iter(grads)
-        full = [next(it) if t.requires_grad else None for t in leaves]
-        return (None, None, *full)
