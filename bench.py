@@ -1,21 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- ray-samples/s of the per-ray rendering hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload black_800|black_400|cfg1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload black_800|black_400|cfg1|fern_high|train_dtu] [--shard images|rays]
 
-A "step" renders ONE full synthetic query image through the hot path (sample_depth -> coarse pass -> fused
-resampling -> fine pass), encoder outputs given.  Workload (config.workload): the geometry BASELINE.json's metric is
-quoted on -- NeRF-synthetic lego "black_800": 800x800 query, 8 reference views 800x800 (feature maps 32ch @ 200x200),
-64 coarse + 64 fine samples, neuray_gen_depth cfg (coarse decoder use_vis:false), random-init weights, synthetic maps.
+Headline (default flags): a "step" renders ONE full synthetic query image through the hot path (sample_depth -> coarse
+pass -> fused resampling -> fine pass), encoder outputs given.  Workload `black_800` = the geometry BASELINE.json's metric
+is quoted on: 800x800 query, 8 reference views 800x800 (feature maps 32ch @ 200x200), 64 coarse + 64 fine samples,
+neuray_gen_depth cfg (coarse decoder use_vis:false), random-init weights, synthetic maps; one image per rank (weak scaling).
 
-  value     ray-samples/s, whole job (N ranks, one image per rank = weak scaling), inputs resident in HBM, device-timed
+  value     ray-samples/s, whole job, inputs resident in HBM, device-timed (CUDA events, max over ranks)
   e2e       same metric through NeuralRayRenderPath.render() from pinned HOST buffers: every step copies all inputs
             host->device and the rendered tiles device->host inside the timed region
   roofline  the dominant kernel (point kernel): algorithmic FLOPs per launch / CUDA-event time, vs MEASURED_PEAKS.json
-  cpu_baseline  the CPU oracle (port of the reference's PyTorch path) on this box's host cores, bounded ray sample
+  cpu_baseline  the reference's own CPU implementation of the path on this box's host cores, bounded ray sample
 
---impl reference times the reference's CPU implementation of the path (the oracle port: /root/reference does not
-exist on the GPU box) on all host cores, same workload/metric, each step a bounded sample of rays.
+Other BASELINE.json configurations (selectable as the main line with --workload, and measured as auxiliary objects
+`aux.fern_high_sharded` / `aux.train_dtu` at every N of the default run so that the driver's 1/2/4/8 scaling runs carry them):
+  fern_high  cfg4: ONE 1008x756 image, 10 reference views, 64+64, rays sharded over the ranks (dist.render_sharded, every
+             output key gathered in one NCCL all-gather) = strong scaling; the collective is timed separately
+  train_dtu  cfg5: one optimisation step per rank on 512 rays of a DTU-shape scene (8 views 304x400), native backward,
+             flat-bucket gradient all-reduce (timed separately), Adam = weak scaling
+
+--impl reference times the UNMODIFIED reference's own implementation of the path (baseline/_ref, the verbatim copy made by
+baseline/install_ref.py: NeuralRayBaseRenderer.render_impl over the chunk loop of renderer.py:237-254, encoder outputs
+given) on the box's host cores; when the copy is absent it falls back to the oracle port and says so (`kind`).
 """
 import argparse
 import json
@@ -30,18 +39,33 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (ref h, ref w, rfn, dn coarse, dn fine, description)
-    "black_800": (800, 800, 8, 64, 64, "nerf_synthetic/lego/black_800 geometry: 800x800 query, 8 ref views, 64+64 samples, neuray_gen_depth cfg"),
-    "black_400": (400, 400, 8, 64, 64, "nerf_synthetic/lego/black_400 geometry: 400x400 query, 8 ref views, 64+64 samples, neuray_gen_depth cfg"),
-    "cfg1": (64, 64, 3, 32, 32, "64x64 query, 3 ref views, 32+32 samples"),
+    # name: dict(scene kwargs for synthetic.make_scene, rfn, dn coarse, dn fine, description)
+    "black_800": dict(scene=dict(h=800, w=800), rfn=8, dn=(64, 64),
+                      desc="nerf_synthetic/lego/black_800 geometry: 800x800 query, 8 ref views, 64+64 samples, neuray_gen_depth cfg"),
+    "black_400": dict(scene=dict(h=400, w=400), rfn=8, dn=(64, 64),
+                      desc="nerf_synthetic/lego/black_400 geometry: 400x400 query, 8 ref views, 64+64 samples, neuray_gen_depth cfg"),
+    "cfg1": dict(scene=dict(h=64, w=64), rfn=3, dn=(32, 32), desc="64x64 query, 3 ref views, 32+32 samples"),
+    "fern_high": dict(scene=dict(h=756, w=1008, depth_range=(1.2, 12.0), arc_deg=100.0, focal=0.83 * 1008), rfn=10, dn=(64, 64),
+                      desc="llff_colmap/fern/high geometry: 1008x756 query, 10 ref views padded to 1008x768, 64+64 samples, depth (1.2,12)"),
+    "train_dtu": dict(scene=dict(h=300, w=400, depth_range=(0.8, 4.0), radius=2.4), rfn=8, dn=(64, 64),
+                      desc="DTU-train shape: 8 ref views 300x400 padded to 304x400, 512 rays per rank, 64+64 samples, training step"),
 }
 METRIC = "ray-samples/sec (800x800x64 coarse+64 fine, 8 ref views)"
+TRAIN_RAYS = 512
 
 
 def model_cfg(dn_c, dn_f):
     return {"use_hierarchical_sampling": True, "dist_decoder_cfg": {"use_vis": False}, "depth_sample_num": dn_c,
             "fine_depth_sample_num": dn_f, "agg_net_cfg": {"sample_num": dn_c}, "fine_agg_net_cfg": {"sample_num": dn_f},
             "render_depth": True, "ray_batch_num": 65536}
+
+
+def make_workload(name, seed=0, with_que_imgs=False, **over):
+    from neuray_b200 import synthetic
+    wl = WORKLOADS[name]
+    kw = dict(wl["scene"], rfn=wl["rfn"], seed=seed, smooth=2, with_que_imgs=with_que_imgs)
+    kw.update(over)
+    return synthetic.make_scene(**kw)
 
 
 def point_kernel_flops_per_sample(rfn, use_vis_head):
@@ -82,67 +106,321 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def training_step(dev, rays=512, steps=8):
-    """Auxiliary number (not the headline metric): one optimisation step on the DTU-train shape of SURVEY.md 8d cfg5
-    (8 reference views 304x400, 512 rays, 64+64 samples): kernel forward + native backward + Adam, inputs resident."""
-    from neuray_b200 import renderer, synthetic
-    cfg = {"use_hierarchical_sampling": True, "fine_dist_decoder_cfg": {"use_vis": True}, "dist_decoder_cfg": {"use_vis": False},
-           "render_depth": True, "ray_batch_num": rays}
-    que, ref = synthetic.make_scene(304, 400, 8, seed=5, smooth=2)
-    net = renderer.NeuralRayRenderPath(cfg)
-    net.load_state_dict(synthetic.make_weights(cfg, seed=1), strict=True)
-    net.to(dev)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
-    dr = synthetic.to_device(ref, dev)
-    gen = torch.Generator().manual_seed(0)
-    n = que["coords"].shape[1]
-    batches = []
-    for _ in range(4):
-        idx = torch.randperm(n, generator=gen)[:rays]
-        q = dict(que)
-        q["coords"] = que["coords"][:, idx]
-        batches.append(synthetic.to_device(q, dev))
+class Ctx:
+    """Process-wide bench state: rank, device, timing helpers."""
 
-    def step(i):
-        out = net.render(batches[i % 4], dr, True)
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, steps, warmup):
+        """W untimed calls, then exactly K calls bracketed by barrier + synchronize; seconds, max over ranks."""
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return ms.item() / 1e3
+
+    def max_over_ranks(self, x):
+        t = torch.tensor([float(x)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.item()
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def build_net(cfg, dev, seed=0):
+    from neuray_b200 import renderer, synthetic
+    net = renderer.NeuralRayRenderPath(cfg)
+    net.load_state_dict(synthetic.make_weights(cfg, seed=seed), strict=True)
+    return net.to(dev)
+
+
+class Uploader:
+    """End-to-end arm: double-buffered uploads.  The inputs of step i+1 go up on a copy stream while step i runs (what a
+    frame / batch loop does); every step still uploads all of its inputs inside the timed region."""
+
+    def __init__(self, dev, host_dicts):
+        self.dev, self.host = dev, host_dicts
+        self.stream = torch.cuda.Stream(device=dev)
+        self.pending = None
+        self.bytes = sum(v.numel() * v.element_size() for d in host_dicts for v in d.values())
+
+    def _upload(self):
+        with torch.cuda.stream(self.stream):
+            out = [{k: v.to(self.dev, non_blocking=True) for k, v in d.items()} for d in self.host]
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return out, ev
+
+    def next(self):
+        out, ev = self.pending if self.pending is not None else self._upload()
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        for d in out:
+            for t in d.values():
+                t.record_stream(cur)
+        self.pending = self._upload()
+        return out
+
+
+def pin(d):
+    return {k: v.pin_memory() for k, v in d.items()}
+
+
+# ---- cfg4: one image, rays sharded over the ranks ---------------------------------------------------------------------------
+
+def sharded_image(ctx, steps, warmup, e2e=True):
+    """fern_high: ONE 1008x756 image, 10 views, 64+64; rank r renders its contiguous ray range, every output key is
+    all-gathered (dist.render_sharded).  Strong scaling: total work fixed as N grows."""
+    from neuray_b200 import dist as nrd
+    wl = WORKLOADS["fern_high"]
+    cfg = model_cfg(*wl["dn"])
+    que, ref = make_workload("fern_high", seed=7)
+    net = build_net(cfg, ctx.dev, seed=5)
+    rays = que["coords"].shape[1]
+    samples = rays * sum(wl["dn"])
+    dq, dr = ({k: v.to(ctx.dev) for k, v in d.items()} for d in (que, ref))
+    coll = []
+
+    @torch.no_grad()
+    def step(q=dq, r=dr):
+        return nrd.render_sharded(lambda a, b, t: net.render(a, b, t), q, r, False, timing=coll)
+
+    t = ctx.timed(step, steps, warmup)
+    coll_ms = [a.elapsed_time(b) for a, b in coll[-steps:]] if coll else []
+    res = {"workload": wl["desc"], "value": samples * steps / t, "unit": "ray-samples/s", "ms_per_step": t / steps * 1e3,
+           "scaling": "strong", "rays": rays, "n_gpus": ctx.world,
+           "allgather_ms": ctx.max_over_ranks(sum(coll_ms) / len(coll_ms)) if coll_ms else 0.0,
+           "allgather_bytes": int(-(-rays // ctx.world) * ctx.world * 4 * 8) if ctx.world > 1 else 0,
+           "parallelism": f"rays of one image sharded over {ctx.world} rank(s); one NCCL all-gather of all output keys per frame"}
+    if e2e:
+        up = Uploader(ctx.dev, [pin(que), pin(ref)])
+        host_out = {}
+
+        def step_e2e():
+            q, r = up.next()
+            out = step(q, r)
+            for k in ("pixel_colors_nr", "pixel_colors_nr_fine", "render_depth_fine", "ray_mask_fine"):
+                if k not in host_out:
+                    host_out[k] = torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory()
+                host_out[k].copy_(out[k], non_blocking=True)
+        t2 = ctx.timed(step_e2e, steps, warmup)
+        res["e2e"] = {"value": samples * steps / t2, "unit": "ray-samples/s", "h2d_bytes_per_step": up.bytes,
+                      "d2h_bytes_per_step": sum(v.numel() * v.element_size() for v in host_out.values()), "ms_per_step": t2 / steps * 1e3}
+    return res
+
+
+# ---- cfg5: data-parallel training step --------------------------------------------------------------------------------------
+
+def train_step_bench(ctx, steps, warmup, e2e=True):
+    """train_dtu: per rank one sampled batch of 512 rays x (64+64) samples on a DTU-shape scene (8 views 304x400): kernel
+    forward (training mode: random fine quantiles, hit_prob kept) + render loss on both passes + native backward
+    (nr_render_pass_bwd + nr_tape_gemms) + flat-bucket gradient all-reduce + Adam.  Weak scaling: 512 rays per rank."""
+    from neuray_b200 import _lib, dist as nrd, synthetic
+    wl = WORKLOADS["train_dtu"]
+    cfg = dict(model_cfg(*wl["dn"]), fine_dist_decoder_cfg={"use_vis": True}, ray_batch_num=TRAIN_RAYS)
+    que, ref = make_workload("train_dtu", seed=5, with_que_imgs=True)
+    net = build_net(cfg, ctx.dev, seed=1)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+    dr = {k: v.to(ctx.dev) for k, v in ref.items()}
+    gen = torch.Generator().manual_seed(100 + ctx.rank)          # distinct batches per rank
+    n = que["coords"].shape[1]
+    host_batches = []
+    for _ in range(4):
+        idx = torch.randperm(n, generator=gen)[:TRAIN_RAYS]
+        host_batches.append(dict(que, coords=que["coords"][:, idx].contiguous()))
+    batches = [synthetic.to_device(b, ctx.dev) for b in host_batches]
+    coll = []
+    state = {"i": 0, "loss": None}
+
+    def step(batch=None):
+        b = batch if batch is not None else batches[state["i"] % 4]
+        state["i"] += 1
+        out = net.render(b, dr, True)
         loss = ((out["pixel_colors_nr"] - out["pixel_colors_gt"]) ** 2).mean() + ((out["pixel_colors_nr_fine"] - out["pixel_colors_gt_fine"]) ** 2).mean()
         opt.zero_grad(set_to_none=True)
         loss.backward()
+        nrd.allreduce_gradients(net.parameters(), timing=coll)
         opt.step()
+        state["loss"] = loss
+        return loss
 
-    for i in range(3):
-        step(i)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(steps):
-        step(i)
-    torch.cuda.synchronize()
-    ms = (time.perf_counter() - t0) / steps * 1e3
-    return {"ms_per_step": ms, "ray_samples_per_s": rays * 128 / ms * 1e3, "rays": rays, "samples_per_ray": 128, "ref_views": 8,
-            "backward": os.environ.get("NR_BACKWARD", "native"),
-            "note": "wall clock incl. host work; kernel forward + nr_render_pass_bwd + nr_tape_gemms + Adam"}
+    l0 = _lib.LAUNCHES
+    t = ctx.timed(step, steps, warmup)
+    launches = (_lib.LAUNCHES - l0) // (steps + warmup)
+    coll_ms = [a.elapsed_time(b) for a, b in coll[-steps:]] if coll else []
+    samples = TRAIN_RAYS * sum(wl["dn"]) * ctx.world
+    res = {"workload": wl["desc"], "value": samples * steps / t, "unit": "ray-samples/s", "ms_per_step": t / steps * 1e3, "scaling": "weak",
+           "rays_per_rank": TRAIN_RAYS, "n_gpus": ctx.world, "kernels_per_step": launches,
+           "allreduce_ms": ctx.max_over_ranks(sum(coll_ms) / len(coll_ms)) if coll_ms else 0.0,
+           "allreduce_bytes": sum(p.numel() for p in net.parameters()) * 4 if ctx.world > 1 else 0,
+           "loss": float(state["loss"]),
+           "parallelism": f"data parallel x{ctx.world}: one 512-ray batch per rank, flat-bucket NCCL all-reduce of the gradients, Adam",
+           "note": "device-timed over whole steps (host work included); forward + nr_render_pass_bwd + nr_tape_gemms + all-reduce + Adam"}
+    if e2e:
+        ups = Uploader(ctx.dev, [pin({"coords": b["coords"]}) for b in host_batches[:1]])
+        host_loss = torch.empty(1).pin_memory()
+
+        def step_e2e():
+            (c,) = ups.next()                    # the sampled ray coordinates of this step come from the host (the data loader's part)
+            loss = step(dict(batches[0], coords=c["coords"]))
+            host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+        t2 = ctx.timed(step_e2e, steps, warmup)
+        res["e2e"] = {"value": samples * steps / t2, "unit": "ray-samples/s", "h2d_bytes_per_step": ups.bytes, "d2h_bytes_per_step": 4,
+                      "ms_per_step": t2 / steps * 1e3}
+    return res
 
 
-def eager_gpu_baseline(net, dq, dr, dn, dev, rays=4096, reps=3):
-    """Auxiliary GPU-vs-GPU number: the same pass as plain PyTorch-eager tensor ops on the same GPU
-    (neuray_b200/autograd_path.render_pass_torch, the restatement of reference renderer.py:168-203 that the tests use as
-    the A/B reference of the backward), coarse pass only, forward only, on a slice of the workload's rays."""
-    from neuray_b200 import render_ops
-    from neuray_b200.autograd_path import render_pass_torch
-    from neuray_b200.weights import posenc_table
+# ---- reference arm / CPU baselines ------------------------------------------------------------------------------------------
+
+def _load_reference():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_import
+    if not ref_import.available():
+        return None
+    return ref_import.load_reference()
+
+
+def reference_net(ref_mod, cfg, seed=0, device="cpu"):
+    from neuray_b200 import synthetic
+    net = ref_mod.NeuralRayBaseRenderer(cfg)
+    missing, unexpected = net.load_state_dict(synthetic.make_weights(cfg, seed=seed), strict=False)
+    assert not unexpected
+    net = net.eval().to(device)
+    for m in net.modules():        # the reference pins this plain attribute to "cuda:0" (ibrnet.py:312); put it where the net runs
+        if hasattr(m, "pos_encoding") and torch.is_tensor(m.pos_encoding):
+            m.pos_encoding = m.pos_encoding.to(device)
+    return net
+
+
+def reference_render_chunks(net, que, ref, ray_batch_num):
+    """The chunk loop of the reference's render() (renderer.py:237-254) with the encoders' outputs given: its own
+    render_impl per chunk, hit_prob keys dropped, chunks concatenated."""
+    coords = que["coords"]
+    acc = {}
+    for s in range(0, coords.shape[1], ray_batch_num):
+        q = dict(que, coords=coords[:, s:s + ray_batch_num])
+        for k, v in net.render_impl(q, dict(ref), False).items():
+            if not k.startswith("hit_prob"):
+                acc.setdefault(k, []).append(v)
+    return {k: torch.cat(v, 1) for k, v in acc.items()}
+
+
+def cpu_arm(wl_name, n_rays, steps, warmup, threads=None):
+    """ray-samples/s of the reference's CPU implementation on `n_rays` rays of the workload (same maps, same weights).
+    Returns (value, seconds per pass, kind, threads).  kind = "reference" (baseline/_ref) or "port" (oracle)."""
+    from neuray_b200 import synthetic, renderer
+    wl = WORKLOADS[wl_name]
+    dn_c, dn_f = wl["dn"]
+    cfg = model_cfg(dn_c, dn_f)
+    que, ref = make_workload(wl_name, seed=0)
+    w = que["coords"][0, :, 0].max().int().item() + 1
+    total = que["coords"].shape[1]
+    start = (total // 2 // w) * w + w // 4         # a stretch of rays through the middle of the image
+    q = synthetic.slice_rays(que, start, start + n_rays)
+    ref_mod = _load_reference()
+    if ref_mod is not None:
+        net = reference_net(ref_mod, cfg)
+        run = lambda: reference_render_chunks(net, q, ref, 4096)
+        kind = "reference"
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import neuray_oracle as orc
+        from gen_golden import flat_cfg
+        W = synthetic.make_weights(cfg, seed=0)
+        ocfg = flat_cfg({**renderer.base_cfg, **cfg})
+        run = lambda: orc.render(W, ocfg, q, ref, False, ray_batch_num=4096)
+        kind = "port"
+    cores = os.cpu_count() or 1
+    with torch.no_grad():
+        if threads is None:
+            # "all the host threads it can use": torch's intra-op pool stops scaling long before 128 threads on this op mix
+            # of many small tensors (round 1: 8 -> 61 k, 16 -> 67 k, 32 -> 63 k, 64 -> 22 k, 128 -> 1.6 k ray-samples/s), so the
+            # arm picks the best of a short scan on a 128-ray probe and reports the count it used
+            probe = synthetic.slice_rays(que, start, start + min(128, n_rays))
+            best = (None, 0.0)
+            for th in [t for t in (8, 16, 32, 64) if t <= cores] or [cores]:
+                torch.set_num_threads(th)
+                fn = (lambda: reference_render_chunks(net, probe, ref, 4096)) if kind == "reference" else (lambda: orc.render(W, ocfg, probe, ref, False, ray_batch_num=4096))
+                fn()
+                t0 = time.perf_counter()
+                fn()
+                rate = 1.0 / (time.perf_counter() - t0)
+                if rate > best[1]:
+                    best = (th, rate)
+            threads = best[0]
+        torch.set_num_threads(threads)
+        times = []
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            run()
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    return n_rays * (dn_c + dn_f) / t, t, kind, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    dn_c, dn_f = wl["dn"]
+    n_rays = args.ref_rays
+    v, t, kind, threads = cpu_arm(args.workload, n_rays, args.steps, max(1, min(args.warmup, 1)))
+    sample = f"{n_rays} rays x ({dn_c}+{dn_f}) samples of the workload per step (a contiguous stretch of image rows)"
+    what = ("the UNMODIFIED reference (baseline/_ref): NeuralRayBaseRenderer.render_impl over render()'s chunk loop, encoder outputs given"
+            if kind == "reference" else "oracle port of the reference's PyTorch path (baseline/_ref missing)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "ray-samples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "rays_per_step": n_rays, "note": what + ", host cores"},
+        "cpu_baseline": {"value": v, "unit": "ray-samples/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": "ray-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def eager_gpu_baseline(dq, dr, cfg, dn, dev, rays=4096, reps=3):
+    """GPU-vs-GPU baseline: the UNMODIFIED reference's own render_impl (coarse + fine pass) as PyTorch-eager
+    CUDA ops on the same B200, on one 4096-ray chunk (render.py's default chunk) of the same workload and weights."""
+    ref_mod = _load_reference()
+    if ref_mod is None:
+        return {"unavailable": "baseline/_ref missing (run baseline/install_ref.py before gpurun)"}
+    net = reference_net(ref_mod, cfg, device=dev)
     n = dq["coords"].shape[1]
     start = max(0, n // 2 - rays // 2)                 # a stretch of rays through the middle of the image
-    coords = dq["coords"][:, start:start + rays].contiguous()
-    depth = render_ops.sample_depth(dq["depth_range"], coords, dn, False)[0]
-    P = {f"dist_decoder.{k}": v for k, v in net.dist_decoder.named_parameters()}
-    P.update({f"agg_net.{k}": v for k, v in net.agg_net.named_parameters()})
-    cfgv = {"use_vis_prob": bool(net.dist_decoder.cfg["use_vis"]), "var_bias": float(net.dist_decoder.cfg["bias_val"])}
-    ref = {k: dr[k] for k in ("poses", "Ks", "depth_range", "imgs", "ray_feats", "img_feats")}
-    pe = posenc_table(dn).to(dev)
+    q = dict(dq, coords=dq["coords"][:, start:start + rays].contiguous())
+    r = {k: v for k, v in dr.items() if torch.is_tensor(v)}
 
     def run():
         with torch.no_grad():
-            return render_pass_torch(P, "dist_decoder", "agg_net", cfgv, depth, coords, dq["poses"], dq["Ks"], dq["depth_range"], ref, pe)
+            return net.render_impl(q, dict(r), False)
 
     run()
     torch.cuda.synchronize()
@@ -153,91 +431,27 @@ def eager_gpu_baseline(net, dq, dr, dn, dev, rays=4096, reps=3):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    return {"value": rays * dn / ms * 1e3, "unit": "ray-samples/s", "ms_per_pass": ms, "rays": rays, "samples_per_ray": dn,
-            "what": "one coarse pass as PyTorch-eager ops on the same GPU (autograd_path.render_pass_torch), forward only"}
+    return {"value": rays * 2 * dn / ms * 1e3, "unit": "ray-samples/s", "ms_per_chunk": ms, "rays": rays, "samples_per_ray": 2 * dn,
+            "kind": "reference", "what": "the unmodified reference's render_impl (coarse + fine) as PyTorch-eager CUDA ops on the same GPU, one 4096-ray chunk"}
 
 
-def cpu_threads():
-    """Threads for the CPU arm: the measured optimum on the GPU box's 128-core host is 16 (8: 61 k, 16: 67 k, 32: 63 k,
-    64: 22 k, 128: 1.6 k ray-samples/s on the same rays, profiles/README.md): beyond that torch's intra-op pool only adds
-    contention on this op mix of many small tensors."""
-    return max(1, min(os.cpu_count() or 1, int(os.environ.get("NR_CPU_THREADS", "16"))))
+# ---- headline -----------------------------------------------------------------------------------------------------------------
 
-
-def oracle_throughput(wl, n_rays, steps, warmup, threads):
-    """ray-samples/s of the CPU oracle on `n_rays` rays of the workload (same maps, same weights)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import neuray_oracle as orc
-    from gen_golden import flat_cfg
-    from neuray_b200 import synthetic, renderer
-    h, w, rfn, dn_c, dn_f, _ = WORKLOADS[wl]
-    torch.set_num_threads(threads)
-    cfg = model_cfg(dn_c, dn_f)
-    que, ref = synthetic.make_scene(h, w, rfn, seed=0, smooth=2, with_que_imgs=False)
-    W = synthetic.make_weights(cfg, seed=0)
-    ocfg = flat_cfg({**renderer.base_cfg, **cfg})
-    total = que["coords"].shape[1]
-    start = (total // 2 // w) * w + w // 4         # a stretch of rays through the middle of the image
-    q = synthetic.slice_rays(que, start, start + n_rays)
-    times = []
-    with torch.no_grad():
-        for i in range(warmup + steps):
-            t0 = time.perf_counter()
-            orc.render(W, ocfg, q, ref, False, ray_batch_num=4096)
-            if i >= warmup:
-                times.append(time.perf_counter() - t0)
-    t = sum(times) / len(times)
-    return n_rays * (dn_c + dn_f) / t, t
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    h, w, rfn, dn_c, dn_f, desc = WORKLOADS[args.workload]
-    threads = cpu_threads()
-    n_rays = args.ref_rays
-    v, t = oracle_throughput(args.workload, n_rays, args.steps, max(1, min(args.warmup, 1)), threads)
-    sample = f"{n_rays} rays x ({dn_c}+{dn_f}) samples of the workload per step (a contiguous stretch of image rows)"
-    line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "ray-samples/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "rays_per_step": n_rays, "note": "reference's PyTorch CPU path (oracle port), host cores"},
-        "cpu_baseline": {"value": v, "unit": "ray-samples/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": v, "unit": "ray-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    print(json.dumps(line))
-
-
-def run_b200(args):
-    import torch.distributed as dist
-    from neuray_b200 import _lib, renderer, synthetic
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    h, w, rfn, dn_c, dn_f, desc = WORKLOADS[args.workload]
+def run_headline(ctx, args):
+    from neuray_b200 import _lib
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
+    wl = WORKLOADS[args.workload]
+    rfn, (dn_c, dn_f) = wl["rfn"], wl["dn"]
     cfg = model_cfg(dn_c, dn_f)
     cfg["ray_batch_num"] = args.ray_batch
     # one image per rank: same reference views, a different query pose per rank (seeded)
-    que, ref = synthetic.make_scene(h, w, rfn, seed=0, smooth=2, with_que_imgs=False)
+    que, ref = make_workload(args.workload, seed=0)
     if rank > 0:
-        q2, _ = synthetic.make_scene(h, w, rfn, seed=0, smooth=2, with_que_imgs=False, arc_deg=60.0 + 3.0 * rank)
+        q2, _ = make_workload(args.workload, seed=0, arc_deg=wl["scene"].get("arc_deg", 60.0) + 3.0 * rank)
         que["poses"] = q2["poses"]
-    W = synthetic.make_weights(cfg, seed=0)
-    net = renderer.NeuralRayRenderPath(cfg)
-    net.load_state_dict(W, strict=True)
-    net.to(dev)
+    net = build_net(cfg, dev, seed=0)
     rays = que["coords"].shape[1]
     samples_per_step = rays * (dn_c + dn_f)
-
-    host_que = {k: v.pin_memory() for k, v in que.items()}
-    host_ref = {k: v.pin_memory() for k, v in ref.items()}
-    h2d = sum(v.numel() * v.element_size() for v in list(host_que.values()) + list(host_ref.values()))
     out_keys = ("pixel_colors_nr", "pixel_colors_nr_fine", "render_depth_fine", "ray_mask_fine")
     host_out = {}
     gathered = [torch.empty(1, rays, 3, device=dev) for _ in range(world)] if world > 1 else None
@@ -246,29 +460,13 @@ def run_b200(args):
     def step_device(dq, dr):
         out = net.render(dq, dr, False)
         if world > 1:   # the rendered tiles of all ranks are gathered (north_star: all-gather of the final tiles)
-            dist.all_gather(gathered, out["pixel_colors_nr_fine"])
+            ctx.dist.all_gather(gathered, out["pixel_colors_nr_fine"])
         return out
 
-    # end-to-end arm: double-buffered uploads.  The inputs of step i+1 go up on a copy stream while step i renders (what a
-    # frame loop does); every step still uploads all of its inputs and reads its result back inside the timed region.
-    copy_stream = torch.cuda.Stream(device=dev)
-    pending = {}
-
-    def upload():
-        with torch.cuda.stream(copy_stream):
-            dq = {k: v.to(dev, non_blocking=True) for k, v in host_que.items()}
-            dr = {k: v.to(dev, non_blocking=True) for k, v in host_ref.items()}
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return dq, dr, ev
+    up = Uploader(dev, [pin(que), pin(ref)])
 
     def step_e2e():
-        dq, dr, ev = pending.pop("next") if "next" in pending else upload()
-        cur = torch.cuda.current_stream()
-        cur.wait_event(ev)
-        for t in list(dq.values()) + list(dr.values()):
-            t.record_stream(cur)
-        pending["next"] = upload()
+        dq, dr = up.next()
         out = step_device(dq, dr)
         for k in out_keys:
             if k not in host_out:
@@ -276,61 +474,53 @@ def run_b200(args):
             host_out[k].copy_(out[k], non_blocking=True)
         return out
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item() / 1e3
-
-    # ---- device-resident arm (value) with per-kernel event timing of the dominant kernel ----
+    # ---- device-resident arm (value) with per-kernel event timing of the two kernels of a pass ----
     dq = {k: v.to(dev) for k, v in que.items()}
     dr = {k: v.to(dev) for k, v in ref.items()}
+    step_resident = lambda: step_device(dict(dq), dr)      # the per-frame map repack runs inside every render() call
 
-    def step_resident():
-        dr.pop(renderer.PACK_KEY, None)       # re-pack the maps every frame: it is part of the per-frame path
-        return step_device(dict(dq), dr)
-
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(ctx.local)
     for _ in range(args.warmup):
         step_resident()
-    barrier()
+    ctx.barrier()
     _lib.PROFILE = []
     l0 = _lib.LAUNCHES
     sampler.start()
-    t_res = timed(step_resident, args.steps, 0)
+    t_res = ctx.timed(step_resident, args.steps, 0)
     sampler.stop_flag = True
     launches = _lib.LAUNCHES - l0
     prof, _lib.PROFILE = _lib.PROFILE, None
-    pk_ms = [a.elapsed_time(b) for a, b, _ in prof]
-    pk_samples = [n for _, _, n in prof]
+    pk_ms = [a.elapsed_time(b) for a, b, *_ in prof]
+    rk_ms = [b.elapsed_time(c) for _, b, _, c in prof]
+    pk_samples = [n for _, _, n, _ in prof]
     value = world * samples_per_step * args.steps / t_res
 
     # ---- end-to-end arm ----
-    t_e2e = timed(step_e2e, args.steps, args.warmup)
+    t_e2e = ctx.timed(step_e2e, args.steps, args.warmup)
     d2h = sum(v.numel() * v.element_size() for v in host_out.values())
     e2e_value = world * samples_per_step * args.steps / t_e2e
 
+    # ---- the other BASELINE configurations, measured at this N too (auxiliary; a failure cannot cost the headline) ----
+    aux = {}
+    if not args.no_aux:
+        del up
+        torch.cuda.empty_cache()
+        for name, fn in (("fern_high_sharded", lambda: sharded_image(ctx, 3, 2, e2e=False)), ("train_dtu", lambda: train_step_bench(ctx, 20, 5, e2e=False))):
+            ok = torch.ones(1, device=dev)
+            try:
+                res = fn()
+            except Exception as e:      # keep the ranks in lock step: if any rank failed, all drop this leg
+                res = {"error": f"{type(e).__name__}: {e}"}
+                ok.zero_()
+            if world > 1:
+                ctx.dist.all_reduce(ok, op=ctx.dist.ReduceOp.MIN)
+            aux[name] = res if ok.item() > 0 or "error" in res else {"error": "failed on another rank"}
+            torch.cuda.empty_cache()
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
 
-    peaks = {}
-    peaks_src = "fallback"
+    peaks, peaks_src = {}, "fallback"
     pth = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pth):
         peaks = json.load(open(pth))
@@ -345,50 +535,70 @@ def run_b200(args):
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only (torchrun pins OMP_NUM_THREADS=1)
-        threads = cpu_threads()
-        v, t = oracle_throughput(args.workload, args.cpu_rays, 1, 1, threads)
-        cpu = {"value": v, "unit": "ray-samples/s", "cores": threads, "kind": "port",
+        v, t, kind, threads = cpu_arm(args.workload, args.cpu_rays, 1, 1)
+        cpu = {"value": v, "unit": "ray-samples/s", "cores": threads, "kind": kind,
                "sample": f"{args.cpu_rays} rays x ({dn_c}+{dn_f}) samples of the same workload, 1 warm-up + 1 timed pass, {t:.1f} s"}
 
-    # DRAM bytes of one point-kernel launch from the ncu --set full capture of this kernel at this launch size
-    # (profiles/r1_point_kernel_pm3_v1_ncu.md: dram__bytes_read 57.7 MB + dram__bytes_write 385.1 MB per 65 536-ray launch;
-    # the algorithmic gather of that launch is 36 GB -- the maps stay L2 resident -- and the record written is 335 MB)
-    traffic = 57697280 + 385050624 if (args.workload == "black_800" and args.ray_batch == 65536) else None
+    # DRAM bytes of one point-kernel launch: from the ncu --set full capture of this kernel at this launch size, kept next
+    # to the other profile summaries (profiles/point_kernel_traffic.json: {"<workload>/<ray_batch>": {...}}); null when no
+    # capture of this exact launch shape has been committed
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "point_kernel_traffic.json")
+    if os.path.exists(tp):
+        ent = json.load(open(tp)).get(f"{args.workload}/{args.ray_batch}")
+        if ent:
+            traffic, traffic_src = ent["dram_bytes_read"] + ent["dram_bytes_write"], ent.get("source")
     line = {
         "metric": METRIC, "value": value, "unit": "ray-samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "rays_per_image": rays, "images_per_step_per_gpu": 1, "ray_batch_num": args.ray_batch,
+        "config": {"workload": wl["desc"], "rays_per_image": rays, "images_per_step_per_gpu": 1, "ray_batch_num": args.ray_batch,
                    "parallelism": f"one image per rank x{world}" + (", NCCL all-gather of rendered tiles" if world > 1 else ""),
-                   "e2e_pipeline": "inputs of step i+1 are uploaded on a copy stream while step i renders", "l2": "inputs (143 MB of maps at black_800) exceed the 126 MB L2; no explicit flush"},
+                   "e2e_pipeline": "inputs of step i+1 are uploaded on a copy stream while step i renders",
+                   "l2": "inputs (143 MB of maps at black_800) exceed the 126 MB L2; no explicit flush"},
         "per_gpu": value / world,
-        "e2e": {"value": e2e_value, "unit": "ray-samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "e2e": {"value": e2e_value, "unit": "ray-samples/s", "h2d_bytes_per_step": up_bytes(que, ref), "d2h_bytes_per_step": d2h,
                 "ms_per_step": t_e2e / args.steps * 1e3},
         "gpu_launches": launches,
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "kernel": "nr::pkt::pm3::point_kernel_pm3", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/r1_point_kernel_pm3_v1_ncu.md)", "peak_source": f"{peaks_src} bf16_tflops_sustained",
+                     "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu --set full)",
+                     "traffic_source": traffic_src, "peak_source": f"{peaks_src} bf16_tflops_sustained",
                      "flops_per_ray_sample": fl, "launches": n_launch, "avg_launch_ms": sum(pk_ms) / max(n_launch, 1),
-                     "share_of_step": pk_time / t_res,
-                     "note": "dense layers on tcgen05 with 3xTF32 (3 MMAs per algorithmic one); the kernel is epilogue/latency bound, not tensor-pipe bound (profiles/README.md)"},
+                     "share_of_step": pk_time / t_res, "ray_kernel_share_of_step": sum(rk_ms) / 1e3 / t_res,
+                     "note": "dense layers on tcgen05 with 3xTF32 (3 MMAs per algorithmic one)"},
         "roofline_gather": {"bound": "hbm", "achieved": gather_gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gather_gbs / peak_hbm,
                             "bytes_per_ray_sample": rfn * 1072,
                             "note": "gather runs inside the point kernel; algorithmic bytes / point-kernel time"},
         "cpu_baseline": cpu,
+        "aux": aux,
     }
-    if world == 1 and not args.no_train_step:
-        try:          # auxiliary numbers: never let them cost the headline line
-            line["eager_gpu_baseline"] = eager_gpu_baseline(net, dq, dr, dn_c, dev)
+    if world == 1 and not args.no_aux:
+        try:          # auxiliary: never let it cost the headline line
+            line["eager_gpu_baseline"] = eager_gpu_baseline(dq, dr, cfg, dn_c, dev)
         except Exception as e:
             line["eager_gpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
-        torch.cuda.empty_cache()
-        try:
-            line["training_step"] = training_step(dev)
-        except Exception as e:
-            line["training_step"] = {"error": f"{type(e).__name__}: {e}"}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+
+
+def up_bytes(que, ref):
+    return sum(v.numel() * v.element_size() for d in (que, ref) for v in d.values())
+
+
+def run_aux_as_main(ctx, args):
+    """--workload fern_high / train_dtu as the main line (same schema)."""
+    sampler = ClockSampler(ctx.local)
+    sampler.start()
+    res = sharded_image(ctx, args.steps, args.warmup) if args.workload == "fern_high" else train_step_bench(ctx, args.steps, args.warmup)
+    sampler.stop_flag = True
+    if ctx.rank != 0:
+        return
+    coll = {k: res[k] for k in ("allgather_ms", "allgather_bytes", "allreduce_ms", "allreduce_bytes", "kernels_per_step", "loss") if k in res}
+    line = {"metric": "ray-samples/sec", "value": res["value"], "unit": "ray-samples/s", "n_gpus": ctx.world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": res["scaling"], "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": res["workload"], "parallelism": res["parallelism"]},
+            "e2e": res.get("e2e"), "collective": coll, "clocks": sampler.summary(), "gpu_launches": None}
+    print(json.dumps(line))
 
 
 def main():
@@ -398,16 +608,26 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="black_800", choices=sorted(WORKLOADS))
+    ap.add_argument("--shard", default=None, choices=["images", "rays"], help="fern_high is always ray-sharded; accepted for explicitness")
     ap.add_argument("--ray-batch", type=int, default=65536)
-    ap.add_argument("--cpu-rays", type=int, default=512, help="rays of the workload timed on the CPU oracle (cpu_baseline)")
+    ap.add_argument("--cpu-rays", type=int, default=512, help="rays of the workload timed on the CPU arm (cpu_baseline)")
     ap.add_argument("--ref-rays", type=int, default=512, help="rays per step for --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-train-step", action="store_true", help="skip the auxiliary training-step timing")
+    ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary legs (fern_high sharded, train_dtu, eager GPU baseline)")
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.workload in ("fern_high", "train_dtu"):
+            args.workload = "fern_high" if args.workload == "fern_high" else "black_800"
         run_reference(args)
-    else:
-        run_b200(args)
+        return
+    ctx = Ctx()
+    try:
+        if args.workload in ("fern_high", "train_dtu"):
+            run_aux_as_main(ctx, args)
+        else:
+            run_headline(ctx, args)
+    finally:
+        ctx.close()
 
 
 if __name__ == "__main__":

@@ -372,7 +372,8 @@ def render_chunks(self, que_imgs_info, ref_imgs_info, is_train):
     ref_imgs_info[PACK_KEY] = FramePack(ref_imgs_info)
     que_imgs_info[CAM_KEY] = camera_blocks(que_imgs_info, None)[0]
     try:
-        for ray_id in range(0, ray_num, ray_batch_num):
+        # an empty ray set still runs one (empty) chunk so that the caller gets every key with a zero-length ray axis
+        for ray_id in range(0, max(ray_num, 1), ray_batch_num):
             que_imgs_info["coords"] = coords[:, ray_id:ray_id + ray_batch_num]
             render_info = render_impl(self, que_imgs_info, ref_imgs_info, is_train)
             for k, v in render_info.items():

@@ -59,3 +59,12 @@ def test_sharded_render_and_grad_allreduce_gloo():
         ret = m.dict()
         mp.spawn(_worker, args=(world, _free_port(), 37, ret), nprocs=world, join=True)   # 37 rays: ragged split
         assert dict(ret) == {0: True, 1: True}
+
+
+def test_fewer_rays_than_ranks_does_not_hang():
+    """One ray, two ranks: rank 1's shard is empty; every rank must still issue the collective and get the full result."""
+    world = 2
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_worker, args=(world, _free_port(), 1, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: True, 1: True}

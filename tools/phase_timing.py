@@ -11,12 +11,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 from neuray_b200 import _lib, renderer, synthetic  # noqa: E402
-from neuray_b200.weights import camera_block  # noqa: E402
+from neuray_b200.weights import camera_blocks  # noqa: E402
 
 rays = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
-h, w, rfn, dn_c, dn_f, _ = bench.WORKLOADS["black_800"]
+wl = bench.WORKLOADS["black_800"]
+w, rfn, (dn_c, dn_f) = wl["scene"]["w"], wl["rfn"], wl["dn"]
 cfg = bench.model_cfg(dn_c, dn_f)
-que, ref = synthetic.make_scene(h, w, rfn, seed=0, smooth=2, with_que_imgs=False)
+que, ref = bench.make_workload("black_800", seed=0)
 n = que["coords"].shape[1]
 start = (n // 2 // w) * w
 que = synthetic.slice_rays(que, start, start + rays)
@@ -29,7 +30,7 @@ out = net.render_impl(dq, dr, False)          # warm-up, builds caches
 depth = renderer.sample_depth(dq["depth_range"], dq["coords"], dn_c, False)[0]
 pack = renderer.frame_pack(dr)
 wp, wr, pe, wt = renderer.pass_weights(net, False, dn_c, depth.device)
-cam = camera_block(dq["poses"][0], dq["Ks"][0], dq["depth_range"][0])
+cam, _ = camera_blocks(dq, None)
 rec = torch.empty(rays * dn_c * 20, device="cuda")
 timing = torch.zeros(64 * 2 * 32, dtype=torch.int64, device="cuda")
 p = _lib.NrPassParams()
@@ -42,27 +43,10 @@ p.use_vis, p.var_bias, p.point_rec = 0, 0.05, rec.data_ptr()
 _lib.check(_lib.lib().nr_point_kernel_timing(C.byref(p), timing.data_ptr(), None), "timing")
 torch.cuda.synchronize()
 t = timing.cpu().reshape(64, 2, 32)
-if os.environ.get("NR_POINT_KERNEL", "pm").startswith("pm"):
-    t = timing.cpu().reshape(64, 2, 32)
-    nm = ["geom+proj", "gather", "RF->A", "dd heads", "cprob+pe0", "pe1+nf+raydir", "pool1+hoist", "base0", "base1", "vis0", "vis1", "v20",
-          "rgb0", "blend", "pool2+geo+rec"]
-    for blk in (0, 1):
-        d = (t[4:40, blk, 1:16] - t[4:40, blk, 0:15]).double().mean(0)
-        tot = (t[4:40, blk, 15] - t[4:40, blk, 0]).double().mean()
-        print(f"block {blk}: tile (16 points x 8 views = 128 rows) total {tot:.0f} cycles")
-        print("  " + "  ".join(f"{nm[i]}:{d[i]:.0f}" for i in range(15)))
-    sys.exit(0)
-names = ["start", "geo-wait", "ph1 proj", "ph2 gather", "RF->A", "dd heads", "cprob+pe0", "pe1+nf+raydir", "w1 syncs", "R1", "hoist", "base0",
-         "base1", "vis0", "vis1", "v20", "rgb0", "w2 syncs", "ph9", "geo0", "geo1", "output"]
+nm = ["geom+proj", "gather", "RF->A", "dd heads", "cprob+pe0", "pe1+nf+raydir", "pool1+hoist", "base0", "base1", "vis0", "vis1", "v20",
+      "rgb0", "blend", "pool2+geo+rec"]
 for blk in (0, 1):
-    d = (t[4:40, blk, 1:22] - t[4:40, blk, 0:21]).double().mean(0)
-    tot = (t[4:40, blk, 21] - t[4:40, blk, 0]).double().mean()
-    print(f"block {blk}: tile total {tot:.0f} cycles")
-    print("  " + "  ".join(f"{names[i + 1]}:{d[i]:.0f}" for i in range(21)))
-for blk in (0, 1):
-    m = t[4:40, blk].double()
-    print(f"block {blk} vis_fc.0 layer: st_wait+bar {float((m[:,24]-m[:,22]).mean()):.0f}  wfull-wait {float((m[:,25]-m[:,24]).mean()):.0f}  "
-          f"issue+commit {float((m[:,26]-m[:,25]).mean()):.0f}  mma-wait {float((m[:,27]-m[:,26]).mean()):.0f}  "
-          f"ld32 {float((m[:,29]-m[:,27]).mean()):.0f}  epilogue {float((m[:,28]-m[:,29]).mean()):.0f}  store_a32 {float((m[:,13]-m[:,28]).mean()):.0f}")
-gap = (t[5:40, 0, 0] - t[4:39, 0, 21]).double().mean()
-print(f"gap between tiles {gap:.0f}")
+    d = (t[4:40, blk, 1:16] - t[4:40, blk, 0:15]).double().mean(0)
+    tot = (t[4:40, blk, 15] - t[4:40, blk, 0]).double().mean()
+    print(f"block {blk}: tile (16 points x 8 views = 128 rows) total {tot:.0f} cycles")
+    print("  " + "  ".join(f"{nm[i]}:{d[i]:.0f}" for i in range(15)))

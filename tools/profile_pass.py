@@ -14,9 +14,9 @@ from neuray_b200 import renderer, synthetic  # noqa: E402
 rays = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 wl = sys.argv[2] if len(sys.argv) > 2 else "black_800"
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-h, w, rfn, dn_c, dn_f, _ = bench.WORKLOADS[wl]
+w, (dn_c, dn_f) = bench.WORKLOADS[wl]["scene"]["w"], bench.WORKLOADS[wl]["dn"]
 cfg = bench.model_cfg(dn_c, dn_f)
-que, ref = synthetic.make_scene(h, w, rfn, seed=0, smooth=2, with_que_imgs=False)
+que, ref = bench.make_workload(wl, seed=0)
 n = que["coords"].shape[1]
 start = (n // 2 // w) * w
 que = synthetic.slice_rays(que, start, start + rays)

@@ -1,6 +1,5 @@
 """Training-step timing on the cfg5 shape of SURVEY.md 8d (DTU-like: 8 reference views 300x400 padded to 304x400, 512 rays,
-64+64 samples, is_train=True): forward through the CUDA kernels, backward through the interim PyTorch recompute
-(neuray_b200/autograd_path.py), Adam step.  usage: python tools/train_step_timing.py [rays] [steps]"""
+64+64 samples, is_train=True): forward through the CUDA kernels, native backward (nr_render_pass_bwd + nr_tape_gemms), Adam step.  usage: python tools/train_step_timing.py [rays] [steps]"""
 import os
 import sys
 import time
@@ -74,4 +73,4 @@ ms_t, loss = timeit(train_step, steps)
 samples = rays * 128
 print(f"cfg5 shape, {rays} rays x (64+64) samples, 8 views 304x400")
 print(f"forward only (kernels, is_train=True): {ms_f:.2f} ms/step  ({samples / ms_f / 1e3:.2f} M ray-samples/s)")
-print(f"training step (kernel forward + backward [NR_BACKWARD=native|torch] + Adam): {ms_t:.2f} ms/step  ({samples / ms_t / 1e3:.3f} M ray-samples/s), loss {float(loss):.5f}")
+print(f"training step (kernel forward + native backward + Adam): {ms_t:.2f} ms/step  ({samples / ms_t / 1e3:.3f} M ray-samples/s), loss {float(loss):.5f}")
