@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libneuray_b200.so")
+# NEURAY_B200_LIB: development switch to load another in-tree build of the same library (A/B runs of kernel variants)
+LIB_PATH = os.environ.get("NEURAY_B200_LIB") or os.path.join(_HERE, "libneuray_b200.so")
 
 ABI_VERSION = 4
 NR_POINT_REC = 20

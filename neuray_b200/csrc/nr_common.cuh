@@ -138,9 +138,9 @@ constexpr int V2R = V01 + STAGE;
 constexpr int RD1 = V2R + STAGE;    // ray_dir_fc.2 as a 48-row x K16 tile (hi 1536 | lo 1536), resident in shared memory
 constexpr int RD1_SIZE = 3072;
 constexpr int HST = RD1 + RD1_SIZE;    // the 140 view-pooled inputs of base_fc.0 as a 64-row x K160 tile: hi 5 slabs | lo 5 slabs; K index
-constexpr int HST_SIZE = 2 * 5 * 2048; //   = 24*round + 6*stat + i  (feature 6*round + i; stat = mean0, var0, mean1, var1), resident in shared memory
+constexpr int HST_SIZE = 2 * 5 * 2048; //   = 32*round + 8*stat + i  (feature 8*round + i; stat = mean0, var0, mean1, var1), resident in shared memory
 constexpr int G0 = HST + HST_SIZE;      // geometry_fc.0 on the view-pooled statistics: three ring stages (hi 2048 | lo 2048), 64 rows x K32 each;
-                                        //   K index = 32*round + 12*stat + i (feature 12*round + i; stat = mean, var); K 72 = mean weight, K 73 = bias
+                                        //   K index = 32*round + 16*stat + i (feature 16*round + i; stat = mean, var); K 64 = mean weight, K 65 = bias
 constexpr int TOTAL = G0 + 3 * STAGE;
 }  // namespace tcl
 

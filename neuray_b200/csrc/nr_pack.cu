@@ -83,8 +83,8 @@ __global__ void pack_weights_kernel(const Jobs jobs, const Out out) {
       case J_B0: {   // base_fc.0 [64,207] = [view-pooled 140 | rgb_feat 35 | neuray_feat 32]
         if (i < 140) {
           wp[lay::HOIST_W + i * 64 + o] = v;
-          const int s = i / 35, f = i - 35 * s, r = f / 6, q = f - 6 * r;     // stat, feature -> K = 24 r + 6 s + q
-          put_tc(wt, tcl::HST, 10240, 2048, o, 24 * r + 6 * s + q, v);
+          const int s = i / 35, f = i - 35 * s, r = f >> 3, q = f & 7;        // stat, feature -> K = 32 r + 8 s + q
+          put_tc(wt, tcl::HST, 10240, 2048, o, 32 * r + 8 * s + q, v);
         } else {
           wp[lay::BASE0_W + (i - 140) * 64 + o] = v;
           const int k = i < 175 ? i - 140 : 40 + (i - 175);                    // rgb_feat 35 | bias | 4 zeros | neuray_feat 32
@@ -106,8 +106,8 @@ __global__ void pack_weights_kernel(const Jobs jobs, const Out out) {
       case J_G0: {   // geometry_fc.0 [64,65] = [mean 32 | var 32 | mean weight]
         wp[lay::GRP_D2 + lay::GEO0_W + i * 64 + o] = v;
         int k;
-        if (i < 64) { const int s = i >> 5, f = i & 31, r = f / 12, q = f - 12 * r; k = 32 * r + 12 * s + q; }
-        else k = 72;
+        if (i < 64) { const int s = i >> 5, f = i & 31, r = f >> 4, q = f & 15; k = 32 * r + 16 * s + q; }
+        else k = 64;
         put_tc(wt, tcl::G0, 2048, tcl::STAGE, o, k, v);
         break;
       }
@@ -149,7 +149,7 @@ __global__ void pack_weights_kernel(const Jobs jobs, const Out out) {
       case J_C0: wp[lay::GRP_D1 + lay::RGB0_B + o] = v; break;
       case J_C1: wp[lay::GRP_D1 + lay::RGB1_B + o] = v; break;
       case J_C2: wp[lay::GRP_D1 + lay::RGB2_B + o] = v; break;
-      case J_G0: wp[lay::GRP_D2 + lay::GEO0_B + o] = v; put_tc(wt, tcl::G0, 2048, tcl::STAGE, o, 73, v); break;   // bias = column 73
+      case J_G0: wp[lay::GRP_D2 + lay::GEO0_B + o] = v; put_tc(wt, tcl::G0, 2048, tcl::STAGE, o, 65, v); break;   // bias = column 65
       case J_G1: wp[lay::GRP_D2 + lay::GEO1_B + o] = v; break;
       case J_OG0: wr[lay::OG0_B + o] = v; break;
       case J_OG1: wr[lay::OG1_B + o] = v; break;

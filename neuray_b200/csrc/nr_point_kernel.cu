@@ -131,6 +131,56 @@ __device__ __forceinline__ void bsum_vec(float (&x)[N]) {
   }
 }
 
+// Sum of N (16 or 32) per-row values over the G rows (views) of each point, result in every lane of the point -- through
+// the warp-private transposition buffer instead of N butterflies (3 shuffles + 3 adds per value at G = 8):
+//   every lane stores its row [N] (128-bit stores, row stride 36 floats: conflict-free), lane v of a point then adds up its
+//   N/G columns over the point's G rows (the G lanes of a point read one contiguous N*4-byte stretch per row), writes the
+//   partial row into the point's first row, and every lane reads the N sums back (broadcast reads).  ~57 instructions for
+//   32 values at G = 8 against 192.  `stg`: this warp's [32][36] buffer; lane0: first lane of the point.
+template <int G, int N>
+__device__ __forceinline__ void pool_rows(float* stg, int lane, int lane0, int v, const float (&in)[N], float (&out)[N]) {
+  static_assert(N == 16 || N == 32, "row length");
+  constexpr int C = N / G > 0 ? N / G : 1;          // columns per lane (G = 32, N = 16: lanes >= 16 idle)
+  constexpr int ROW = 36;
+#pragma unroll
+  for (int q = 0; q < N / 4; ++q) *reinterpret_cast<float4*>(stg + lane * ROW + 4 * q) = make_float4(in[4 * q], in[4 * q + 1], in[4 * q + 2], in[4 * q + 3]);
+  __syncwarp();
+  float acc[C];
+#pragma unroll
+  for (int j = 0; j < C; ++j) acc[j] = 0.f;
+  const bool active = v * C < N;
+  if (active) {
+#pragma unroll
+    for (int t = 0; t < G; ++t) {
+      const float* __restrict__ src = stg + (lane0 + t) * ROW + v * C;
+      if constexpr (C >= 4) {
+#pragma unroll
+        for (int j = 0; j < C; j += 4) {
+          const float4 x = *reinterpret_cast<const float4*>(src + j);
+          acc[j] += x.x; acc[j + 1] += x.y; acc[j + 2] += x.z; acc[j + 3] += x.w;
+        }
+      } else if constexpr (C == 2) {
+        const float2 x = *reinterpret_cast<const float2*>(src);
+        acc[0] += x.x; acc[1] += x.y;
+      } else {
+        acc[0] += src[0];
+      }
+    }
+  }
+  __syncwarp();
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < C; ++j) stg[lane0 * ROW + v * C + j] = acc[j];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < N / 4; ++q) {
+    const float4 x = *reinterpret_cast<const float4*>(stg + lane0 * ROW + 4 * q);
+    out[4 * q] = x.x; out[4 * q + 1] = x.y; out[4 * q + 2] = x.z; out[4 * q + 3] = x.w;
+  }
+  __syncwarp();
+}
+
 // The 64/G output columns a lane owns in the streamed per-point layers.  Lane v takes, for q = 0..CPL/4-1, the float4
 // at columns q*4G + 4v: the G lanes of a point then read G consecutive 16-byte chunks (one conflict-free wavefront) for
 // every q, instead of 32-byte chunks whose second halves collide in the banks.  (G = 32: two columns 2v, 2v+1.)

@@ -19,7 +19,12 @@ using pm::bmax;
 using pm::bsum_vec;
 using pm::own_col;
 using pm::ld_cols;
+using pm::pool_rows;
 
+#ifndef NR_GATHER_BATCH
+#define NR_GATHER_BATCH 2     // 4 (16 loads in flight per lane) cost 520 B of spills per thread and 12 % of the kernel (profiles/README.md)
+#endif
+constexpr int GB = NR_GATHER_BATCH;                           // rows whose 4 taps a quarter-warp keeps in flight at once (4 x GB 128-bit loads per lane)
 constexpr int NBLK = 3;
 constexpr int NCOMP = NBLK * 128;
 constexpr int NTHR = NCOMP;
@@ -263,8 +268,11 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
     b.prod = tid == 0 ? &prod : nullptr;
     if (tid == 0) prod.feed(0);
 
-#define PM_TICK(id)                                                                          \
-  if (kp.timing != nullptr && blockIdx.x == 0 && b.leader && b.blk < 2 && it < 64) kp.timing[(it * 2 + b.blk) * 32 + (id)] = clock64();
+  // phase stamps exist only in the DEBUG instantiation (nr_point_kernel_timing / nr_point_kernel_debug)
+#define PM_TICK(id)                                                                                      \
+  if constexpr (DEBUG) {                                                                                 \
+    if (kp.timing != nullptr && blockIdx.x == 0 && b.leader && b.blk < 2 && it < 64) kp.timing[(it * 2 + b.blk) * 32 + (id)] = clock64(); \
+  }
     for (int it = 0; it < iters; ++it) {
       const int tile = (it * int(gridDim.x) + int(blockIdx.x)) * NBLK + b.blk;
       if (tile >= n_tiles) {
@@ -372,12 +380,12 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
         const int qw = lane >> 3, l = lane & 7;
         __syncwarp();
 #pragma unroll 1
-        for (int rb = 0; rb < 32; rb += 16) {
-          float4 t[4][4];
-          float wq[4][4];
-          bool on[4];
+        for (int rb = 0; rb < 32; rb += 4 * GB) {
+          float4 t[GB][4];
+          float wq[GB][4];
+          bool on[GB];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < GB; ++u) {
             const int j = rb + 4 * u + qw;                                   // row (= lane) whose texels this quarter-warp fetches
             const int code = __shfl_sync(0xffffffffu, tcode, j);
 #pragma unroll
@@ -391,7 +399,7 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
             }
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < GB; ++u) {
             const int j = rb + 4 * u + qw;
             float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
             if (on[u]) {
@@ -566,46 +574,40 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
       }
 
       PM_TICK(6)
-      // ---------------- view pooling #1 (ibrnet.py:336-339) -> six more K rounds of base_fc.0 ----------------
-      // Every lane of a point ends the butterflies with the point's statistics, which is exactly its row of the
-      // view-invariant operand: 6 features x (mean0, var0, mean1, var1) = K 24 per round go to A[0:24] and are
-      // multiplied into the same accumulator.  The previous round's MMAs finish under this round's butterflies.
+      // ---------------- view pooling #1 (ibrnet.py:336-339) -> five more K rounds of base_fc.0 ----------------
+      // Every lane of a point ends a round with the point's statistics, which is exactly its row of the view-invariant
+      // operand: 8 features x (mean0, var0, mean1, var1) = K 32 per round go to A[0:32) and are multiplied into the same
+      // accumulator.  The previous round's MMAs finish under this round's reduction.  The sums over the views go through the
+      // warp's transposition buffer (pool_rows); the variance comes from the weighted second moment:
+      //   sum_v w (x - mu)^2 = sum_v w x^2 - mu^2 (2 - sum_v w),  mu = sum_v w x   (the reference's mean is NOT normalised)
       const float msum = bsum<G>(mrow);
       const float w1 = mrow / (msum + 1e-8f);
       const float w0 = sigmoidf_(gate) * w1;
       {
+        const float c1 = 2.f - bsum<G>(w1), c0 = 2.f - bsum<G>(w0);
         const uint32_t hst = tc::smem_u32(smem + OFF_HST);
         const int wq = __shfl_sync(0xffffffffu, warp, 0) & 3;
         auto round = [&](auto rc) {
           constexpr int R = decltype(rc)::value;
-          float val[6], st[24];
+          float in[32], st[32];
 #pragma unroll
-          for (int i = 0; i < 6; ++i) {
-            val[i] = (6 * R + i < 35) ? rf[6 * R + i] : 0.f;
-            st[i] = val[i] * w0; st[12 + i] = val[i] * w1;
+          for (int i = 0; i < 8; ++i) {
+            const float x = (8 * R + i < 35) ? rf[8 * R + i] : 0.f;
+            const float p0 = x * w0, p1 = x * w1;
+            in[i] = p0; in[8 + i] = p0 * x; in[16 + i] = p1; in[24 + i] = p1 * x;
           }
-          {
-            float mm[12];
+          pool_rows<G, 32>(stg, lane, lane0, v, in, st);
 #pragma unroll
-            for (int i = 0; i < 6; ++i) { mm[i] = st[i]; mm[6 + i] = st[12 + i]; }
-            bsum_vec<G, 12>(mm);
-            float vv_[12];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-              const float d0 = val[i] - mm[i], d1 = val[i] - mm[6 + i];
-              vv_[i] = w0 * d0 * d0; vv_[6 + i] = w1 * d1 * d1;
-            }
-            bsum_vec<G, 12>(vv_);
-#pragma unroll
-            for (int i = 0; i < 6; ++i) { st[i] = mm[i]; st[6 + i] = vv_[i]; st[12 + i] = mm[6 + i]; st[18 + i] = vv_[6 + i]; }
+          for (int i = 0; i < 8; ++i) {
+            st[8 + i] = fmaf(-st[i] * st[i], c0, st[8 + i]);
+            st[24 + i] = fmaf(-st[16 + i] * st[16 + i], c1, st[24 + i]);
           }
-          wait_layer(b);                                                             // the MMAs reading A[0:48) have completed
-          st16(b, 0, 24, st);
-          st8(b, 16, 40, st + 16);
-          issue_layer_resident<64, 3, 0, 24, 96, 3 * R, 10240 * 4, 2048 * 4, true>(b, hst, wq == (R & 3));
+          wait_layer(b);                                                             // the MMAs reading A[0:96) have completed
+          st32(b, 0, 32, st);
+          issue_layer_resident<64, 4, 0, 32, 96, 4 * R, 10240 * 4, 2048 * 4, true>(b, hst, wq == (R & 3));
         };
         round(std::integral_constant<int, 0>{}); round(std::integral_constant<int, 1>{}); round(std::integral_constant<int, 2>{});
-        round(std::integral_constant<int, 3>{}); round(std::integral_constant<int, 4>{}); round(std::integral_constant<int, 5>{});
+        round(std::integral_constant<int, 3>{}); round(std::integral_constant<int, 4>{});
       }
 
       PM_TICK(7)
@@ -718,34 +720,33 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
       {
         const float vs = bsum<G>(vis2);
         const float w2 = vis2 / (vs + 1e-8f);
-        const float wmean = bsum<G>(w2) / float(rfn);
-        // three K rounds of 12 features x (mean, var), one ring stage each; the last one also carries the mean weight
-        // and the constant that multiplies the bias column
+        const float sw2 = bsum<G>(w2);
+        const float wmean = sw2 / float(rfn);
+        // two K rounds of 16 features x (mean, var) and a third with the mean weight and the constant that multiplies the
+        // bias column, one ring stage each; sums over the views through pool_rows, variance from the second moment (above)
+        const float c2 = 2.f - sw2;
         auto ground = [&](auto rc) {
           constexpr int R = decltype(rc)::value;
-          constexpr int NF = R == 2 ? 8 : 12;
-          float st[24];
+          float in[32], st[32];
 #pragma unroll
-          for (int i = 0; i < 24; ++i) st[i] = 0.f;
-          {
-            float mm[NF];
+          for (int i = 0; i < 16; ++i) { const float p = xr[16 * R + i] * w2; in[i] = p; in[16 + i] = p * xr[16 * R + i]; }
+          pool_rows<G, 32>(stg, lane, lane0, v, in, st);
 #pragma unroll
-            for (int i = 0; i < NF; ++i) mm[i] = xr[12 * R + i] * w2;
-            bsum_vec<G, NF>(mm);
-            float vv_[NF];
-#pragma unroll
-            for (int i = 0; i < NF; ++i) { const float d0 = xr[12 * R + i] - mm[i]; vv_[i] = w2 * d0 * d0; }
-            bsum_vec<G, NF>(vv_);
-#pragma unroll
-            for (int i = 0; i < NF; ++i) { st[i] = mm[i]; st[12 + i] = vv_[i]; }
-            if (R == 2) { st[8] = wmean; st[9] = 1.f; }
-          }
-          if (R > 0) wait_layer(b);                                                  // the previous round has read A[0:48)
-          st16(b, 0, 24, st);
-          st8(b, 16, 40, st + 16);
-          issue_layer<64, 3, 0, 24, 3, 0, 96, 0, 1, 0, 2048 * 4, 0, true, true, (R > 0)>(b);
+          for (int i = 0; i < 16; ++i) st[16 + i] = fmaf(-st[i] * st[i], c2, st[16 + i]);
+          if (R > 0) wait_layer(b);                                                  // the previous round has read A[0:64)
+          st32(b, 0, 32, st);
+          issue_layer<64, 4, 0, 32, 4, 0, 96, 0, 1, 0, 2048 * 4, 0, true, true, (R > 0)>(b);
         };
-        ground(std::integral_constant<int, 0>{}); ground(std::integral_constant<int, 1>{}); ground(std::integral_constant<int, 2>{});
+        ground(std::integral_constant<int, 0>{}); ground(std::integral_constant<int, 1>{});
+        {
+          float st[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) st[i] = 0.f;
+          st[0] = wmean; st[1] = 1.f;
+          wait_layer(b);
+          st8(b, 0, 32, st);
+          issue_layer<64, 1, 0, 32, 1, 0, 96, 0, 1, 0, 2048 * 4, 0, true, true, true>(b);
+        }
         wait_layer(b);
         // all G rows of a point hold the same 64 hidden pre-activations; lane v keeps columns [v*CPL, (v+1)*CPL)
         float hh[CPL];
@@ -771,9 +772,12 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
 #pragma unroll
           for (int j = 0; j < CPL; ++j) out[k] = fmaf(wk[j], hh[j], out[k]);
         }
-        bsum_vec<G, 16>(out);
+        {
+          float sum[16];
+          pool_rows<G, 16>(stg, lane, lane0, v, out, sum);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) out[k] = elu(out[k] + sWg1[64 * 16 + k]);
+          for (int k = 0; k < 16; ++k) out[k] = elu(sum[k] + sWg1[64 * 16 + k]);
+        }
         if (v == 0 && pt_ok) {
           float4* __restrict__ dst = reinterpret_cast<float4*>(pp.point_rec + size_t(n) * REC);
           dst[0] = make_float4(out[0], out[1], out[2], out[3]); dst[1] = make_float4(out[4], out[5], out[6], out[7]);

@@ -24,7 +24,7 @@ struct KParams {
 
 __device__ __forceinline__ float warp_sum(float v) { return warp_sum_f(v); }
 
-__global__ void __launch_bounds__(256) ray_kernel(const KParams kp) {
+__global__ void __launch_bounds__(512) ray_kernel(const KParams kp) {
   extern __shared__ __align__(16) float smem[];
   const NrPassParams& pp = kp.p;
   const int dn = pp.dn, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -32,8 +32,10 @@ __global__ void __launch_bounds__(256) ray_kernel(const KParams kp) {
   float* const sW = smem;                                   // lay::TOTAL_RAY
   float* const sPE = sW + lay::TOTAL_RAY;                   // [dn][ROW]
   float* const wbase = sPE + dn * ROW + size_t(warp) * kp.per_warp;
-  float* const sX = wbase;                                  // [dn][ROW] attention input (residual)
-  float* const sK = sX + dn * ROW;
+  // per warp: K and V rows of the ray's samples.  The attention input x = g + pos_enc is NOT kept: a lane re-reads its own
+  // sample's 64 bytes (L2 hit) when it needs them again, which brings a warp's footprint from 16.4 KB to 11.3 KB at dn = 64
+  // and lets 16 warps share an SM instead of 8 (the kernel is latency bound: ncu short_scoreboard 2.2 per issue at 12 % occupancy)
+  float* const sK = wbase;                                  // [dn][ROW]
   float* const sV = sK + dn * ROW;
   float* const sHit = sV + dn * ROW;                        // [dn]
   float* const sT = sHit + dn;                              // [dn]   normalised inverse depth
@@ -71,7 +73,6 @@ __global__ void __launch_bounds__(256) ray_kernel(const KParams kp) {
       }
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
-        *reinterpret_cast<float4*>(sX + s * ROW + 4 * q4) = make_float4(x[4 * q4], x[4 * q4 + 1], x[4 * q4 + 2], x[4 * q4 + 3]);
         *reinterpret_cast<float4*>(sK + s * ROW + 4 * q4) = make_float4(kk[4 * q4], kk[4 * q4 + 1], kk[4 * q4 + 2], kk[4 * q4 + 3]);
         *reinterpret_cast<float4*>(sV + s * ROW + 4 * q4) = make_float4(vv[4 * q4], vv[4 * q4 + 1], vv[4 * q4 + 2], vv[4 * q4 + 3]);
       }
@@ -85,9 +86,10 @@ __global__ void __launch_bounds__(256) ray_kernel(const KParams kp) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) q[j] = 0.f;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const float4 t4 = *reinterpret_cast<const float4*>(sX + s * ROW + 4 * q4);
-          x[4 * q4] = t4.x; x[4 * q4 + 1] = t4.y; x[4 * q4 + 2] = t4.z; x[4 * q4 + 3] = t4.w;
+        for (int q4 = 0; q4 < 4; ++q4) {      // the same expression as in phase A: bit-identical x
+          const float4 g = __ldg(reinterpret_cast<const float4*>(rec + s * REC) + q4);
+          const float4 pe = *reinterpret_cast<const float4*>(sPE + s * ROW + 4 * q4);
+          x[4 * q4 + 0] = g.x + pe.x; x[4 * q4 + 1] = g.y + pe.y; x[4 * q4 + 2] = g.z + pe.z; x[4 * q4 + 3] = g.w + pe.w;
         }
 #pragma unroll
         for (int k = 0; k < 16; ++k)
@@ -237,11 +239,11 @@ int launch_ray_kernel(const NrPassParams* p, cudaStream_t stream) {
   if (p->fine_dn > 0) {
     kp.sort_n = sort_size_for(p->fine_dn + (p->fine_use_all ? p->dn : 0));
   }
-  kp.per_warp = p->dn * 3 * rk::ROW + p->dn * 3 + 8 + kp.sort_n;
+  kp.per_warp = p->dn * 2 * rk::ROW + p->dn * 3 + 8 + kp.sort_n;
   kp.per_warp = (kp.per_warp + 3) & ~3;
   const int shared_common = lay::TOTAL_RAY + p->dn * rk::ROW;
-  int warps = 8;
-  while (warps > 1 && size_t(shared_common + warps * kp.per_warp) * 4 > 200 * 1024) warps >>= 1;
+  int warps = 16;
+  while (warps > 1 && size_t(shared_common + warps * kp.per_warp) * 4 > 216 * 1024) warps >>= 1;
   kp.warps = warps;
   const size_t smem = size_t(shared_common + warps * kp.per_warp) * 4;
   NR_CHECK_ARG(smem <= 227 * 1024, "ray kernel shared memory");
@@ -251,7 +253,7 @@ int launch_ray_kernel(const NrPassParams* p, cudaStream_t stream) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int grid = (p->rn + warps - 1) / warps;
-  const int cap = sms * 8;
+  const int cap = sms * 4;
   if (grid > cap) grid = cap;
   rk::ray_kernel<<<grid, warps * 32, smem, stream>>>(kp);
   NR_CHECK_LAUNCH("ray_kernel");

@@ -195,24 +195,24 @@ def pack_tc_weights(params, dec, agg, device=None, _comp=None):
     wrd = torch.zeros(48, 16, dtype=torch.float32, device=device)         # ray_dir_fc.2 [35, 16] -> 48 rows (MMA N % 16 == 0)
     wrd[:35] = g(f"{ib}.ray_dir_fc.2.weight").detach().float().to(device)
     put(T.rd1, wrd, 16, 1536)
-    # view-pooled inputs of base_fc.0 (ibrnet.py:338-342): K = 24*round + 6*stat + i <-> reference column stat*35 + 6*round + i
+    # view-pooled inputs of base_fc.0 (ibrnet.py:338-342): K = 32*round + 8*stat + i <-> reference column stat*35 + 8*round + i
     bh = torch.zeros(64, 160, dtype=torch.float32, device=device)
-    for r_ in range(6):
+    for r_ in range(5):
         for s_ in range(4):
-            n_ = min(6, 35 - 6 * r_)
-            bh[:, 24 * r_ + 6 * s_: 24 * r_ + 6 * s_ + n_] = w0[:, s_ * 35 + 6 * r_: s_ * 35 + 6 * r_ + n_]
+            n_ = min(8, 35 - 8 * r_)
+            bh[:, 32 * r_ + 8 * s_: 32 * r_ + 8 * s_ + n_] = w0[:, s_ * 35 + 8 * r_: s_ * 35 + 8 * r_ + n_]
     hi, lo = _tc_tiles(bh, 160)
     buf[T.hst: T.hst + 10240] = hi
     buf[T.hst + 10240: T.hst + 20480] = lo
-    # geometry_fc.0 on the second view pooling (ibrnet.py:352-354): K = 32*round + 12*stat + i <-> reference column stat*32 + 12*round + i
+    # geometry_fc.0 on the second view pooling (ibrnet.py:352-354): K = 32*round + 16*stat + i <-> reference column stat*32 + 16*round + i;
+    # third stage: K 64 = mean weight, K 65 = bias (constant-1 input)
     wg = g(f"{ib}.geometry_fc.0.weight").detach().float().to(device)     # [64, 65]: mean 32 | var 32 | mean weight
     bg = torch.zeros(64, 96, dtype=torch.float32, device=device)
-    for r_ in range(3):
-        n_ = min(12, 32 - 12 * r_)
+    for r_ in range(2):
         for s_ in range(2):
-            bg[:, 32 * r_ + 12 * s_: 32 * r_ + 12 * s_ + n_] = wg[:, s_ * 32 + 12 * r_: s_ * 32 + 12 * r_ + n_]
-    bg[:, 72] = wg[:, 64]
-    bg[:, 73] = g(f"{ib}.geometry_fc.0.bias").detach().float().to(device)
+            bg[:, 32 * r_ + 16 * s_: 32 * r_ + 16 * s_ + 16] = wg[:, s_ * 32 + 16 * r_: s_ * 32 + 16 * r_ + 16]
+    bg[:, 64] = wg[:, 64]
+    bg[:, 65] = g(f"{ib}.geometry_fc.0.bias").detach().float().to(device)
     hi, lo = _tc_tiles(bg, 96)
     for s_ in range(3):
         buf[T.g0 + s_ * T.stage: T.g0 + s_ * T.stage + 2048] = hi[s_ * 2048:(s_ + 1) * 2048]

@@ -104,16 +104,17 @@ def test_tc_weight_pack_roundtrip():
     assert torch.equal(rec[:, 35], W["agg_net.agg_impl.base_fc.0.bias"])             # bias column (constant-1 input)
     assert float(rec[:, 36:40].abs().sum()) == 0.0 and float(rec[:, 72:].abs().sum()) == 0.0
     hst = unswz(buf[T.hst:T.hst + 10240], 64) + unswz(buf[T.hst + 10240:T.hst + 20480], 64)          # [64, 160]
-    for r_, s_, i_ in ((0, 0, 0), (2, 1, 3), (5, 3, 4), (4, 2, 5)):
-        assert torch.equal(hst[:, 24 * r_ + 6 * s_ + i_], w0[:, s_ * 35 + 6 * r_ + i_])
-    assert float(hst[:, 24 * 5 + 5].abs().sum()) == 0.0 and float(hst[:, 144:].abs().sum()) == 0.0    # feature 35 does not exist
+    for r_, s_, i_ in ((0, 0, 0), (2, 1, 3), (4, 3, 2), (3, 2, 7)):
+        assert torch.equal(hst[:, 32 * r_ + 8 * s_ + i_], w0[:, s_ * 35 + 8 * r_ + i_])
+    for s_ in range(4):                                                                                  # features 35..39 do not exist
+        assert float(hst[:, 32 * 4 + 8 * s_ + 3: 32 * 4 + 8 * s_ + 8].abs().sum()) == 0.0
     wg = W["agg_net.agg_impl.geometry_fc.0.weight"]
     geo = torch.cat([unswz(buf[T.g0 + s * T.stage:T.g0 + s * T.stage + 2048], 64) +
                      unswz(buf[T.g0 + s * T.stage + 2048:T.g0 + (s + 1) * T.stage], 64) for s in range(3)], 1)      # [64, 96]
-    for r_, s_, i_ in ((0, 0, 0), (1, 1, 11), (2, 0, 7), (2, 1, 7)):
-        assert torch.equal(geo[:, 32 * r_ + 12 * s_ + i_], wg[:, s_ * 32 + 12 * r_ + i_])
-    assert torch.equal(geo[:, 72], wg[:, 64]) and torch.equal(geo[:, 73], W["agg_net.agg_impl.geometry_fc.0.bias"])
-    assert float(geo[:, 24:32].abs().sum()) == 0.0 and float(geo[:, 74:76].abs().sum()) == 0.0 and float(geo[:, 84:].abs().sum()) == 0.0
+    for r_, s_, i_ in ((0, 0, 0), (1, 1, 15), (1, 0, 7), (0, 1, 7)):
+        assert torch.equal(geo[:, 32 * r_ + 16 * s_ + i_], wg[:, s_ * 32 + 16 * r_ + i_])
+    assert torch.equal(geo[:, 64], wg[:, 64]) and torch.equal(geo[:, 65], W["agg_net.agg_impl.geometry_fc.0.bias"])
+    assert float(geo[:, 66:].abs().sum()) == 0.0
     # prob_embed.2 + neuray_fc.0 behind it: 48-row tile, hi 0..1536, lo 1536..3072
     rec = unswz(buf[T.pe1:T.pe1 + 1536], 48) + unswz(buf[T.pe1 + 1536:T.pe1 + 3072], 48)
     wpe, wnf = W["agg_net.prob_embed.2.weight"], W["agg_net.agg_impl.neuray_fc.0.weight"]

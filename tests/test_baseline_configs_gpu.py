@@ -96,10 +96,11 @@ def test_cfg2_black_400():
 def test_benched_workload_black_800():
     sys.path.insert(0, ROOT)
     import bench
-    h, w, rfn, dn_c, dn_f, _ = bench.WORKLOADS["black_800"]
-    cfg = bench.model_cfg(dn_c, dn_f)
-    check(dict(h=h, w=w, rfn=rfn, seed=0, smooth=2, with_que_imgs=False), cfg, 0, w, h, head={})       # exactly what bench.py renders
-    check(dict(h=h, w=w, rfn=rfn, seed=0, smooth=2, with_que_imgs=False), cfg, 0, w, h)                # same maps, softer density head
+    wl = bench.WORKLOADS["black_800"]
+    cfg = bench.model_cfg(*wl["dn"])
+    scene = dict(wl["scene"], rfn=wl["rfn"], seed=0, smooth=2, with_que_imgs=False)                     # = bench.make_workload("black_800")
+    check(scene, cfg, 0, 800, 800, head={})       # exactly what bench.py renders
+    check(scene, cfg, 0, 800, 800)                # same maps, softer density head
 
 
 def test_cfg3_black_800_fine_use_all_128():

@@ -12,9 +12,9 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def setup():
-    h, w, rfn, dn_c, dn_f, _ = bench.WORKLOADS["black_800"]
+    w, (dn_c, dn_f) = bench.WORKLOADS["black_800"]["scene"]["w"], bench.WORKLOADS["black_800"]["dn"]
     cfg = bench.model_cfg(dn_c, dn_f)
-    que, ref = synthetic.make_scene(h, w, rfn, seed=0, smooth=2, with_que_imgs=False)
+    que, ref = bench.make_workload("black_800", seed=0)
     n = que["coords"].shape[1]
     start = (n // 2 // w) * w + 123
     que = synthetic.slice_rays(que, start, start + 12345)          # ragged: not a multiple of the 32-point tile or the chunk

@@ -17,6 +17,17 @@ from neuray_b200 import patch, synthetic
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def fp32_convolutions():
+    """cuDNN runs fp32 convolutions through TF32 by default; the encoders in front of the path would then turn a 1e-6
+    difference in the feature-map gradients into a 1e-2 difference of their own weight gradients (sums with heavy
+    cancellation), which says nothing about the path under test."""
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = old
+
 DN = 24
 CFG = {"init_net_type": "depth", "use_hierarchical_sampling": True, "use_depth_loss": True, "dist_decoder_cfg": {"use_vis": False},
        "depth_sample_num": DN, "fine_depth_sample_num": DN, "agg_net_cfg": {"sample_num": DN}, "fine_agg_net_cfg": {"sample_num": DN},
@@ -50,7 +61,9 @@ def make_data(rfn=6, rays=384, self_feats=False, seed=3):
 def build(ref_mod, cfg, seed=0):
     torch.manual_seed(seed)
     net = ref_mod.NeuralRayGenRenderer(cfg)
-    W = synthetic.make_weights(cfg, seed=seed)            # hot-path modules: random init with a density head that terminates rays
+    # hot-path modules: random init with a density head that terminates rays gradually (the default head of make_weights
+    # multiplies the last density layer by 8, which also multiplies fp32 summation-order noise between cuBLAS and the kernels)
+    W = synthetic.make_weights(cfg, seed=seed, sigma_gain=1.0, sigma_bias=0.02)
     missing, unexpected = net.load_state_dict(W, strict=False)
     assert not unexpected
     return net.cuda()
@@ -110,7 +123,7 @@ def test_training_forward_and_every_gradient(ref_mod, self_hit):
     net = build(ref_mod, cfg).train()
     grads = {}
     outs = {}
-    for mode in ("reference", "patched"):
+    for mode in ("reference", "reference_again", "patched"):       # the second reference run measures the run-to-run noise floor
         if mode == "patched":
             patch.install()
         try:
@@ -123,7 +136,7 @@ def test_training_forward_and_every_gradient(ref_mod, self_hit):
         outs[mode] = {k: v.detach().clone() for k, v in out.items()}
         grads[mode] = {k: (p.grad.detach().clone() if p.grad is not None else None) for k, p in net.named_parameters()}
     compare_outputs(outs["patched"], outs["reference"], fine_bad_frac=0.01)
-    checked, flows_upstream = 0, 0
+    checked, flows_upstream, worst = 0, 0, (0.0, "")
     for k, g_ref in grads["reference"].items():
         g = grads["patched"][k]
         if g_ref is None or float(g_ref.abs().max()) == 0.0:
@@ -132,10 +145,13 @@ def test_training_forward_and_every_gradient(ref_mod, self_hit):
         assert g is not None, f"{k}: the patched network sends no gradient here"
         scale = float(g_ref.abs().max())
         err = float((g - g_ref).abs().max())
-        assert err <= 2e-3 * scale + 1e-7, (k, err, scale)
+        floor = float((grads["reference_again"][k] - g_ref).abs().max())      # atomics / algorithm choice in the reference itself
+        worst = max(worst, (err / scale, k))
+        assert err <= 2e-3 * scale + 4 * floor + 1e-7, (k, err, scale, floor)
         checked += 1
         if k.split(".")[0] in ("image_encoder", "vis_encoder", "init_net"):
             flows_upstream += 1
+    print(f"worst relative gradient difference {worst[0]:.2e} ({worst[1]}), {checked} parameters, {flows_upstream} upstream of the path")
     assert checked > 250 and flows_upstream > 100, (checked, flows_upstream)
 
 
