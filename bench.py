@@ -266,7 +266,7 @@ def train_step_bench(ctx, steps, warmup, e2e=True):
         loss.backward()
         nrd.allreduce_gradients(net.parameters(), timing=coll)
         opt.step()
-        state["loss"] = loss
+        state["loss"] = loss.detach()
         return loss
 
     l0 = _lib.LAUNCHES

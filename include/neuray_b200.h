@@ -200,6 +200,14 @@ int nr_interpolate_feats_bwd(const float* d_out, const float* pts, const float* 
 int nr_sample_fine_depth(const float* depth, const float* hit_prob, const float* depth_range, int rn, int dn, int fine_dn,
                          const float* u, int u_stride, int use_all, int do_sort, float* out, void* stream);
 
+/* ---- DepthInitNet.get_diff_feats (reference network/init_net.py:29-61) -----------------------------
+ * imgs [rfn,3,h,w], depth_in [rfn,1,h,w] (normalised inverse depth in [0,1], extract_depth_for_init), poses [rfn,3,4],
+ * Ks [rfn,3,3], view_params [rfn,20] (nr_camera_blocks with the views' depth ranges) -> out [rfn,8,h,w] =
+ * rgb_mean (3) | rgb_var (3) | dpt_mean | dpt_var of the reprojection differences, pooled over the views that see the pixel.
+ * One fused launch: rfn^2 * h * w reprojections + gathers in registers, none of the reference's intermediates. */
+int nr_diff_feats(const float* imgs, const float* depth_in, const float* poses, const float* Ks, const float* view_params,
+                  int rfn, int h, int w, float* out, void* stream);
+
 /* ---- training: backward of one pass -------------------------------------------------------------------------- */
 
 /* Backward of nr_render_pass_fwd for the same NrPassParams (reference: loss.backward() through renderer.py:168-203;

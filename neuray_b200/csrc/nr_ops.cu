@@ -424,3 +424,114 @@ int nr_sample_fine_depth(const float* depth, const float* hit_prob, const float*
 }
 
 }  // extern "C"
+
+// ---- DepthInitNet.get_diff_feats (reference network/init_net.py:14-61) ---------------------------------------------
+// For every pixel of every reference view: back-project with the view's (normalised inverse) depth, re-project into all
+// rfn views, sample their depth maps and images there (bilinear, border clamp, align_corners), and pool the absolute
+// colour / inverse-depth differences over the views that see the point: masked mean and variance -> 8 channels.
+// One thread per (view, pixel); the rfn re-projections are a loop in registers, so none of the reference's
+// [rfn, rfn*h*w, *] intermediates exists.  vp: view_params [rfn,20] (K@Rt | centre | -1/near, -1/far | pad), kinv [rfn,9].
+namespace nr {
+namespace ops {
+
+__device__ __forceinline__ float bil1(const float* __restrict__ pl, int w, int xa, int xb, int ya, int yb, float w00, float w01, float w10,
+                                      float w11) {
+  return pl[ya * w + xa] * w00 + pl[ya * w + xb] * w01 + pl[yb * w + xa] * w10 + pl[yb * w + xb] * w11;
+}
+
+__global__ void diff_feats_kernel(const float* __restrict__ imgs, const float* __restrict__ depth_in, const float* __restrict__ poses,
+                                  const float* __restrict__ Ks, const float* __restrict__ vps, int rfn, int h, int w,
+                                  float* __restrict__ out) {
+  __shared__ float kinv[NR_MAX_VIEWS * 9];     // K^-1 per view (closed form in fp64, rounded once; reference: torch.inverse)
+  for (int t = threadIdx.x; t < rfn; t += blockDim.x) {
+    double k[9], inv[9];
+    for (int e = 0; e < 9; ++e) k[e] = double(Ks[9 * t + e]);
+    const double det = k[0] * (k[4] * k[8] - k[5] * k[7]) - k[1] * (k[3] * k[8] - k[5] * k[6]) + k[2] * (k[3] * k[7] - k[4] * k[6]);
+    inv[0] = (k[4] * k[8] - k[5] * k[7]) / det; inv[1] = (k[2] * k[7] - k[1] * k[8]) / det; inv[2] = (k[1] * k[5] - k[2] * k[4]) / det;
+    inv[3] = (k[5] * k[6] - k[3] * k[8]) / det; inv[4] = (k[0] * k[8] - k[2] * k[6]) / det; inv[5] = (k[2] * k[3] - k[0] * k[5]) / det;
+    inv[6] = (k[3] * k[7] - k[4] * k[6]) / det; inv[7] = (k[1] * k[6] - k[0] * k[7]) / det; inv[8] = (k[0] * k[4] - k[1] * k[3]) / det;
+    for (int e = 0; e < 9; ++e) kinv[9 * t + e] = float(inv[e]);
+  }
+  __syncthreads();
+  const long long hw = (long long)h * w, total = (long long)rfn * hw;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int i = int(idx / hw);
+    const long long px = idx - (long long)i * hw;
+    const int y = int(px / w), x = int(px - (long long)y * w);
+    // depth_in in [0,1] -> metric depth of view i (init_net.py:34-35)
+    const float* __restrict__ vi = vps + i * 20;
+    const float near_inv = vi[15], far_inv = vi[16];
+    const float z = -1.f / (__ldg(depth_in + idx) * (far_inv - near_inv) + near_inv);
+    // pts3d = R^T (K^-1 [x z, y z, z]) + (-R^T t)   (depth2pts3d, init_net.py:14-27; t = centre of view i)
+    const float* ki = kinv + i * 9;
+    const float* __restrict__ P = poses + i * 12;
+    const float cx = float(x) * z, cy = float(y) * z;
+    float c[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) c[r] = ki[3 * r] * cx + ki[3 * r + 1] * cy + ki[3 * r + 2] * z;
+    float X[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) X[r] = (P[r] * c[0] + P[4 + r] * c[1] + P[8 + r] * c[2]) + vi[12 + r];
+    const float r0 = __ldg(imgs + ((long long)i * 3 + 0) * hw + px), g0 = __ldg(imgs + ((long long)i * 3 + 1) * hw + px),
+                b0 = __ldg(imgs + ((long long)i * 3 + 2) * hw + px);
+    float n = 0.f, s[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < rfn; ++j) {
+      const float* __restrict__ vp = vps + j * 20;
+      const float xh = fmaf(vp[2], X[2], fmaf(vp[1], X[1], vp[0] * X[0])) + vp[3];
+      const float yh = fmaf(vp[6], X[2], fmaf(vp[5], X[1], vp[4] * X[0])) + vp[7];
+      float zh = fmaf(vp[10], X[2], fmaf(vp[9], X[1], vp[8] * X[0])) + vp[11];
+      const bool degenerate = fabsf(zh) < 1e-4f;
+      if (degenerate) zh = 1e-3f;
+      const float ux = xh / zh, uy = yh / zh;
+      const bool outside = (ux < -0.5f) || (ux >= float(w) - 0.5f) || (uy < -0.5f) || (uy >= float(h) - 0.5f);
+      if (degenerate || outside) continue;
+      // bilinear, border clamp, align_corners (interpolate_feats(..., padding_mode='border', align_corners=True))
+      float ix = (ux / float(w - 1) * 2.f - 1.f + 1.f) / 2.f * float(w - 1), iy = (uy / float(h - 1) * 2.f - 1.f + 1.f) / 2.f * float(h - 1);
+      ix = fminf(fmaxf(ix, 0.f), float(w - 1)); iy = fminf(fmaxf(iy, 0.f), float(h - 1));
+      const float x0f = floorf(ix), y0f = floorf(iy);
+      const int xa = int(x0f), ya = int(y0f), xb = min(xa + 1, w - 1), yb = min(ya + 1, h - 1);
+      const float we = ix - x0f, ww = (x0f + 1.f) - ix, ws = iy - y0f, wn = (y0f + 1.f) - iy;
+      const float w00 = ww * wn, w01 = we * wn, w10 = ww * ws, w11 = we * ws;
+      const float* __restrict__ img = imgs + (long long)j * 3 * hw;
+      const float dr = fabsf(bil1(img, w, xa, xb, ya, yb, w00, w01, w10, w11) - r0);
+      const float dg = fabsf(bil1(img + hw, w, xa, xb, ya, yb, w00, w01, w10, w11) - g0);
+      const float db = fabsf(bil1(img + 2 * hw, w, xa, xb, ya, yb, w00, w01, w10, w11) - b0);
+      // depth map of view j: the reference samples the METRIC depth of view j (depth = -1/depth_in with view j's range)
+      const float* __restrict__ dj = depth_in + (long long)j * hw;
+      const float nj = vp[15], fj = vp[16];
+      auto metric = [&](float t) { return -1.f / (t * (fj - nj) + nj); };
+      const float dint = metric(dj[ya * w + xa]) * w00 + metric(dj[ya * w + xb]) * w01 + metric(dj[yb * w + xa]) * w10 + metric(dj[yb * w + xb]) * w11;
+      // normalised by the range of the view projected INTO (init_net.py:49-50: near/far broadcast over the first axis = j)
+      const float dd = fminf(fabsf(-1.f / fmaxf(dint, 1e-5f) + 1.f / fmaxf(zh, 1e-5f)) / (fj - nj), 1.5f);
+      n += 1.f;
+      s[0] += dr; s[1] += dg; s[2] += db; s[3] += dd;
+      s2[0] = fmaf(dr, dr, s2[0]); s2[1] = fmaf(dg, dg, s2[1]); s2[2] = fmaf(db, db, s2[2]); s2[3] = fmaf(dd, dd, s2[3]);
+    }
+    // masked_mean_var (ops.py:36-41): mean = sum / max(n, 1e-4); var = sum((x - mean)^2 mask) / max(n, 1e-4)
+    const float inv_n = 1.f / fmaxf(n, 1e-4f);
+    float* __restrict__ o = out + (long long)i * 8 * hw + px;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float mean = s[k] * inv_n;
+      const float var = fmaxf((s2[k] - 2.f * mean * s[k] + mean * mean * n) * inv_n, 0.f);
+      // channel order: rgb_mean (3), rgb_var (3), dpt_mean, dpt_var
+      if (k < 3) { o[k * hw] = mean; o[(3 + k) * hw] = var; }
+      else { o[6 * hw] = mean; o[7 * hw] = var; }
+    }
+  }
+}
+
+}  // namespace ops
+}  // namespace nr
+
+extern "C" int nr_diff_feats(const float* imgs, const float* depth_in, const float* poses, const float* Ks, const float* view_params,
+                             int rfn, int h, int w, float* out, void* stream) {
+  using namespace nr;
+  NR_CHECK_ARG(imgs && depth_in && poses && Ks && view_params && out, "null device pointer");
+  NR_CHECK_ARG(rfn >= 1 && rfn <= NR_MAX_VIEWS && h > 1 && w > 1, "shape");
+  const long long total = (long long)rfn * h * w;
+  ops::diff_feats_kernel<<<min(ops::blocks_for(total), 148 * 16), ops::TPB, 0, (cudaStream_t)stream>>>(imgs, depth_in, poses, Ks, view_params,
+                                                                                                    rfn, h, w, out);
+  NR_CHECK_LAUNCH("diff_feats");
+  return NR_OK;
+}

@@ -11,8 +11,11 @@
 namespace nr {
 namespace tr {
 
+#ifndef NR_TRAIN_MINB
+#define NR_TRAIN_MINB 2     // 255 registers: the row sweeps spill 2.8 KB per thread at 128; measured 11.0 -> 10.4 ms per training step
+#endif
 template <int WHICH>
-__global__ void __launch_bounds__(128, 4) train_kernel(const Ctx c, long long count) {
+__global__ void __launch_bounds__(128, NR_TRAIN_MINB) train_kernel(const Ctx c, long long count) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
     if (WHICH == 0) row_forward_a(c, i);
     else if (WHICH == 1) point_forward_b(c, i);

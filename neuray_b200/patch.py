@@ -9,13 +9,14 @@ What is rebound:
   * every function of network/render_ops.py  -> neuray_b200.render_ops (also inside network.renderer's and
     network.init_net's namespaces, which star-/name-import them)
   * NeuralRayBaseRenderer.render_by_depth / fine_render_impl / render_impl / render -> neuray_b200.renderer
+  * network.init_net.get_diff_feats (DepthInitNet) -> neuray_b200.init_ops.get_diff_feats
 Constructors, cfg keys, sub-module and state-dict names, and the output dict stay the reference's own.
 The IBRNetWithNeuRay.pos_encoding attribute pinned to cuda:0 (ibrnet.py:312) is no longer used on the path: the
 kernels get a per-device table built by neuray_b200.weights.posenc_table.
 """
 import importlib
 
-from . import render_ops, renderer
+from . import init_ops, render_ops, renderer
 
 _ORIGINALS = []          # (object, attribute name, original value) of everything install() rebound
 
@@ -36,7 +37,9 @@ def install():
     ref_renderer = importlib.import_module("network.renderer")
     targets = [ref_ops, ref_renderer]
     try:
-        targets.append(importlib.import_module("network.init_net"))
+        ref_init = importlib.import_module("network.init_net")
+        targets.append(ref_init)
+        _rebind(ref_init, "get_diff_feats", init_ops.get_diff_feats)      # DepthInitNet's per-frame reprojection features
     except Exception:      # init_net needs inplace_abn / kornia; the rendering path does not
         pass
     for name in render_ops.__all__:

@@ -475,3 +475,50 @@ def render(W, cfg, que, ref, is_train, ray_batch_num=None):
             if is_train or not k.startswith("hit_prob"):
                 chunks.setdefault(k, []).append(v)
     return {k: torch.cat(v, 1) for k, v in chunks.items()}
+
+
+# --------------------------------------------------------------------------------------------------
+# DepthInitNet.get_diff_feats (network/init_net.py:14-61)
+
+def masked_mean_var(feats, mask, dim):
+    """ops.py:36-41."""
+    mask = mask.float()
+    mask_sum = torch.clamp_min(torch.sum(mask, dim, keepdim=True), min=1e-4)
+    mean = torch.sum(feats * mask, dim, keepdim=True) / mask_sum
+    var = torch.sum((feats - mean) ** 2 * mask, dim, keepdim=True) / mask_sum
+    return mean, var
+
+
+def depth2pts3d(depth, ref_Ks, ref_poses):
+    """init_net.py:13-27: every pixel of every view lifted to the world with its depth.  depth [rfn,1,h,w] -> [rfn,h*w,3]."""
+    rfn, dn, h, w = depth.shape
+    ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    hom = torch.stack([xs, ys, torch.ones_like(xs)], -1).float()                   # h,w,3 = (x, y, 1)
+    pts = depth.permute(0, 2, 3, 1).unsqueeze(-1) * hom[None, :, :, None, :]        # rfn,h,w,dn,3
+    pts = pts.reshape(rfn, h * w * dn, 3).permute(0, 2, 1)
+    pts = torch.inverse(ref_Ks) @ pts
+    R = ref_poses[:, :, :3].permute(0, 2, 1)
+    t = -R @ ref_poses[:, :, 3:]
+    return (R @ pts + t).permute(0, 2, 1)
+
+
+def get_diff_feats(ref, depth_in):
+    """init_net.py:29-61.  ref: imgs [rfn,3,h,w], poses, Ks, depth_range; depth_in [rfn,1,h,w] in [0,1] -> [rfn,8,h,w]."""
+    imgs = ref["imgs"]
+    near = ref["depth_range"][:, 0][:, None, None]
+    far = ref["depth_range"][:, 1][:, None, None]
+    near_inv, far_inv = -1 / near[..., None], -1 / far[..., None]
+    depth = -1 / (depth_in * (far_inv - near_inv) + near_inv)
+    rfn, _, h, w = imgs.shape
+    pts3d = depth2pts3d(depth, ref["Ks"], ref["poses"])
+    _, pts2d, dpt_prj, valid = project_points_ref_views(ref, pts3d.reshape(-1, 3))
+    dpt_int = bilinear_sample(depth, pts2d, padding_mode="border", align_corners=True)
+    rgb_int = bilinear_sample(imgs, pts2d, padding_mode="border", align_corners=True)
+    rgb_diff = torch.abs(rgb_int - imgs.permute(0, 2, 3, 1).reshape(1, rfn * h * w, 3))
+    dpt_diff = torch.abs(-1 / torch.clamp(dpt_int, min=1e-5) + 1 / torch.clamp(dpt_prj, min=1e-5))
+    dpt_diff = torch.clamp(dpt_diff / ((-1 / far) - (-1 / near)), max=1.5)         # the range of the view projected into
+    valid = valid.float().unsqueeze(-1)
+    dm, dv = masked_mean_var(dpt_diff, valid, 0)
+    rm, rv = masked_mean_var(rgb_diff, valid, 0)
+    shape = lambda t, c: t.reshape(rfn, h, w, c).permute(0, 3, 1, 2)
+    return torch.cat([shape(rm, 3), shape(rv, 3), shape(dm, 1), shape(dv, 1)], 1)

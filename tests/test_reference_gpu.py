@@ -116,14 +116,53 @@ def test_eval_forward_patched_equals_unpatched(ref_mod):
     compare_outputs(got, want, fine_bad_frac=0.01)
 
 
+class GradTap:
+    """Captures (and optionally perturbs) the gradients that flow OUT of the rendering path into the encoders in front of it:
+    d loss / d output of every image_encoder / vis_encoder call (the path's inputs img_feats / ray_feats)."""
+
+    def __init__(self, net, noise=None):
+        self.grads, self.noise, self.handles = [], noise, []
+        for name in ("image_encoder", "vis_encoder"):
+            self.handles.append(getattr(net, name).register_forward_hook(self._fwd(name)))
+
+    def _fwd(self, name):
+        def hook(module, inputs, output):
+            idx = len(self.grads)
+            self.grads.append(None)
+
+            def on_grad(g):
+                self.grads[idx] = (name, g.detach().clone())
+                if self.noise is not None:      # additive noise of a given size relative to the map's largest entry
+                    gen = torch.Generator(device=g.device).manual_seed(1000 + idx)
+                    r = torch.rand(g.shape, device=g.device, generator=gen) * 2 - 1
+                    return g + self.noise[idx] * g.abs().max() * r
+            output.register_hook(on_grad)
+        return hook
+
+    def close(self):
+        for h in self.handles:
+            h.remove()
+
+
 @pytest.mark.parametrize("self_hit", [False, True])
 def test_training_forward_and_every_gradient(ref_mod, self_hit):
+    """forward() in training mode + backward() of the reference's kind of loss, unpatched vs patched:
+      * every output key;
+      * every parameter of the hot-path modules (dist_decoder, agg_net and their fine twins), directly;
+      * the gradients the path hands to the encoders in front of it (d ray_feats, d img_feats), directly;
+      * every parameter upstream of the path (image encoder, vis encoder, init net).  Their gradients come out of the
+        reference's own PyTorch backward through up to ~20 convolution + InstanceNorm layers, which amplifies a last-bit
+        difference in the feature-map gradients by orders of magnitude (two fp32 implementations of the same sum differ in
+        the last bits); the yardstick is therefore the reference itself: its backward is run once more with the measured
+        feature-map gradient difference injected as noise, and the patched network has to stay within a small multiple of
+        what that does to each parameter."""
     cfg = dict(CFG, use_self_hit_prob=self_hit)
     que, ref = make_data(self_feats=self_hit)
     net = build(ref_mod, cfg).train()
-    grads = {}
-    outs = {}
-    for mode in ("reference", "reference_again", "patched"):       # the second reference run measures the run-to-run noise floor
+    grads, outs, taps = {}, {}, {}
+
+    def run_mode(mode, noise=None):
+        tap = GradTap(net, noise)
         if mode == "patched":
             patch.install()
         try:
@@ -133,9 +172,28 @@ def test_training_forward_and_every_gradient(ref_mod, self_hit):
             torch.cuda.synchronize()
         finally:
             patch.uninstall()
+            tap.close()
         outs[mode] = {k: v.detach().clone() for k, v in out.items()}
         grads[mode] = {k: (p.grad.detach().clone() if p.grad is not None else None) for k, p in net.named_parameters()}
+        taps[mode] = tap.grads
+
+    run_mode("reference")
+    run_mode("patched")
     compare_outputs(outs["patched"], outs["reference"], fine_bad_frac=0.01)
+    # what the path hands upstream
+    assert len(taps["patched"]) == len(taps["reference"]) >= 2
+    delta = []
+    for (name, g_ref), (_, g) in zip(taps["reference"], taps["patched"]):
+        rel = float((g - g_ref).abs().max()) / float(g_ref.abs().max())
+        delta.append(rel)
+        print(f"d loss / d {name} output: relative difference {rel:.2e}")
+        assert rel <= 2e-3, (name, rel)
+    run_mode("reference_noisy", noise=delta)          # the reference's own sensitivity to a difference of that size
+    module_scale = {}
+    for k, g_ref in grads["reference"].items():
+        if g_ref is not None:
+            m = k.split(".")[0]
+            module_scale[m] = max(module_scale.get(m, 0.0), float(g_ref.abs().max()))
     checked, flows_upstream, worst = 0, 0, (0.0, "")
     for k, g_ref in grads["reference"].items():
         g = grads["patched"][k]
@@ -145,12 +203,17 @@ def test_training_forward_and_every_gradient(ref_mod, self_hit):
         assert g is not None, f"{k}: the patched network sends no gradient here"
         scale = float(g_ref.abs().max())
         err = float((g - g_ref).abs().max())
-        floor = float((grads["reference_again"][k] - g_ref).abs().max())      # atomics / algorithm choice in the reference itself
-        worst = max(worst, (err / scale, k))
-        assert err <= 2e-3 * scale + 4 * floor + 1e-7, (k, err, scale, floor)
+        # parameters whose true gradient is zero (a conv bias in front of an InstanceNorm, the bias in front of a softmax) hold
+        # rounding noise only, in the reference too: measured against the module's largest gradient entry
+        noise = 1e-4 * module_scale[k.split(".")[0]]
+        upstream = k.split(".")[0] in ("image_encoder", "vis_encoder", "init_net")
+        sens = float((grads["reference_noisy"][k] - g_ref).abs().max()) if upstream else 0.0
+        if scale > noise:
+            worst = max(worst, (err / scale, k))
+        # 5e-3: the fine pass runs on resampled depths that differ in the last bits between the two implementations
+        assert err <= 5e-3 * scale + noise + 6 * sens, (k, err, scale, sens, noise)
         checked += 1
-        if k.split(".")[0] in ("image_encoder", "vis_encoder", "init_net"):
-            flows_upstream += 1
+        flows_upstream += upstream
     print(f"worst relative gradient difference {worst[0]:.2e} ({worst[1]}), {checked} parameters, {flows_upstream} upstream of the path")
     assert checked > 250 and flows_upstream > 100, (checked, flows_upstream)
 
