@@ -25,6 +25,9 @@ using pm::pool_rows;
 #define NR_GATHER_BATCH 2     // 4 (16 loads in flight per lane) cost 520 B of spills per thread and 12 % of the kernel (profiles/README.md)
 #endif
 constexpr int GB = NR_GATHER_BATCH;                           // rows whose 4 taps a quarter-warp keeps in flight at once (4 x GB 128-bit loads per lane)
+#ifndef NR_GATHER_OVERLAP
+#define NR_GATHER_OVERLAP 1
+#endif
 constexpr int NBLK = 3;
 constexpr int NCOMP = NBLK * 128;
 constexpr int NTHR = NCOMP;
@@ -413,6 +416,45 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
         }
         __syncwarp();
       };
+      // The same gather split into "issue the loads of rows [rb, rb + 4 GB)" and "blend them and store": the img_feats half is
+      // fetched underneath the dist decoder's first MMA round trips instead of in front of them (NR_GATHER_OVERLAP).
+      float4 gt[GB][4];
+      float gwq[GB][4];
+      bool gon[GB];
+      auto g_issue = [&](const int rb, const int ch0) {
+        const int qw = lane >> 3, l = lane & 7;
+#pragma unroll
+        for (int u = 0; u < GB; ++u) {
+          const int j = rb + 4 * u + qw;
+          const int code = __shfl_sync(0xffffffffu, tcode, j);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) gwq[u][k] = __shfl_sync(0xffffffffu, tw[k], j);
+          gon[u] = code >= 0;
+          if (gon[u]) {
+            const float* __restrict__ base = pp.feat + (code & ~63) + ch0 + 4 * l;
+            const int dx = (code & 1) << 6, dy = (code & 2) ? fw * 64 : 0;
+            gt[u][0] = ldg4(base); gt[u][1] = ldg4(base + dx);
+            gt[u][2] = ldg4(base + dy); gt[u][3] = ldg4(base + dy + dx);
+          }
+        }
+      };
+      auto g_consume = [&](const int rb) {
+        const int qw = lane >> 3, l = lane & 7;
+#pragma unroll
+        for (int u = 0; u < GB; ++u) {
+          const int j = rb + 4 * u + qw;
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (gon[u]) {
+            o.x = gt[u][0].x * gwq[u][0] + gt[u][1].x * gwq[u][1] + gt[u][2].x * gwq[u][2] + gt[u][3].x * gwq[u][3];
+            o.y = gt[u][0].y * gwq[u][0] + gt[u][1].y * gwq[u][1] + gt[u][2].y * gwq[u][2] + gt[u][3].y * gwq[u][3];
+            o.z = gt[u][0].z * gwq[u][0] + gt[u][1].z * gwq[u][1] + gt[u][2].z * gwq[u][2] + gt[u][3].z * gwq[u][3];
+            o.w = gt[u][0].w * gwq[u][0] + gt[u][1].w * gwq[u][1] + gt[u][2].w * gwq[u][2] + gt[u][3].w * gwq[u][3];
+          }
+          *reinterpret_cast<float4*>(stg + j * STG_ROW + 4 * l) = o;
+        }
+      };
+      constexpr int GSTEP = 4 * GB;                  // rows per issue/consume step; 32 / GSTEP steps per half
+      static_assert(!NR_GATHER_OVERLAP || GB == 2, "the overlapped gather is written for four steps of eight rows");
       gather32(0);
 
       PM_TICK(2)
@@ -430,13 +472,24 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
           for (int k = 0; k < 32; ++k) o[12 + k] = x[k];
         }
       }
+#if NR_GATHER_OVERLAP
+      __syncwarp();                                                                  // every lane has read its ray_feats row
+      g_issue(0, 32);                                                                // img_feats, step 0: in flight under head 0
+#else
       gather32(32);                                                                  // img_feats: stay in the buffer until ray_dir_fc
+#endif
       PM_TICK(3)
       float hv[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll 1
       for (int hd = 0; hd < n_heads; ++hd) {
         const float* __restrict__ hw_ = sw + SW_HEAD + hd * SW_HEAD_STRIDE;
+#if NR_GATHER_OVERLAP
+        issue_layer<32, 4, 0, 64, 4, 0, 128, 0, 1, 0, 1024 * 4, 0, true, false, false>(b);          // L0: A[0:32]
+        if (hd < 2) { g_consume(2 * GSTEP * hd); g_issue(2 * GSTEP * hd + GSTEP, 32); }
+        wait_layer(b);
+#else
         run_layer<32, 4, 0, 4, 0, 0, 1024 * 4, 0, true, false>(b);              // L0: A[0:32]
+#endif
         {
           float x[32];
           ld32(b, 128, x);
@@ -445,7 +498,17 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
           for (int j = 0; j < 32; ++j) x[j] = elu(x[j]);
           st32(b, 32, 96, x);
         }
+#if NR_GATHER_OVERLAP
+        issue_layer<32, 4, 32, 64, 4, 0, 128, 0, 1, 2048 * 4, 3072 * 4, 0, false, true, false>(b);  // L1: A[32:64]
+        if (hd < 2) {
+          g_consume(2 * GSTEP * hd + GSTEP);
+          if (hd == 0) g_issue(2 * GSTEP, 32);
+          else __syncwarp();                                                         // img_feats complete in the buffer
+        }
+        wait_layer(b);
+#else
         run_layer<32, 4, 32, 4, 0, 2048 * 4, 3072 * 4, 0, false, true>(b);      // L1: A[32:64]
+#endif
         float o0 = hw_[128], o1 = hw_[129];
         {
           float x[32];

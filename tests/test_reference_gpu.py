@@ -23,10 +23,14 @@ def fp32_convolutions():
     """cuDNN runs fp32 convolutions through TF32 by default; the encoders in front of the path would then turn a 1e-6
     difference in the feature-map gradients into a 1e-2 difference of their own weight gradients (sums with heavy
     cancellation), which says nothing about the path under test."""
-    old = torch.backends.cudnn.allow_tf32
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark)
     torch.backends.cudnn.allow_tf32 = False
+    # one fixed cuDNN algorithm per convolution: otherwise the heuristics may pick different ones in the two runs (the choice
+    # depends on the free workspace memory), and the encoders' own outputs already differ by 1e-5 between two runs of the
+    # UNMODIFIED reference -- which their ill-conditioned backward turns into 1e-2 (tools/debug_initnet.py)
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False
     yield
-    torch.backends.cudnn.allow_tf32 = old
+    torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = old
 
 DN = 24
 CFG = {"init_net_type": "depth", "use_hierarchical_sampling": True, "use_depth_loss": True, "dist_decoder_cfg": {"use_vis": False},
@@ -43,12 +47,22 @@ def ref_mod():
     patch.uninstall()
 
 
+def _smooth(rs, shape, lo, hi, cells=8):
+    """Low-frequency random field (bilinear upsampling of a coarse grid): images and depth maps of real scenes are smooth at
+    the pixel scale; white noise would make every bilinear lookup hypersensitive to the last bit of its coordinates."""
+    n, c, h, w = shape
+    coarse = torch.from_numpy(rs.uniform(lo, hi, (n, c, max(2, h // cells), max(2, w // cells))).astype(np.float32))
+    return torch.nn.functional.interpolate(coarse, size=(h, w), mode="bilinear", align_corners=True)
+
+
 def make_data(rfn=6, rays=384, self_feats=False, seed=3):
     que, ref = synthetic.make_scene(64, 80, rfn, seed=seed, smooth=2)
     ref = dict(ref)
     ref.pop("ray_feats"), ref.pop("img_feats")
     rs = np.random.RandomState(seed)
-    ref["depth"] = torch.from_numpy(rs.uniform(2.5, 5.0, (rfn, 1, 64, 80)).astype(np.float32))
+    ref["imgs"] = _smooth(rs, tuple(ref["imgs"].shape), 0.0, 1.0)
+    que = dict(que, imgs=_smooth(rs, tuple(que["imgs"].shape), 0.0, 1.0))
+    ref["depth"] = _smooth(rs, (rfn, 1, 64, 80), 2.5, 5.0)
     ref["true_depth"] = ref["depth"]
     n = que["coords"].shape[1]
     idx = torch.from_numpy(rs.permutation(n)[:rays])
@@ -120,8 +134,8 @@ class GradTap:
     """Captures (and optionally perturbs) the gradients that flow OUT of the rendering path into the encoders in front of it:
     d loss / d output of every image_encoder / vis_encoder call (the path's inputs img_feats / ray_feats)."""
 
-    def __init__(self, net, noise=None):
-        self.grads, self.noise, self.handles = [], noise, []
+    def __init__(self, net, inject=None):
+        self.grads, self.inject, self.handles = [], inject, []
         for name in ("image_encoder", "vis_encoder"):
             self.handles.append(getattr(net, name).register_forward_hook(self._fwd(name)))
 
@@ -132,10 +146,8 @@ class GradTap:
 
             def on_grad(g):
                 self.grads[idx] = (name, g.detach().clone())
-                if self.noise is not None:      # additive noise of a given size relative to the map's largest entry
-                    gen = torch.Generator(device=g.device).manual_seed(1000 + idx)
-                    r = torch.rand(g.shape, device=g.device, generator=gen) * 2 - 1
-                    return g + self.noise[idx] * g.abs().max() * r
+                if self.inject is not None:     # replace what arrives here by a given gradient (see the test below)
+                    return g + self.inject[idx]
             output.register_hook(on_grad)
         return hook
 
@@ -150,19 +162,21 @@ def test_training_forward_and_every_gradient(ref_mod, self_hit):
       * every output key;
       * every parameter of the hot-path modules (dist_decoder, agg_net and their fine twins), directly;
       * the gradients the path hands to the encoders in front of it (d ray_feats, d img_feats), directly;
-      * every parameter upstream of the path (image encoder, vis encoder, init net).  Their gradients come out of the
-        reference's own PyTorch backward through up to ~20 convolution + InstanceNorm layers, which amplifies a last-bit
-        difference in the feature-map gradients by orders of magnitude (two fp32 implementations of the same sum differ in
-        the last bits); the yardstick is therefore the reference itself: its backward is run once more with the measured
-        feature-map gradient difference injected as noise, and the patched network has to stay within a small multiple of
-        what that does to each parameter."""
+      * every parameter upstream of the path (image encoder, vis encoder, init net).  The encoders' backward is the
+        reference's own PyTorch code in both runs and LINEAR in the gradient it receives, so their parameter gradients must be
+        exactly what that backward makes of the path's output gradients: the reference is run once more with the measured
+        difference of the feature-map gradients (patched - reference, 1e-5 .. 2e-4 of the maps' largest entry: last-bit
+        differences of the fine-pass sample positions) added where the path hands them over, and every upstream parameter
+        gradient of the patched network has to agree with that run to fp32 accuracy.  (Comparing them with the plain reference
+        run instead would test the conditioning of ~20 convolution + InstanceNorm layers, which turn a 1e-4 difference into
+        1e-2: tools/debug_ref_grads.py.)"""
     cfg = dict(CFG, use_self_hit_prob=self_hit)
     que, ref = make_data(self_feats=self_hit)
     net = build(ref_mod, cfg).train()
     grads, outs, taps = {}, {}, {}
 
-    def run_mode(mode, noise=None):
-        tap = GradTap(net, noise)
+    def run_mode(mode, inject=None):
+        tap = GradTap(net, inject)
         if mode == "patched":
             patch.install()
         try:
@@ -185,10 +199,10 @@ def test_training_forward_and_every_gradient(ref_mod, self_hit):
     delta = []
     for (name, g_ref), (_, g) in zip(taps["reference"], taps["patched"]):
         rel = float((g - g_ref).abs().max()) / float(g_ref.abs().max())
-        delta.append(rel)
+        delta.append(g - g_ref)
         print(f"d loss / d {name} output: relative difference {rel:.2e}")
         assert rel <= 2e-3, (name, rel)
-    run_mode("reference_noisy", noise=delta)          # the reference's own sensitivity to a difference of that size
+    run_mode("reference_plus_delta", inject=delta)    # the reference's backward fed with the patched path's output gradients
     module_scale = {}
     for k, g_ref in grads["reference"].items():
         if g_ref is not None:
@@ -207,11 +221,16 @@ def test_training_forward_and_every_gradient(ref_mod, self_hit):
         # rounding noise only, in the reference too: measured against the module's largest gradient entry
         noise = 1e-4 * module_scale[k.split(".")[0]]
         upstream = k.split(".")[0] in ("image_encoder", "vis_encoder", "init_net")
-        sens = float((grads["reference_noisy"][k] - g_ref).abs().max()) if upstream else 0.0
+        if upstream:
+            # 2e-2: init_net additionally sees its own inputs through the CUDA get_diff_feats (1e-6-level differences of the
+            # reprojection features), and its backward runs through ~20 convolution + InstanceNorm layers (tools/debug_initnet2.py)
+            err = float((g - grads["reference_plus_delta"][k]).abs().max())
+            assert err <= 2e-2 * scale + noise, (k, err, scale, noise)
+        else:
+            # 5e-3: the fine pass runs on resampled depths that differ in the last bits between the two implementations
+            assert err <= 5e-3 * scale + noise, (k, err, scale, noise)
         if scale > noise:
             worst = max(worst, (err / scale, k))
-        # 5e-3: the fine pass runs on resampled depths that differ in the last bits between the two implementations
-        assert err <= 5e-3 * scale + noise + 6 * sens, (k, err, scale, sens, noise)
         checked += 1
         flows_upstream += upstream
     print(f"worst relative gradient difference {worst[0]:.2e} ({worst[1]}), {checked} parameters, {flows_upstream} upstream of the path")
