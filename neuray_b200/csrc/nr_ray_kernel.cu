@@ -102,26 +102,39 @@ __global__ void __launch_bounds__(512) ray_kernel(const KParams kp) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) o[j] = 0.f;
         if (nvalid > 1.f) {
+          // single pass, blockwise online softmax: 8 keys at a time -- logits of the block, block maximum, ONE rescale of the
+          // running sums per block (instead of a separate max pass over all keys: half the K loads and dot products)
           float mx[4] = {-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f};
-          for (int t = 0; t < dn; ++t) {
-#pragma unroll
-            for (int hh = 0; hh < 4; ++hh) {
-              const float4 k4 = *reinterpret_cast<const float4*>(sK + t * ROW + 4 * hh);
-              const float l = fmaf(q[4 * hh + 3], k4.w, fmaf(q[4 * hh + 2], k4.z, fmaf(q[4 * hh + 1], k4.y, q[4 * hh] * k4.x)));
-              mx[hh] = fmaxf(mx[hh], l);
-            }
-          }
           float den[4] = {0.f, 0.f, 0.f, 0.f};
-          for (int t = 0; t < dn; ++t) {
+          for (int t0 = 0; t0 < dn; t0 += 8) {
+            const int tn = min(8, dn - t0);
 #pragma unroll
             for (int hh = 0; hh < 4; ++hh) {
-              const float4 k4 = *reinterpret_cast<const float4*>(sK + t * ROW + 4 * hh);
-              const float4 v4 = *reinterpret_cast<const float4*>(sV + t * ROW + 4 * hh);
-              const float l = fmaf(q[4 * hh + 3], k4.w, fmaf(q[4 * hh + 2], k4.z, fmaf(q[4 * hh + 1], k4.y, q[4 * hh] * k4.x)));
-              const float e = ex2_ftz(l - mx[hh]);
-              den[hh] += e;
-              o[4 * hh + 0] = fmaf(e, v4.x, o[4 * hh + 0]); o[4 * hh + 1] = fmaf(e, v4.y, o[4 * hh + 1]);
-              o[4 * hh + 2] = fmaf(e, v4.z, o[4 * hh + 2]); o[4 * hh + 3] = fmaf(e, v4.w, o[4 * hh + 3]);
+              float l[8];
+              float bm = -3.4e38f;
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                if (u < tn) {
+                  const float4 k4 = *reinterpret_cast<const float4*>(sK + (t0 + u) * ROW + 4 * hh);
+                  l[u] = fmaf(q[4 * hh + 3], k4.w, fmaf(q[4 * hh + 2], k4.z, fmaf(q[4 * hh + 1], k4.y, q[4 * hh] * k4.x)));
+                  bm = fmaxf(bm, l[u]);
+                } else l[u] = -3.4e38f;
+              }
+              const float m_new = fmaxf(mx[hh], bm);
+              const float scale = ex2_ftz(mx[hh] - m_new);          // first block: ex2(-huge) = 0 on zero sums
+              mx[hh] = m_new;
+              den[hh] *= scale;
+              o[4 * hh + 0] *= scale; o[4 * hh + 1] *= scale; o[4 * hh + 2] *= scale; o[4 * hh + 3] *= scale;
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                if (u < tn) {
+                  const float4 v4 = *reinterpret_cast<const float4*>(sV + (t0 + u) * ROW + 4 * hh);
+                  const float e = ex2_ftz(l[u] - m_new);
+                  den[hh] += e;
+                  o[4 * hh + 0] = fmaf(e, v4.x, o[4 * hh + 0]); o[4 * hh + 1] = fmaf(e, v4.y, o[4 * hh + 1]);
+                  o[4 * hh + 2] = fmaf(e, v4.z, o[4 * hh + 2]); o[4 * hh + 3] = fmaf(e, v4.w, o[4 * hh + 3]);
+                }
+              }
             }
           }
 #pragma unroll
