@@ -209,11 +209,15 @@ def fine_sample_u(fdn):
     return 0.5 * step + torch.arange(fdn) * step
 
 
-def sample_fine_depth(depth, hit_prob, depth_range, sample_num, random_sample, u=None):
-    """render_ops.py:172-229 (inv_mode=True).  `u` [qn,rn,fdn] replaces torch.rand when random_sample."""
-    a = -1 / depth_range[0, 0]
-    b = -1 / depth_range[0, 1]
-    t = (-1 / depth - a) / (b - a)
+def sample_fine_depth(depth, hit_prob, depth_range, sample_num, random_sample, u=None, inv_mode=True):
+    """render_ops.py:172-229.  `u` [qn,rn,fdn] replaces torch.rand when random_sample.  inv_mode=False (render_ops.py:182,224):
+    the resampling runs directly in depth instead of normalised inverse depth."""
+    if inv_mode:
+        a = -1 / depth_range[0, 0]
+        b = -1 / depth_range[0, 1]
+        t = (-1 / depth - a) / (b - a)
+    else:
+        t = depth
     edges = torch.cat([t[..., :1], (t[..., 1:] + t[..., :-1]) / 2, t[..., -1:]], -1)   # dn+1
     p = hit_prob + 1e-5
     pdf = p / p.sum(-1, keepdim=True)
@@ -229,7 +233,7 @@ def sample_fine_depth(depth, hit_prob, depth_range, sample_num, random_sample, u
     den = c1 - c0
     den = torch.where(den < 1e-5, torch.ones_like(den), den)
     tf = e0 + (u - c0) / den * (e1 - e0)
-    return -1 / (tf * (b - a) + a)
+    return -1 / (tf * (b - a) + a) if inv_mode else tf
 
 
 # --------------------------------------------------------------------------------------------------

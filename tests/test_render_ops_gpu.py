@@ -74,3 +74,32 @@ def test_compositing_and_resampling(scene):
     fd_o = orc.sample_fine_depth(depth, hit, que["depth_range"], 16, False)
     fd_g = render_ops.sample_fine_depth(depth.cuda(), hit.cuda(), que["depth_range"].cuda(), 16, False)
     close(fd_g, fd_o, atol=2e-5, what="sample_fine_depth")
+    # inv_mode=False (render_ops.py:182,224): resampling directly in depth; pinned to the unmodified reference where it is present
+    fd_o2 = orc.sample_fine_depth(depth, hit, que["depth_range"], 16, False, inv_mode=False)
+    fd_g2 = render_ops.sample_fine_depth(depth.cuda(), hit.cuda(), que["depth_range"].cuda(), 16, False, inv_mode=False)
+    close(fd_g2, fd_o2, atol=2e-5, what="sample_fine_depth inv_mode=False")
+    import ref_import
+    if ref_import.available():
+        ref_import.load_reference()
+        import network.render_ops as ref_ops
+        close(fd_o2, ref_ops.sample_fine_depth(depth, hit, que["depth_range"], 16, False, inv_mode=False), atol=1e-6, what="oracle vs reference, inv_mode=False")
+        close(fd_o, ref_ops.sample_fine_depth(depth, hit, que["depth_range"], 16, False), atol=1e-5, what="oracle vs reference, inv_mode=True")
+
+
+def test_interpolation_backward_matches_the_oracle_autograd(scene):
+    """d out / d map of interpolate_feature_map (nr_interpolate_feats_bwd) against autograd over the oracle's bilinear taps, for
+    the quarter-resolution maps (align_corners=False branch) and a full-resolution map, with a mask."""
+    que, ref, dq, dr = scene
+    torch.manual_seed(3)
+    h, w = ref["imgs"].shape[-2:]
+    for fmap in (ref["ray_feats"], torch.randn(5, 7, h, w)):
+        pts = torch.rand(5, 300, 2) * torch.tensor([w + 4.0, h + 4.0]) - 2.0          # some outside: border clamp
+        mask = (torch.rand(5, 300) > 0.25).float()
+        g_out = torch.randn(5, 300, fmap.shape[1])
+        fo = fmap.clone().requires_grad_(True)
+        (orc.interpolate_feature_map(fo, pts, mask, h, w) * g_out).sum().backward()
+        fg = fmap.cuda().requires_grad_(True)
+        out = render_ops.interpolate_feature_map(fg, pts.cuda(), mask.cuda(), h, w)
+        (out * g_out.cuda()).sum().backward()
+        close(out, orc.interpolate_feature_map(fmap, pts, mask, h, w), atol=2e-5, what="forward")
+        close(fg.grad, fo.grad, atol=2e-5, rtol=1e-4, what="d map")
