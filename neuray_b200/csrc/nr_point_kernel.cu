@@ -181,6 +181,87 @@ __device__ __forceinline__ void pool_rows(float* stg, int lane, int lane0, int v
   __syncwarp();
 }
 
+// ---- lane groups that are not a power of two (G = 5, 6, 10: PPW = 32 / G points per warp, the last 32 - PPW * G lanes idle) ----
+// Butterflies do not exist for them; a group's scalars are summed through columns 32..35 of the group's rows in the same
+// warp-private buffer (pool_rows only touches columns 0..31).  `idle` lanes take part in the warp syncs only.
+template <int G>
+__device__ __forceinline__ float gsum_np2(float* stg, int lane, int lane0, bool idle, float x) {
+  stg[lane * 36 + 32] = x;
+  __syncwarp();
+  float s = 0.f;
+  if (!idle) {
+#pragma unroll
+    for (int t = 0; t < G; ++t) s += stg[(lane0 + t) * 36 + 32];
+  }
+  __syncwarp();
+  return s;
+}
+template <int G>
+__device__ __forceinline__ float gmax_np2(float* stg, int lane, int lane0, bool idle, float x) {
+  stg[lane * 36 + 32] = x;
+  __syncwarp();
+  float s = x;
+  if (!idle) {
+#pragma unroll
+    for (int t = 0; t < G; ++t) s = fmaxf(s, stg[(lane0 + t) * 36 + 32]);
+  }
+  __syncwarp();
+  return s;
+}
+template <int G>
+__device__ __forceinline__ void gsum4_np2(float* stg, int lane, int lane0, bool idle, float (&x)[4]) {
+  *reinterpret_cast<float4*>(stg + lane * 36 + 32) = make_float4(x[0], x[1], x[2], x[3]);
+  __syncwarp();
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!idle) {
+#pragma unroll
+    for (int t = 0; t < G; ++t) {
+      const float4 y = *reinterpret_cast<const float4*>(stg + (lane0 + t) * 36 + 32);
+      s.x += y.x; s.y += y.y; s.z += y.z; s.w += y.w;
+    }
+  }
+  __syncwarp();
+  x[0] = s.x; x[1] = s.y; x[2] = s.z; x[3] = s.w;
+}
+// pool_rows for such a group: lane v adds up columns v, v + G, v + 2G, ... of the group's G rows
+template <int G, int N>
+__device__ __forceinline__ void pool_rows_np2(float* stg, int lane, int lane0, int v, bool idle, const float (&in)[N], float (&out)[N]) {
+  constexpr int ROW = 36;
+  constexpr int C = (N + G - 1) / G;
+#pragma unroll
+  for (int q = 0; q < N / 4; ++q) *reinterpret_cast<float4*>(stg + lane * ROW + 4 * q) = make_float4(in[4 * q], in[4 * q + 1], in[4 * q + 2], in[4 * q + 3]);
+  __syncwarp();
+  float acc[C];
+#pragma unroll
+  for (int j = 0; j < C; ++j) acc[j] = 0.f;
+  if (!idle) {
+#pragma unroll
+    for (int t = 0; t < G; ++t) {
+#pragma unroll
+      for (int j = 0; j < C; ++j)
+        if (v + G * j < N) acc[j] += stg[(lane0 + t) * ROW + v + G * j];
+    }
+  }
+  __syncwarp();
+  if (!idle) {
+#pragma unroll
+    for (int j = 0; j < C; ++j)
+      if (v + G * j < N) stg[lane0 * ROW + v + G * j] = acc[j];
+  }
+  __syncwarp();
+  if (!idle) {
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) {
+      const float4 x = *reinterpret_cast<const float4*>(stg + lane0 * ROW + 4 * q);
+      out[4 * q] = x.x; out[4 * q + 1] = x.y; out[4 * q + 2] = x.z; out[4 * q + 3] = x.w;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < N; ++q) out[q] = 0.f;
+  }
+  __syncwarp();
+}
+
 // The 64/G output columns a lane owns in the streamed per-point layers.  Lane v takes, for q = 0..CPL/4-1, the float4
 // at columns q*4G + 4v: the G lanes of a point then read G consecutive 16-byte chunks (one conflict-free wavefront) for
 // every q, instead of 32-byte chunks whose second halves collide in the banks.  (G = 32: two columns 2v, 2v+1.)
@@ -236,7 +317,7 @@ static int launch_pm3_inst(const pkt::KParams& kp, int grid, cudaStream_t stream
 
 template <int G>
 static int launch_pm3(pkt::KParams kp, cudaStream_t stream) {
-  constexpr int PB = 128 / G;
+  constexpr int PB = 4 * (32 / G);       // points per 128-row block: 32 / G per warp (G not a power of two leaves 32 % G lanes idle)
   const long long N = (long long)kp.p.rn * kp.p.dn;
   kp.P = PB;
   kp.n_tiles = int((N + PB - 1) / PB);
@@ -264,8 +345,12 @@ int launch_point_kernel(const NrPassParams* p, float* dbg, long long* timing, cu
   kp.dbg = dbg;
   kp.timing = timing;
   kp.n_heads = p->use_vis ? 4 : 3;
+  // lanes per point: the smallest group size that holds the views and wastes the fewest of a warp's 32 lanes
   if (p->rfn <= 4) return launch_pm3<4>(kp, stream);
+  if (p->rfn == 5) return launch_pm3<5>(kp, stream);      // 6 points per warp (30 lanes) instead of 4 groups of 8
+  if (p->rfn == 6) return launch_pm3<6>(kp, stream);      // 5 points per warp
   if (p->rfn <= 8) return launch_pm3<8>(kp, stream);
+  if (p->rfn <= 10) return launch_pm3<10>(kp, stream);    // 3 points per warp instead of 2 groups of 16 (cfg4: 10 views)
   if (p->rfn <= 16) return launch_pm3<16>(kp, stream);
   return launch_pm3<32>(kp, stream);
 }

@@ -20,6 +20,10 @@ using pm::bsum_vec;
 using pm::own_col;
 using pm::ld_cols;
 using pm::pool_rows;
+using pm::pool_rows_np2;
+using pm::gsum_np2;
+using pm::gmax_np2;
+using pm::gsum4_np2;
 
 #ifndef NR_GATHER_BATCH
 #define NR_GATHER_BATCH 2     // 4 (16 loads in flight per lane) cost 520 B of spills per thread and 12 % of the kernel (profiles/README.md)
@@ -171,9 +175,12 @@ __device__ __forceinline__ void st8(const Blk& b, int hi, int lo, const float* v
 template <int G, bool DEBUG>
 __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
   extern __shared__ __align__(1024) float smem[];
-  constexpr int PB = 128 / G;          // points per block
-  constexpr int CPL = 64 / G;          // hoist / geometry_fc.0 output columns per lane
-  static_assert(G == 4 || G == 8 || G == 16 || G == 32, "lanes per point");
+  constexpr bool P2 = (G & (G - 1)) == 0;      // power-of-two lane groups reduce with butterflies, the others through shared memory
+  constexpr int PPW = 32 / G;                   // points per warp (G = 10: 3, two lanes idle)
+  constexpr int PB = 4 * PPW;                   // points per block
+  constexpr int GE = G >= 32 ? 32 : G >= 16 ? 16 : G >= 8 ? 8 : 4;   // lanes of a point that share geometry_fc's 64 hidden units
+  constexpr int CPL = 64 / GE;                  // geometry_fc.0 output columns per such lane
+  static_assert(G == 4 || G == 5 || G == 6 || G == 8 || G == 10 || G == 16 || G == 32, "lanes per point");
   const NrPassParams& pp = kp.p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -224,7 +231,7 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
     cp(sw + SW_RGB1B, gd + lay::RGB1_B, 8); cp(sw + SW_RGB2W, gd + lay::RGB2_W, 8); cp(sw + SW_RGB2B, gd + lay::RGB2_B, 4);
     // WT[64][16] -> [16][64]; hidden unit c = v*CPL + j sits where lane v's j-th own column is (conflict-free ld_cols)
     for (int i = tid; i < 64 * 16; i += NCOMP)
-      sWg1[(i & 15) * 64 + own_col<G>((i >> 4) / CPL, (i >> 4) % CPL)] = __ldg(W + lay::GRP_D2 + lay::GEO1_W + i);
+      sWg1[(i & 15) * 64 + own_col<GE>((i >> 4) / CPL, (i >> 4) % CPL)] = __ldg(W + lay::GRP_D2 + lay::GEO1_W + i);
     cp(sWg1 + 64 * 16, lay::GRP_D2 + lay::GEO1_B, 16);
   }
   tc::fence_before_thread_sync();
@@ -243,10 +250,18 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
     // ---------------- compute warps (thread 0 also feeds the weight ring, see Producer) ----------------
     const int fh = pp.fh, fw = pp.fw, h = pp.h, w = pp.w;
     const bool feat_align = (fh == h && fw == w);
-    const int v = lane % G;                         // view of this row (>= rfn: padding lane)
-    const int pl = (tid & 127) / G;                 // point inside the block
+    const int grp = lane / G;                       // point of this lane inside the warp (>= PPW: idle lane)
+    const bool idle = P2 ? false : grp >= PPW;     // a compile-time false for the power-of-two groups
+    const int v = P2 ? lane % G : lane - grp * G;   // view of this row (>= rfn: padding lane)
+    const int pl = P2 ? (tid & 127) / G : (warp & 3) * PPW + grp;   // point inside the block
     const int lane0 = lane - v;                     // first lane of this point's group
     float* const stg = smem + OFF_STG + warp * 32 * STG_ROW;
+    // sums / maxima over the lanes of a point
+    auto gsum = [&](float x) { if constexpr (P2) return bsum<G>(x); else return gsum_np2<G>(stg, lane, lane0, idle, x); };
+    auto gmax = [&](float x) { if constexpr (P2) return bmax<G>(x); else return gmax_np2<G>(stg, lane, lane0, idle, x); };
+    auto gpool32 = [&](const float (&in)[32], float (&out)[32]) {
+      if constexpr (P2) pool_rows<G, 32>(stg, lane, lane0, v, in, out); else pool_rows_np2<G, 32>(stg, lane, lane0, v, idle, in, out);
+    };
 
     Blk b;
     b.blk = warp >> 2;
@@ -292,7 +307,7 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
         continue;
       }
       const int n = tile * PB + pl;
-      const bool pt_ok = n < N;
+      const bool pt_ok = P2 ? n < N : (n < N && !idle);
       const bool row_ok = pt_ok && v < rfn;
 
       PM_TICK(0)
@@ -643,11 +658,11 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
       // accumulator.  The previous round's MMAs finish under this round's reduction.  The sums over the views go through the
       // warp's transposition buffer (pool_rows); the variance comes from the weighted second moment:
       //   sum_v w (x - mu)^2 = sum_v w x^2 - mu^2 (2 - sum_v w),  mu = sum_v w x   (the reference's mean is NOT normalised)
-      const float msum = bsum<G>(mrow);
+      const float msum = gsum(mrow);
       const float w1 = mrow / (msum + 1e-8f);
       const float w0 = sigmoidf_(gate) * w1;
       {
-        const float c1 = 2.f - bsum<G>(w1), c0 = 2.f - bsum<G>(w0);
+        const float c1 = 2.f - gsum(w1), c0 = 2.f - gsum(w0);
         const uint32_t hst = tc::smem_u32(smem + OFF_HST);
         const int wq = __shfl_sync(0xffffffffu, warp, 0) & 3;
         auto round = [&](auto rc) {
@@ -659,7 +674,7 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
             const float p0 = x * w0, p1 = x * w1;
             in[i] = p0; in[8 + i] = p0 * x; in[16 + i] = p1; in[24 + i] = p1 * x;
           }
-          pool_rows<G, 32>(stg, lane, lane0, v, in, st);
+          gpool32(in, st);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             st[8 + i] = fmaf(-st[i] * st[i], c0, st[8 + i]);
@@ -770,10 +785,10 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
       // ---------------- softmax colour blend over the views (ibrnet.py:365-367) ----------------
       float rgbo[3];
       {
-        const float mx = bmax<G>(logit);
+        const float mx = gmax(logit);
         const float e = v >= rfn ? 0.f : expf(logit - mx);
         float acc[4] = {e, e * rgbin[0], e * rgbin[1], e * rgbin[2]};
-        bsum_vec<G, 4>(acc);
+        if constexpr (P2) bsum_vec<G, 4>(acc); else gsum4_np2<G>(stg, lane, lane0, idle, acc);
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) rgbo[cc] = acc[1 + cc] / acc[0];
       }
@@ -781,9 +796,9 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
       PM_TICK(14)
       // ---------------- view pooling #2 (ibrnet.py:352-353) -> geometry_fc.0 on the tensor cores, geometry_fc.2 across the lanes ----------------
       {
-        const float vs = bsum<G>(vis2);
+        const float vs = gsum(vis2);
         const float w2 = vis2 / (vs + 1e-8f);
-        const float sw2 = bsum<G>(w2);
+        const float sw2 = gsum(w2);
         const float wmean = sw2 / float(rfn);
         // two K rounds of 16 features x (mean, var) and a third with the mean weight and the constant that multiplies the
         // bias column, one ring stage each; sums over the views through pool_rows, variance from the second moment (above)
@@ -793,7 +808,7 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
           float in[32], st[32];
 #pragma unroll
           for (int i = 0; i < 16; ++i) { const float p = xr[16 * R + i] * w2; in[i] = p; in[16 + i] = p * xr[16 * R + i]; }
-          pool_rows<G, 32>(stg, lane, lane0, v, in, st);
+          gpool32(in, st);
 #pragma unroll
           for (int i = 0; i < 16; ++i) st[16 + i] = fmaf(-st[i] * st[i], c2, st[16 + i]);
           if (R > 0) wait_layer(b);                                                  // the previous round has read A[0:64)
@@ -817,13 +832,14 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
           float d[64];
           ld32(b, 96, d);
           ld32(b, 128, d + 32);
+          // GE = the lanes of the point that take part (all G of a power-of-two group, else the first 8 / 4)
 #pragma unroll
-          for (int m = G >> 1, len = 32; m >= 1; m >>= 1, len >>= 1) {
+          for (int m = GE >> 1, len = 32; m >= 1; m >>= 1, len >>= 1) {
 #pragma unroll
             for (int k = 0; k < len; ++k) d[k] = (v & m) ? d[len + k] : d[k];
           }
 #pragma unroll
-          for (int j = 0; j < CPL; ++j) hh[j] = elu(d[j]);
+          for (int j = 0; j < CPL; ++j) hh[j] = (P2 || v < GE) ? elu(d[j]) : 0.f;
         }
         float out[16];
 #pragma unroll
@@ -831,13 +847,13 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) {                                               // sWg1 is stored output-major: [16][64]
           float wk[CPL];
-          ld_cols<G>(sWg1 + k * 64, v, wk);
+          ld_cols<GE>(sWg1 + k * 64, (P2 || v < GE) ? v : 0, wk);
 #pragma unroll
           for (int j = 0; j < CPL; ++j) out[k] = fmaf(wk[j], hh[j], out[k]);
         }
         {
           float sum[16];
-          pool_rows<G, 16>(stg, lane, lane0, v, out, sum);
+          if constexpr (P2) pool_rows<G, 16>(stg, lane, lane0, v, out, sum); else pool_rows_np2<G, 16>(stg, lane, lane0, v, idle, out, sum);
 #pragma unroll
           for (int k = 0; k < 16; ++k) out[k] = elu(sum[k] + sWg1[64 * 16 + k]);
         }

@@ -193,10 +193,11 @@ def test_against_oracle_mid_size():
     assert torch.equal(out["ray_mask"].cpu(), gold["ray_mask"])
 
 
-@pytest.mark.parametrize("rfn", [1, 2, 5, 10, 16, 20, 32])
+@pytest.mark.parametrize("rfn", [1, 2, 3, 5, 6, 8, 9, 10, 16, 20, 32])
 def test_view_counts(rfn):
     """Every lanes-per-point instantiation of the point kernel (4, 8, 16, 32 lanes; padding lanes when the view count
-    is not a power of two -- cfg4 of SURVEY.md 8d renders with 10 views) against the CPU oracle on a small seeded case."""
+    is not a power of two; groups of 5, 6 and 10 lanes that are reduced through shared memory -- cfg4 of SURVEY.md 8d renders with 10 views)
+    against the CPU oracle on a small seeded case."""
     cfg = {"use_hierarchical_sampling": True, "dist_decoder_cfg": {"use_vis": False}, "render_depth": True}
     que, ref = synthetic.make_scene(48, 64, rfn, seed=100 + rfn, smooth=2)
     que = synthetic.slice_rays(que, 1000, 1048)
