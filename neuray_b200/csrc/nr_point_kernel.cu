@@ -21,7 +21,11 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 
 constexpr int REC = NR_POINT_REC;
 constexpr int RING_STAGE = 4096;    // 16 KB
-constexpr int NBUF = 3;
+constexpr int NBUF = 4;             // depth of the shared weight ring.  The three blocks of a CTA consume every stage, so the depth bounds how far
+                                    // they can drift apart: 3 -> 4 slots = +1.9 % (166.6 -> 169.8 M); more does not fit next to the resident
+                                    // base_fc.0 tile, and streaming that tile too (19 stages per tile, 6..9 slots) costs 13..18 %.
+                                    // Also measured and rejected (profiles/README.md): feeding from all three blocks through a shared
+                                    // claim counter (-9 %), feeding from a non-issuing warp of block 0 (-2.5 %), a non-inlined feed (-12 %)
 constexpr int SW = 2048;
 
 // ---- small resident weights (floats inside `sw`) ----
