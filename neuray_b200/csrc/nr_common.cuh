@@ -164,7 +164,9 @@ __device__ __forceinline__ float elu(float x) {
   return y;
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
-__device__ __forceinline__ float softplusf_(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+// softplus(x) = max(x, 0) + log(1 + exp(-|x|)): the exponential is in (0, 1], so the fast ex2/lg2 paths are accurate to ~2e-7
+// absolute here (log1pf(expf(x)) costs two slow-path libm calls per value)
+__device__ __forceinline__ float softplusf_(float x) { return x > 20.f ? x : fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x))); }
 // 0.5 + 0.5 tanh(x), accurate to ~1e-7 absolute (tanh.approx is only ~5e-4)
 __device__ __forceinline__ float logistic_cdf(float x) {
   // 0.5 + 0.5*tanh(x) = 1/(1+exp(-2x))

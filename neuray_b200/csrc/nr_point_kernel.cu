@@ -50,24 +50,28 @@ struct Producer {
   const float* w_tc;
   float* ring;
   uint64_t *wfull, *wempty;
+  const int2* table;      // shared: per stage of a tile (source offset in floats, bytes), built once at kernel start
   uint32_t next;          // next stage index to issue
   uint32_t total;         // iters * stages_per_tile
-  int stages_per_tile, n_heads;
+  int stages_per_tile;
+  int s;                  // next % stages_per_tile, kept as a running counter (this code runs on one lane, inside block 0's MMA-issue
+                          // path: every instruction counts)
 
+  // (source offset, bytes) of stage s of a tile: heads, prob_embed x2, base_fc.0 x3, base_fc.2, vis, vis2+rgb, geometry_fc.0 x3
+  __device__ static int2 stage_source(int s, int n_heads) {
+    if (s < n_heads) return make_int2(tcl::HEAD0 + s * RING_STAGE, RING_STAGE * 4);
+    const int t = s - n_heads;
+    const int src = t == 0 ? tcl::PE0 : t == 1 ? tcl::PE1 : t <= 4 ? tcl::B0 + (t - 2) * RING_STAGE : t == 5 ? tcl::B1 : t == 6 ? tcl::V01
+                  : t == 7 ? tcl::V2R : tcl::G0 + (t - 8) * RING_STAGE;
+    return make_int2(src, t == 1 ? 3072 * 4 : RING_STAGE * 4);
+  }
   __device__ __forceinline__ void issue() {
-    const int s = int(next % uint32_t(stages_per_tile));
-    int src, bytes = RING_STAGE * 4;
-    if (s < n_heads) src = tcl::HEAD0 + s * RING_STAGE;
-    else {
-      const int t = s - n_heads;
-      src = t == 0 ? tcl::PE0 : t == 1 ? tcl::PE1 : t <= 4 ? tcl::B0 + (t - 2) * RING_STAGE : t == 5 ? tcl::B1 : t == 6 ? tcl::V01 : t == 7 ? tcl::V2R
-                                                                                                                       : tcl::G0 + (t - 8) * RING_STAGE;   // pm3 only
-      if (t == 1) bytes = 3072 * 4;
-    }
+    const int2 e = table[s];
     const uint32_t buf = next % NBUF;
-    tc::mbar_arrive_expect_tx(wfull + buf, bytes);
-    tc::bulk_g2s(ring + buf * RING_STAGE, w_tc + src, bytes, wfull + buf);
+    tc::mbar_arrive_expect_tx(wfull + buf, e.y);
+    tc::bulk_g2s(ring + buf * RING_STAGE, w_tc + e.x, e.y, wfull + buf);
     ++next;
+    if (++s == stages_per_tile) s = 0;
   }
   // make sure stages [.., last] are in flight; then try to run ahead without blocking
   __device__ __forceinline__ void feed(uint32_t last) {

@@ -47,7 +47,10 @@ constexpr int OFF_SW = OFF_WG1 + WG1;                         // small resident 
 constexpr int OFF_STG = OFF_SW + SW;                          // gather transposition: per warp [32 rows][36]
 constexpr int STG_ROW = 36;
 constexpr int STG = (NCOMP / 32) * 32 * STG_ROW;
-constexpr int OFF_BAR = OFF_STG + STG;
+constexpr int OFF_CAM = OFF_STG + STG;                        // que_cam [24] (padded to 32) | view_params [NR_MAX_VIEWS][20]
+constexpr int CAM = 32 + NR_MAX_VIEWS * 20;
+constexpr int OFF_STAB = OFF_CAM + CAM;                       // Producer::table: int2 per stage of a tile (at most 4 + 11)
+constexpr int OFF_BAR = OFF_STAB + 32;
 constexpr int SMEM_FLOATS = OFF_BAR + 32;
 constexpr size_t SMEM_BYTES = size_t(SMEM_FLOATS) * 4;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -233,6 +236,9 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
     for (int i = tid; i < 64 * 16; i += NCOMP)
       sWg1[(i & 15) * 64 + own_col<GE>((i >> 4) / CPL, (i >> 4) % CPL)] = __ldg(W + lay::GRP_D2 + lay::GEO1_W + i);
     cp(sWg1 + 64 * 16, lay::GRP_D2 + lay::GEO1_B, 16);
+    if (tid < stages_per_tile) reinterpret_cast<int2*>(smem + OFF_STAB)[tid] = Producer::stage_source(tid, n_heads);
+    for (int i = tid; i < 24; i += NCOMP) smem[OFF_CAM + i] = __ldg(pp.que_cam + i);
+    for (int i = tid; i < pp.rfn * 20; i += NCOMP) smem[OFF_CAM + 32 + i] = __ldg(pp.view_params + i);
   }
   tc::fence_before_thread_sync();
   __syncthreads();
@@ -282,7 +288,7 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
     Producer prod;
     prod.w_tc = pp.w_tc; prod.ring = ring; prod.wfull = wfull; prod.wempty = wempty;
     prod.next = 0; prod.total = uint32_t(iters) * uint32_t(stages_per_tile);
-    prod.stages_per_tile = stages_per_tile; prod.n_heads = n_heads;
+    prod.stages_per_tile = stages_per_tile; prod.s = 0; prod.table = reinterpret_cast<const int2*>(smem + OFF_STAB);
     b.prod = tid == 0 ? &prod : nullptr;
     if (tid == 0) prod.feed(0);
 
@@ -314,7 +320,7 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
       // ---------------- ray geometry of this row's point (every lane of the group computes the same values) ----------------
       float X = 0.f, Y = 0.f, Z = 0.f, qx = 0.f, qy = 0.f, qz = 0.f, ihp = 0.f, ihc = 0.f;
       if (pt_ok) {
-        const float* __restrict__ cam = pp.que_cam;
+        const float* cam = smem + OFF_CAM;
         const int ray = n / dn, s = n - ray * dn;
         const float cx = __ldg(pp.coords + 2 * ray), cy = __ldg(pp.coords + 2 * ray + 1);
         float cm[3], d[3];
@@ -344,10 +350,10 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
       int tcode = -1;
       float tw[4] = {0.f, 0.f, 0.f, 0.f};
       if (row_ok) {
-        const float* __restrict__ vp = pp.view_params + v * 20;
-        const float xh = fmaf(__ldg(vp + 2), Z, fmaf(__ldg(vp + 1), Y, __ldg(vp + 0) * X)) + __ldg(vp + 3);
-        const float yh = fmaf(__ldg(vp + 6), Z, fmaf(__ldg(vp + 5), Y, __ldg(vp + 4) * X)) + __ldg(vp + 7);
-        float zh = fmaf(__ldg(vp + 10), Z, fmaf(__ldg(vp + 9), Y, __ldg(vp + 8) * X)) + __ldg(vp + 11);
+        const float* vp = smem + OFF_CAM + 32 + v * 20;
+        const float xh = fmaf(vp[2], Z, fmaf(vp[1], Y, vp[0] * X)) + vp[3];
+        const float yh = fmaf(vp[6], Z, fmaf(vp[5], Y, vp[4] * X)) + vp[7];
+        float zh = fmaf(vp[10], Z, fmaf(vp[9], Y, vp[8] * X)) + vp[11];
         const bool degenerate = fabsf(zh) < 1e-4f;
         if (degenerate) zh = 1e-3f;
         const float ux = xh / zh, uy = yh / zh;
@@ -355,7 +361,7 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
         const bool valid = !degenerate && !outside;
         mrow = valid ? 1.f : 0.f;
         zrow = zh;
-        const float dx = X - __ldg(vp + 12), dy = Y - __ldg(vp + 13), dz = Z - __ldg(vp + 14);
+        const float dx = X - vp[12], dy = Y - vp[13], dz = Z - vp[14];
         const float inv = -1.f / fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-5f);
         const float ex = dx * inv, ey = dy * inv, ez = dz * inv;
         dd[0] = ex - qx; dd[1] = ey - qy; dd[2] = ez - qz; dd[3] = ex * qx + ey * qy + ez * qz;
@@ -546,9 +552,9 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
       PM_TICK(4)
       float hit = 0.f, visib = 0.f;
       {
-        const float* __restrict__ vp = pp.view_params + (v < rfn ? v : 0) * 20;
+        const float* vp = smem + OFF_CAM + 32 + (v < rfn ? v : 0) * 20;
         const float zc = fmaxf(zrow, 1e-5f);
-        const float a = __ldg(vp + 15), bb = __ldg(vp + 16);
+        const float a = vp[15], bb = vp[16];
         const float tz = (-1.f / zc - a) / (bb - a);
         const float lo = tz - ihp, hi = tz + ihc;
         const float aw = sigmoidf_(hv[2][0]);
