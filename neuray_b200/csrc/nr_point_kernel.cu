@@ -332,7 +332,7 @@ static int launch_pm3(pkt::KParams kp, cudaStream_t stream) {
   const int groups = (kp.n_tiles + pkt::pm3::NBLK - 1) / pkt::pm3::NBLK;
   const int sms = device_sms();
   const int grid = groups < sms ? groups : sms;
-  return kp.dbg ? launch_pm3_inst<G, true>(kp, grid, stream) : launch_pm3_inst<G, false>(kp, grid, stream);
+  return (kp.dbg || kp.timing) ? launch_pm3_inst<G, true>(kp, grid, stream) : launch_pm3_inst<G, false>(kp, grid, stream);
 }
 
 // `timing`: optional clock64() stamps at the phase boundaries (nr_point_kernel_timing), passed per call
