@@ -212,8 +212,20 @@ def sharded_image(ctx, steps, warmup, e2e=True):
 
     t = ctx.timed(step, steps, warmup)
     coll_ms = [a.elapsed_time(b) for a, b in coll[-steps:]] if coll else []
+    # correctness of the sharded path, checked where it is measured (the driver's GPU test box has one GPU): every rank renders
+    # the same 4096-ray stretch that straddles a shard boundary on its own and compares it with the gathered image, bit for bit
+    identical = None
+    if ctx.world > 1:
+        full = step()
+        lo = max(0, nrd.ray_range(rays, 1, ctx.world)[0] - 2048)
+        q = dict(dq, coords=dq["coords"][:, lo:lo + 4096].contiguous())
+        with torch.no_grad():
+            local = net.render(q, dr, False)
+        same = torch.tensor([float(all(torch.equal(local[k], full[k][:, lo:lo + 4096]) for k in local))], device=ctx.dev)
+        ctx.dist.all_reduce(same, op=ctx.dist.ReduceOp.MIN)
+        identical = bool(same.item())
     res = {"workload": wl["desc"], "value": samples * steps / t, "unit": "ray-samples/s", "ms_per_step": t / steps * 1e3,
-           "scaling": "strong", "rays": rays, "n_gpus": ctx.world,
+           "scaling": "strong", "rays": rays, "n_gpus": ctx.world, "sharded_equals_single_gpu_bitwise": identical,
            "allgather_ms": ctx.max_over_ranks(sum(coll_ms) / len(coll_ms)) if coll_ms else 0.0,
            "allgather_bytes": int(-(-rays // ctx.world) * ctx.world * 4 * 8) if ctx.world > 1 else 0,
            "parallelism": f"rays of one image sharded over {ctx.world} rank(s); one NCCL all-gather of all output keys per frame"}
@@ -272,10 +284,19 @@ def train_step_bench(ctx, steps, warmup, e2e=True):
     l0 = _lib.LAUNCHES
     t = ctx.timed(step, steps, warmup)
     launches = (_lib.LAUNCHES - l0) // (steps + warmup)
+    # after the all-reduce every rank must hold the same gradients (checked here because the driver's GPU test box has one GPU)
+    grads_agree = None
+    if ctx.world > 1:
+        flat = torch.cat([p.grad.reshape(-1) for p in net.parameters() if p.grad is not None])
+        ref_flat = flat.clone()
+        ctx.dist.broadcast(ref_flat, 0)
+        diff = (flat - ref_flat).abs().max().reshape(1)
+        ctx.dist.all_reduce(diff, op=ctx.dist.ReduceOp.MAX)
+        grads_agree = bool(diff.item() == 0.0)
     coll_ms = [a.elapsed_time(b) for a, b in coll[-steps:]] if coll else []
     samples = TRAIN_RAYS * sum(wl["dn"]) * ctx.world
     res = {"workload": wl["desc"], "value": samples * steps / t, "unit": "ray-samples/s", "ms_per_step": t / steps * 1e3, "scaling": "weak",
-           "rays_per_rank": TRAIN_RAYS, "n_gpus": ctx.world, "kernels_per_step": launches,
+           "rays_per_rank": TRAIN_RAYS, "n_gpus": ctx.world, "kernels_per_step": launches, "gradients_identical_on_all_ranks": grads_agree,
            "allreduce_ms": ctx.max_over_ranks(sum(coll_ms) / len(coll_ms)) if coll_ms else 0.0,
            "allreduce_bytes": sum(p.numel() for p in net.parameters()) * 4 if ctx.world > 1 else 0,
            "loss": float(state["loss"]),

@@ -110,8 +110,15 @@ enum PointGrad {
 // K-chunk of a Linear's input is one contiguous block of n_in x 512 bytes for the weight-gradient GEMMs (with a plain
 // slot-major layout every slot of a row is a megabyte apart).
 constexpr int TILE = 128;
+#ifndef NR_TAPE_RESTRICT
+#define NR_TAPE_RESTRICT 0
+#endif
 struct Tape {
+#if NR_TAPE_RESTRICT
+  float* __restrict__ p;
+#else
   float* p;
+#endif
   long long rows;     // logical rows (the buffer holds ceil(rows / 128) * 128)
   int slots;
   NR_HD float& at(int slot, long long i) const { return p[((i >> 7) * slots + slot) * TILE + (i & (TILE - 1))]; }
@@ -193,6 +200,15 @@ NR_HD void atomic_add(float* p, float v) {
   atomicAdd(p, v);
 #else
   *p += v;
+#endif
+}
+
+// four consecutive floats (16-byte aligned) in one reduction: red.global.add.v4.f32 on the device
+NR_HD void atomic_add4(float* p, float a, float b, float c, float d) {
+#ifdef __CUDA_ARCH__
+  atomicAdd(reinterpret_cast<float4*>(p), make_float4(a, b, c, d));
+#else
+  p[0] += a; p[1] += b; p[2] += c; p[3] += d;
 #endif
 }
 
@@ -992,7 +1008,10 @@ NR_HD void row_backward_d(const Ctx& c, long long r) {
       const int off[4] = {0, dxo, dyo, dyo + dxo};
       for (int t = 0; t < 4; ++t) {
         if (tw[t] == 0.f) continue;
-        for (int k = 0; k < 32; ++k) { atomic_add(base + off[t] + k, drf[k] * tw[t]); atomic_add(base + off[t] + 32 + k, dimf[k] * tw[t]); }
+        for (int k = 0; k < 32; k += 4) {          // 16 vector reductions per tap instead of 64 scalar ones
+          atomic_add4(base + off[t] + k, drf[k] * tw[t], drf[k + 1] * tw[t], drf[k + 2] * tw[t], drf[k + 3] * tw[t]);
+          atomic_add4(base + off[t] + 32 + k, dimf[k] * tw[t], dimf[k + 1] * tw[t], dimf[k + 2] * tw[t], dimf[k + 3] * tw[t]);
+        }
       }
     }
   }
