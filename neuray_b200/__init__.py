@@ -3,10 +3,12 @@
 Drop-in surface:
     neuray_b200.render_ops      mirrors reference network/render_ops.py (same 12 function names)
     neuray_b200.renderer        NeuralRayBaseRenderer-compatible render_by_depth / render_impl / render
-    neuray_b200.patch           installs both into an importable reference tree (render.py / run_training.py unchanged)
+    neuray_b200.init_ops        get_diff_feats of the reference's DepthInitNet (network/init_net.py:29-61)
+    neuray_b200.patch           installs them into an importable reference tree (render.py / run_training.py unchanged)
+    neuray_b200.dist            ray-sharded rendering + gradient all-reduce over torch.distributed (NCCL)
 
 All arithmetic runs in hand-written CUDA kernels behind the C-ABI declared in include/neuray_b200.h
 (libneuray_b200.so, loaded with ctypes).  There is no CPU or PyTorch fallback: calling any op without the
 built library, or with non-CUDA tensors, raises.
 """
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -1,15 +1,19 @@
-// Point kernel, point-major tensor-core version with THREE 128-row blocks per SM (namespace nr::pkt::pm3).
+// Point kernel (namespace nr::pkt::pm3): point-major rows, tcgen05 layers, THREE independent 128-row blocks per SM.
 //
-// Same row ownership and arithmetic as point_kernel_pm (nr_point_kernel_pm.cuh); what changes is the resource plan, so
-// that a third block fits next to the other two and fills the issue slots they leave idle while they wait for their MMAs:
-//   * tensor memory: 160 columns per block instead of 224.  Activations: hi parts at columns [0,64), lo parts at
-//     [64,128), accumulator at [128,160).  base_fc.0 (N = 64) is issued in two K rounds into one accumulator at
-//     [96,160): round A (the 32 neuray_feat inputs) right after prob_embed.2 while they are still the only live A
-//     operand, round B (the 40 rgb_feat inputs, lo parts at [48,88)) after the first view pooling.  Its epilogue reads
-//     the accumulator half by half and writes base_fc.2's operand over the columns it has already consumed.
-//   * shared memory: the gather is transposed in two channel passes (ray_feats, then img_feats) through a per-warp
-//     [32][36] buffer instead of one [32][68] pass; img_feats stay there until ray_dir_fc needs them.
+// Row = point * G + view inside a block (G lanes per point: 4, 5, 6, 8, 10, 16 or 32), thread r = row r = TMEM lane r; a thread
+// keeps its row in registers from the gather to the output record.  Resource plan (one CTA of 384 threads per SM):
+//   * tensor memory: 160 columns per block.  Activations: hi parts at columns [0,64), lo parts at [64,128), accumulator at
+//     [128,160).  base_fc.0 (N = 64) is issued in K rounds into one accumulator at [96,160): round A (the 32 neuray_feat
+//     inputs) right after prob_embed.2 while they are still the only live A operand, round B (the 40 rgb_feat inputs, lo parts
+//     at [48,88)) after ray_dir_fc, then five rounds of view-pooled statistics (K 32 each).  Its epilogue reads the accumulator
+//     half by half and writes base_fc.2's operand over the columns it has already consumed.
+//   * shared memory (230 KB): 4 x 16 KB weight ring (TMA bulk copies, fed by thread 0), the resident tiles of the pooled
+//     base_fc.0 inputs (80 KB) and of ray_dir_fc.2, small weights, camera blocks, and one [32][36] transposition buffer per warp:
+//     gather (two channel passes: ray_feats, then img_feats, which stay there until ray_dir_fc needs them), the cross-view
+//     pooling (pm::pool_rows) and the lane-group sums of the non-power-of-two groups all go through it.
 //   * 384 threads: three warps per SM sub-partition, i.e. at most 168 registers per thread.
+// The three blocks exist to fill each other's bubbles: a block has ~25 MMA round trips per tile during which its four warps
+// have nothing to do (profiles/r2_point_kernel_v4_lines.txt).
 #pragma once
 
 namespace pm3 {
@@ -43,7 +47,7 @@ constexpr int OFF_HST = OFF_RING + NBUF * RING_STAGE;         // view-pooled par
 constexpr int OFF_RD1 = OFF_HST + tcl::HST_SIZE;              // ray_dir_fc.2 tensor-core tile (resident, 1024-byte aligned)
 constexpr int OFF_WG1 = OFF_RD1 + tcl::RD1_SIZE;              // geometry_fc.2: [16][64] (output-major, columns in own_col order) | bias[16]
 constexpr int WG1 = 64 * 16 + 16;
-constexpr int OFF_SW = OFF_WG1 + WG1;                         // small resident weights (same layout as point_kernel_tc)
+constexpr int OFF_SW = OFF_WG1 + WG1;                         // small resident weights (offsets SW_*, nr_point_kernel.cu)
 constexpr int OFF_STG = OFF_SW + SW;                          // gather transposition: per warp [32 rows][36]
 constexpr int STG_ROW = 36;
 constexpr int STG = (NCOMP / 32) * 32 * STG_ROW;

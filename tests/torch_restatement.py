@@ -141,7 +141,7 @@ def render_pass_torch(P, dec, agg, cfgv, que_depth, coords, que_pose, que_K, que
 def self_hit_prob_torch(P, dec, use_vis_prob, var_bias, que_ray_feats, coords, h, w, que_depth, que_range):
     """predict_self_hit_prob (reference renderer.py:137-155 + dist_decoder.py compute_prob with is_ref=False): the query
     view's own visibility features decoded along its rays (fine-tuning configs).  PyTorch restatement: the A/B reference of
-    nr_self_hit_prob (NR_BACKWARD=torch selects it).
+    nr_self_hit_prob.
     que_ray_feats [qn,32,fh,fw], coords [qn,rn,2], que_depth [qn,rn,dn] -> hit_prob_self [qn,rn,dn]."""
     fh, fw = que_ray_feats.shape[-2:]
     feats = _bilinear(que_ray_feats, coords, h, w, fh == h and fw == w)                      # [qn,rn,32]
