@@ -67,9 +67,13 @@ static_assert((OFF_HST * 4) % 1024 == 0 && (OFF_RD1 * 4) % 1024 == 0 && OFF_WG1 
 template <int N, int NCH, int AHI, int LOOFF, int NLIN, int TAILHI, int DCOL, int CB0, int NSTG, uint32_t OFF_HI, uint32_t OFF_LO,
           uint32_t SLAB, bool WAIT_FULL, bool RELEASE, bool ACC>
 __device__ __forceinline__ void issue_layer(Blk& b) {
+  // b.tk: diagnostics of ONE layer's round trip (debug instantiation only; a compile-time null otherwise)
+  if (b.tk) b.tk[0] = clock64();
   tc::tmem_st_wait();
   tc::fence_before_thread_sync();
+  if (b.tk) b.tk[1] = clock64();
   tc::named_sync(2 + b.blk, 128);
+  if (b.tk) b.tk[2] = clock64();
   if (b.issuer_warp) {                       // warp-uniform branch; one elected lane issues
     tc::fence_after_thread_sync();
     const uint32_t st0 = b.wi % NBUF;
@@ -79,6 +83,7 @@ __device__ __forceinline__ void issue_layer(Blk& b) {
 #pragma unroll
       for (int s = 0; s < NSTG; ++s) tc::mbar_wait(b.wfull + ((st0 + s) % NBUF), ((b.wi + s) / NBUF) & 1);
     }
+    if (b.tk) b.tk[3] = clock64();
     if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::idesc_tf32(N);
       uint64_t dhi[NSTG], dlo[NSTG];
@@ -107,6 +112,7 @@ __device__ __forceinline__ void issue_layer(Blk& b) {
       tc::mma_commit(b.mma_bar);
     }
     __syncwarp();
+    if (b.tk) b.tk[4] = clock64();
   }
   if (RELEASE) b.wi += NSTG;
 }
@@ -142,6 +148,7 @@ __device__ __forceinline__ void wait_layer(Blk& b) {
   tc::mbar_wait(b.mma_bar, b.phase);
   b.phase ^= 1;
   tc::fence_after_thread_sync();
+  if (b.tk) b.tk[5] = clock64();
 }
 // the common case: activations hi [0,64) / lo [64,128), accumulator at 128, one ring stage
 template <int N, int NCH, int AHI, int NLIN, int TAILHI, uint32_t OFF_HI, uint32_t OFF_LO, uint32_t SLAB, bool WAIT_FULL, bool RELEASE>
@@ -720,11 +727,15 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
 
       PM_TICK(9)
       // ---------------- vis_fc, vis_fc2, rgb_fc ----------------
+      if constexpr (DEBUG) {
+        if (kp.timing != nullptr && blockIdx.x == 0 && b.leader && b.blk < 2 && it < 64) b.tk = kp.timing + (it * 2 + b.blk) * 32 + 16;
+      }
       run_layer<32, 4, 0, 4, 0, 0, 1024 * 4, 0, true, false>(b);                     // vis_fc.0 (row scale folded into the epilogue)
       float lg = sw[SW_V1LB];
       {
         float x[32];
         ld32(b, 128, x);
+        if (b.tk) b.tk[6] = clock64();
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float4 bb = *reinterpret_cast<const float4*>(sw + SW_V0B + 4 * q);
@@ -733,7 +744,9 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
           x[4 * q + 2] = elu(fmaf(w1, x[4 * q + 2], bb.z)); x[4 * q + 3] = elu(fmaf(w1, x[4 * q + 3], bb.w));
           lg = fmaf(wl.w, x[4 * q + 3], fmaf(wl.z, x[4 * q + 2], fmaf(wl.y, x[4 * q + 1], fmaf(wl.x, x[4 * q], lg))));
         }
+        if (b.tk) b.tk[7] = clock64();
         st32(b, 32, 96, x);
+        if (b.tk) { b.tk[8] = clock64(); b.tk = nullptr; }
       }
       PM_TICK(10)
       const float visa = sigmoidf_(elu(lg)) * mrow;
