@@ -37,8 +37,14 @@ constexpr int GB = NR_GATHER_BATCH;                           // rows whose 4 ta
 #define NR_GATHER_OVERLAP 1
 #endif
 constexpr int NBLK = 3;
+#ifndef NR_PRODUCER_WARP
+#define NR_PRODUCER_WARP 1
+#endif
 constexpr int NCOMP = NBLK * 128;
-constexpr int NTHR = NCOMP;
+// + one warp group whose lane 0 does nothing but keep the weight ring full.  Registers are handed out per 4 warps, so the
+// CTA launches at 512 x 128 and the producer group gives its registers to the compute groups (setmaxnreg below).
+constexpr int NTHR = NCOMP + (NR_PRODUCER_WARP ? 128 : 0);
+constexpr int REGS_COMPUTE = 160, REGS_PRODUCER = 24;
 constexpr int TCOLS = 160;                                    // tensor-memory columns per block
 
 // ---- shared memory map (floats) ----
@@ -263,8 +269,33 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
   }
   __syncthreads();
 
+#if NR_PRODUCER_WARP
+  if (tid >= NCOMP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
+    // ---------------- producer warp: a stage goes out the moment its ring slot is free ----------------
+    // (fed from a compute thread's issue path, a load only started at that thread's next layer: ~500-850 cycles of every
+    // layer's round trip were the issuing lane waiting for weights, profiles/r2_phase_timing.md)
+    if (tid == NCOMP) {
+      const int2* table = reinterpret_cast<const int2*>(smem + OFF_STAB);
+      const uint32_t total = uint32_t(iters) * uint32_t(stages_per_tile);
+      int s = 0;
+      for (uint32_t n = 0; n < total; ++n) {
+        const uint32_t buf = n % NBUF;
+        if (n >= NBUF) tc::mbar_wait(wempty + buf, ((n / NBUF) - 1) & 1);
+        const int2 e = table[s];
+        tc::mbar_arrive_expect_tx(wfull + buf, e.y);
+        tc::bulk_g2s(ring + buf * RING_STAGE, pp.w_tc + e.x, e.y, wfull + buf);
+        if (++s == stages_per_tile) s = 0;
+      }
+    }
+    __syncwarp();
+  } else
+#endif
   {
-    // ---------------- compute warps (thread 0 also feeds the weight ring, see Producer) ----------------
+#if NR_PRODUCER_WARP
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_COMPUTE));
+#endif
+    // ---------------- compute warps ----------------
     const int fh = pp.fh, fw = pp.fw, h = pp.h, w = pp.w;
     const bool feat_align = (fh == h && fw == w);
     const int grp = lane / G;                       // point of this lane inside the warp (>= PPW: idle lane)
@@ -300,8 +331,13 @@ __global__ void __launch_bounds__(NTHR, 1) point_kernel_pm3(const KParams kp) {
     prod.w_tc = pp.w_tc; prod.ring = ring; prod.wfull = wfull; prod.wempty = wempty;
     prod.next = 0; prod.total = uint32_t(iters) * uint32_t(stages_per_tile);
     prod.stages_per_tile = stages_per_tile; prod.s = 0; prod.table = reinterpret_cast<const int2*>(smem + OFF_STAB);
-    b.prod = tid == 0 ? &prod : nullptr;
+#if NR_PRODUCER_WARP
+    b.prod = nullptr;
+    (void)prod;
+#else
+    b.prod = tid == 0 ? &prod : nullptr;                       // thread 0 feeds the ring from inside its own issue path
     if (tid == 0) prod.feed(0);
+#endif
 
   // phase stamps exist only in the DEBUG instantiation (nr_point_kernel_timing / nr_point_kernel_debug)
 #define PM_TICK(id)                                                                                      \
