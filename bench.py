@@ -456,6 +456,80 @@ def eager_gpu_baseline(dq, dr, cfg, dn, dev, rays=4096, reps=3):
             "kind": "reference", "what": "the unmodified reference's render_impl (coarse + fine) as PyTorch-eager CUDA ops on the same GPU, one 4096-ray chunk"}
 
 
+def encoder_flops(h, w):
+    """Algorithmic FLOP (2 x MAC, convolutions only) of image_encoder + vis_encoder for one h x w view
+    (ResUNetLight(3,[1,2,6,4],32,inplanes=16), ops.py:150-230; DefaultVisEncoder, vis_encoder.py:6-21)."""
+    c = lambda n: (n - 1) // 2 + 1
+    h0, w0 = c(h), c(w); h1, w1 = c(h0), c(w0); h2, w2 = c(h1), c(w1); h3, w3 = c(h2), c(w2)
+    u3, u2 = (2 * h3) * (2 * w3), (4 * h3) * (4 * w3)
+    mac = h0 * w0 * 16 * 147
+    mac += h1 * w1 * (32 * 16 * 9 + 32 * 32 * 9 + 32 * 16)
+    mac += h2 * w2 * (64 * 32 * 9 + 64 * 64 * 9 + 64 * 32 + 2 * 64 * 64 * 9)
+    mac += h3 * w3 * (128 * 64 * 9 + 128 * 128 * 9 + 128 * 64 + 10 * 128 * 128 * 9)
+    mac += u3 * 2 * 64 * 128 * 9 + u2 * (2 * 32 * 64 * 9 + 32 * 32)
+    mac += u2 * (32 * 64 * 9 + 4 * 32 * 32 * 9 + 32 * 32)
+    return 2 * mac
+
+
+def encoders_bench(dr, dev, reps=5):
+    """Auxiliary: the per-frame encoders of the headline workload's reference views -- native
+    (nr_image_encoder_fwd + nr_vis_encoder_fwd writing the frame pack in place) against the UNMODIFIED reference modules as
+    PyTorch / cuDNN ops on the same GPU, same random-init parameters, same inputs."""
+    import types
+    from neuray_b200 import encoders
+    imgs, ray_in = dr["imgs"], dr["ray_feats"]
+    rfn, _, h, w = imgs.shape
+    fh, fw = encoders.image_dims(h, w)
+    torch.manual_seed(0)
+    owner = types.SimpleNamespace(image_encoder=encoders.ImageEncoder().to(dev), vis_encoder=encoders.VisEncoder().to(dev))
+    feat = torch.empty(rfn, fh, fw, 64, device=dev)
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    info = {"imgs": imgs, "ray_feats": ray_in}
+    with torch.no_grad():
+        ms = timed(lambda: encoders.encode_frame(owner, dict(info), feat))
+    fl = encoder_flops(h, w) * rfn
+    res = {"ms_per_frame": ms, "views": rfn, "image": [h, w], "algorithmic_tflops": fl / ms / 1e9, "flop_per_frame": fl,
+           "kernels_per_frame": encoders.IMAGE_LAUNCHES + encoders.VIS_LAUNCHES + 3,
+           "what": "image_encoder + vis_encoder of all reference views into the channel-last frame pack (3xTF32 tensor-core convolutions: fp32 accuracy)"}
+    ref_mod = _load_reference()
+    if ref_mod is None:
+        res["reference"] = {"unavailable": "baseline/_ref missing"}
+        return res
+    from network.ops import ResUNetLight
+    from network.vis_encoder import DefaultVisEncoder
+    ie, ve = ResUNetLight(3, [1, 2, 6, 4], 32, inplanes=16).to(dev).eval(), DefaultVisEncoder({}).to(dev).eval()
+    ie.load_state_dict(owner.image_encoder.state_dict(), strict=True)
+    ve.load_state_dict(owner.vis_encoder.state_dict(), strict=True)
+
+    def ref_run():
+        f = ie(imgs)
+        return f, ve(ray_in, f)
+
+    old = torch.backends.cudnn.allow_tf32
+    with torch.no_grad():
+        ms_tf32 = timed(ref_run)                       # torch default: cuDNN may use TF32 for fp32 convolutions
+        torch.backends.cudnn.allow_tf32 = False
+        ms_fp32 = timed(ref_run)
+        f_img, f_ray = ref_run()
+        torch.backends.cudnn.allow_tf32 = old
+    res["reference"] = {"ms_per_frame_cudnn_default_tf32": ms_tf32, "ms_per_frame_cudnn_fp32": ms_fp32, "kind": "reference",
+                        "max_abs_diff_img_feats": float((feat[..., 32:].permute(0, 3, 1, 2) - f_img).abs().max()),
+                        "max_abs_diff_ray_feats": float((feat[..., :32].permute(0, 3, 1, 2) - f_ray).abs().max()),
+                        "what": "the unmodified reference's ResUNetLight + DefaultVisEncoder (PyTorch eager / cuDNN) on the same GPU"}
+    return res
+
+
 # ---- headline -----------------------------------------------------------------------------------------------------------------
 
 def run_headline(ctx, args):
@@ -599,6 +673,11 @@ def run_headline(ctx, args):
             line["eager_gpu_baseline"] = eager_gpu_baseline(dq, dr, cfg, dn_c, dev)
         except Exception as e:
             line["eager_gpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
+        try:
+            torch.cuda.empty_cache()
+            line["aux"]["encoders"] = encoders_bench(dr, dev)
+        except Exception as e:
+            line["aux"]["encoders"] = {"error": f"{type(e).__name__}: {e}"}
     print(json.dumps(line))
 
 

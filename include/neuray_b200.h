@@ -107,7 +107,9 @@ int nr_camera_blocks(const float* que_pose, const float* que_K, const float* que
  *   ray_feats, img_feats : [rfn,32,fh,fw]   (reference: ref_imgs_info['ray_feats'|'img_feats'], renderer.py:229-231)
  *   imgs                 : [rfn,3,h,w]
  *   out_feat             : [rfn,fh,fw,64]   ray_feats in channels 0..31, img_feats in 32..63 (256 B per texel)
- *   out_rgb              : [rfn,h,w,4]      rgb + zero pad (16 B per texel)                                      */
+ *   out_rgb              : [rfn,h,w,4]      rgb + zero pad (16 B per texel)
+ * ray_feats == img_feats == NULL: only out_rgb is written (out_feat was filled in place by nr_image_encoder_fwd /
+ * nr_vis_encoder_fwd).                                                                                             */
 int nr_pack_feature_maps(const float* ray_feats, const float* img_feats, const float* imgs, int rfn, int h, int w,
                          int fh, int fw, float* out_feat, float* out_rgb, void* stream);
 
@@ -261,6 +263,105 @@ typedef struct NrSelfParams {
   float* d_map;              /* [32,fh,fw] accumulated, or NULL */
 } NrSelfParams;
 int nr_self_hit_prob(const NrSelfParams* p, void* stream);
+
+/* ---- encoders upstream of the ray path ------------------------------------------------
+ * image_encoder = ResUNetLight(3, [1,2,6,4], 32, inplanes=16)  (reference network/ops.py:150-230, built at renderer.py:59,
+ * called at renderer.py:229,233) and vis_encoder = DefaultVisEncoder (network/vis_encoder.py:6-21, called at
+ * renderer.py:231,234), forward only (inference; training keeps the torch modules upstream of the boundary).
+ * Everything runs channel-last; the last layer of each encoder writes straight into the [rfn,fh,fw,64] frame pack of
+ * NrPassParams.feat (ray_feats in channels 0..31, img_feats in 32..63), so a frame needs no NCHW->NHWC repack.
+ *
+ * Parameters: `params` is a HOST array of DEVICE pointers to the module's tensors in state_dict() order (conv weights
+ * [cout][cin][kh][kw], InstanceNorm weight / bias, conv bias; image encoder: 84 tensors, vis encoder: 14).  nr_*_pack
+ * re-lays them once per checkpoint into one flat buffer (conv weights as [tap][cin][cout]). */
+typedef struct NrEncoderLayout {
+  int32_t image_tensors, vis_tensors;
+  int64_t image_packed_floats, vis_packed_floats;
+} NrEncoderLayout;
+int nr_encoder_layout(NrEncoderLayout* out);
+int nr_image_encoder_pack(const float* const* params, int n_params, float* packed, void* stream);
+int nr_vis_encoder_pack(const float* const* params, int n_params, float* packed, void* stream);
+/* output map size for h x w images (h/4 x w/4 when h, w are multiples of 16; the decoder's skip connections pad otherwise,
+ * ops.py:199-208) */
+int nr_image_encoder_dims(int h, int w, int* fh, int* fw);
+long long nr_image_encoder_workspace(int n, int h, int w);     /* bytes */
+long long nr_vis_encoder_workspace(int n, int fh, int fw);     /* bytes */
+/* imgs [n,3,h,w] (NCHW as the reference holds them) -> out[(view, y, x) * out_stride + out_off + c], c < 32. */
+int nr_image_encoder_fwd(const float* packed, const float* imgs, int n, int h, int w, float* out, int out_stride, int out_off,
+                         void* workspace, long long workspace_bytes, void* stream);
+/* feat [n,fh,fw,64]: channels 0..31 = the init net's ray_feats, 32..63 = img_feats; channels 0..31 are overwritten with
+ * vis_encoder(ray_feats, img_feats). */
+int nr_vis_encoder_fwd(const float* packed, float* feat, int n, int fh, int fw, void* workspace, long long workspace_bytes, void* stream);
+
+/* Building blocks (channel-last).  nr_conv2d_nhwc: 1x1 / 3x3 convolution, stride 1 / 2, reflect or zero padding of
+ * (ks-1)/2, cout in {32, 64, 128}, cin a multiple of 16, as an implicit GEMM on the tensor cores (3xTF32: fp32 accuracy);
+ * y = conv(x) [+ bias] [+ res]; when `stats` is given, sum and sum of squares of y per (image, channel) are ADDED to
+ * stats [n][cout][2] (fp64) for a following nr_instance_norm_act.  Pixel (i, y, x) channel c of a tensor sits at
+ * base[((i*H + y)*W + x) * stride + off + c]. */
+typedef struct NrConv2d {
+  const float* x; const float* w_packed; const float* bias; const float* res;
+  float* y; double* stats;
+  int32_t n, h, w, cin, cout, ks, stride, reflect;
+  int32_t x_stride, x_off, y_stride, y_off, res_stride, res_off;
+} NrConv2d;
+int nr_conv2d_nhwc(const NrConv2d* c, void* stream);
+/* [cout][cin][ks][ks] -> [tap][cin][cout]; packed input channel c reads reference channel (c + cin_rot) % cin */
+int nr_conv_pack_weight(const float* w, int cout, int cin, int ks, int cin_rot, float* packed, void* stream);
+/* y = act(IN(x) * gamma + beta [+ res | + IN(res) * res_gamma + res_beta]) on dense [n,hw,c] tensors; act 0 none, 1 ReLU,
+ * 2 ELU; statistics from nr_conv2d_nhwc (biased variance, eps 1e-5 = nn.InstanceNorm2d). */
+int nr_instance_norm_act(const float* x, const double* stats, const float* gamma, const float* beta, const float* res,
+                         const double* res_stats, const float* res_gamma, const float* res_beta, int n, int hw, int c, int act, float* y,
+                         void* stream);
+int nr_nchw_to_nhwc(const float* x, int n, int c, int h, int w, float* y, int y_stride, int y_off, void* stream);
+int nr_nhwc_to_nchw(const float* x, int n, int c, int h, int w, int x_stride, int x_off, float* y, void* stream);
+
+/* ---- training extras next to the ray path ------------------------------------------------ */
+
+/* NeuralRayGenRenderer.predict_mean_for_depth_loss (reference renderer.py:280-316): per reference view, the view's
+ * ray_feats sampled at `coords` (interpolate_feature_map, border clamp) and decoded by the MEAN head of the coarse
+ * (index 0) and, optionally, the fine (index 1) dist decoder.  d_mean[k] == NULL: forward only (writes mean[k]);
+ * otherwise also the backward of decoder k: weight gradients are ADDED to d_w_point[k] (packed w_point layout), the map
+ * gradient to d_map (may be NULL). */
+typedef struct NrDepthMeanParams {
+  const float* map;            /* [rfn,32,fh,fw] ray_feats */
+  const float* coords;         /* [rfn,pn,2], pixels of the h x w reference images, in the order the reference passes them */
+  const float* w_point[2];     /* packed weights of the coarse / fine pass (fine may be NULL) */
+  int32_t rfn, pn, h, w, fh, fw;
+  float* mean[2];              /* [rfn,pn,2] softplus outputs (depth_mean = [...,0], depth_mean_2 = [...,1]) */
+  const float* d_mean[2];      /* [rfn,pn,2] or NULL */
+  float* d_w_point[2];         /* [NrWeightLayout.total_point] accumulated */
+  float* d_map;                /* [rfn,32,fh,fw] accumulated, or NULL */
+} NrDepthMeanParams;
+int nr_depth_mean(const NrDepthMeanParams* p, void* stream);
+
+/* RenderLoss (reference network/loss.py:46-76): loss[q] = sum_r mask * |pr - gt|^2 / (sum_r mask + 1e-3), or the plain mean
+ * over rays when ray_mask == NULL.  g == NULL: forward (writes loss [qn]); otherwise the backward: d_pr [qn,rn,3] =
+ * g[q] * d loss[q] / d pr. */
+int nr_render_loss(const float* pr, const float* gt, const uint8_t* ray_mask, int qn, int rn, float* loss, const float* g, float* d_pr,
+                   void* stream);
+
+/* DepthLoss (reference network/loss.py:78-132): the decoder means against the ground-truth depth maps sampled at the same
+ * coordinates, both in normalised inverse depth; loss_type 0 = l2, 1 = smooth_l1(beta); aug_depth != NULL = the 'gso'
+ * branch (mean over the coordinates whose augmented depth agrees with the true depth within correct_thresh).
+ * g == NULL: forward (loss [rfn]); otherwise d_depth_pr [rfn,pn] = g[view] * d loss / d depth_pr. */
+typedef struct NrDepthLossParams {
+  const float* depth_pr;       /* [rfn,pn] */
+  const float* coords;         /* [rfn,pn,2] */
+  const float* true_depth;     /* [rfn,h,w] */
+  const float* aug_depth;      /* [rfn,h,w] or NULL */
+  const float* depth_range;    /* [rfn,2] */
+  int32_t rfn, pn, h, w, loss_type;
+  float beta, correct_thresh;
+  float* loss;                 /* [rfn] */
+  const float* g;              /* [rfn] or NULL */
+  float* d_depth_pr;           /* [rfn,pn] */
+} NrDepthLossParams;
+int nr_depth_loss(const NrDepthLossParams* p, void* stream);
+
+/* ConsistencyLoss (reference network/loss.py:17-44): loss[q] = mean over rays and samples of the cross entropy between
+ * prob0 (the rendered hit probability, a constant) and prob1 (hit_prob_self).  g == NULL: forward; otherwise d_prob1. */
+int nr_consistency_loss(const float* prob0, const float* prob1, int qn, int rn, int dn, float* loss, const float* g, float* d_prob1,
+                        void* stream);
 
 /* ---- diagnostics ------------------------------------------------------------------------------------------- */
 

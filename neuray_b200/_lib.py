@@ -90,7 +90,45 @@ SIGNATURES = {
     "nr_bwd_slot": (C.c_int, [C.c_char_p]),
     "nr_tape_gemms": (C.c_int, [_vp, _i, _vp, _vp, C.c_longlong, _vp, _vp, C.c_longlong, _vp, _vp]),
     "nr_self_hit_prob": (C.c_int, [_vp, _vp]),
+    "nr_encoder_layout": (C.c_int, [_vp]),
+    "nr_image_encoder_pack": (C.c_int, [_vp, _i, _vp, _vp]),
+    "nr_vis_encoder_pack": (C.c_int, [_vp, _i, _vp, _vp]),
+    "nr_image_encoder_dims": (C.c_int, [_i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "nr_image_encoder_workspace": (C.c_longlong, [_i, _i, _i]),
+    "nr_vis_encoder_workspace": (C.c_longlong, [_i, _i, _i]),
+    "nr_image_encoder_fwd": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, C.c_longlong, _vp]),
+    "nr_vis_encoder_fwd": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, C.c_longlong, _vp]),
+    "nr_conv2d_nhwc": (C.c_int, [_vp, _vp]),
+    "nr_conv_pack_weight": (C.c_int, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "nr_instance_norm_act": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "nr_nchw_to_nhwc": (C.c_int, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
+    "nr_nhwc_to_nchw": (C.c_int, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "nr_depth_mean": (C.c_int, [_vp, _vp]),
+    "nr_render_loss": (C.c_int, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "nr_depth_loss": (C.c_int, [_vp, _vp]),
+    "nr_consistency_loss": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
 }
+
+
+class NrDepthMeanParams(C.Structure):
+    _fields_ = [("map", C.c_void_p), ("coords", C.c_void_p), ("w_point", C.c_void_p * 2)] + \
+               [(n, C.c_int32) for n in "rfn pn h w fh fw".split()] + \
+               [("mean", C.c_void_p * 2), ("d_mean", C.c_void_p * 2), ("d_w_point", C.c_void_p * 2), ("d_map", C.c_void_p)]
+
+
+class NrDepthLossParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in "depth_pr coords true_depth aug_depth depth_range".split()] + \
+               [(n, C.c_int32) for n in "rfn pn h w loss_type".split()] + [("beta", C.c_float), ("correct_thresh", C.c_float)] + \
+               [("loss", C.c_void_p), ("g", C.c_void_p), ("d_depth_pr", C.c_void_p)]
+
+
+class NrEncoderLayout(C.Structure):
+    _fields_ = [("image_tensors", C.c_int32), ("vis_tensors", C.c_int32), ("image_packed_floats", C.c_int64), ("vis_packed_floats", C.c_int64)]
+
+
+class NrConv2d(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("w_packed", C.c_void_p), ("bias", C.c_void_p), ("res", C.c_void_p), ("y", C.c_void_p), ("stats", C.c_void_p)] + \
+               [(n, C.c_int32) for n in "n h w cin cout ks stride reflect x_stride x_off y_stride y_off res_stride res_off".split()]
 
 
 class NrSelfParams(C.Structure):

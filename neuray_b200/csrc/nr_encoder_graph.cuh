@@ -1,0 +1,357 @@
+// The two encoder networks as layer graphs over the building blocks of nr_conv.cuh.  The graph is a template over an
+// `Ops` backend: csrc/nr_encoder.cu instantiates it with kernel launches on a stream (the product), and
+// tests/cpu_harness/conv_cpu_harness.cu with host loops over the same __host__ __device__ routines (CPU parity tests of the
+// wiring, the weight layout and the index math against the reference's torch modules).
+//
+//   image_encoder = ResUNetLight(3, [1,2,6,4], 32, inplanes=16)   reference network/ops.py:150-230 (renderer.py:59)
+//   vis_encoder   = DefaultVisEncoder                              reference network/vis_encoder.py:6-21
+#pragma once
+#include <stddef.h>
+
+#include "nr_conv.cuh"
+
+namespace nr {
+namespace enc {
+
+// ---- parameter tensors in state_dict() order, and where each lands in the packed buffer ----------------------------
+struct TensorSpec {
+  int kind;        // 0 conv weight [cout][cin][ks][ks] -> packed [tap][cin][cout]; 1 vector [n] copied
+  int cout, cin, ks;
+  int rot;         // packed input channel c reads reference channel (c + rot) % cin
+  int cin_major;   // packed as [cin][tap][cout] (the 7x7 first layer)
+  long long off;   // floats, multiple of 4
+  long long n;     // elements
+};
+struct NetSpec {
+  TensorSpec t[96];
+  int count;
+  long long total;
+  int conv(int cout, int cin, int ks, int rot = 0, int cin_major = 0) {
+    TensorSpec& s = t[count];
+    s.kind = 0; s.cout = cout; s.cin = cin; s.ks = ks; s.rot = rot; s.cin_major = cin_major;
+    s.off = total; s.n = (long long)cout * cin * ks * ks;
+    total += (s.n + 3) & ~3LL;
+    return count++;
+  }
+  int vec(int n) {
+    TensorSpec& s = t[count];
+    s.kind = 1; s.cout = n; s.cin = 1; s.ks = 1; s.rot = 0; s.cin_major = 0;
+    s.off = total; s.n = n;
+    total += (s.n + 3) & ~3LL;
+    return count++;
+  }
+};
+
+// packed element e of tensor s <- index into the reference tensor
+NR_HD long long pack_source(const TensorSpec& s, long long e) {
+  if (s.kind == 1) return e;
+  const int taps = s.ks * s.ks;
+  int tap, c, o;
+  o = int(e % s.cout);
+  const long long r = e / s.cout;
+  if (s.cin_major) { tap = int(r % taps); c = int(r / taps); }
+  else { c = int(r % s.cin); tap = int(r / s.cin); }
+  const int c_ref = (c + s.rot) % s.cin;
+  return ((long long)o * s.cin + c_ref) * taps + tap;
+}
+
+struct BasicBlockIdx { int c1, n1w, n1b, c2, n2w, n2b, ds, dsw, dsb; int cin, cout, stride; };
+struct ConvBnIdx { int w, b, nw, nb; int cin, cout; };
+
+struct ImageNet {
+  NetSpec spec;
+  int conv1, bn1w, bn1b;
+  BasicBlockIdx blocks[9];     // layer1: 1, layer2: 2, layer3: 6   (layers = [1,2,6,4]; the fourth entry is unused, ops.py:166-170)
+  ConvBnIdx upconv3, iconv3, upconv2, iconv2;
+  int out_w, out_b;
+};
+
+inline BasicBlockIdx basic_block(NetSpec& s, int cin, int cout, int stride) {
+  BasicBlockIdx b;
+  b.cin = cin; b.cout = cout; b.stride = stride;
+  b.c1 = s.conv(cout, cin, 3); b.n1w = s.vec(cout); b.n1b = s.vec(cout);
+  b.c2 = s.conv(cout, cout, 3); b.n2w = s.vec(cout); b.n2b = s.vec(cout);
+  if (stride != 1 || cin != cout) { b.ds = s.conv(cout, cin, 1); b.dsw = s.vec(cout); b.dsb = s.vec(cout); }
+  else b.ds = b.dsw = b.dsb = -1;
+  return b;
+}
+inline ConvBnIdx conv_bn(NetSpec& s, int cin, int cout) {
+  ConvBnIdx c;
+  c.cin = cin; c.cout = cout;
+  c.w = s.conv(cout, cin, 3); c.b = s.vec(cout); c.nw = s.vec(cout); c.nb = s.vec(cout);
+  return c;
+}
+
+inline void build_image_net(ImageNet& n) {
+  NetSpec& s = n.spec;
+  s.count = 0; s.total = 0;
+  n.conv1 = s.conv(16, 3, 7, 0, 1); n.bn1w = s.vec(16); n.bn1b = s.vec(16);
+  int k = 0;
+  n.blocks[k++] = basic_block(s, 16, 32, 2);
+  n.blocks[k++] = basic_block(s, 32, 64, 2);
+  n.blocks[k++] = basic_block(s, 64, 64, 1);
+  n.blocks[k++] = basic_block(s, 64, 128, 2);
+  for (int i = 0; i < 5; ++i) n.blocks[k++] = basic_block(s, 128, 128, 1);
+  n.upconv3 = conv_bn(s, 128, 64);
+  n.iconv3 = conv_bn(s, 128, 64);
+  n.upconv2 = conv_bn(s, 64, 32);
+  n.iconv2 = conv_bn(s, 64, 32);
+  n.out_w = s.conv(32, 32, 1); n.out_b = s.vec(32);
+}
+
+struct ResidualIdx { int n0w, n0b, c0, n1w, n1b, c1; };
+struct VisNet {
+  NetSpec spec;
+  int conv0;                  // conv3x3(64, 32): the packed input order is [ray_feats | img_feats] (the frame pack's), the reference
+                              // concatenates [img_feats, ray_feats] (vis_encoder.py:20) -> rot 32
+  ResidualIdx rb[2];
+  int conv_out;
+};
+inline void build_vis_net(VisNet& n) {
+  NetSpec& s = n.spec;
+  s.count = 0; s.total = 0;
+  n.conv0 = s.conv(32, 64, 3, 32);
+  for (int i = 0; i < 2; ++i) {
+    ResidualIdx& r = n.rb[i];
+    r.n0w = s.vec(32); r.n0b = s.vec(32); r.c0 = s.conv(32, 32, 3);
+    r.n1w = s.vec(32); r.n1b = s.vec(32); r.c1 = s.conv(32, 32, 3);
+  }
+  n.conv_out = s.conv(32, 32, 1);
+}
+
+// ---- geometry ---------------------------------------------------------------------------------------------------------
+inline int conv_out(int n, int ks, int stride) { return (n + 2 * ((ks - 1) / 2) - ks) / stride + 1; }
+struct ImageDims {
+  int h0, w0, h1, w1, h2, w2, h3, w3;   // after conv1 (/2), layer1 (/4), layer2 (/8), layer3 (/16)
+  int u3h, u3w, u2h, u2w;               // after the two x2 upsamplings; (u2h, u2w) is the output size
+};
+inline ImageDims image_dims(int H, int W) {
+  ImageDims d;
+  d.h0 = conv_out(H, 7, 2); d.w0 = conv_out(W, 7, 2);
+  d.h1 = conv_out(d.h0, 3, 2); d.w1 = conv_out(d.w0, 3, 2);
+  d.h2 = conv_out(d.h1, 3, 2); d.w2 = conv_out(d.w1, 3, 2);
+  d.h3 = conv_out(d.h2, 3, 2); d.w3 = conv_out(d.w2, 3, 2);
+  d.u3h = 2 * d.h3; d.u3w = 2 * d.w3;
+  d.u2h = 2 * d.u3h; d.u2w = 2 * d.u3w;
+  return d;
+}
+
+struct CopyP {     // y[n, yo, xo, y_off + c] = (yo - py, xo - px) inside the source ? x[n, yo - py, xo - px, x_off + c] : 0
+  const float* x; float* y;
+  int N, H, W, Ho, Wo, C, py, px, x_stride, x_off, y_stride, y_off;
+};
+
+// bump allocator over the caller's workspace (256-byte granules)
+struct Arena {
+  char* base; size_t size, used;
+  bool ok;
+  void* take(size_t bytes) {
+    const size_t a = (used + 255) & ~size_t(255);
+    if (base != nullptr && a + bytes > size) { ok = false; return base; }
+    used = a + bytes;
+    return base != nullptr ? base + a : nullptr;
+  }
+  float* floats(long long n) { return (float*)take(size_t(n) * sizeof(float)); }
+  double* doubles(long long n) { return (double*)take(size_t(n) * sizeof(double)); }
+};
+
+template <class Ops>
+struct Builder {
+  Ops& ops;
+  Arena& ar;
+  const float* W;      // packed parameters
+  int N;
+  double* stats_base; long long stats_used, stats_cap;
+
+  const float* w(const NetSpec& s, int i) const { return i < 0 ? nullptr : W + s.t[i].off; }
+  double* stats(int C) {
+    double* p = stats_base != nullptr ? stats_base + stats_used : nullptr;
+    stats_used += (long long)N * C * 2;
+    if (stats_base != nullptr && stats_used > stats_cap) ar.ok = false;
+    return p;
+  }
+  // y (dense [N,Ho,Wo,cout] unless y/y_stride/y_off say otherwise) = conv(x)
+  float* conv(const float* x, int x_stride, int x_off, int H, int Wd, int cin, int cout, int ks, int stride, const float* wt, const float* bias,
+              const float* res, int res_stride, int res_off, double* st, float* y, int y_stride, int y_off, int& Ho, int& Wo) {
+    Ho = conv_out(H, ks, stride); Wo = conv_out(Wd, ks, stride);
+    if (y == nullptr) { y = ar.floats((long long)N * Ho * Wo * cout); y_stride = cout; y_off = 0; }
+    cv::ConvP p;
+    p.x = x; p.w = wt; p.bias = bias; p.res = res; p.y = y; p.stats = st;
+    p.N = N; p.H = H; p.W = Wd; p.Ho = Ho; p.Wo = Wo; p.Cin = cin; p.Cout = cout; p.ks = ks; p.stride = stride; p.reflect = 1;
+    p.x_stride = x_stride; p.x_off = x_off; p.y_stride = y_stride; p.y_off = y_off; p.res_stride = res_stride; p.res_off = res_off;
+    ops.conv(p);
+    return y;
+  }
+  // y = act(IN(x) gamma + beta [+ res | + IN(res) rg + rb])
+  float* norm(const float* x, int C, int HW, const double* st, const float* g, const float* b, const float* res, int res_stride, int res_off,
+              const double* rst, const float* rg, const float* rb, int act, float* y, int y_stride, int y_off) {
+    if (y == nullptr) { y = ar.floats((long long)N * HW * C); y_stride = C; y_off = 0; }
+    cv::NormP p;
+    p.x = x; p.stats = st; p.gamma = g; p.beta = b; p.res = res; p.res_stats = rst; p.res_gamma = rg; p.res_beta = rb; p.y = y;
+    p.N = N; p.HW = HW; p.C = C; p.act = act; p.x_stride = C; p.x_off = 0; p.res_stride = res_stride; p.res_off = res_off;
+    p.y_stride = y_stride; p.y_off = y_off; p.eps = 1e-5f;
+    ops.norm(p);
+    return y;
+  }
+};
+
+// BasicBlock (ops.py:86-124): relu(IN(conv2(relu(IN(conv1(x))))) + identity), identity = x or IN(conv1x1(x))
+template <class Ops>
+float* run_basic_block(Builder<Ops>& b, const NetSpec& s, const BasicBlockIdx& k, const float* x, int& H, int& Wd) {
+  int Ho, Wo, h2, w2;
+  double* st1 = b.stats(k.cout);
+  float* t1 = b.conv(x, k.cin, 0, H, Wd, k.cin, k.cout, 3, k.stride, b.w(s, k.c1), nullptr, nullptr, 0, 0, st1, nullptr, 0, 0, Ho, Wo);
+  float* a1 = b.norm(t1, k.cout, Ho * Wo, st1, b.w(s, k.n1w), b.w(s, k.n1b), nullptr, 0, 0, nullptr, nullptr, nullptr, 1, t1, k.cout, 0);
+  double* st2 = b.stats(k.cout);
+  float* t2 = b.conv(a1, k.cout, 0, Ho, Wo, k.cout, k.cout, 3, 1, b.w(s, k.c2), nullptr, nullptr, 0, 0, st2, nullptr, 0, 0, h2, w2);
+  float* out;
+  if (k.ds >= 0) {
+    double* st3 = b.stats(k.cout);
+    int h3, w3;
+    float* d = b.conv(x, k.cin, 0, H, Wd, k.cin, k.cout, 1, k.stride, b.w(s, k.ds), nullptr, nullptr, 0, 0, st3, nullptr, 0, 0, h3, w3);
+    out = b.norm(t2, k.cout, Ho * Wo, st2, b.w(s, k.n2w), b.w(s, k.n2b), d, k.cout, 0, st3, b.w(s, k.dsw), b.w(s, k.dsb), 1, t2, k.cout, 0);
+  } else {
+    out = b.norm(t2, k.cout, Ho * Wo, st2, b.w(s, k.n2w), b.w(s, k.n2b), x, k.cin, 0, nullptr, nullptr, nullptr, 1, t2, k.cout, 0);
+  }
+  H = Ho; Wd = Wo;
+  return out;
+}
+
+// `conv` of ops.py:126-138: ELU(IN(conv3x3 reflect + bias)); the result goes to channels [y_off, y_off + cout) of y
+template <class Ops>
+void run_conv_bn_elu(Builder<Ops>& b, const NetSpec& s, const ConvBnIdx& k, const float* x, int H, int Wd, float* y, int y_stride, int y_off) {
+  int Ho, Wo;
+  double* st = b.stats(k.cout);
+  float* t = b.conv(x, k.cin, 0, H, Wd, k.cin, k.cout, 3, 1, b.w(s, k.w), b.w(s, k.b), nullptr, 0, 0, st, nullptr, 0, 0, Ho, Wo);
+  b.norm(t, k.cout, Ho * Wo, st, b.w(s, k.nw), b.w(s, k.nb), nullptr, 0, 0, nullptr, nullptr, nullptr, 2, y, y_stride, y_off);
+}
+
+// ResUNetLight.forward (ops.py:210-228).  imgs [N,3,H,W] (NCHW, as the reference holds them) -> out[n, y, x, out_off + c],
+// c < 32, at image_dims(H, W).u2h x u2w (= H/4 x W/4 for sizes that are multiples of 16).
+template <class Ops>
+bool image_encoder_graph(Ops& ops, Arena& ar, const ImageNet& net, const float* packed, const float* imgs, int N, int H, int Wd, float* out,
+                         int out_stride, int out_off, long long stats_cap, long long* stats_used) {
+  const NetSpec& s = net.spec;
+  const ImageDims d = image_dims(H, Wd);
+  if (d.u3h < d.h2 || d.u3w < d.w2 || d.u2h < d.h1 || d.u2w < d.w1) return false;
+  Builder<Ops> b{ops, ar, packed, N, nullptr, 0, stats_cap};
+  // InstanceNorm sums of every normalised conv output in one block, zeroed once (stats_cap == 0: a dry run that counts)
+  if (stats_cap > 0) {
+    b.stats_base = ar.doubles(stats_cap);
+    ops.zero(b.stats_base, size_t(stats_cap) * sizeof(double));
+  }
+  // conv1 + bn1 + relu
+  double* st0 = b.stats(16);
+  float* c1 = ar.floats((long long)N * d.h0 * d.w0 * 16);
+  cv::Conv7P p7;
+  p7.img = imgs; p7.w = b.w(s, net.conv1); p7.y = c1; p7.stats = st0; p7.N = N; p7.H = H; p7.W = Wd; p7.Ho = d.h0; p7.Wo = d.w0;
+  ops.conv7(p7);
+  float* x = b.norm(c1, 16, d.h0 * d.w0, st0, b.w(s, net.bn1w), b.w(s, net.bn1b), nullptr, 0, 0, nullptr, nullptr, nullptr, 1, c1, 16, 0);
+  int h = d.h0, w = d.w0;
+  float* x1 = run_basic_block(b, s, net.blocks[0], x, h, w);                 // layer1: [N,h1,w1,32]
+  int h1 = h, w1 = w;
+  float* x2 = run_basic_block(b, s, net.blocks[1], x1, h, w);
+  x2 = run_basic_block(b, s, net.blocks[2], x2, h, w);                       // layer2: [N,h2,w2,64]
+  int h2 = h, w2 = w;
+  float* x3 = x2;
+  for (int i = 3; i < 9; ++i) x3 = run_basic_block(b, s, net.blocks[i], x3, h, w);   // layer3: [N,h3,w3,128]
+  // upconv3 -> skipconnect(x2, .) -> iconv3
+  float* up3 = ar.floats((long long)N * d.u3h * d.u3w * 128);
+  cv::UpP u;
+  u.x = x3; u.y = up3; u.N = N; u.H = h; u.W = w; u.Ho = d.u3h; u.Wo = d.u3w; u.C = 128; u.x_stride = 128; u.x_off = 0; u.y_stride = 128; u.y_off = 0;
+  ops.upsample(u);
+  float* cat3 = ar.floats((long long)N * d.u3h * d.u3w * 128);               // [upconv3 out (64) | x2 (64)]  (torch.cat([x2_up, x1_skip]), ops.py:207)
+  run_conv_bn_elu(b, s, net.upconv3, up3, d.u3h, d.u3w, cat3, 128, 0);
+  CopyP cp;
+  cp.x = x2; cp.y = cat3; cp.N = N; cp.H = h2; cp.W = w2; cp.Ho = d.u3h; cp.Wo = d.u3w; cp.C = 64;
+  cp.py = (d.u3h - h2) / 2; cp.px = (d.u3w - w2) / 2; cp.x_stride = 64; cp.x_off = 0; cp.y_stride = 128; cp.y_off = 64;
+  ops.copy_pad(cp);
+  float* i3 = ar.floats((long long)N * d.u3h * d.u3w * 64);
+  run_conv_bn_elu(b, s, net.iconv3, cat3, d.u3h, d.u3w, i3, 64, 0);
+  // upconv2 -> skipconnect(x1, .) -> iconv2
+  float* up2 = ar.floats((long long)N * d.u2h * d.u2w * 64);
+  u.x = i3; u.y = up2; u.H = d.u3h; u.W = d.u3w; u.Ho = d.u2h; u.Wo = d.u2w; u.C = 64; u.x_stride = 64; u.y_stride = 64;
+  ops.upsample(u);
+  float* cat2 = ar.floats((long long)N * d.u2h * d.u2w * 64);
+  run_conv_bn_elu(b, s, net.upconv2, up2, d.u2h, d.u2w, cat2, 64, 0);
+  cp.x = x1; cp.y = cat2; cp.H = h1; cp.W = w1; cp.Ho = d.u2h; cp.Wo = d.u2w; cp.C = 32;
+  cp.py = (d.u2h - h1) / 2; cp.px = (d.u2w - w1) / 2; cp.x_stride = 32; cp.y_stride = 64; cp.y_off = 32;
+  ops.copy_pad(cp);
+  float* i2 = ar.floats((long long)N * d.u2h * d.u2w * 32);
+  run_conv_bn_elu(b, s, net.iconv2, cat2, d.u2h, d.u2w, i2, 32, 0);
+  // out_conv (1x1 + bias) straight into the caller's channel-last destination
+  int Ho, Wo;
+  b.conv(i2, 32, 0, d.u2h, d.u2w, 32, 32, 1, 1, b.w(s, net.out_w), b.w(s, net.out_b), nullptr, 0, 0, nullptr, out, out_stride, out_off, Ho, Wo);
+  if (stats_used != nullptr) *stats_used = b.stats_used;
+  return ar.ok;
+}
+
+// DefaultVisEncoder.forward (vis_encoder.py:19-21) on the channel-last frame pack: feat [N,fh,fw,64] holds the init-net
+// ray_feats in channels 0..31 and the image encoder's img_feats in 32..63; the result overwrites channels 0..31.
+template <class Ops>
+bool vis_encoder_graph(Ops& ops, Arena& ar, const VisNet& net, const float* packed, float* feat, int N, int fh, int fw, long long stats_cap,
+                       long long* stats_used) {
+  const NetSpec& s = net.spec;
+  Builder<Ops> b{ops, ar, packed, N, nullptr, 0, stats_cap};
+  if (stats_cap > 0) {
+    b.stats_base = ar.doubles(stats_cap);
+    ops.zero(b.stats_base, size_t(stats_cap) * sizeof(double));
+  }
+  int Ho, Wo;
+  const int HW = fh * fw;
+  double* st = b.stats(32);
+  float* x = b.conv(feat, 64, 0, fh, fw, 64, 32, 3, 1, b.w(s, net.conv0), nullptr, nullptr, 0, 0, st, nullptr, 0, 0, Ho, Wo);
+  for (int i = 0; i < 2; ++i) {       // ResidualBlock (ops.py:43-76): x + conv(relu(IN(conv(relu(IN(x))))))
+    const ResidualIdx& r = net.rb[i];
+    float* a0 = b.norm(x, 32, HW, st, b.w(s, r.n0w), b.w(s, r.n0b), nullptr, 0, 0, nullptr, nullptr, nullptr, 1, nullptr, 0, 0);
+    double* st1 = b.stats(32);
+    float* t = b.conv(a0, 32, 0, fh, fw, 32, 32, 3, 1, b.w(s, r.c0), nullptr, nullptr, 0, 0, st1, nullptr, 0, 0, Ho, Wo);
+    b.norm(t, 32, HW, st1, b.w(s, r.n1w), b.w(s, r.n1b), nullptr, 0, 0, nullptr, nullptr, nullptr, 1, t, 32, 0);
+    st = i == 0 ? b.stats(32) : nullptr;   // the second block's output is not normalised again
+    x = b.conv(t, 32, 0, fh, fw, 32, 32, 3, 1, b.w(s, r.c1), nullptr, x, 32, 0, st, a0, 32, 0, Ho, Wo);   // a0 is free by now
+  }
+  b.conv(x, 32, 0, fh, fw, 32, 32, 1, 1, b.w(s, net.conv_out), nullptr, nullptr, 0, 0, nullptr, feat, 64, 0, Ho, Wo);
+  if (stats_used != nullptr) *stats_used = b.stats_used;
+  return ar.ok;
+}
+
+// dry runs: the arena hands out fake (never dereferenced) addresses so that in-place reuse is counted once
+static char* const DRY_BASE = (char*)0x100000;
+struct NullOps {
+  void conv(const cv::ConvP&) {}
+  void conv7(const cv::Conv7P&) {}
+  void norm(const cv::NormP&) {}
+  void upsample(const cv::UpP&) {}
+  void copy_pad(const CopyP&) {}
+  void zero(void*, size_t) {}
+};
+// doubles of InstanceNorm sums a forward needs (dry run of the graph)
+inline long long image_stats_doubles(const ImageNet& net, int N, int H, int W) {
+  NullOps ops;
+  Arena ar{DRY_BASE, ~size_t(0) / 2, 0, true};
+  long long used = 0;
+  image_encoder_graph(ops, ar, net, nullptr, nullptr, N, H, W, (float*)DRY_BASE, 32, 0, 0, &used);
+  return used;
+}
+inline long long vis_stats_doubles(const VisNet& net, int N, int fh, int fw) {
+  NullOps ops;
+  Arena ar{DRY_BASE, ~size_t(0) / 2, 0, true};
+  long long used = 0;
+  vis_encoder_graph(ops, ar, net, nullptr, (float*)DRY_BASE, N, fh, fw, 0, &used);
+  return used;
+}
+inline size_t image_workspace_bytes(const ImageNet& net, int N, int H, int W) {
+  NullOps ops;
+  Arena ar{DRY_BASE, ~size_t(0) / 2, 0, true};
+  image_encoder_graph(ops, ar, net, nullptr, nullptr, N, H, W, (float*)DRY_BASE, 32, 0, image_stats_doubles(net, N, H, W), nullptr);
+  return ar.used + 256;
+}
+inline size_t vis_workspace_bytes(const VisNet& net, int N, int fh, int fw) {
+  NullOps ops;
+  Arena ar{DRY_BASE, ~size_t(0) / 2, 0, true};
+  vis_encoder_graph(ops, ar, net, nullptr, (float*)DRY_BASE, N, fh, fw, vis_stats_doubles(net, N, fh, fw), nullptr);
+  return ar.used + 256;
+}
+
+}  // namespace enc
+}  // namespace nr

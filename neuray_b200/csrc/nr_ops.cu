@@ -296,11 +296,14 @@ int nr_tc_layout(NrTcLayout* o) {
 
 int nr_pack_feature_maps(const float* ray_feats, const float* img_feats, const float* imgs, int rfn, int h, int w, int fh,
                          int fw, float* out_feat, float* out_rgb, void* stream) {
-  NR_CHECK_ARG(ray_feats && img_feats && imgs && out_feat && out_rgb, "null device pointer");
+  // ray_feats == img_feats == NULL: the frame pack was written in place by the native encoders (nr_image_encoder_fwd /
+  // nr_vis_encoder_fwd), only the rgb pack is produced
+  const bool maps = ray_feats != nullptr || img_feats != nullptr;
+  NR_CHECK_ARG(imgs && out_rgb && (!maps || (ray_feats && img_feats && out_feat)), "null device pointer");
   NR_CHECK_ARG(rfn >= 1 && rfn <= NR_MAX_VIEWS && h > 1 && w > 1 && fh > 0 && fw > 0, "shape");
   cudaStream_t s = (cudaStream_t)stream;
   const long long nf = (long long)rfn * fh * fw * 16, nr_ = (long long)rfn * h * w;
-  pack_feat_kernel<<<min(blocks_for(nf), 148 * 16), TPB, 0, s>>>(ray_feats, img_feats, rfn, fh, fw, out_feat);
+  if (maps) pack_feat_kernel<<<min(blocks_for(nf), 148 * 16), TPB, 0, s>>>(ray_feats, img_feats, rfn, fh, fw, out_feat);
   pack_rgb_kernel<<<min(blocks_for(nr_), 148 * 16), TPB, 0, s>>>(imgs, rfn, h, w, out_rgb);
   NR_CHECK_LAUNCH("pack_feature_maps");
   return NR_OK;

@@ -21,7 +21,7 @@ import ctypes as C
 import torch
 import torch.nn as nn
 
-from . import _lib, modules
+from . import _lib, encoders, modules
 from .render_ops import fine_sample_u, interpolate_feats, sample_depth
 from .weights import camera_blocks, pack_pass, point_index_map, posenc_table
 
@@ -80,12 +80,22 @@ class FramePack:
         except Exception:      # interpreter shutdown
             pass
 
-    def __init__(self, ref_imgs_info):
+    def __init__(self, ref_imgs_info, encoder_owner=None):
+        """encoder_owner: a module with image_encoder / vis_encoder (reference parameter names).  The pack then takes the INIT
+        net's ray_feats from ref_imgs_info, runs both encoders natively into the channel-last buffer (encoders.encode_frame,
+        reference renderer.py:229-231) and leaves their NCHW results in ref_imgs_info['img_feats'] / ['ray_feats']."""
         imgs = ref_imgs_info["imgs"]
-        rf, imf = ref_imgs_info["ray_feats"], ref_imgs_info["img_feats"]
         if not imgs.is_cuda:
             raise _lib.NeurayB200Error("the rendering path needs CUDA tensors (no CPU fallback)")
         rfn, _, h, w = imgs.shape
+        rf = ref_imgs_info["ray_feats"]
+        if encoder_owner is not None:
+            if tuple(rf.shape[-2:]) != encoders.image_dims(h, w) or rf.shape[1] != 32:
+                raise _lib.NeurayB200Error(f"ray_feats {tuple(rf.shape)} do not match the image encoder's output size "
+                                           f"{encoders.image_dims(h, w)} for {h}x{w} images")
+            imf = rf
+        else:
+            imf = ref_imgs_info["img_feats"]
         if rf.shape != imf.shape or rf.shape[1] != 32:
             raise _lib.NeurayB200Error(f"ray_feats {tuple(rf.shape)} and img_feats {tuple(imf.shape)} must both be [rfn,32,fh,fw]")
         if rfn > _lib.NR_MAX_VIEWS:
@@ -100,12 +110,19 @@ class FramePack:
         else:
             self.feat = torch.empty(rfn, fh, fw, 64, dtype=torch.float32, device=dev)
             self.rgb = torch.empty(rfn, h, w, 4, dtype=torch.float32, device=dev)
-        with _lib.on_device(imgs):
-            _lib.check(_lib.lib().nr_pack_feature_maps(
-                _lib.ptr(rf.detach().contiguous().float()), _lib.ptr(imf.detach().contiguous().float()),
-                _lib.ptr(imgs.detach().contiguous().float()), rfn, h, w, fh, fw, _lib.ptr(self.feat), _lib.ptr(self.rgb),
-                _lib.stream_of(imgs)), "nr_pack_feature_maps")
-        _lib.count_launches(2)
+        if encoder_owner is not None:
+            encoders.encode_frame(encoder_owner, ref_imgs_info, self.feat)
+            with _lib.on_device(imgs):
+                _lib.check(_lib.lib().nr_pack_feature_maps(None, None, _lib.ptr(imgs.detach().contiguous().float()), rfn, h, w, fh, fw,
+                                                           None, _lib.ptr(self.rgb), _lib.stream_of(imgs)), "nr_pack_feature_maps (rgb)")
+            _lib.count_launches(1)
+        else:
+            with _lib.on_device(imgs):
+                _lib.check(_lib.lib().nr_pack_feature_maps(
+                    _lib.ptr(rf.detach().contiguous().float()), _lib.ptr(imf.detach().contiguous().float()),
+                    _lib.ptr(imgs.detach().contiguous().float()), rfn, h, w, fh, fw, _lib.ptr(self.feat), _lib.ptr(self.rgb),
+                    _lib.stream_of(imgs)), "nr_pack_feature_maps")
+            _lib.count_launches(2)
         _, self.view_params = camera_blocks(None, ref_imgs_info)
         self.src = tuple((ref_imgs_info[k], ref_imgs_info[k]._version) for k in _PACK_SOURCES)
 
@@ -154,6 +171,18 @@ def pass_weights(owner, is_fine, dn, device):
         pe = posenc_table(dn).to(device).contiguous()
         hit[3][dn] = pe
     return hit[1], hit[2], pe, hit[4]
+
+
+def pass_index_map(owner, is_fine, dev):
+    """weights.point_index_map of a pass (packed w_point position -> parameter element), cached on the owner."""
+    dec, agg, dec_name, agg_name = _pass_modules(owner, is_fine)
+    allp = {f"{dec_name}.{k}": v for k, v in dec.named_parameters()}
+    allp.update({f"{agg_name}.{k}": v for k, v in agg.named_parameters()})
+    maps = owner.__dict__.setdefault("_nr_index_maps", {})
+    key = (is_fine, str(dev), tuple(allp))
+    if key not in maps:
+        maps[key] = point_index_map(allp, dec_name, agg_name)
+    return maps[key]
 
 
 def _check_supported(owner):
@@ -286,13 +315,7 @@ def _self_hit_prob(self, que_depth, que_imgs_info, is_fine):
     _, rn, dn = que_depth.shape
     w_point = pass_weights(self, is_fine, dn, dev)[0]
     dec_params = {f"{dec_name}.{k}": v for k, v in dec.named_parameters()}
-    maps = self.__dict__.setdefault("_nr_index_maps", {})
-    key = (is_fine, str(dev), tuple(dec_params))
-    if key not in maps:
-        _, agg, _, agg_name = _pass_modules(self, is_fine)
-        allp = dict(dec_params)
-        allp.update({f"{agg_name}.{k}": v for k, v in agg.named_parameters()})
-        maps[key] = point_index_map(allp, dec_name, agg_name)
+    index_map = pass_index_map(self, is_fine, dev)
     fmap = feats[0].detach().contiguous().float()
     cc, qd = coords[0].detach().contiguous().float(), que_depth[0].detach().contiguous().float()
     rng = que_imgs_info["depth_range"][0].detach().float().contiguous()
@@ -306,7 +329,7 @@ def _self_hit_prob(self, que_depth, que_imgs_info, is_fine):
         return p
 
     named = list(dec_params.items())
-    meta = {"params": params, "index_map": maps[key], "stream": _lib.stream_of(coords), "map_shape": tuple(fmap.shape),
+    meta = {"params": params, "index_map": index_map, "stream": _lib.stream_of(coords), "map_shape": tuple(fmap.shape),
             "dec_names": [n for n, _ in named], "keep": (fmap, cc, qd, w_point, rng)}
     return SelfHitProbFn.apply(meta, feats, *[v for _, v in named])
 
@@ -361,7 +384,7 @@ def render_impl(self, que_imgs_info, ref_imgs_info, is_train):
     return outputs
 
 
-def render_chunks(self, que_imgs_info, ref_imgs_info, is_train):
+def render_chunks(self, que_imgs_info, ref_imgs_info, is_train, pack=None):
     """The chunk loop of reference renderer.py:236-254 (everything after the encoders).  The per-frame pack (channel-last
     maps, per-view parameters) and the query camera block are built once here and live exactly as long as this call: they
     are handed to the per-chunk functions through the two info dicts and removed again before returning."""
@@ -369,7 +392,7 @@ def render_chunks(self, que_imgs_info, ref_imgs_info, is_train):
     coords = que_imgs_info["coords"]
     ray_num = coords.shape[1]
     render_info_all = {}
-    ref_imgs_info[PACK_KEY] = FramePack(ref_imgs_info)
+    ref_imgs_info[PACK_KEY] = pack if pack is not None else FramePack(ref_imgs_info)
     que_imgs_info[CAM_KEY] = camera_blocks(que_imgs_info, None)[0]
     try:
         # an empty ray set still runs one (empty) chunk so that the caller gets every key with a zero-length ray axis
@@ -387,14 +410,20 @@ def render_chunks(self, que_imgs_info, ref_imgs_info, is_train):
 
 
 def render(self, que_imgs_info, ref_imgs_info, is_train):
-    """reference renderer.py:228-254, for an owner that has the reference's encoders."""
-    ref_img_feats = self.image_encoder(ref_imgs_info["imgs"])
-    ref_imgs_info["img_feats"] = ref_img_feats
-    ref_imgs_info["ray_feats"] = self.vis_encoder(ref_imgs_info["ray_feats"], ref_img_feats)
+    """reference renderer.py:228-254, for an owner that has the reference's encoders.  Inference runs the two encoders
+    natively, straight into the channel-last frame pack (encoders.encode_frame); when a gradient is wanted through them
+    (training) the owner's own torch modules run, upstream of the boundary, exactly as in the reference."""
+    pack = None
+    if encoders.usable(self, ref_imgs_info):
+        pack = FramePack(ref_imgs_info, encoder_owner=self)
+    else:
+        ref_img_feats = self.image_encoder(ref_imgs_info["imgs"])
+        ref_imgs_info["img_feats"] = ref_img_feats
+        ref_imgs_info["ray_feats"] = self.vis_encoder(ref_imgs_info["ray_feats"], ref_img_feats)
     if is_train and self.cfg["use_self_hit_prob"]:
         que_img_feats = self.image_encoder(que_imgs_info["imgs"])
         que_imgs_info["ray_feats"] = self.vis_encoder(que_imgs_info["ray_feats"], que_img_feats)
-    return render_chunks(self, que_imgs_info, ref_imgs_info, is_train)
+    return render_chunks(self, que_imgs_info, ref_imgs_info, is_train, pack)
 
 
 class NeuralRayRenderPath(nn.Module):
@@ -424,3 +453,17 @@ class NeuralRayRenderPath(nn.Module):
     def forward(self, data):
         is_train = "eval" not in data
         return self.render(data["que_imgs_info"].copy(), data["ref_imgs_info"].copy(), is_train)
+
+
+class NeuralRayFrameRenderer(NeuralRayRenderPath):
+    """NeuralRayRenderPath plus the two encoders of NeuralRayBaseRenderer (renderer.py:56-59), under the reference's
+    state-dict names `image_encoder.*` / `vis_encoder.*`: `render()` is the reference's `render` (renderer.py:228-254) --
+    ref_imgs_info carries the INIT net's 'ray_feats' [rfn,32,H/4,W/4]; both encoders run natively into the frame pack."""
+
+    def __init__(self, cfg):
+        super().__init__(cfg)
+        self.image_encoder = encoders.ImageEncoder()
+        self.vis_encoder = encoders.VisEncoder(self.cfg["vis_encoder_cfg"])
+
+    def render(self, que_imgs_info, ref_imgs_info, is_train):
+        return render(self, dict(que_imgs_info), ref_imgs_info, is_train)

@@ -526,3 +526,146 @@ def get_diff_feats(ref, depth_in):
     rm, rv = masked_mean_var(rgb_diff, valid, 0)
     shape = lambda t, c: t.reshape(rfn, h, w, c).permute(0, 3, 1, 2)
     return torch.cat([shape(rm, 3), shape(rv, 3), shape(dm, 1), shape(dv, 1)], 1)
+
+
+# --------------------------------------------------------------------------------------------------
+# encoders upstream of the ray path: functional restatement of
+#   ResUNetLight(3, [1,2,6,4], 32, inplanes=16)   network/ops.py:150-230 (built at renderer.py:59)
+#   DefaultVisEncoder                              network/vis_encoder.py:6-21
+# pinned by tests/golden/encoders.npz (oracle/gen_golden_encoders.py runs the unmodified modules).
+
+
+def _conv2d(x, w, b=None, stride=1):
+    """nn.Conv2d(k, stride, padding=(k-1)//2, padding_mode='reflect') (ops.py:129-134, conv3x3 / conv1x1)."""
+    p = (w.shape[-1] - 1) // 2
+    if p:
+        x = F.pad(x, (p, p, p, p), mode="reflect")
+    return F.conv2d(x, w, b, stride=stride)
+
+
+def _inorm(W, name, x, eps=1e-5):
+    """nn.InstanceNorm2d(C, track_running_stats=False, affine=True): per-(image, channel) biased statistics."""
+    m = x.mean((2, 3), keepdim=True)
+    v = ((x - m) ** 2).mean((2, 3), keepdim=True)
+    return (x - m) / torch.sqrt(v + eps) * W[name + ".weight"][None, :, None, None] + W[name + ".bias"][None, :, None, None]
+
+
+def _basic_block(W, pre, x, stride):
+    """BasicBlock.forward (ops.py:107-124)."""
+    out = torch.relu(_inorm(W, pre + ".bn1", _conv2d(x, W[pre + ".conv1.weight"], None, stride)))
+    out = _inorm(W, pre + ".bn2", _conv2d(out, W[pre + ".conv2.weight"]))
+    if pre + ".downsample.0.weight" in W:
+        x = _inorm(W, pre + ".downsample.1", _conv2d(x, W[pre + ".downsample.0.weight"], None, stride))
+    return torch.relu(out + x)
+
+
+def _conv_bn_elu(W, pre, x):
+    """`conv` module (ops.py:126-138): ELU(IN(conv3x3 reflect + bias))."""
+    return F.elu(_inorm(W, pre + ".bn", _conv2d(x, W[pre + ".conv.weight"], W[pre + ".conv.bias"])))
+
+
+def _skipconnect(x1, x2):
+    """ops.py:199-208: zero-pad the skip to the upsampled size, upsampled first."""
+    dy, dx = x2.shape[2] - x1.shape[2], x2.shape[3] - x1.shape[3]
+    x1 = F.pad(x1, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
+    return torch.cat([x2, x1], 1)
+
+
+def res_unet_light(W, pre, imgs, blocks=(1, 2, 6)):
+    """ResUNetLight.forward (ops.py:210-228); W keyed by state-dict names under `pre` ('' or 'image_encoder.')."""
+    W = {k[len(pre):]: v for k, v in W.items() if k.startswith(pre)}
+    x = torch.relu(_inorm(W, "bn1", _conv2d(imgs, W["conv1.weight"], None, 2)))
+    feats = []
+    for li, nb in enumerate(blocks):
+        for bi in range(nb):
+            x = _basic_block(W, f"layer{li + 1}.{bi}", x, 2 if bi == 0 else 1)
+        feats.append(x)
+    x1, x2, x3 = feats
+    up = lambda t: F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=True)
+    x = _conv_bn_elu(W, "upconv3.conv", up(x3))
+    x = _conv_bn_elu(W, "iconv3", _skipconnect(x2, x))
+    x = _conv_bn_elu(W, "upconv2.conv", up(x))
+    x = _conv_bn_elu(W, "iconv2", _skipconnect(x1, x))
+    return F.conv2d(x, W["out_conv.weight"], W["out_conv.bias"])
+
+
+def vis_encoder(W, pre, ray_feats, img_feats):
+    """DefaultVisEncoder.forward (vis_encoder.py:19-21) with ResidualBlock (ops.py:43-76, use_norm, no shortcut conv)."""
+    W = {k[len(pre):]: v for k, v in W.items() if k.startswith(pre)}
+    x = _conv2d(torch.cat([img_feats, ray_feats], 1), W["out_conv.0.weight"])
+    for i in (1, 2):
+        p = f"out_conv.{i}.conv"
+        t = _conv2d(torch.relu(_inorm(W, p + ".0", x)), W[p + ".2.weight"])
+        t = _conv2d(torch.relu(_inorm(W, p + ".3", t)), W[p + ".5.weight"])
+        x = t + x
+    return F.conv2d(x, W["out_conv.3.weight"])
+
+
+def encoder_test_weights(template, seed):
+    """Deterministic non-trivial parameters for a state dict `template` ({name: shape}): conv weights ~ N(0, 2/fan_in),
+    norm weights ~ U(0.5, 1.5), biases ~ N(0, 0.1).  numpy RandomState keeps the stream stable across versions, so the
+    goldens store only inputs and outputs, not the 2 M parameters."""
+    rs = np.random.RandomState(seed)
+    out = {}
+    for name, shape in template.items():
+        shape = tuple(shape)
+        if len(shape) == 4:
+            fan_in = shape[1] * shape[2] * shape[3]
+            a = rs.standard_normal(shape) * math.sqrt(2.0 / fan_in)
+        elif name.endswith(".weight"):
+            a = rs.uniform(0.5, 1.5, shape)
+        else:
+            a = rs.standard_normal(shape) * 0.1
+        out[name] = torch.from_numpy(a.astype(np.float32))
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# training extras (SURVEY.md section 8f row 3): network/renderer.py:280-316 and network/loss.py:17-132,
+# pinned by tests/golden/losses.npz (oracle/gen_golden_losses.py runs the unmodified classes).
+
+
+def predict_mean(W, pre, ray_feats, coords, h, w):
+    """renderer.py:291-296: interpolate_feature_map(ray_feats, coords, ones, h, w) + dist_decoder.predict_mean -> [rfn,pn,2]."""
+    mask = torch.ones(coords.shape[:2], dtype=torch.float32)
+    f = interpolate_feature_map(ray_feats, coords.float(), mask, h, w)
+    x = _elu(_lin(W, pre + ".mean_decoder.0", f))
+    x = _elu(_lin(W, pre + ".mean_decoder.2", x))
+    return _softplus(_lin(W, pre + ".mean_decoder.4", x))
+
+
+def render_loss(pr, gt, ray_mask=None):
+    """RenderLoss.compute_loss (loss.py:58-66)."""
+    loss = torch.sum((pr - gt) ** 2, -1)
+    if ray_mask is None:
+        return torch.mean(loss, 1)
+    m = ray_mask.float()
+    return torch.sum(loss * m, 1) / (torch.sum(m, 1) + 1e-3)
+
+
+def depth_loss(depth_pr, coords, true_depth, depth_range, loss_type="l2", beta=0.05, aug_depth=None, thresh=0.02):
+    """DepthLoss.__call__ (loss.py:92-127); aug_depth = the 'gso' branch."""
+    rfn, _, h, w = true_depth.shape
+    near, far = -1 / depth_range[:, 0:1], -1 / depth_range[:, 1:2]
+
+    def process(d):
+        d = -1 / torch.clamp(d, min=1e-5)
+        return torch.clamp((d - near) / (far - near), min=0, max=1.0)
+
+    at = lambda m: bilinear_sample(m, coords.float(), h, w, padding_mode="border", align_corners=True)[..., 0]
+    gt = process(at(true_depth))
+    if loss_type == "l2":
+        loss = (gt - depth_pr) ** 2
+    else:
+        d = (gt - depth_pr).abs()
+        loss = torch.where(d < beta, 0.5 * d * d / beta, d - 0.5 * beta)
+    if aug_depth is None:
+        return torch.mean(loss, 1)
+    m = ((process(at(aug_depth)) - gt).abs() < thresh).float()
+    return torch.sum(loss * m, 1) / (torch.sum(m, 1) + 1e-4)
+
+
+def consistency_loss(prob0, prob1):
+    """ConsistencyLoss.__call__ (loss.py:30-37)."""
+    ce = -prob0 * torch.log(prob1 + 1e-5) - (1 - prob0) * torch.log(1 - prob1 + 1e-5)
+    return torch.mean(torch.mean(ce, -1), 1)

@@ -1,0 +1,157 @@
+"""GPU: the native encoders (csrc/nr_encoder.cu) through the C-ABI against
+  * torch's fp32 conv2d for the tensor-core convolution alone (cuDNN with TF32 switched off),
+  * the golden outputs of the UNMODIFIED reference modules (tests/golden/encoders.npz),
+  * the oracle's restatement at the BASELINE configurations' image sizes,
+and the whole frame path (init-net ray_feats -> image_encoder + vis_encoder -> coarse + fine render) against the oracle."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import neuray_oracle as orc
+from gen_golden import flat_cfg
+from golden_io import GOLDEN_DIR
+from neuray_b200 import _lib, encoders, renderer, synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def golden():
+    z = np.load(os.path.join(GOLDEN_DIR, "encoders.npz"))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    cases = {tag: {k[2:]: t(z[k]) for k in z.files if k.startswith(tag + "_")} for tag in ("a", "b")}
+    return cases, orc.encoder_test_weights(json.loads(str(z["image_shapes"])), 11), orc.encoder_test_weights(json.loads(str(z["vis_shapes"])), 12)
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,ks,stride,reflect,rot", [
+    (2, 9, 11, 16, 32, 3, 2, 1, 0),
+    (3, 7, 9, 32, 64, 3, 1, 0, 0),
+    (1, 12, 13, 64, 128, 3, 1, 1, 32),
+    (2, 8, 8, 32, 32, 1, 2, 1, 0),
+    (1, 20, 20, 128, 64, 3, 1, 1, 0),
+    (8, 100, 100, 64, 64, 3, 1, 1, 0),       # layer2 of black_800: 625 CTAs
+    (8, 50, 50, 128, 128, 3, 1, 1, 0),       # layer3 of black_800
+    (4, 101, 75, 16, 32, 3, 2, 1, 0),        # layer1.0.conv1 shape family, odd sizes
+])
+def test_conv2d_matches_torch(n, h, w, cin, cout, ks, stride, reflect, rot):
+    g = torch.Generator().manual_seed(cin * 1000 + cout + ks)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5
+    bias = torch.randn(cout, generator=g)
+    p = (ks - 1) // 2
+    xp = F.pad(x, (p, p, p, p), mode="reflect") if (reflect and p) else x
+    want = F.conv2d(xp.double(), wt.double(), bias.double(), stride=stride, padding=0 if (reflect or not p) else p)
+    ho, wo = want.shape[2:]
+    res = torch.randn(n, ho, wo, cout, generator=g)
+    want = want + res.permute(0, 3, 1, 2).double()
+    xs, xo, ys, yo = cin + 8, 4, cout + 8, 4
+    xbuf = torch.full((n, h, w, xs), 7.0)
+    xbuf[..., xo:xo + cin] = _nhwc(x if rot == 0 else torch.roll(x, -rot, 1))
+    d = lambda t: t.cuda().contiguous()
+    xbuf, wt_d, b_d, r_d = d(xbuf), d(wt), d(bias), d(res)
+    ybuf = torch.full((n, ho, wo, ys), -3.0, device="cuda")
+    stats = torch.zeros(n, cout, 2, dtype=torch.float64, device="cuda")
+    packed = torch.empty(cout * cin * ks * ks, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(_lib.lib().nr_conv_pack_weight(_lib.ptr(wt_d), cout, cin, ks, rot, _lib.ptr(packed), st), "nr_conv_pack_weight")
+    c = _lib.NrConv2d()
+    c.x, c.w_packed, c.bias, c.res, c.y, c.stats = xbuf.data_ptr(), packed.data_ptr(), b_d.data_ptr(), r_d.data_ptr(), ybuf.data_ptr(), stats.data_ptr()
+    c.n, c.h, c.w, c.cin, c.cout, c.ks, c.stride, c.reflect = n, h, w, cin, cout, ks, stride, reflect
+    c.x_stride, c.x_off, c.y_stride, c.y_off, c.res_stride, c.res_off = xs, xo, ys, yo, cout, 0
+    _lib.check(_lib.lib().nr_conv2d_nhwc(C.byref(c), st), "nr_conv2d_nhwc")
+    torch.cuda.synchronize()
+    got = ybuf[..., yo:yo + cout].permute(0, 3, 1, 2).cpu().double()
+    err = float((got - want).abs().max())
+    assert err < 1e-5, err                                                    # 3xTF32: fp32 accuracy (one TF32 pass: ~1e-3)
+    assert bool(torch.all(ybuf[..., :yo] == -3.0)) and bool(torch.all(ybuf[..., yo + cout:] == -3.0))
+    assert torch.allclose(stats[..., 0].cpu(), want.sum((2, 3)), atol=1e-3, rtol=1e-6)
+    assert torch.allclose(stats[..., 1].cpu(), (want ** 2).sum((2, 3)), rtol=1e-5, atol=1e-3)
+
+
+def _modules(img_w, vis_w):
+    ie, ve = encoders.ImageEncoder(), encoders.VisEncoder()
+    ie.load_state_dict(img_w, strict=True)
+    ve.load_state_dict(vis_w, strict=True)
+    return ie.cuda(), ve.cuda()
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_encoders_match_the_reference_golden(tag):
+    cases, img_w, vis_w = golden()
+    c = cases[tag]
+    ie, ve = _modules(img_w, vis_w)
+    with torch.no_grad():
+        img_feats = ie(c["imgs"].cuda())
+        ray_feats = ve(c["ray_in"].cuda(), img_feats)
+    torch.cuda.synchronize()
+    assert img_feats.shape == c["img_feats"].shape
+    e1 = float((img_feats.cpu() - c["img_feats"]).abs().max())
+    e2 = float((ray_feats.cpu() - c["ray_feats"]).abs().max())
+    assert e1 < 5e-5 and e2 < 1e-4, (e1, e2)
+    with pytest.raises(_lib.NeurayB200Error):          # forward-only: no silent graph cut in training
+        ie(c["imgs"].cuda())
+
+
+@pytest.mark.parametrize("n,h,w", [(8, 304, 400), (2, 800, 800), (3, 768, 1008)])
+def test_encoders_match_the_oracle_at_baseline_sizes(n, h, w):
+    """cfg5 (DTU 300x400 padded to 304x400, 8 views), black_800 (2 of the 8 views), fern_high (3 of the 10 views)."""
+    _, img_w, vis_w = golden()
+    rs = np.random.RandomState(h + w)
+    coarse = torch.from_numpy(rs.uniform(0, 1, (n, 3, h // 8, w // 8)).astype(np.float32))
+    imgs = (F.interpolate(coarse, size=(h, w), mode="bilinear", align_corners=True) + torch.from_numpy(rs.uniform(-0.05, 0.05, (n, 3, h, w)).astype(np.float32))).clamp(0, 1)
+    ray_in = torch.from_numpy(rs.standard_normal((n, 32, h // 4, w // 4)).astype(np.float32))
+    want_i = orc.res_unet_light(img_w, "", imgs)
+    want_r = orc.vis_encoder(vis_w, "", ray_in, want_i)
+    ie, ve = _modules(img_w, vis_w)
+    with torch.no_grad():
+        got_i = ie(imgs.cuda())
+        got_r = ve(ray_in.cuda(), got_i)
+    torch.cuda.synchronize()
+    for got, want, tol in ((got_i, want_i, 1e-4), (got_r, want_r, 2e-4)):
+        err = (got.cpu() - want).abs()
+        assert float(err.max()) < tol * max(1.0, float(want.abs().max())), (float(err.max()), float(want.abs().max()))
+        assert float(err.mean()) < 5e-6
+
+
+def test_frame_renderer_with_native_encoders_matches_the_oracle():
+    """renderer.render (reference renderer.py:228-254): init-net ray_feats + images -> both encoders written straight into the
+    frame pack -> coarse + fine pass, against oracle encoders + oracle render."""
+    cfg = {"use_hierarchical_sampling": True, "dist_decoder_cfg": {"use_vis": False}, "depth_sample_num": 32, "fine_depth_sample_num": 32,
+           "agg_net_cfg": {"sample_num": 32}, "fine_agg_net_cfg": {"sample_num": 32}, "render_depth": True, "ray_batch_num": 160}
+    _, img_w, vis_w = golden()
+    que, ref = synthetic.make_scene(64, 80, 5, seed=4, smooth=2)
+    que = synthetic.slice_rays(que, 2000, 2400)
+    ref = dict(ref)
+    ray_in = ref.pop("ray_feats")          # plays the init net's output
+    ref.pop("img_feats")
+    W = synthetic.make_weights(cfg, seed=4)
+    net = renderer.NeuralRayFrameRenderer(cfg)
+    full = dict(W)
+    full.update({"image_encoder." + k: v for k, v in img_w.items()})
+    full.update({"vis_encoder." + k: v for k, v in vis_w.items()})
+    net.load_state_dict(full, strict=True)
+    net.cuda().eval()
+    dref = synthetic.to_device(dict(ref, ray_feats=ray_in), "cuda")
+    with torch.no_grad():
+        out = net.render(synthetic.to_device(que, "cuda"), dref, False)
+    torch.cuda.synchronize()
+    img_feats = orc.res_unet_light(img_w, "", ref["imgs"])
+    ray_feats = orc.vis_encoder(vis_w, "", ray_in, img_feats)
+    # the NCHW maps the reference's later callers read are left in the dict
+    assert float((dref["img_feats"].cpu() - img_feats).abs().max()) < 1e-4
+    assert float((dref["ray_feats"].cpu() - ray_feats).abs().max()) < 2e-4
+    gold = orc.render(W, flat_cfg({**renderer.base_cfg, **cfg}), que, dict(ref, ray_feats=ray_feats, img_feats=img_feats), False, ray_batch_num=160)
+    assert set(out) == set(gold)
+    err = float((out["pixel_colors_nr"].cpu() - gold["pixel_colors_nr"]).abs().max())
+    assert err < 2e-4, err
+    fine = (out["pixel_colors_nr_fine"].cpu() - gold["pixel_colors_nr_fine"]).abs()
+    assert float(torch.quantile(fine.flatten(), 0.99)) < 2e-4 and float((fine > 1e-3).float().mean()) < 0.01
+    assert torch.equal(out["ray_mask"].cpu(), gold["ray_mask"])
