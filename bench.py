@@ -498,9 +498,19 @@ def encoders_bench(dr, dev, reps=5):
     info = {"imgs": imgs, "ray_feats": ray_in}
     with torch.no_grad():
         ms = timed(lambda: encoders.encode_frame(owner, dict(info), feat))
+        feat32 = feat.clone()
+        encoders.set_precision("tf32")
+        try:
+            ms_tf32x1 = timed(lambda: encoders.encode_frame(owner, dict(info), feat))
+            tf32_diff = float((feat - feat32).abs().max())
+        finally:
+            encoders.set_precision("fp32")
+        encoders.encode_frame(owner, dict(info), feat)
     fl = encoder_flops(h, w) * rfn
     res = {"ms_per_frame": ms, "views": rfn, "image": [h, w], "algorithmic_tflops": fl / ms / 1e9, "flop_per_frame": fl,
            "kernels_per_frame": encoders.IMAGE_LAUNCHES + encoders.VIS_LAUNCHES + 3,
+           "single_pass_tf32": {"ms_per_frame": ms_tf32x1, "algorithmic_tflops": fl / ms_tf32x1 / 1e9, "max_abs_diff_to_fp32_mode": tf32_diff,
+                                "what": "encoders.set_precision('tf32'): one TF32 pass per product, the arithmetic of cuDNN under torch's default allow_tf32"},
            "what": "image_encoder + vis_encoder of all reference views into the channel-last frame pack (3xTF32 tensor-core convolutions: fp32 accuracy)"}
     ref_mod = _load_reference()
     if ref_mod is None:

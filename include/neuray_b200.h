@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NR_ABI_VERSION 4
+#define NR_ABI_VERSION 5
 
 #define NR_OK 0
 #define NR_E_INVALID (-1)   /* bad argument (null pointer, unsupported shape) */
@@ -286,12 +286,16 @@ int nr_vis_encoder_pack(const float* const* params, int n_params, float* packed,
 int nr_image_encoder_dims(int h, int w, int* fh, int* fw);
 long long nr_image_encoder_workspace(int n, int h, int w);     /* bytes */
 long long nr_vis_encoder_workspace(int n, int fh, int fw);     /* bytes */
-/* imgs [n,3,h,w] (NCHW as the reference holds them) -> out[(view, y, x) * out_stride + out_off + c], c < 32. */
+/* imgs [n,3,h,w] (NCHW as the reference holds them) -> out[(view, y, x) * out_stride + out_off + c], c < 32.
+ * tf32x1: 0 = 3xTF32 tensor-core products (fp32 accuracy: parity with the fp32 reference, the default of the Python layer);
+ * 1 = one TF32 pass per product, i.e. what the reference computes on a GPU under torch's default
+ * torch.backends.cudnn.allow_tf32 = True (~1e-3 relative). */
 int nr_image_encoder_fwd(const float* packed, const float* imgs, int n, int h, int w, float* out, int out_stride, int out_off,
-                         void* workspace, long long workspace_bytes, void* stream);
+                         int tf32x1, void* workspace, long long workspace_bytes, void* stream);
 /* feat [n,fh,fw,64]: channels 0..31 = the init net's ray_feats, 32..63 = img_feats; channels 0..31 are overwritten with
  * vis_encoder(ray_feats, img_feats). */
-int nr_vis_encoder_fwd(const float* packed, float* feat, int n, int fh, int fw, void* workspace, long long workspace_bytes, void* stream);
+int nr_vis_encoder_fwd(const float* packed, float* feat, int n, int fh, int fw, int tf32x1, void* workspace, long long workspace_bytes,
+                       void* stream);
 
 /* Building blocks (channel-last).  nr_conv2d_nhwc: 1x1 / 3x3 convolution, stride 1 / 2, reflect or zero padding of
  * (ks-1)/2, cout in {32, 64, 128}, cin a multiple of 16, as an implicit GEMM on the tensor cores (3xTF32: fp32 accuracy);
@@ -303,6 +307,7 @@ typedef struct NrConv2d {
   float* y; double* stats;
   int32_t n, h, w, cin, cout, ks, stride, reflect;
   int32_t x_stride, x_off, y_stride, y_off, res_stride, res_off;
+  int32_t tf32x1;            /* 0: 3xTF32 (fp32 accuracy); 1: one TF32 pass */
 } NrConv2d;
 int nr_conv2d_nhwc(const NrConv2d* c, void* stream);
 /* [cout][cin][ks][ks] -> [tap][cin][cout]; packed input channel c reads reference channel (c + cin_rot) % cin */

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # NEURAY_B200_LIB: development switch to load another in-tree build of the same library (A/B runs of kernel variants)
 LIB_PATH = os.environ.get("NEURAY_B200_LIB") or os.path.join(_HERE, "libneuray_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 NR_POINT_REC = 20
 NR_MAX_VIEWS = 32
 NR_MAX_SAMPLES = 256
@@ -96,8 +96,8 @@ SIGNATURES = {
     "nr_image_encoder_dims": (C.c_int, [_i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "nr_image_encoder_workspace": (C.c_longlong, [_i, _i, _i]),
     "nr_vis_encoder_workspace": (C.c_longlong, [_i, _i, _i]),
-    "nr_image_encoder_fwd": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, C.c_longlong, _vp]),
-    "nr_vis_encoder_fwd": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, C.c_longlong, _vp]),
+    "nr_image_encoder_fwd": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp, C.c_longlong, _vp]),
+    "nr_vis_encoder_fwd": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp, C.c_longlong, _vp]),
     "nr_conv2d_nhwc": (C.c_int, [_vp, _vp]),
     "nr_conv_pack_weight": (C.c_int, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "nr_instance_norm_act": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
@@ -128,7 +128,7 @@ class NrEncoderLayout(C.Structure):
 
 class NrConv2d(C.Structure):
     _fields_ = [("x", C.c_void_p), ("w_packed", C.c_void_p), ("bias", C.c_void_p), ("res", C.c_void_p), ("y", C.c_void_p), ("stats", C.c_void_p)] + \
-               [(n, C.c_int32) for n in "n h w cin cout ks stride reflect x_stride x_off y_stride y_off res_stride res_off".split()]
+               [(n, C.c_int32) for n in "n h w cin cout ks stride reflect x_stride x_off y_stride y_off res_stride res_off tf32x1".split()]
 
 
 class NrSelfParams(C.Structure):

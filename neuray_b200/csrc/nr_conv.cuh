@@ -39,6 +39,7 @@ struct ConvP {
   double* stats;        // [N][Cout][2]: sum, sum of squares (accumulated; the caller zeroes it) or null
   int N, H, W, Ho, Wo, Cin, Cout, ks, stride, reflect;
   int x_stride, x_off, y_stride, y_off, res_stride, res_off;
+  int tf32x1;           // 0: 3xTF32 (fp32 accuracy, the default); 1: one TF32 pass, what cuDNN does under torch's default allow_tf32
 };
 
 struct RowInfo {

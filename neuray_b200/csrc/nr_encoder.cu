@@ -26,7 +26,15 @@ __device__ __forceinline__ void split(float x, uint32_t& hi, uint32_t& lo) {
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
-template <int BN, int KC>
+__device__ __forceinline__ uint32_t to_tf32(float x) {      // round to nearest (the MMA itself would truncate)
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+// FAST = one TF32 pass per product (operands rounded to TF32: ~1e-3 relative, torch's default for cuDNN convolutions);
+// otherwise the 3xTF32 split (fp32 accuracy, what the parity tests run)
+template <int BN, int KC, bool FAST>
 __global__ void __launch_bounds__(THREADS, BN >= 64 ? 1 : 2) conv_mma_kernel(const __grid_constant__ ConvP p) {
   extern __shared__ __align__(16) float sm[];
   constexpr int MT = BN / 32, WN = BN / 32;
@@ -92,27 +100,35 @@ __global__ void __launch_bounds__(THREADS, BN >= 64 ? 1 : 2) conv_mma_kernel(con
         for (int e = 0; e < 4; ++e) part[i][j][e] = 0.f;
 #pragma unroll
     for (int k8 = 0; k8 < KC / 8; ++k8) {
-      uint32_t ah[MT][4], al[MT][4], bh[4][2], bl[4][2];
+      uint32_t ah[MT][4], al[FAST ? 1 : MT][4], bh[4][2], bl[FAST ? 1 : 4][2];
 #pragma unroll
       for (int i = 0; i < MT; ++i) {
         int off[4];
         a_frag<KC>(warp_m * (16 * MT) + 16 * i, lane, k8, off);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) split(A[off[e]], ah[i][e], al[i][e]);
+        for (int e = 0; e < 4; ++e) {
+          if constexpr (FAST) ah[i][e] = to_tf32(A[off[e]]);
+          else split(A[off[e]], ah[i][e], al[i][e]);
+        }
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         int off[2];
         b_frag<BN>(warp_n * 32 + 8 * j, lane, k8, off);
 #pragma unroll
-        for (int e = 0; e < 2; ++e) split(B[off[e]], bh[j][e], bl[j][e]);
+        for (int e = 0; e < 2; ++e) {
+          if constexpr (FAST) bh[j][e] = to_tf32(B[off[e]]);
+          else split(B[off[e]], bh[j][e], bl[j][e]);
+        }
       }
 #pragma unroll
       for (int i = 0; i < MT; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          mma_tf32(part[i][j], al[i], bh[j]);      // small terms first
-          mma_tf32(part[i][j], ah[i], bl[j]);
+          if constexpr (!FAST) {
+            mma_tf32(part[i][j], al[i], bh[j]);      // small terms first
+            mma_tf32(part[i][j], ah[i], bl[j]);
+          }
           mma_tf32(part[i][j], ah[i], bh[j]);
         }
     }
@@ -125,14 +141,25 @@ __global__ void __launch_bounds__(THREADS, BN >= 64 ? 1 : 2) conv_mma_kernel(con
   }
   cp_async_wait<0>();
 
+  // InstanceNorm sums: thread partials -> the 8 row lanes of a warp (shuffles) -> the CTA (shared memory) -> ONE fp64 atomic
+  // per (column, sum) and CTA.  Thousands of CTAs adding to the same 2 x Cout addresses of an image serialise in L2: with one
+  // atomic per warp the 2 500-CTA layers spent 300 us of their 420 us on them (profiles/r2_encoders_v0_launches.md).
+  __shared__ double cta_sums[2 * 128];
+  const long long M = (long long)p.N * p.Ho * p.Wo;
+  const long long plane = (long long)p.Ho * p.Wo;
+  const long long last_row = m0 + BM - 1 < M ? m0 + BM - 1 : M - 1;
+  const bool cta_uniform = p.stats != nullptr && m0 / plane == last_row / plane;      // all rows of the CTA in one image
+  if (cta_uniform) {
+    for (int i = tid; i < 2 * BN; i += THREADS) cta_sums[i] = 0.0;
+    __syncthreads();
+  }
   const bool uniform = warp_rows_uniform<BN>(p, m0, warp);
   float s[4][2], q[4][2];
   epilogue_thread<BN>(p, m0, warp, lane, acc, uniform, s, q);
   if (p.stats != nullptr && uniform) {
     const long long first = m0 + warp_m * (16 * MT);
-    const long long M = (long long)p.N * p.Ho * p.Wo;
     if (first < M) {                  // warp-uniform
-      const int n = int(first / ((long long)p.Ho * p.Wo));
+      const int n = int(first / plane);
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -145,12 +172,22 @@ __global__ void __launch_bounds__(THREADS, BN >= 64 ? 1 : 2) conv_mma_kernel(con
           }
           if ((lane >> 2) == 0) {
             const int col = warp_n * 32 + 8 * j + 2 * (lane & 3) + b;
-            double* st = p.stats + ((long long)n * BN + col) * 2;
-            atomicAdd(st, sd);
-            atomicAdd(st + 1, qd);
+            if (cta_uniform) {
+              atomicAdd(&cta_sums[2 * col], sd);
+              atomicAdd(&cta_sums[2 * col + 1], qd);
+            } else {
+              double* st = p.stats + ((long long)n * BN + col) * 2;
+              atomicAdd(st, sd);
+              atomicAdd(st + 1, qd);
+            }
           }
         }
     }
+  }
+  if (cta_uniform) {
+    __syncthreads();
+    const int n = int(m0 / plane);
+    for (int i = tid; i < 2 * BN; i += THREADS) atomicAdd(p.stats + (long long)n * BN * 2 + i, cta_sums[i]);
   }
 }
 
@@ -169,7 +206,11 @@ __global__ void __launch_bounds__(256) conv7_kernel(const __grid_constant__ Conv
 #pragma unroll
     for (int c = 0; c < 4; ++c) o[c] = make_float4(out[4 * c], out[4 * c + 1], out[4 * c + 2], out[4 * c + 3]);
   }
-  // InstanceNorm sums of the block's pixels (one image per blockIdx.y): warp sums in fp32, one fp64 atomic per warp and channel
+  // InstanceNorm sums of the block's pixels (one image per blockIdx.y): warp sums in fp32 -> block sums in shared memory ->
+  // one fp64 atomic per channel, sum and block
+  __shared__ double cta_sums[32];
+  if (threadIdx.x < 32) cta_sums[threadIdx.x] = 0.0;
+  __syncthreads();
 #pragma unroll
   for (int c = 0; c < 16; ++c) {
     float sv = out[c], qv = out[c] * out[c];
@@ -179,10 +220,12 @@ __global__ void __launch_bounds__(256) conv7_kernel(const __grid_constant__ Conv
       qv += __shfl_xor_sync(0xffffffffu, qv, o);
     }
     if ((threadIdx.x & 31) == 0) {
-      atomicAdd(p.stats + ((long long)n * 16 + c) * 2, double(sv));
-      atomicAdd(p.stats + ((long long)n * 16 + c) * 2 + 1, double(qv));
+      atomicAdd(&cta_sums[2 * c], double(sv));
+      atomicAdd(&cta_sums[2 * c + 1], double(qv));
     }
   }
+  __syncthreads();
+  if (threadIdx.x < 32) atomicAdd(p.stats + (long long)n * 32 + threadIdx.x, cta_sums[threadIdx.x]);
 }
 
 __global__ void __launch_bounds__(256) norm_act_kernel(const __grid_constant__ NormP p) {
@@ -310,14 +353,18 @@ __global__ void __launch_bounds__(256) pack_params_kernel(const __grid_constant_
     a.out[j.spec.off + e] = j.src[enc::pack_source(j.spec, e)];
 }
 
-template <int BN, int KC>
-int launch_conv_t(const ConvP& p, cudaStream_t st) {
+template <int BN, int KC, bool FAST>
+int launch_conv_f(const ConvP& p, cudaStream_t st) {
   constexpr size_t smem = size_t(STAGES) * (BM * (KC + 4) + KC * (BN + 8)) * sizeof(float);
-  cudaFuncSetAttribute(conv_mma_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));   // per device, per launch
+  cudaFuncSetAttribute(conv_mma_kernel<BN, KC, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));   // per device, per launch
   const long long M = (long long)p.N * p.Ho * p.Wo;
-  conv_mma_kernel<BN, KC><<<unsigned((M + BM - 1) / BM), THREADS, smem, st>>>(p);
+  conv_mma_kernel<BN, KC, FAST><<<unsigned((M + BM - 1) / BM), THREADS, smem, st>>>(p);
   NR_CHECK_LAUNCH("conv_mma_kernel");
   return NR_OK;
+}
+template <int BN, int KC>
+int launch_conv_t(const ConvP& p, cudaStream_t st) {
+  return p.tf32x1 ? launch_conv_f<BN, KC, true>(p, st) : launch_conv_f<BN, KC, false>(p, st);
 }
 
 int check_conv(const ConvP& p) {
@@ -355,7 +402,13 @@ struct StreamOps {
   cudaStream_t st;
   int sms;
   int rc;
-  void conv(const ConvP& p) { if (rc == NR_OK) rc = launch_conv(p, st); }
+  int tf32x1;
+  void conv(const ConvP& p) {
+    if (rc != NR_OK) return;
+    ConvP q = p;
+    q.tf32x1 = tf32x1;
+    rc = launch_conv(q, st);
+  }
   void conv7(const Conv7P& p) {
     if (rc != NR_OK) return;
     conv7_kernel<<<dim3(unsigned((p.Ho * p.Wo + 255) / 256), p.N), 256, 0, st>>>(p);
@@ -455,7 +508,7 @@ extern "C" int nr_vis_encoder_pack(const float* const* params, int n_params, flo
 }
 
 extern "C" int nr_image_encoder_fwd(const float* packed, const float* imgs, int n, int h, int w, float* out, int out_stride, int out_off,
-                                    void* workspace, long long workspace_bytes, void* stream) {
+                                    int tf32x1, void* workspace, long long workspace_bytes, void* stream) {
   if (n == 0) return NR_OK;
   NR_CHECK_ARG(packed != nullptr && imgs != nullptr && out != nullptr && workspace != nullptr, "image_encoder: null pointer");
   NR_CHECK_ARG(n >= 1 && h >= 32 && w >= 32, "image_encoder: images must be at least 32 x 32");
@@ -465,7 +518,7 @@ extern "C" int nr_image_encoder_fwd(const float* packed, const float* imgs, int 
   const long long stats = enc::image_stats_doubles(net, n, h, w);
   NR_CHECK_ARG(stats > 0, "image_encoder: image size the decoder's skip connections cannot take (ops.py:199-208)");
   enc::Arena ar{(char*)workspace, size_t(workspace_bytes), 0, true};
-  cv::StreamOps ops{(cudaStream_t)stream, cv::sm_count(), NR_OK};
+  cv::StreamOps ops{(cudaStream_t)stream, cv::sm_count(), NR_OK, tf32x1 != 0};
   const bool ok = enc::image_encoder_graph(ops, ar, net, packed, imgs, n, h, w, out, out_stride, out_off, stats, nullptr);
   if (ops.rc != NR_OK) return ops.rc;
   NR_CHECK_ARG(ok, "image_encoder: workspace too small (nr_image_encoder_workspace)");
@@ -473,7 +526,8 @@ extern "C" int nr_image_encoder_fwd(const float* packed, const float* imgs, int 
   return NR_OK;
 }
 
-extern "C" int nr_vis_encoder_fwd(const float* packed, float* feat, int n, int fh, int fw, void* workspace, long long workspace_bytes, void* stream) {
+extern "C" int nr_vis_encoder_fwd(const float* packed, float* feat, int n, int fh, int fw, int tf32x1, void* workspace, long long workspace_bytes,
+                                  void* stream) {
   if (n == 0) return NR_OK;
   NR_CHECK_ARG(packed != nullptr && feat != nullptr && workspace != nullptr, "vis_encoder: null pointer");
   NR_CHECK_ARG(n >= 1 && fh >= 2 && fw >= 2, "vis_encoder: empty maps");
@@ -481,7 +535,7 @@ extern "C" int nr_vis_encoder_fwd(const float* packed, float* feat, int n, int f
   enc::build_vis_net(net);
   const long long stats = enc::vis_stats_doubles(net, n, fh, fw);
   enc::Arena ar{(char*)workspace, size_t(workspace_bytes), 0, true};
-  cv::StreamOps ops{(cudaStream_t)stream, cv::sm_count(), NR_OK};
+  cv::StreamOps ops{(cudaStream_t)stream, cv::sm_count(), NR_OK, tf32x1 != 0};
   const bool ok = enc::vis_encoder_graph(ops, ar, net, packed, feat, n, fh, fw, stats, nullptr);
   if (ops.rc != NR_OK) return ops.rc;
   NR_CHECK_ARG(ok, "vis_encoder: workspace too small (nr_vis_encoder_workspace)");
@@ -499,6 +553,7 @@ extern "C" int nr_conv2d_nhwc(const NrConv2d* c, void* stream) {
   NR_CHECK_ARG(p.stride == 1 || p.stride == 2, "conv: stride 1 or 2");
   p.Ho = enc::conv_out(p.H, p.ks, p.stride); p.Wo = enc::conv_out(p.W, p.ks, p.stride);
   p.x_stride = c->x_stride; p.x_off = c->x_off; p.y_stride = c->y_stride; p.y_off = c->y_off; p.res_stride = c->res_stride; p.res_off = c->res_off;
+  p.tf32x1 = c->tf32x1 != 0;
   if (p.N == 0) return NR_OK;
   return cv::launch_conv(p, (cudaStream_t)stream);
 }
@@ -524,7 +579,7 @@ extern "C" int nr_instance_norm_act(const float* x, const double* stats, const f
   p.x = x; p.stats = stats; p.gamma = gamma; p.beta = beta; p.res = res; p.res_stats = res_stats; p.res_gamma = res_gamma; p.res_beta = res_beta;
   p.y = y; p.N = n; p.HW = hw; p.C = c; p.act = act; p.x_stride = c; p.x_off = 0; p.res_stride = c; p.res_off = 0; p.y_stride = c; p.y_off = 0;
   p.eps = 1e-5f;
-  cv::StreamOps ops{(cudaStream_t)stream, cv::sm_count(), NR_OK};
+  cv::StreamOps ops{(cudaStream_t)stream, cv::sm_count(), NR_OK, 0};
   ops.norm(p);
   NR_CHECK_LAUNCH("norm_act_kernel");
   return NR_OK;

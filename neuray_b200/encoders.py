@@ -105,6 +105,18 @@ def _plant(root, shapes):
 IMAGE_LAUNCHES = 2 + 15 + 24 + 2 + 8 + 2 + 1
 VIS_LAUNCHES = 10
 
+# Convolution arithmetic: "fp32" = 3xTF32 tensor-core products (fp32 accuracy: parity with the fp32 reference; the default),
+# "tf32" = one TF32 pass per product -- what the reference's cuDNN convolutions do on a GPU under torch's default
+# torch.backends.cudnn.allow_tf32 = True (~1e-3 relative error), roughly three times fewer MMAs.
+PRECISION = "fp32"
+
+
+def set_precision(mode):
+    global PRECISION
+    if mode not in ("fp32", "tf32"):
+        raise ValueError(f"encoder precision {mode!r}: 'fp32' or 'tf32'")
+    PRECISION = mode
+
 _WS = {}
 
 
@@ -163,8 +175,8 @@ def image_encoder_into(module, imgs, out, out_off):
     ws = _workspace("image", nbytes, dev)
     x = imgs.detach().contiguous().float()
     with _lib.on_device(imgs):
-        _lib.check(_lib.lib().nr_image_encoder_fwd(_lib.ptr(packed), _lib.ptr(x), n, h, w, _lib.ptr(out), out.shape[-1], out_off, ws.data_ptr(),
-                                                   nbytes, _lib.stream_of(imgs)), "nr_image_encoder_fwd")
+        _lib.check(_lib.lib().nr_image_encoder_fwd(_lib.ptr(packed), _lib.ptr(x), n, h, w, _lib.ptr(out), out.shape[-1], out_off, int(PRECISION == "tf32"),
+                                                   ws.data_ptr(), nbytes, _lib.stream_of(imgs)), "nr_image_encoder_fwd")
     _lib.count_launches(IMAGE_LAUNCHES)
     return out
 
@@ -179,7 +191,7 @@ def vis_encoder_inplace(module, feat):
     nbytes = _lib.lib().nr_vis_encoder_workspace(n, fh, fw)
     ws = _workspace("vis", nbytes, dev)
     with _lib.on_device(feat):
-        _lib.check(_lib.lib().nr_vis_encoder_fwd(_lib.ptr(packed), _lib.ptr(feat), n, fh, fw, ws.data_ptr(), nbytes, _lib.stream_of(feat)),
+        _lib.check(_lib.lib().nr_vis_encoder_fwd(_lib.ptr(packed), _lib.ptr(feat), n, fh, fw, int(PRECISION == "tf32"), ws.data_ptr(), nbytes, _lib.stream_of(feat)),
                    "nr_vis_encoder_fwd")
     _lib.count_launches(VIS_LAUNCHES)
     return feat

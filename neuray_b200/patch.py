@@ -10,18 +10,26 @@ What is rebound:
     network.init_net's namespaces, which star-/name-import them)
   * NeuralRayBaseRenderer.render_by_depth / fine_render_impl / render_impl / render -> neuray_b200.renderer
   * network.init_net.get_diff_feats (DepthInitNet) -> neuray_b200.init_ops.get_diff_feats
+  * NeuralRayGenRenderer.predict_mean_for_depth_loss and network.loss.{RenderLoss, DepthLoss, ConsistencyLoss, name2loss}
+     -> neuray_b200.losses
+  * inference only: `render` runs image_encoder / vis_encoder natively into the frame pack (SURVEY.md 8f row 1,
+    neuray_b200.encoders); with a gradient wanted through them the reference's own torch modules run
 Constructors, cfg keys, sub-module and state-dict names, and the output dict stay the reference's own.
 The IBRNetWithNeuRay.pos_encoding attribute pinned to cuda:0 (ibrnet.py:312) is no longer used on the path: the
 kernels get a per-device table built by neuray_b200.weights.posenc_table.
 """
 import importlib
 
-from . import init_ops, render_ops, renderer
+from . import init_ops, losses, render_ops, renderer
 
 _ORIGINALS = []          # (object, attribute name, original value) of everything install() rebound
 
 
 def _rebind(obj, name, value):
+    if isinstance(obj, dict):
+        _ORIGINALS.append((obj, name, obj[name]))
+        obj[name] = value
+        return
     _ORIGINALS.append((obj, name, getattr(obj, name)))
     setattr(obj, name, value)
 
@@ -52,6 +60,14 @@ def install():
     _rebind(base, "fine_render_impl", renderer.fine_render_impl)
     _rebind(base, "render_impl", renderer.render_impl)
     _rebind(base, "render", renderer.render)
+    _rebind(ref_renderer.NeuralRayGenRenderer, "predict_mean_for_depth_loss", losses.predict_mean_for_depth_loss)
+    try:
+        ref_loss = importlib.import_module("network.loss")
+        for key, cls in losses.name2loss.items():
+            _rebind(ref_loss.name2loss, key, cls)
+            _rebind(ref_loss, cls.__name__, cls)
+    except Exception:      # a trimmed reference tree without the training code
+        pass
     return base
 
 
@@ -59,4 +75,7 @@ def uninstall():
     """Puts the reference's own functions back (tests compare patched and unpatched runs in one process)."""
     while _ORIGINALS:
         obj, name, value = _ORIGINALS.pop()
-        setattr(obj, name, value)
+        if isinstance(obj, dict):
+            obj[name] = value
+        else:
+            setattr(obj, name, value)

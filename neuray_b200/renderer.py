@@ -38,6 +38,8 @@ base_cfg = {
     "use_dr_prediction": False, "use_nr_color_for_dr": False, "use_self_hit_prob": False,
     "use_ray_mask": True, "ray_mask_view_num": 2, "ray_mask_point_num": 8,
     "render_depth": False,
+    # NeuralRayGenRenderer.default_cfg (renderer.py:256-261), read by predict_mean_for_depth_loss
+    "use_depth_loss": False, "depth_loss_coords_num": 8192,
 }
 
 
@@ -446,6 +448,11 @@ class NeuralRayRenderPath(nn.Module):
     render_by_depth = render_by_depth
     fine_render_impl = fine_render_impl
     render_impl = render_impl
+
+    def predict_mean_for_depth_loss(self, ref_imgs_info):
+        """NeuralRayGenRenderer.predict_mean_for_depth_loss (reference renderer.py:280-316); cfg 'depth_loss_coords_num'."""
+        from . import losses
+        return losses.predict_mean_for_depth_loss(self, ref_imgs_info)
 
     def render(self, que_imgs_info, ref_imgs_info, is_train):
         return render_chunks(self, dict(que_imgs_info), ref_imgs_info, is_train)

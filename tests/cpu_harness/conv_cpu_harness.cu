@@ -235,6 +235,7 @@ extern "C" int nr_cpu_conv2d(const float* x, const float* w, const float* bias, 
   p.N = n; p.H = h; p.W = wd; p.Cin = cin; p.Cout = cout; p.ks = ks; p.stride = stride; p.reflect = reflect;
   p.Ho = enc::conv_out(h, ks, stride); p.Wo = enc::conv_out(wd, ks, stride);
   p.x_stride = x_stride; p.x_off = x_off; p.y_stride = y_stride; p.y_off = y_off; p.res_stride = cout; p.res_off = 0;
+  p.tf32x1 = 0;
   HostOps ops;
   ops.conv(p);
   return 0;

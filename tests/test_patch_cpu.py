@@ -13,9 +13,15 @@ def test_install_rebinds_reference_api():
     import network.render_ops as ref_ops
     orig_ops = {n: getattr(ref_ops, n) for n in render_ops.__all__ if hasattr(ref_ops, n)}
     orig_ren = {n: getattr(ref_renderer, n) for n in render_ops.__all__ if hasattr(ref_renderer, n)}
+    import network.loss as ref_loss
+    from neuray_b200 import losses
+    orig_loss = dict(ref_loss.name2loss)
+    orig_pm = ref_renderer.NeuralRayGenRenderer.predict_mean_for_depth_loss
     try:
         base = patch.install()
         assert base.render_impl is renderer.render_impl and base.render is renderer.render
+        assert ref_loss.name2loss == losses.name2loss and ref_loss.DepthLoss is losses.DepthLoss
+        assert ref_renderer.NeuralRayGenRenderer.predict_mean_for_depth_loss is losses.predict_mean_for_depth_loss
         for n in orig_ops:
             assert getattr(ref_ops, n) is getattr(render_ops, n), n
         # the reference's own constructor still builds the network; the hot path now refuses CPU tensors (no fallback)
@@ -29,6 +35,7 @@ def test_install_rebinds_reference_api():
         patch.uninstall()
     for k, v in orig.items():
         assert getattr(ref_renderer.NeuralRayBaseRenderer, k) is v, k
+    assert ref_loss.name2loss == orig_loss and ref_renderer.NeuralRayGenRenderer.predict_mean_for_depth_loss is orig_pm
     for n, v in orig_ops.items():
         assert getattr(ref_ops, n) is v, n
     for n, v in orig_ren.items():

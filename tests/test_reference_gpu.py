@@ -256,3 +256,45 @@ def test_render_ops_refuse_to_cut_a_graph(ref_mod):
     want = ref_ops.interpolate_feature_map(fm2, pts, mask, 48, 64)
     want.square().sum().backward()
     assert torch.allclose(out, want, atol=1e-5) and torch.allclose(fm.grad, fm2.grad, atol=1e-4, rtol=1e-4)
+
+
+def test_losses_patched_equal_unpatched(ref_mod):
+    """network.loss.name2loss (what train/trainer.py builds its losses from) before and after patch.install(): the three
+    losses on the outputs of one training-mode forward of the reference network, values and the gradients with respect to
+    every output tensor they read."""
+    import network.loss as ref_loss
+    cfg = dict(CFG, use_self_hit_prob=True)
+    que, ref = make_data(self_feats=True)
+    net = build(ref_mod, cfg).train()
+    with torch.no_grad():
+        out = run(net, que, ref, True)
+    dref = synthetic.to_device(ref, "cuda")
+    data_gt = {"ref_imgs_info": dref, "scene_name": "dtu_train/scan1"}
+    reads = ("pixel_colors_nr", "pixel_colors_nr_fine", "depth_mean", "depth_mean_fine", "hit_prob_self", "hit_prob_self_fine")
+    cfgs = {"render": {"use_nr_fine_loss": True}, "depth": {"depth_loss_type": "smooth_l1"}, "consist": {}}
+
+    def evaluate():
+        data_pr = {k: (v.detach().clone().requires_grad_(True) if k in reads else v) for k, v in out.items()}
+        res = {}
+        for name, c in cfgs.items():
+            res.update(ref_loss.name2loss[name](c)(data_pr, data_gt, 0))
+        total = sum((i + 1.0) * v.sum() for i, v in enumerate(res.values()))
+        total.backward()
+        return {k: v.detach() for k, v in res.items()}, {k: data_pr[k].grad for k in reads}
+
+    want, gwant = evaluate()
+    patch.install()
+    try:
+        from neuray_b200 import losses
+        assert ref_loss.name2loss["depth"] is losses.DepthLoss
+        got, ggot = evaluate()
+    finally:
+        patch.uninstall()
+    assert ref_loss.name2loss["depth"] is not losses.DepthLoss
+    assert set(got) == set(want) == {"loss_rgb_nr", "loss_rgb_nr_fine", "loss_depth", "loss_depth_fine", "loss_prob", "loss_prob_fine"}
+    for k in want:
+        assert torch.allclose(got[k], want[k], rtol=2e-5, atol=1e-6), (k, got[k], want[k])
+    for k in reads:
+        assert gwant[k] is not None and ggot[k] is not None, k
+        err, scale = float((ggot[k] - gwant[k]).abs().max()), float(gwant[k].abs().max())
+        assert err <= 1e-4 * scale + 1e-9, (k, err, scale)
