@@ -35,7 +35,7 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {      // round to nearest 
 // FAST = one TF32 pass per product (operands rounded to TF32: ~1e-3 relative, torch's default for cuDNN convolutions);
 // otherwise the 3xTF32 split (fp32 accuracy, what the parity tests run)
 template <int BN, int KC, bool FAST>
-__global__ void __launch_bounds__(THREADS, BN >= 64 ? 1 : 2) conv_mma_kernel(const __grid_constant__ ConvP p) {
+__global__ void __launch_bounds__(THREADS, BN >= 128 ? 1 : 2) conv_mma_kernel(const __grid_constant__ ConvP p) {
   extern __shared__ __align__(16) float sm[];
   constexpr int MT = BN / 32, WN = BN / 32;
   constexpr int A_ST = BM * (KC + 4), B_ST = KC * (BN + 8), ST = A_ST + B_ST;
