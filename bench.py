@@ -537,7 +537,49 @@ def encoders_bench(dr, dev, reps=5):
                         "max_abs_diff_img_feats": float((feat[..., 32:].permute(0, 3, 1, 2) - f_img).abs().max()),
                         "max_abs_diff_ray_feats": float((feat[..., :32].permute(0, 3, 1, 2) - f_ray).abs().max()),
                         "what": "the unmodified reference's ResUNetLight + DefaultVisEncoder (PyTorch eager / cuDNN) on the same GPU"}
+    try:
+        res["depth_init_net"] = init_net_bench(dr, dev, reps, timed)
+    except Exception as e:
+        res["depth_init_net"] = {"error": f"{type(e).__name__}: {e}"}
     return res
+
+
+def init_net_bench(dr, dev, reps, timed):
+    """DepthInitNet of the same frame (init_net.py:63-101: extract_depth + get_diff_feats + ResEncoder + depth_skip + conv_out),
+    native against the unmodified reference module on the same GPU; the depth maps are synthetic smooth fields inside the range."""
+    from neuray_b200 import init_nets
+    imgs = dr["imgs"]
+    rfn, _, h, w = imgs.shape
+    g = torch.Generator(device="cpu").manual_seed(4)
+    rng = dr["depth_range"]
+    base = torch.rand(rfn, 1, h // 16, w // 16, generator=g).to(dev)
+    depth = rng[:, 0].view(-1, 1, 1, 1) + (rng[:, 1] - rng[:, 0]).view(-1, 1, 1, 1) * (0.15 + 0.7 * torch.nn.functional.interpolate(base, size=(h, w), mode="bilinear", align_corners=True))
+    ref = {"imgs": imgs, "depth": depth, "depth_range": rng, "poses": dr["poses"], "Ks": dr["Ks"]}
+    torch.manual_seed(0)
+    net = init_nets.DepthInitNet().to(dev)
+    fh, fw = init_nets.dims(h, w)
+    buf = torch.empty(rfn, fh, fw, 64, device=dev)
+    with torch.no_grad():
+        ms = timed(lambda: init_nets.forward_into(net, ref, buf, 0))
+    out = {"ms_per_frame": ms, "what": "nr_extract_depth + nr_diff_feats + nr_depth_init_fwd (ResEncoder on the tensor cores, fp32 accuracy) into the frame pack"}
+    ref_mod = _load_reference()
+    if ref_mod is None:
+        return out
+    import network.init_net as ref_init
+    rnet = ref_init.DepthInitNet({}).to(dev).eval()
+    rnet.load_state_dict(net.state_dict(), strict=True)
+    old = torch.backends.cudnn.allow_tf32
+    with torch.no_grad():
+        ms_tf32 = timed(lambda: rnet(dict(ref), None, False))
+        torch.backends.cudnn.allow_tf32 = False
+        ms_fp32 = timed(lambda: rnet(dict(ref), None, False))
+        want = rnet(dict(ref), None, False)
+        torch.backends.cudnn.allow_tf32 = old
+    err = (buf[..., :32].permute(0, 3, 1, 2) - want).abs()
+    out["reference"] = {"ms_per_frame_cudnn_default_tf32": ms_tf32, "ms_per_frame_cudnn_fp32": ms_fp32, "kind": "reference",
+                        "max_abs_diff": float(err.max()), "frac_above_1e-3": float((err > 1e-3).float().mean()),
+                        "what": "the unmodified reference's DepthInitNet (PyTorch eager: get_diff_feats as torch ops + cuDNN) on the same GPU"}
+    return out
 
 
 # ---- headline -----------------------------------------------------------------------------------------------------------------

@@ -277,6 +277,8 @@ int nr_self_hit_prob(const NrSelfParams* p, void* stream);
 typedef struct NrEncoderLayout {
   int32_t image_tensors, vis_tensors;
   int64_t image_packed_floats, vis_packed_floats;
+  int32_t depth_init_tensors, reserved;
+  int64_t depth_init_packed_floats;
 } NrEncoderLayout;
 int nr_encoder_layout(NrEncoderLayout* out);
 int nr_image_encoder_pack(const float* const* params, int n_params, float* packed, void* stream);
@@ -297,8 +299,22 @@ int nr_image_encoder_fwd(const float* packed, const float* imgs, int n, int h, i
 int nr_vis_encoder_fwd(const float* packed, float* feat, int n, int fh, int fw, int tf32x1, void* workspace, long long workspace_bytes,
                        void* stream);
 
-/* Building blocks (channel-last).  nr_conv2d_nhwc: 1x1 / 3x3 convolution, stride 1 / 2, reflect or zero padding of
- * (ks-1)/2, cout in {32, 64, 128}, cin a multiple of 16, as an implicit GEMM on the tensor cores (3xTF32: fp32 accuracy);
+/* DepthInitNet (reference network/init_net.py:63-101; the init net of the neuray_gen_depth model), forward only:
+ *   nr_extract_depth  extract_depth_for_init_impl (:63-74): metric depth [n,1,h,w] + depth_range [n,2] -> normalised inverse depth
+ *   nr_diff_feats     get_diff_feats (:29-61), declared above
+ *   nr_depth_init_fwd res_net = ResEncoder (ops.py:232-312) on cat([imgs, depth, diff_feats]), depth_skip, conv_out (:93-101)
+ * `params`: the module's 72 tensors in state_dict() order (res_net.*, depth_skip.*, conv_out.*).  The 32 output channels go to
+ * out[(view, y, x) * out_stride + out_off + c] at nr_depth_init_dims (h/4 x w/4 for multiples of 16), e.g. straight into
+ * channels 0..31 of the frame pack, where nr_vis_encoder_fwd expects the init net's ray_feats. */
+int nr_extract_depth(const float* depth, const float* depth_range, int n, int h, int w, float* out, void* stream);
+int nr_depth_init_dims(int h, int w, int* fh, int* fw);
+long long nr_depth_init_workspace(int n, int h, int w);        /* bytes */
+int nr_depth_init_pack(const float* const* params, int n_params, float* packed, void* stream);
+int nr_depth_init_fwd(const float* packed, const float* imgs, const float* depth_norm, const float* diff_feats, int n, int h, int w,
+                      float* out, int out_stride, int out_off, int tf32x1, void* workspace, long long workspace_bytes, void* stream);
+
+/* Building blocks (channel-last).  nr_conv2d_nhwc: k x k convolution (k <= 8), stride 1 / 2, reflect or zero padding of
+ * `pad` (-1: (ks-1)/2), cout in {32, 64, 128}, cin a multiple of 16, as an implicit GEMM on the tensor cores (3xTF32: fp32 accuracy);
  * y = conv(x) [+ bias] [+ res]; when `stats` is given, sum and sum of squares of y per (image, channel) are ADDED to
  * stats [n][cout][2] (fp64) for a following nr_instance_norm_act.  Pixel (i, y, x) channel c of a tensor sits at
  * base[((i*H + y)*W + x) * stride + off + c]. */
@@ -308,6 +324,7 @@ typedef struct NrConv2d {
   int32_t n, h, w, cin, cout, ks, stride, reflect;
   int32_t x_stride, x_off, y_stride, y_off, res_stride, res_off;
   int32_t tf32x1;            /* 0: 3xTF32 (fp32 accuracy); 1: one TF32 pass */
+  int32_t pad;               /* -1: (ks-1)/2 */
 } NrConv2d;
 int nr_conv2d_nhwc(const NrConv2d* c, void* stream);
 /* [cout][cin][ks][ks] -> [tap][cin][cout]; packed input channel c reads reference channel (c + cin_rot) % cin */

@@ -103,6 +103,11 @@ SIGNATURES = {
     "nr_instance_norm_act": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "nr_nchw_to_nhwc": (C.c_int, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "nr_nhwc_to_nchw": (C.c_int, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "nr_extract_depth": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "nr_depth_init_dims": (C.c_int, [_i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "nr_depth_init_workspace": (C.c_longlong, [_i, _i, _i]),
+    "nr_depth_init_pack": (C.c_int, [_vp, _i, _vp, _vp]),
+    "nr_depth_init_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp, C.c_longlong, _vp]),
     "nr_depth_mean": (C.c_int, [_vp, _vp]),
     "nr_render_loss": (C.c_int, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "nr_depth_loss": (C.c_int, [_vp, _vp]),
@@ -123,12 +128,13 @@ class NrDepthLossParams(C.Structure):
 
 
 class NrEncoderLayout(C.Structure):
-    _fields_ = [("image_tensors", C.c_int32), ("vis_tensors", C.c_int32), ("image_packed_floats", C.c_int64), ("vis_packed_floats", C.c_int64)]
+    _fields_ = [("image_tensors", C.c_int32), ("vis_tensors", C.c_int32), ("image_packed_floats", C.c_int64), ("vis_packed_floats", C.c_int64),
+                ("depth_init_tensors", C.c_int32), ("reserved", C.c_int32), ("depth_init_packed_floats", C.c_int64)]
 
 
 class NrConv2d(C.Structure):
     _fields_ = [("x", C.c_void_p), ("w_packed", C.c_void_p), ("bias", C.c_void_p), ("res", C.c_void_p), ("y", C.c_void_p), ("stats", C.c_void_p)] + \
-               [(n, C.c_int32) for n in "n h w cin cout ks stride reflect x_stride x_off y_stride y_off res_stride res_off tf32x1".split()]
+               [(n, C.c_int32) for n in "n h w cin cout ks stride reflect x_stride x_off y_stride y_off res_stride res_off tf32x1 pad".split()]
 
 
 class NrSelfParams(C.Structure):

@@ -37,7 +37,7 @@ struct ConvP {
   const float* res;     // residual added before the store / the statistics, output geometry, or null
   float* y;             // output: pixel m (linear) channel c at y[m * y_stride + y_off + c]
   double* stats;        // [N][Cout][2]: sum, sum of squares (accumulated; the caller zeroes it) or null
-  int N, H, W, Ho, Wo, Cin, Cout, ks, stride, reflect;
+  int N, H, W, Ho, Wo, Cin, Cout, ks, stride, pad, reflect;
   int x_stride, x_off, y_stride, y_off, res_stride, res_off;
   int tf32x1;           // 0: 3xTF32 (fp32 accuracy, the default); 1: one TF32 pass, what cuDNN does under torch's default allow_tf32
 };
@@ -54,9 +54,8 @@ NR_HD RowInfo row_info(const ConvP& p, long long m) {
   r.n = int(m / plane);
   const int rem = int(m - (long long)r.n * plane);
   const int yo = rem / p.Wo, xo = rem - yo * p.Wo;
-  const int pad = (p.ks - 1) / 2;
-  r.y0 = yo * p.stride - pad;
-  r.x0 = xo * p.stride - pad;
+  r.y0 = yo * p.stride - p.pad;
+  r.x0 = xo * p.stride - p.pad;
   return r;
 }
 
@@ -65,7 +64,7 @@ NR_HD long long src_pixel(const ConvP& p, const RowInfo& r, int tap) {
   if (r.n < 0) return -1;
   const int dy = tap / p.ks, dx = tap - dy * p.ks;
   int yi = r.y0 + dy, xi = r.x0 + dx;
-  if (p.reflect) {   // padding_mode='reflect': -1 -> 1, H -> H-2
+  if (p.reflect) {   // padding_mode='reflect': -1 -> 1, H -> H-2 (one reflection: pad < H)
     yi = yi < 0 ? -yi : (yi >= p.H ? 2 * (p.H - 1) - yi : yi);
     xi = xi < 0 ? -xi : (xi >= p.W ? 2 * (p.W - 1) - xi : xi);
   } else if (yi < 0 || yi >= p.H || xi < 0 || xi >= p.W) {
@@ -233,6 +232,32 @@ NR_HD float act_f(float v, int act) {
   if (act == 1) return v > 0.f ? v : 0.f;
   if (act == 2) return v > 0.f ? v : expm1f(v);
   return v;
+}
+
+// ---- DepthInitNet.depth_skip (init_net.py:85-89): Conv2d(1,8,2,2) ReLU Conv2d(8,16,2,2) on the normalised depth map -----------
+struct DepthSkipP {
+  const float* depth;   // [N,H,W]
+  const float* w0; const float* b0;   // [8][1][2][2], [8]
+  const float* w1; const float* b1;   // [16][8][2][2], [16]
+  float* y;             // channels [y_off, y_off + 16) of [N,Ho,Wo,y_stride], Ho = (H/2)/2
+  int N, H, W, Ho, Wo, y_stride, y_off;
+};
+NR_HD void depth_skip_pixel(const DepthSkipP& p, int n, int yo, int xo, float (&out)[16]) {
+  for (int o = 0; o < 16; ++o) out[o] = p.b1[o];
+  const float* d = p.depth + (long long)n * p.H * p.W;
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {          // the four outputs of the first conv under this output pixel
+      const int y1 = 2 * yo + py, x1 = 2 * xo + px;
+      float h[8];
+      for (int c = 0; c < 8; ++c) {
+        float a = p.b0[c];
+        for (int ky = 0; ky < 2; ++ky)
+          for (int kx = 0; kx < 2; ++kx) a = fmaf(p.w0[(c * 2 + ky) * 2 + kx], d[(long long)(2 * y1 + ky) * p.W + 2 * x1 + kx], a);
+        h[c] = a > 0.f ? a : 0.f;
+      }
+      for (int o = 0; o < 16; ++o)
+        for (int c = 0; c < 8; ++c) out[o] = fmaf(p.w1[((o * 8 + c) * 2 + py) * 2 + px], h[c], out[o]);
+    }
 }
 
 // ---- bilinear x2 upsampling, align_corners=True (reference ops.py:147, nn.functional.interpolate) ----------------

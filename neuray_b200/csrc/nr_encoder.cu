@@ -338,6 +338,32 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float* __restri
   }
 }
 
+__global__ void __launch_bounds__(256) depth_skip_kernel(const __grid_constant__ DepthSkipP p) {
+  const long long total = (long long)p.N * p.Ho * p.Wo;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int xo = int(i % p.Wo);
+    const long long t = i / p.Wo;
+    const int yo = int(t % p.Ho), n = int(t / p.Ho);
+    float out[16];
+    depth_skip_pixel(p, n, yo, xo, out);
+    float4* o = reinterpret_cast<float4*>(p.y + i * p.y_stride + p.y_off);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o[c] = make_float4(out[4 * c], out[4 * c + 1], out[4 * c + 2], out[4 * c + 3]);
+  }
+}
+
+// extract_depth_for_init_impl (init_net.py:63-74): metric depth -> normalised inverse depth in [0, 1], per view
+__global__ void __launch_bounds__(256) extract_depth_kernel(const float* __restrict__ depth, const float* __restrict__ range, int N, long long HW,
+                                                            float* __restrict__ out) {
+  const long long total = (long long)N * HW;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int n = int(i / HW);
+    const float a = -1.f / range[2 * n], b = -1.f / range[2 * n + 1];
+    const float d = -1.f / fmaxf(depth[i], 1e-5f);
+    out[i] = fminf(fmaxf((d - a) / (b - a), 0.f), 1.f);
+  }
+}
+
 struct PackJob {
   enc::TensorSpec spec;
   const float* src;
@@ -350,7 +376,10 @@ struct PackArgs {
 __global__ void __launch_bounds__(256) pack_params_kernel(const __grid_constant__ PackArgs a) {
   const PackJob& j = a.job[blockIdx.y];
   for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < j.spec.n; e += (long long)gridDim.x * 256)
-    a.out[j.spec.off + e] = j.src[enc::pack_source(j.spec, e)];
+  {
+    const long long src = enc::pack_source(j.spec, e);
+    a.out[j.spec.off + e] = src >= 0 ? j.src[src] : 0.f;
+  }
 }
 
 template <int BN, int KC, bool FAST>
@@ -371,8 +400,9 @@ int check_conv(const ConvP& p) {
   NR_CHECK_ARG(p.x != nullptr && p.w != nullptr && p.y != nullptr, "conv: null pointer");
   NR_CHECK_ARG(p.Cout == 32 || p.Cout == 64 || p.Cout == 128, "conv: Cout must be 32, 64 or 128");
   NR_CHECK_ARG(p.Cin >= 16 && p.Cin % 16 == 0, "conv: Cin must be a multiple of 16");
-  NR_CHECK_ARG(p.ks == 1 || p.ks == 3, "conv: kernel size 1 or 3");
+  NR_CHECK_ARG(p.ks >= 1 && p.ks <= 8, "conv: kernel size 1 .. 8");
   NR_CHECK_ARG(p.stride == 1 || p.stride == 2, "conv: stride 1 or 2");
+  NR_CHECK_ARG(p.pad >= 0 && p.pad < p.ks && p.pad < p.H && p.pad < p.W, "conv: padding (one reflection: pad < H, W)");
   NR_CHECK_ARG(p.N >= 1 && p.H >= 2 && p.W >= 2 && p.Ho >= 1 && p.Wo >= 1, "conv: empty input");
   NR_CHECK_ARG(p.x_stride % 4 == 0 && p.x_off % 4 == 0 && p.y_stride % 2 == 0 && p.y_off % 2 == 0, "conv: channel strides / offsets must keep 16-byte alignment");
   NR_CHECK_ARG(p.res == nullptr || (p.res_stride % 2 == 0 && p.res_off % 2 == 0), "conv: residual alignment");
@@ -425,6 +455,10 @@ struct StreamOps {
     if (rc != NR_OK) return;
     copy_pad_kernel<<<grid_for((long long)p.N * p.Ho * p.Wo * (p.C / 4), 16 * sms), 256, 0, st>>>(p);
   }
+  void depth_skip(const DepthSkipP& p) {
+    if (rc != NR_OK) return;
+    depth_skip_kernel<<<grid_for((long long)p.N * p.Ho * p.Wo, 16 * sms), 256, 0, st>>>(p);
+  }
   void zero(void* ptr, size_t bytes) {
     if (rc != NR_OK) return;
     cudaMemsetAsync(ptr, 0, bytes, st);
@@ -472,6 +506,11 @@ extern "C" int nr_encoder_layout(NrEncoderLayout* out) {
   out->image_packed_floats = in.spec.total;
   out->vis_tensors = vn.spec.count;
   out->vis_packed_floats = vn.spec.total;
+  enc::DepthInitNet* dn = new enc::DepthInitNet;
+  enc::build_depth_init_net(*dn);
+  out->depth_init_tensors = dn->res.spec.count;
+  out->depth_init_packed_floats = dn->res.spec.total;
+  delete dn;
   return NR_OK;
 }
 
@@ -543,15 +582,82 @@ extern "C" int nr_vis_encoder_fwd(const float* packed, float* feat, int n, int f
   return NR_OK;
 }
 
+extern "C" int nr_extract_depth(const float* depth, const float* depth_range, int n, int h, int w, float* out, void* stream) {
+  if (n == 0) return NR_OK;
+  NR_CHECK_ARG(depth && depth_range && out && n >= 1 && h >= 1 && w >= 1, "extract_depth");
+  const long long hw = (long long)h * w;
+  cv::extract_depth_kernel<<<cv::grid_for((long long)n * hw, 16 * cv::sm_count()), 256, 0, (cudaStream_t)stream>>>(depth, depth_range, n, hw, out);
+  NR_CHECK_LAUNCH("extract_depth_kernel");
+  return NR_OK;
+}
+
+extern "C" int nr_depth_init_dims(int h, int w, int* fh, int* fw) {
+  NR_CHECK_ARG(h >= 32 && w >= 32 && fh != nullptr && fw != nullptr, "depth_init_dims");
+  const enc::ImageDims d = enc::depth_init_dims(h, w);
+  *fh = d.u2h;
+  *fw = d.u2w;
+  return NR_OK;
+}
+extern "C" long long nr_depth_init_workspace(int n, int h, int w) {
+  if (n < 1 || h < 32 || w < 32) return 0;
+  enc::DepthInitNet* net = new enc::DepthInitNet;
+  enc::build_depth_init_net(*net);
+  const long long bytes = (long long)enc::depth_init_workspace_bytes(*net, n, h, w) + ((long long)n * h * w * 16 * 4 + 256);   // + the 16-channel input
+  delete net;
+  return bytes;
+}
+extern "C" int nr_depth_init_pack(const float* const* params, int n_params, float* packed, void* stream) {
+  enc::DepthInitNet* net = new enc::DepthInitNet;
+  enc::build_depth_init_net(*net);
+  const int rc = cv::pack_params(net->res.spec, params, n_params, packed, (cudaStream_t)stream);
+  delete net;
+  return rc;
+}
+extern "C" int nr_depth_init_fwd(const float* packed, const float* imgs, const float* depth_norm, const float* diff_feats, int n, int h, int w,
+                                 float* out, int out_stride, int out_off, int tf32x1, void* workspace, long long workspace_bytes, void* stream) {
+  if (n == 0) return NR_OK;
+  NR_CHECK_ARG(packed && imgs && depth_norm && diff_feats && out && workspace, "depth_init: null pointer");
+  NR_CHECK_ARG(n >= 1 && h >= 32 && w >= 32, "depth_init: images must be at least 32 x 32");
+  NR_CHECK_ARG(out_stride >= 32 && out_stride % 4 == 0 && out_off % 4 == 0 && out_off + 32 <= out_stride, "depth_init: output channel slot");
+  enc::DepthInitNet* net = new enc::DepthInitNet;
+  enc::build_depth_init_net(*net);
+  const long long stats = enc::depth_init_stats_doubles(*net, n, h, w);
+  int rc = NR_OK;
+  bool ok = false;
+  if (stats > 0) {
+    enc::Arena ar{(char*)workspace, size_t(workspace_bytes), 0, true};
+    cudaStream_t st = (cudaStream_t)stream;
+    // the 12 input channels of ResEncoder.conv1 (init_net.py:98: cat([imgs, depth, diff_feats])) channel-last, padded to 16
+    const long long hw = (long long)h * w;
+    float* x16 = ar.floats((long long)n * hw * 16);
+    if (ar.ok) {
+      cudaMemsetAsync(x16, 0, size_t(n) * hw * 16 * sizeof(float), st);
+      cv::nchw_to_nhwc_kernel<<<dim3(unsigned((hw + 31) / 32), 1, n), 256, 0, st>>>(imgs, x16, n, 3, hw, 16, 0);
+      cv::nchw_to_nhwc_kernel<<<dim3(unsigned((hw + 31) / 32), 1, n), 256, 0, st>>>(depth_norm, x16, n, 1, hw, 16, 3);
+      cv::nchw_to_nhwc_kernel<<<dim3(unsigned((hw + 31) / 32), 1, n), 256, 0, st>>>(diff_feats, x16, n, 8, hw, 16, 4);
+      cv::StreamOps ops{st, cv::sm_count(), NR_OK, tf32x1 != 0};
+      ok = enc::depth_init_graph(ops, ar, *net, packed, x16, depth_norm, n, h, w, out, out_stride, out_off, stats, nullptr);
+      rc = ops.rc;
+    }
+  }
+  delete net;
+  if (rc != NR_OK) return rc;
+  NR_CHECK_ARG(stats > 0, "depth_init: image size whose depth_skip and ResEncoder outputs differ (init_net.py:101 would fail too)");
+  NR_CHECK_ARG(ok, "depth_init: workspace too small (nr_depth_init_workspace)");
+  NR_CHECK_LAUNCH("depth_init");
+  return NR_OK;
+}
+
 /* ---- single building blocks (tests, and hosts that run other conv stacks) ---- */
 extern "C" int nr_conv2d_nhwc(const NrConv2d* c, void* stream) {
   NR_CHECK_ARG(c != nullptr, "null conv descriptor");
   cv::ConvP p;
   p.x = c->x; p.w = c->w_packed; p.bias = c->bias; p.res = c->res; p.y = c->y; p.stats = c->stats;
   p.N = c->n; p.H = c->h; p.W = c->w; p.Cin = c->cin; p.Cout = c->cout; p.ks = c->ks; p.stride = c->stride; p.reflect = c->reflect;
-  NR_CHECK_ARG(p.ks == 1 || p.ks == 3, "conv: kernel size 1 or 3");
+  NR_CHECK_ARG(p.ks >= 1 && p.ks <= 8, "conv: kernel size 1 .. 8");
   NR_CHECK_ARG(p.stride == 1 || p.stride == 2, "conv: stride 1 or 2");
-  p.Ho = enc::conv_out(p.H, p.ks, p.stride); p.Wo = enc::conv_out(p.W, p.ks, p.stride);
+  p.pad = c->pad >= 0 ? c->pad : (p.ks - 1) / 2;
+  p.Ho = enc::conv_out(p.H, p.ks, p.stride, p.pad); p.Wo = enc::conv_out(p.W, p.ks, p.stride, p.pad);
   p.x_stride = c->x_stride; p.x_off = c->x_off; p.y_stride = c->y_stride; p.y_off = c->y_off; p.res_stride = c->res_stride; p.res_off = c->res_off;
   p.tf32x1 = c->tf32x1 != 0;
   if (p.N == 0) return NR_OK;

@@ -19,6 +19,7 @@ struct TensorSpec {
   int cout, cin, ks;
   int rot;         // packed input channel c reads reference channel (c + rot) % cin
   int cin_major;   // packed as [cin][tap][cout] (the 7x7 first layer)
+  int cin_ref;     // input channels of the reference tensor (< cin: the packed tensor has zero rows for the padding channels)
   long long off;   // floats, multiple of 4
   long long n;     // elements
 };
@@ -26,23 +27,23 @@ struct NetSpec {
   TensorSpec t[96];
   int count;
   long long total;
-  int conv(int cout, int cin, int ks, int rot = 0, int cin_major = 0) {
+  int conv(int cout, int cin, int ks, int rot = 0, int cin_major = 0, int cin_ref = 0) {
     TensorSpec& s = t[count];
-    s.kind = 0; s.cout = cout; s.cin = cin; s.ks = ks; s.rot = rot; s.cin_major = cin_major;
+    s.kind = 0; s.cout = cout; s.cin = cin; s.ks = ks; s.rot = rot; s.cin_major = cin_major; s.cin_ref = cin_ref > 0 ? cin_ref : cin;
     s.off = total; s.n = (long long)cout * cin * ks * ks;
     total += (s.n + 3) & ~3LL;
     return count++;
   }
   int vec(int n) {
     TensorSpec& s = t[count];
-    s.kind = 1; s.cout = n; s.cin = 1; s.ks = 1; s.rot = 0; s.cin_major = 0;
+    s.kind = 1; s.cout = n; s.cin = 1; s.ks = 1; s.rot = 0; s.cin_major = 0; s.cin_ref = 1;
     s.off = total; s.n = n;
     total += (s.n + 3) & ~3LL;
     return count++;
   }
 };
 
-// packed element e of tensor s <- index into the reference tensor
+// packed element e of tensor s <- index into the reference tensor (-1: a padding channel, packed as zero)
 NR_HD long long pack_source(const TensorSpec& s, long long e) {
   if (s.kind == 1) return e;
   const int taps = s.ks * s.ks;
@@ -52,19 +53,25 @@ NR_HD long long pack_source(const TensorSpec& s, long long e) {
   if (s.cin_major) { tap = int(r % taps); c = int(r / taps); }
   else { c = int(r % s.cin); tap = int(r / s.cin); }
   const int c_ref = (c + s.rot) % s.cin;
-  return ((long long)o * s.cin + c_ref) * taps + tap;
+  if (c_ref >= s.cin_ref) return -1;
+  return ((long long)o * s.cin_ref + c_ref) * taps + tap;
 }
 
 struct BasicBlockIdx { int c1, n1w, n1b, c2, n2w, n2b, ds, dsw, dsb; int cin, cout, stride; };
 struct ConvBnIdx { int w, b, nw, nb; int cin, cout; };
 
-struct ImageNet {
+// The U-shaped residual encoder both networks share (ops.py:150-230 ResUNetLight, :232-312 ResEncoder): first conv + IN + ReLU,
+// three stages of BasicBlocks (the first block of a stage has stride 2 and a 1x1 downsample branch), two
+// upsample-conv / skip / conv decoder steps, a 1x1 output conv.
+struct UNet {
   NetSpec spec;
-  int conv1, bn1w, bn1b;
-  BasicBlockIdx blocks[9];     // layer1: 1, layer2: 2, layer3: 6   (layers = [1,2,6,4]; the fourth entry is unused, ops.py:166-170)
+  int conv1, bn1w, bn1b, inplanes;
+  BasicBlockIdx blocks[12];
+  int nb[3];                   // blocks per stage
   ConvBnIdx upconv3, iconv3, upconv2, iconv2;
-  int out_w, out_b;
+  int out_w, out_b, out_planes;
 };
+typedef UNet ImageNet;
 
 inline BasicBlockIdx basic_block(NetSpec& s, int cin, int cout, int stride) {
   BasicBlockIdx b;
@@ -81,22 +88,46 @@ inline ConvBnIdx conv_bn(NetSpec& s, int cin, int cout) {
   c.w = s.conv(cout, cin, 3); c.b = s.vec(cout); c.nw = s.vec(cout); c.nb = s.vec(cout);
   return c;
 }
+// everything after the first conv + norm, in state_dict() order
+inline void build_unet_tail(UNet& n, int inplanes, int nb0, int nb1, int nb2, int out_planes) {
+  NetSpec& s = n.spec;
+  const int planes[3] = {32, 64, 128};
+  n.inplanes = inplanes; n.nb[0] = nb0; n.nb[1] = nb1; n.nb[2] = nb2; n.out_planes = out_planes;
+  int k = 0, cin = inplanes;
+  for (int st = 0; st < 3; ++st)
+    for (int i = 0; i < n.nb[st]; ++i) {
+      n.blocks[k++] = basic_block(s, cin, planes[st], i == 0 ? 2 : 1);
+      cin = planes[st];
+    }
+  n.upconv3 = conv_bn(s, 128, 64);
+  n.iconv3 = conv_bn(s, 128, 64);
+  n.upconv2 = conv_bn(s, 64, 32);
+  n.iconv2 = conv_bn(s, 64, out_planes);
+  n.out_w = s.conv(out_planes, out_planes, 1); n.out_b = s.vec(out_planes);
+}
 
+// image_encoder = ResUNetLight(3, [1,2,6,4], 32, inplanes=16): layers [1,2,6] are used (the fourth entry never is, ops.py:166-170)
 inline void build_image_net(ImageNet& n) {
   NetSpec& s = n.spec;
   s.count = 0; s.total = 0;
   n.conv1 = s.conv(16, 3, 7, 0, 1); n.bn1w = s.vec(16); n.bn1b = s.vec(16);
-  int k = 0;
-  n.blocks[k++] = basic_block(s, 16, 32, 2);
-  n.blocks[k++] = basic_block(s, 32, 64, 2);
-  n.blocks[k++] = basic_block(s, 64, 64, 1);
-  n.blocks[k++] = basic_block(s, 64, 128, 2);
-  for (int i = 0; i < 5; ++i) n.blocks[k++] = basic_block(s, 128, 128, 1);
-  n.upconv3 = conv_bn(s, 128, 64);
-  n.iconv3 = conv_bn(s, 128, 64);
-  n.upconv2 = conv_bn(s, 64, 32);
-  n.iconv2 = conv_bn(s, 64, 32);
-  n.out_w = s.conv(32, 32, 1); n.out_b = s.vec(32);
+  build_unet_tail(n, 16, 1, 2, 6, 32);
+}
+
+// DepthInitNet (init_net.py:78-101): res_net = ResEncoder (ops.py:232-312: conv1 8x8 stride 2 pad 2 on 12 channels = imgs 3 |
+// normalised depth 1 | diff_feats 8, packed with 4 zero channels; stages [2,2,2]), depth_skip, conv_out (1x1, 48 -> 32)
+struct DepthInitNet {
+  UNet res;                    // its spec holds ALL tensors of the module in state_dict() order
+  int skip_w0, skip_b0, skip_w1, skip_b1, out_w, out_b;
+};
+inline void build_depth_init_net(DepthInitNet& n) {
+  NetSpec& s = n.res.spec;
+  s.count = 0; s.total = 0;
+  n.res.conv1 = s.conv(32, 16, 8, 0, 0, 12); n.res.bn1w = s.vec(32); n.res.bn1b = s.vec(32);
+  build_unet_tail(n.res, 32, 2, 2, 2, 32);
+  n.skip_w0 = s.vec(8 * 1 * 2 * 2); n.skip_b0 = s.vec(8);          // depth_skip.0 (copied as is: the SIMT routine reads PyTorch layout)
+  n.skip_w1 = s.vec(16 * 8 * 2 * 2); n.skip_b1 = s.vec(16);        // depth_skip.2
+  n.out_w = s.conv(32, 48, 1); n.out_b = s.vec(32);                // conv_out on cat([depth_feats 16, feats 32])
 }
 
 struct ResidualIdx { int n0w, n0b, c0, n1w, n1b, c1; };
@@ -120,14 +151,14 @@ inline void build_vis_net(VisNet& n) {
 }
 
 // ---- geometry ---------------------------------------------------------------------------------------------------------
-inline int conv_out(int n, int ks, int stride) { return (n + 2 * ((ks - 1) / 2) - ks) / stride + 1; }
+inline int conv_out(int n, int ks, int stride, int pad = -1) { return (n + 2 * (pad < 0 ? (ks - 1) / 2 : pad) - ks) / stride + 1; }
 struct ImageDims {
   int h0, w0, h1, w1, h2, w2, h3, w3;   // after conv1 (/2), layer1 (/4), layer2 (/8), layer3 (/16)
   int u3h, u3w, u2h, u2w;               // after the two x2 upsamplings; (u2h, u2w) is the output size
 };
-inline ImageDims image_dims(int H, int W) {
+inline ImageDims unet_dims(int H, int W, int ks, int pad) {        // first conv: ks x ks, stride 2, padding pad
   ImageDims d;
-  d.h0 = conv_out(H, 7, 2); d.w0 = conv_out(W, 7, 2);
+  d.h0 = conv_out(H, ks, 2, pad); d.w0 = conv_out(W, ks, 2, pad);
   d.h1 = conv_out(d.h0, 3, 2); d.w1 = conv_out(d.w0, 3, 2);
   d.h2 = conv_out(d.h1, 3, 2); d.w2 = conv_out(d.w1, 3, 2);
   d.h3 = conv_out(d.h2, 3, 2); d.w3 = conv_out(d.w2, 3, 2);
@@ -135,6 +166,10 @@ inline ImageDims image_dims(int H, int W) {
   d.u2h = 2 * d.u3h; d.u2w = 2 * d.u3w;
   return d;
 }
+inline bool dims_ok(const ImageDims& d) {      // the skip connections pad the encoder feature up to the decoder's size, never crop (ops.py:199-208)
+  return d.h3 >= 2 && d.w3 >= 2 && d.u3h >= d.h2 && d.u3w >= d.w2 && d.u2h >= d.h1 && d.u2w >= d.w1;
+}
+inline ImageDims image_dims(int H, int W) { return unet_dims(H, W, 7, 3); }
 
 struct CopyP {     // y[n, yo, xo, y_off + c] = (yo - py, xo - px) inside the source ? x[n, yo - py, xo - px, x_off + c] : 0
   const float* x; float* y;
@@ -172,12 +207,13 @@ struct Builder {
   }
   // y (dense [N,Ho,Wo,cout] unless y/y_stride/y_off say otherwise) = conv(x)
   float* conv(const float* x, int x_stride, int x_off, int H, int Wd, int cin, int cout, int ks, int stride, const float* wt, const float* bias,
-              const float* res, int res_stride, int res_off, double* st, float* y, int y_stride, int y_off, int& Ho, int& Wo) {
-    Ho = conv_out(H, ks, stride); Wo = conv_out(Wd, ks, stride);
+              const float* res, int res_stride, int res_off, double* st, float* y, int y_stride, int y_off, int& Ho, int& Wo, int pad = -1) {
+    if (pad < 0) pad = (ks - 1) / 2;
+    Ho = conv_out(H, ks, stride, pad); Wo = conv_out(Wd, ks, stride, pad);
     if (y == nullptr) { y = ar.floats((long long)N * Ho * Wo * cout); y_stride = cout; y_off = 0; }
     cv::ConvP p;
     p.x = x; p.w = wt; p.bias = bias; p.res = res; p.y = y; p.stats = st;
-    p.N = N; p.H = H; p.W = Wd; p.Ho = Ho; p.Wo = Wo; p.Cin = cin; p.Cout = cout; p.ks = ks; p.stride = stride; p.reflect = 1;
+    p.N = N; p.H = H; p.W = Wd; p.Ho = Ho; p.Wo = Wo; p.Cin = cin; p.Cout = cout; p.ks = ks; p.stride = stride; p.pad = pad; p.reflect = 1;
     p.x_stride = x_stride; p.x_off = x_off; p.y_stride = y_stride; p.y_off = y_off; p.res_stride = res_stride; p.res_off = res_off;
     p.tf32x1 = 0;      // the backend decides (StreamOps)
     ops.conv(p);
@@ -227,35 +263,21 @@ void run_conv_bn_elu(Builder<Ops>& b, const NetSpec& s, const ConvBnIdx& k, cons
   b.norm(t, k.cout, Ho * Wo, st, b.w(s, k.nw), b.w(s, k.nb), nullptr, 0, 0, nullptr, nullptr, nullptr, 2, y, y_stride, y_off);
 }
 
-// ResUNetLight.forward (ops.py:210-228).  imgs [N,3,H,W] (NCHW, as the reference holds them) -> out[n, y, x, out_off + c],
-// c < 32, at image_dims(H, W).u2h x u2w (= H/4 x W/4 for sizes that are multiples of 16).
+// Everything of the U-shaped encoder after conv1 + bn1 + relu (ops.py:213-228): x [N,h0,w0,inplanes] -> out slot
 template <class Ops>
-bool image_encoder_graph(Ops& ops, Arena& ar, const ImageNet& net, const float* packed, const float* imgs, int N, int H, int Wd, float* out,
-                         int out_stride, int out_off, long long stats_cap, long long* stats_used) {
+void unet_body(Builder<Ops>& b, Arena& ar, const UNet& net, const ImageDims& d, float* x, float* out, int out_stride, int out_off) {
+  Ops& ops = b.ops;
   const NetSpec& s = net.spec;
-  const ImageDims d = image_dims(H, Wd);
-  if (d.u3h < d.h2 || d.u3w < d.w2 || d.u2h < d.h1 || d.u2w < d.w1) return false;
-  Builder<Ops> b{ops, ar, packed, N, nullptr, 0, stats_cap};
-  // InstanceNorm sums of every normalised conv output in one block, zeroed once (stats_cap == 0: a dry run that counts)
-  if (stats_cap > 0) {
-    b.stats_base = ar.doubles(stats_cap);
-    ops.zero(b.stats_base, size_t(stats_cap) * sizeof(double));
-  }
-  // conv1 + bn1 + relu
-  double* st0 = b.stats(16);
-  float* c1 = ar.floats((long long)N * d.h0 * d.w0 * 16);
-  cv::Conv7P p7;
-  p7.img = imgs; p7.w = b.w(s, net.conv1); p7.y = c1; p7.stats = st0; p7.N = N; p7.H = H; p7.W = Wd; p7.Ho = d.h0; p7.Wo = d.w0;
-  ops.conv7(p7);
-  float* x = b.norm(c1, 16, d.h0 * d.w0, st0, b.w(s, net.bn1w), b.w(s, net.bn1b), nullptr, 0, 0, nullptr, nullptr, nullptr, 1, c1, 16, 0);
-  int h = d.h0, w = d.w0;
-  float* x1 = run_basic_block(b, s, net.blocks[0], x, h, w);                 // layer1: [N,h1,w1,32]
-  int h1 = h, w1 = w;
-  float* x2 = run_basic_block(b, s, net.blocks[1], x1, h, w);
-  x2 = run_basic_block(b, s, net.blocks[2], x2, h, w);                       // layer2: [N,h2,w2,64]
-  int h2 = h, w2 = w;
+  const int N = b.N;
+  int h = d.h0, w = d.w0, k = 0;
+  float* x1 = x;
+  for (int i = 0; i < net.nb[0]; ++i) x1 = run_basic_block(b, s, net.blocks[k++], x1, h, w);     // layer1: [N,h1,w1,32]
+  const int h1 = h, w1 = w;
+  float* x2 = x1;
+  for (int i = 0; i < net.nb[1]; ++i) x2 = run_basic_block(b, s, net.blocks[k++], x2, h, w);     // layer2: [N,h2,w2,64]
+  const int h2 = h, w2 = w;
   float* x3 = x2;
-  for (int i = 3; i < 9; ++i) x3 = run_basic_block(b, s, net.blocks[i], x3, h, w);   // layer3: [N,h3,w3,128]
+  for (int i = 0; i < net.nb[2]; ++i) x3 = run_basic_block(b, s, net.blocks[k++], x3, h, w);     // layer3: [N,h3,w3,128]
   // upconv3 -> skipconnect(x2, .) -> iconv3
   float* up3 = ar.floats((long long)N * d.u3h * d.u3w * 128);
   cv::UpP u;
@@ -278,11 +300,67 @@ bool image_encoder_graph(Ops& ops, Arena& ar, const ImageNet& net, const float* 
   cp.x = x1; cp.y = cat2; cp.H = h1; cp.W = w1; cp.Ho = d.u2h; cp.Wo = d.u2w; cp.C = 32;
   cp.py = (d.u2h - h1) / 2; cp.px = (d.u2w - w1) / 2; cp.x_stride = 32; cp.y_stride = 64; cp.y_off = 32;
   ops.copy_pad(cp);
-  float* i2 = ar.floats((long long)N * d.u2h * d.u2w * 32);
-  run_conv_bn_elu(b, s, net.iconv2, cat2, d.u2h, d.u2w, i2, 32, 0);
+  float* i2 = ar.floats((long long)N * d.u2h * d.u2w * net.out_planes);
+  run_conv_bn_elu(b, s, net.iconv2, cat2, d.u2h, d.u2w, i2, net.out_planes, 0);
   // out_conv (1x1 + bias) straight into the caller's channel-last destination
   int Ho, Wo;
-  b.conv(i2, 32, 0, d.u2h, d.u2w, 32, 32, 1, 1, b.w(s, net.out_w), b.w(s, net.out_b), nullptr, 0, 0, nullptr, out, out_stride, out_off, Ho, Wo);
+  b.conv(i2, net.out_planes, 0, d.u2h, d.u2w, net.out_planes, net.out_planes, 1, 1, b.w(s, net.out_w), b.w(s, net.out_b), nullptr, 0, 0, nullptr, out,
+         out_stride, out_off, Ho, Wo);
+}
+
+// ResUNetLight.forward (ops.py:210-228).  imgs [N,3,H,W] (NCHW, as the reference holds them) -> out[n, y, x, out_off + c],
+// c < 32, at image_dims(H, W).u2h x u2w (= H/4 x W/4 for sizes that are multiples of 16).
+template <class Ops>
+bool image_encoder_graph(Ops& ops, Arena& ar, const ImageNet& net, const float* packed, const float* imgs, int N, int H, int Wd, float* out,
+                         int out_stride, int out_off, long long stats_cap, long long* stats_used) {
+  const NetSpec& s = net.spec;
+  const ImageDims d = image_dims(H, Wd);
+  if (!dims_ok(d)) return false;
+  Builder<Ops> b{ops, ar, packed, N, nullptr, 0, stats_cap};
+  // InstanceNorm sums of every normalised conv output in one block, zeroed once (stats_cap == 0: a dry run that counts)
+  if (stats_cap > 0) {
+    b.stats_base = ar.doubles(stats_cap);
+    ops.zero(b.stats_base, size_t(stats_cap) * sizeof(double));
+  }
+  // conv1 + bn1 + relu
+  double* st0 = b.stats(16);
+  float* c1 = ar.floats((long long)N * d.h0 * d.w0 * 16);
+  cv::Conv7P p7;
+  p7.img = imgs; p7.w = b.w(s, net.conv1); p7.y = c1; p7.stats = st0; p7.N = N; p7.H = H; p7.W = Wd; p7.Ho = d.h0; p7.Wo = d.w0;
+  ops.conv7(p7);
+  float* x = b.norm(c1, 16, d.h0 * d.w0, st0, b.w(s, net.bn1w), b.w(s, net.bn1b), nullptr, 0, 0, nullptr, nullptr, nullptr, 1, c1, 16, 0);
+  unet_body(b, ar, net, d, x, out, out_stride, out_off);
+  if (stats_used != nullptr) *stats_used = b.stats_used;
+  return ar.ok;
+}
+
+// DepthInitNet.forward after extract_depth_for_init and get_diff_feats (init_net.py:93-101).  x16 [N,H,W,16] = imgs (3) |
+// normalised depth (1) | diff_feats (8) | zeros (4), channel-last (the caller assembles it); depth [N,H,W] = the
+// normalised depth again for depth_skip.  out[n, y, x, out_off + c], c < 32, at unet_dims(H, W, 8, 2).u2h x u2w.
+inline ImageDims depth_init_dims(int H, int W) { return unet_dims(H, W, 8, 2); }
+template <class Ops>
+bool depth_init_graph(Ops& ops, Arena& ar, const DepthInitNet& net, const float* packed, const float* x16, const float* depth, int N, int H, int Wd,
+                      float* out, int out_stride, int out_off, long long stats_cap, long long* stats_used) {
+  const NetSpec& s = net.res.spec;
+  const ImageDims d = depth_init_dims(H, Wd);
+  // depth_skip halves twice without padding; torch.cat (init_net.py:101) needs the two maps to agree
+  if (!dims_ok(d) || (H / 2) / 2 != d.u2h || (Wd / 2) / 2 != d.u2w) return false;
+  Builder<Ops> b{ops, ar, packed, N, nullptr, 0, stats_cap};
+  if (stats_cap > 0) {
+    b.stats_base = ar.doubles(stats_cap);
+    ops.zero(b.stats_base, size_t(stats_cap) * sizeof(double));
+  }
+  int Ho, Wo;
+  double* st0 = b.stats(32);
+  float* c1 = b.conv(x16, 16, 0, H, Wd, 16, 32, 8, 2, b.w(s, net.res.conv1), nullptr, nullptr, 0, 0, st0, nullptr, 0, 0, Ho, Wo, 2);
+  float* x = b.norm(c1, 32, Ho * Wo, st0, b.w(s, net.res.bn1w), b.w(s, net.res.bn1b), nullptr, 0, 0, nullptr, nullptr, nullptr, 1, c1, 32, 0);
+  float* cat = ar.floats((long long)N * d.u2h * d.u2w * 48);                 // [depth_feats 16 | feats 32]
+  unet_body(b, ar, net.res, d, x, cat, 48, 16);
+  cv::DepthSkipP ds;
+  ds.depth = depth; ds.w0 = b.w(s, net.skip_w0); ds.b0 = b.w(s, net.skip_b0); ds.w1 = b.w(s, net.skip_w1); ds.b1 = b.w(s, net.skip_b1);
+  ds.y = cat; ds.N = N; ds.H = H; ds.W = Wd; ds.Ho = d.u2h; ds.Wo = d.u2w; ds.y_stride = 48; ds.y_off = 0;
+  ops.depth_skip(ds);
+  b.conv(cat, 48, 0, d.u2h, d.u2w, 48, 32, 1, 1, b.w(s, net.out_w), b.w(s, net.out_b), nullptr, 0, 0, nullptr, out, out_stride, out_off, Ho, Wo);
   if (stats_used != nullptr) *stats_used = b.stats_used;
   return ar.ok;
 }
@@ -324,6 +402,7 @@ struct NullOps {
   void norm(const cv::NormP&) {}
   void upsample(const cv::UpP&) {}
   void copy_pad(const CopyP&) {}
+  void depth_skip(const cv::DepthSkipP&) {}
   void zero(void*, size_t) {}
 };
 // doubles of InstanceNorm sums a forward needs (dry run of the graph)
@@ -340,6 +419,19 @@ inline long long vis_stats_doubles(const VisNet& net, int N, int fh, int fw) {
   long long used = 0;
   vis_encoder_graph(ops, ar, net, nullptr, (float*)DRY_BASE, N, fh, fw, 0, &used);
   return used;
+}
+inline long long depth_init_stats_doubles(const DepthInitNet& net, int N, int H, int W) {
+  NullOps ops;
+  Arena ar{DRY_BASE, ~size_t(0) / 2, 0, true};
+  long long used = 0;
+  depth_init_graph(ops, ar, net, nullptr, nullptr, nullptr, N, H, W, (float*)DRY_BASE, 32, 0, 0, &used);
+  return used;
+}
+inline size_t depth_init_workspace_bytes(const DepthInitNet& net, int N, int H, int W) {
+  NullOps ops;
+  Arena ar{DRY_BASE, ~size_t(0) / 2, 0, true};
+  depth_init_graph(ops, ar, net, nullptr, nullptr, nullptr, N, H, W, (float*)DRY_BASE, 32, 0, depth_init_stats_doubles(net, N, H, W), nullptr);
+  return ar.used + 256;
 }
 inline size_t image_workspace_bytes(const ImageNet& net, int N, int H, int W) {
   NullOps ops;

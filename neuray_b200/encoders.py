@@ -22,11 +22,12 @@ import torch.nn as nn
 from . import _lib
 
 
-def image_param_names():
-    """state_dict() order of ResUNetLight(3, [1,2,6,4], 32, inplanes=16) = the order nr_image_encoder_pack expects."""
+def unet_param_names(blocks):
+    """state_dict() order of the U-shaped residual encoder (ResUNetLight / ResEncoder, ops.py:150-312) with `blocks` BasicBlocks
+    per stage: the first block of a stage carries the 1x1 downsample branch."""
     names = ["conv1.weight", "bn1.weight", "bn1.bias"]
-    for layer, blocks in ((1, 1), (2, 2), (3, 6)):
-        for b in range(blocks):
+    for layer, nb in enumerate(blocks, 1):
+        for b in range(nb):
             p = f"layer{layer}.{b}"
             names += [f"{p}.conv1.weight", f"{p}.bn1.weight", f"{p}.bn1.bias", f"{p}.conv2.weight", f"{p}.bn2.weight", f"{p}.bn2.bias"]
             if b == 0:
@@ -36,20 +37,12 @@ def image_param_names():
     return names + ["out_conv.weight", "out_conv.bias"]
 
 
-def vis_param_names():
-    """state_dict() order of DefaultVisEncoder = the order nr_vis_encoder_pack expects."""
-    names = ["out_conv.0.weight"]
-    for i in (1, 2):
-        p = f"out_conv.{i}.conv"
-        names += [f"{p}.0.weight", f"{p}.0.bias", f"{p}.2.weight", f"{p}.3.weight", f"{p}.3.bias", f"{p}.5.weight"]
-    return names + ["out_conv.3.weight"]
-
-
-def _image_shapes():
-    shapes = {"conv1.weight": (16, 3, 7, 7), "bn1.weight": (16,), "bn1.bias": (16,)}
-    cin = 16
-    for layer, blocks, cout in ((1, 1, 32), (2, 2, 64), (3, 6, 128)):
-        for b in range(blocks):
+def unet_param_shapes(conv1_shape, blocks):
+    inplanes = conv1_shape[0]
+    shapes = {"conv1.weight": tuple(conv1_shape), "bn1.weight": (inplanes,), "bn1.bias": (inplanes,)}
+    cin = inplanes
+    for layer, (nb, cout) in enumerate(zip(blocks, (32, 64, 128)), 1):
+        for b in range(nb):
             p = f"layer{layer}.{b}"
             shapes[f"{p}.conv1.weight"] = (cout, cin, 3, 3)
             shapes[f"{p}.conv2.weight"] = (cout, cout, 3, 3)
@@ -64,7 +57,25 @@ def _image_shapes():
         shapes[f"{p}.conv.bias"] = shapes[f"{p}.bn.weight"] = shapes[f"{p}.bn.bias"] = (co,)
     shapes["out_conv.weight"] = (32, 32, 1, 1)
     shapes["out_conv.bias"] = (32,)
-    return {n: shapes[n] for n in image_param_names()}
+    return {n: shapes[n] for n in unet_param_names(blocks)}
+
+
+def image_param_names():
+    """state_dict() order of ResUNetLight(3, [1,2,6,4], 32, inplanes=16) = the order nr_image_encoder_pack expects."""
+    return unet_param_names((1, 2, 6))
+
+
+def vis_param_names():
+    """state_dict() order of DefaultVisEncoder = the order nr_vis_encoder_pack expects."""
+    names = ["out_conv.0.weight"]
+    for i in (1, 2):
+        p = f"out_conv.{i}.conv"
+        names += [f"{p}.0.weight", f"{p}.0.bias", f"{p}.2.weight", f"{p}.3.weight", f"{p}.3.bias", f"{p}.5.weight"]
+    return names + ["out_conv.3.weight"]
+
+
+def _image_shapes():
+    return unet_param_shapes((16, 3, 7, 7), (1, 2, 6))
 
 
 def _vis_shapes():
@@ -82,6 +93,11 @@ class _Node(nn.Module):
 
 
 def _plant(root, shapes):
+    # biases that sit next to a 4-D weight of the same module belong to a convolution
+    conv_biases = {}
+    for dotted, shape in shapes.items():
+        if dotted.endswith(".weight") and len(shape) == 4 and dotted[:-6] + "bias" in shapes:
+            conv_biases[dotted[:-6] + "bias"] = 1.0 / (shape[1] * shape[2] * shape[3]) ** 0.5
     for dotted, shape in shapes.items():
         node = root
         *path, leaf = dotted.split(".")
@@ -95,6 +111,9 @@ def _plant(root, shapes):
             nn.init.uniform_(t, -bound, bound)
         elif leaf == "weight":     # InstanceNorm2d(affine=True)
             t = torch.ones(shape)
+        elif dotted in conv_biases:        # nn.Conv2d default bias init: U(-1/sqrt(fan_in), 1/sqrt(fan_in))
+            t = torch.empty(shape)
+            nn.init.uniform_(t, -conv_biases[dotted], conv_biases[dotted])
         else:
             t = torch.zeros(shape)
         node.register_parameter(leaf, nn.Parameter(t))
@@ -143,13 +162,13 @@ def _packed(module, names, which, dev):
             raise _lib.NeurayB200Error(f"{which} encoder parameters live on {params[0].device} but the images are on {dev}")
         lay = _lib.NrEncoderLayout()
         _lib.check(_lib.lib().nr_encoder_layout(C.byref(lay)), "nr_encoder_layout")
-        n_floats = lay.image_packed_floats if which == "image" else lay.vis_packed_floats
+        n_floats = {"image": lay.image_packed_floats, "vis": lay.vis_packed_floats, "depth_init": lay.depth_init_packed_floats}[which]
         keep = [p.detach().contiguous().float() for p in params]
         ptrs = (C.c_void_p * len(keep))(*[t.data_ptr() for t in keep])
         out = torch.empty(n_floats, dtype=torch.float32, device=dev)
-        fn = _lib.lib().nr_image_encoder_pack if which == "image" else _lib.lib().nr_vis_encoder_pack
+        fn = {"image": _lib.lib().nr_image_encoder_pack, "vis": _lib.lib().nr_vis_encoder_pack, "depth_init": _lib.lib().nr_depth_init_pack}[which]
         with torch.cuda.device(dev):
-            _lib.check(fn(ptrs, len(keep), _lib.ptr(out), torch.cuda.current_stream(dev).cuda_stream), f"nr_{which}_encoder_pack")
+            _lib.check(fn(ptrs, len(keep), _lib.ptr(out), torch.cuda.current_stream(dev).cuda_stream), f"nr_{which}_pack")
         _lib.count_launches(1)
         hit = (stamp, out)
         module.__dict__["_nr_enc_pack"] = hit
@@ -263,8 +282,13 @@ def usable(owner, ref_imgs_info):
     ie, ve = getattr(owner, "image_encoder", None), getattr(owner, "vis_encoder", None)
     if ie is None or ve is None or not ref_imgs_info["imgs"].is_cuda:
         return False
+    rf = ref_imgs_info.get("ray_feats")
+    if rf is None:
+        from . import init_nets
+        if getattr(owner, "init_net", None) is None or not init_nets.usable(owner.init_net, ref_imgs_info):
+            return False
     if torch.is_grad_enabled() and (any(p.requires_grad for p in ie.parameters()) or any(p.requires_grad for p in ve.parameters())
-                                    or ref_imgs_info["ray_feats"].requires_grad):
+                                    or (rf is not None and rf.requires_grad)):
         return False
     have_i, have_v = dict(ie.named_parameters()), dict(ve.named_parameters())
     return all(n in have_i for n in image_param_names()) and all(n in have_v for n in vis_param_names())
@@ -275,7 +299,11 @@ def encode_frame(owner, ref_imgs_info, feat):
     Also leaves NCHW 'img_feats' / 'ray_feats' in ref_imgs_info, which later callers of the reference read
     (predict_mean_for_depth_loss, renderer.py:281)."""
     imgs = ref_imgs_info["imgs"]
-    to_channel_last(ref_imgs_info["ray_feats"], feat, 0)
+    if ref_imgs_info.get("ray_feats") is not None:
+        to_channel_last(ref_imgs_info["ray_feats"], feat, 0)
+    else:                                  # renderer.py:269 -- the owner's init net, channel-last in place
+        from . import init_nets
+        init_nets.forward_into(owner.init_net, ref_imgs_info, feat, 0)
     image_encoder_into(owner.image_encoder, imgs, feat, 32)
     vis_encoder_inplace(owner.vis_encoder, feat)
     ref_imgs_info["img_feats"] = from_channel_last(feat, 32, 32)

@@ -9,7 +9,8 @@ What is rebound:
   * every function of network/render_ops.py  -> neuray_b200.render_ops (also inside network.renderer's and
     network.init_net's namespaces, which star-/name-import them)
   * NeuralRayBaseRenderer.render_by_depth / fine_render_impl / render_impl / render -> neuray_b200.renderer
-  * network.init_net.get_diff_feats (DepthInitNet) -> neuray_b200.init_ops.get_diff_feats
+  * network.init_net.get_diff_feats (DepthInitNet, SURVEY.md 8f row 2) -> neuray_b200.init_ops.get_diff_feats;
+    DepthInitNet.forward -> neuray_b200.init_nets (inference: the whole init net natively)
   * NeuralRayGenRenderer.predict_mean_for_depth_loss and network.loss.{RenderLoss, DepthLoss, ConsistencyLoss, name2loss}
      -> neuray_b200.losses
   * inference only: `render` runs image_encoder / vis_encoder natively into the frame pack (SURVEY.md 8f row 1,
@@ -20,7 +21,7 @@ kernels get a per-device table built by neuray_b200.weights.posenc_table.
 """
 import importlib
 
-from . import init_ops, losses, render_ops, renderer
+from . import init_nets, init_ops, losses, render_ops, renderer
 
 _ORIGINALS = []          # (object, attribute name, original value) of everything install() rebound
 
@@ -48,6 +49,8 @@ def install():
         ref_init = importlib.import_module("network.init_net")
         targets.append(ref_init)
         _rebind(ref_init, "get_diff_feats", init_ops.get_diff_feats)      # DepthInitNet's per-frame reprojection features
+        # inference: the whole DepthInitNet natively (ResEncoder on the tensor cores); with a gradient wanted, the reference's
+        _rebind(ref_init.DepthInitNet, "forward", init_nets.forward_or_reference(ref_init.DepthInitNet.forward))
     except Exception:      # init_net needs inplace_abn / kornia; the rendering path does not
         pass
     for name in render_ops.__all__:

@@ -21,7 +21,7 @@ import ctypes as C
 import torch
 import torch.nn as nn
 
-from . import _lib, encoders, modules
+from . import _lib, encoders, init_nets, modules
 from .render_ops import fine_sample_u, interpolate_feats, sample_depth
 from .weights import camera_blocks, pack_pass, point_index_map, posenc_table
 
@@ -90,19 +90,21 @@ class FramePack:
         if not imgs.is_cuda:
             raise _lib.NeurayB200Error("the rendering path needs CUDA tensors (no CPU fallback)")
         rfn, _, h, w = imgs.shape
-        rf = ref_imgs_info["ray_feats"]
+        rf = ref_imgs_info.get("ray_feats")
         if encoder_owner is not None:
-            if tuple(rf.shape[-2:]) != encoders.image_dims(h, w) or rf.shape[1] != 32:
-                raise _lib.NeurayB200Error(f"ray_feats {tuple(rf.shape)} do not match the image encoder's output size "
-                                           f"{encoders.image_dims(h, w)} for {h}x{w} images")
-            imf = rf
+            fh, fw = encoders.image_dims(h, w)
+            if rf is None:       # the owner's init net writes its ray_feats straight into the pack (encoders.encode_frame)
+                if init_nets.dims(h, w) != (fh, fw):
+                    raise _lib.NeurayB200Error(f"init net and image encoder disagree on the map size for {h}x{w} images")
+            elif tuple(rf.shape[-2:]) != (fh, fw) or rf.shape[1] != 32:
+                raise _lib.NeurayB200Error(f"ray_feats {tuple(rf.shape)} do not match the image encoder's output size {(fh, fw)} for {h}x{w} images")
         else:
             imf = ref_imgs_info["img_feats"]
-        if rf.shape != imf.shape or rf.shape[1] != 32:
-            raise _lib.NeurayB200Error(f"ray_feats {tuple(rf.shape)} and img_feats {tuple(imf.shape)} must both be [rfn,32,fh,fw]")
+            if rf.shape != imf.shape or rf.shape[1] != 32:
+                raise _lib.NeurayB200Error(f"ray_feats {tuple(rf.shape)} and img_feats {tuple(imf.shape)} must both be [rfn,32,fh,fw]")
+            fh, fw = rf.shape[-2:]
         if rfn > _lib.NR_MAX_VIEWS:
             raise _lib.NeurayB200Error(f"at most {_lib.NR_MAX_VIEWS} reference views per call, got {rfn}")
-        fh, fw = rf.shape[-2:]
         dev = imgs.device
         self.rfn, self.h, self.w, self.fh, self.fw = rfn, h, w, fh, fw
         self._pool_key = (str(dev), (rfn, fh, fw, 64), (rfn, h, w, 4))
@@ -474,3 +476,33 @@ class NeuralRayFrameRenderer(NeuralRayRenderPath):
 
     def render(self, que_imgs_info, ref_imgs_info, is_train):
         return render(self, dict(que_imgs_info), ref_imgs_info, is_train)
+
+
+class NeuralRayGenFrameRenderer(NeuralRayFrameRenderer):
+    """The inference frame path of NeuralRayGenRenderer with init_net_type 'depth' (reference renderer.py:255-327, the
+    neuray_gen_depth model): DepthInitNet -> image_encoder + vis_encoder -> chunk loop, every stage native, the three front
+    stages writing the channel-last frame pack in place.  State-dict names are the reference's (`init_net.*`,
+    `image_encoder.*`, `vis_encoder.*`, `dist_decoder.*`, ...), so a gen-model checkpoint loads unchanged.
+    ref_imgs_info carries imgs, depth, depth_range, poses, Ks (the init net's inputs); forward(data) like the reference."""
+
+    def __init__(self, cfg):
+        super().__init__(cfg)
+        if self.cfg.get("init_net_type", "depth") != "depth":
+            raise NotImplementedError("only init_net_type 'depth' (DepthInitNet) is native; CostVolumeInitNet / MVSNet is not built (DESIGN.md 7)")
+        self.init_net = init_nets.DepthInitNet(self.cfg.get("init_net_cfg", {}))
+
+    def render_call(self, que_imgs_info, ref_imgs_info, is_train, src_imgs_info=None):
+        """renderer.py:268-270: the init net's ray_feats go straight into the frame pack (no 'ray_feats' entry needed)."""
+        ref_imgs_info.pop("ray_feats", None)
+        if not encoders.usable(self, ref_imgs_info):
+            raise _lib.NeurayB200Error("NeuralRayGenFrameRenderer is the INFERENCE frame path (CUDA tensors, torch.no_grad() or frozen front-end "
+                                       "parameters); training goes through patch.install() on the reference's NeuralRayGenRenderer")
+        return render(self, dict(que_imgs_info), ref_imgs_info, is_train)
+
+    def forward(self, data):
+        ref_imgs_info, que_imgs_info = data["ref_imgs_info"].copy(), data["que_imgs_info"].copy()
+        is_train = "eval" not in data
+        out = self.render_call(que_imgs_info, ref_imgs_info, is_train, data.get("src_imgs_info"))
+        if (self.cfg["use_depth_loss"] and "true_depth" in ref_imgs_info) or (not is_train):
+            out.update(self.predict_mean_for_depth_loss(ref_imgs_info))
+        return out

@@ -535,9 +535,9 @@ def get_diff_feats(ref, depth_in):
 # pinned by tests/golden/encoders.npz (oracle/gen_golden_encoders.py runs the unmodified modules).
 
 
-def _conv2d(x, w, b=None, stride=1):
-    """nn.Conv2d(k, stride, padding=(k-1)//2, padding_mode='reflect') (ops.py:129-134, conv3x3 / conv1x1)."""
-    p = (w.shape[-1] - 1) // 2
+def _conv2d(x, w, b=None, stride=1, pad=None):
+    """nn.Conv2d(k, stride, padding=(k-1)//2 unless given, padding_mode='reflect') (ops.py:129-134, conv3x3 / conv1x1)."""
+    p = (w.shape[-1] - 1) // 2 if pad is None else pad
     if p:
         x = F.pad(x, (p, p, p, p), mode="reflect")
     return F.conv2d(x, w, b, stride=stride)
@@ -571,10 +571,11 @@ def _skipconnect(x1, x2):
     return torch.cat([x2, x1], 1)
 
 
-def res_unet_light(W, pre, imgs, blocks=(1, 2, 6)):
-    """ResUNetLight.forward (ops.py:210-228); W keyed by state-dict names under `pre` ('' or 'image_encoder.')."""
+def res_unet_light(W, pre, imgs, blocks=(1, 2, 6), first_pad=None):
+    """ResUNetLight.forward (ops.py:210-228); W keyed by state-dict names under `pre` ('' or 'image_encoder.').
+    ResEncoder.forward (ops.py:296-312) is the same graph with blocks (2, 2, 2) and an 8x8 stride-2 first conv of padding 2."""
     W = {k[len(pre):]: v for k, v in W.items() if k.startswith(pre)}
-    x = torch.relu(_inorm(W, "bn1", _conv2d(imgs, W["conv1.weight"], None, 2)))
+    x = torch.relu(_inorm(W, "bn1", _conv2d(imgs, W["conv1.weight"], None, 2, first_pad)))
     feats = []
     for li, nb in enumerate(blocks):
         for bi in range(nb):
@@ -669,3 +670,21 @@ def consistency_loss(prob0, prob1):
     """ConsistencyLoss.__call__ (loss.py:30-37)."""
     ce = -prob0 * torch.log(prob1 + 1e-5) - (1 - prob0) * torch.log(1 - prob1 + 1e-5)
     return torch.mean(torch.mean(ce, -1), 1)
+
+
+def extract_depth_for_init(depth_range, depth):
+    """init_net.py:63-74: metric depth [rfn,1,h,w] -> normalised inverse depth in [0, 1]."""
+    near, far = -1 / depth_range[:, 0][:, None, None, None], -1 / depth_range[:, 1][:, None, None, None]
+    d = -1 / torch.clamp(depth, min=1e-5)
+    return torch.clamp((d - near) / (far - near), min=0, max=1.0)
+
+
+def depth_init_net(W, pre, ref):
+    """DepthInitNet.forward (init_net.py:93-101); ref = {imgs, depth, depth_range, poses, Ks}; W under `pre` ('' or 'init_net.')."""
+    W = {k[len(pre):]: v for k, v in W.items() if k.startswith(pre)}
+    depth = extract_depth_for_init(ref["depth_range"], ref["depth"])
+    diff = get_diff_feats(ref, depth)
+    feats = res_unet_light(W, "res_net.", torch.cat([ref["imgs"], depth, diff], 1), blocks=(2, 2, 2), first_pad=2)
+    d = torch.relu(F.conv2d(depth, W["depth_skip.0.weight"], W["depth_skip.0.bias"], stride=2))
+    d = F.conv2d(d, W["depth_skip.2.weight"], W["depth_skip.2.bias"], stride=2)
+    return F.conv2d(torch.cat([d, feats], 1), W["conv_out.weight"], W["conv_out.bias"])

@@ -161,13 +161,25 @@ struct HostOps {
                 in ? p.x[(((long long)n * p.H + yi) * p.W + xi) * p.x_stride + p.x_off + c] : 0.f;
         }
   }
+  void depth_skip(const DepthSkipP& p) {
+    for (int n = 0; n < p.N; ++n)
+      for (int yo = 0; yo < p.Ho; ++yo)
+        for (int xo = 0; xo < p.Wo; ++xo) {
+          float out[16];
+          depth_skip_pixel(p, n, yo, xo, out);
+          for (int c = 0; c < 16; ++c) p.y[(((long long)n * p.Ho + yo) * p.Wo + xo) * p.y_stride + p.y_off + c] = out[c];
+        }
+  }
   void zero(void* ptr, size_t bytes) { memset(ptr, 0, bytes); }
 };
 
 static void host_pack(const enc::NetSpec& spec, const float* const* params, float* packed) {
   memset(packed, 0, size_t(spec.total) * sizeof(float));
   for (int i = 0; i < spec.count; ++i)
-    for (long long e = 0; e < spec.t[i].n; ++e) packed[spec.t[i].off + e] = params[i][enc::pack_source(spec.t[i], e)];
+    for (long long e = 0; e < spec.t[i].n; ++e) {
+      const long long src = enc::pack_source(spec.t[i], e);
+      packed[spec.t[i].off + e] = src >= 0 ? params[i][src] : 0.f;
+    }
 }
 
 extern "C" int nr_cpu_encoder_counts(int* image_tensors, int* vis_tensors) {
@@ -220,12 +232,50 @@ extern "C" int nr_cpu_vis_encoder(const float* const* params, int n_params, floa
   return ok ? 0 : -2;
 }
 
+// DepthInitNet after extract_depth / get_diff_feats: imgs [n,3,h,w], depth_norm [n,1,h,w], diff_feats [n,8,h,w] (NCHW) -> out slot
+extern "C" int nr_cpu_depth_init(const float* const* params, int n_params, const float* imgs, const float* depth_norm, const float* diff_feats, int n,
+                                 int h, int w, float* out, int out_stride, int out_off) {
+  enc::DepthInitNet* net = new enc::DepthInitNet;
+  enc::build_depth_init_net(*net);
+  if (n_params != net->res.spec.count) return -1;
+  std::vector<float> packed(net->res.spec.total);
+  host_pack(net->res.spec, params, packed.data());
+  const long long hw = (long long)h * w;
+  std::vector<float> x16(size_t(n) * hw * 16, 0.f);
+  for (int i = 0; i < n; ++i)
+    for (long long p = 0; p < hw; ++p) {
+      float* px = &x16[(size_t(i) * hw + p) * 16];
+      for (int c = 0; c < 3; ++c) px[c] = imgs[(size_t(i) * 3 + c) * hw + p];
+      px[3] = depth_norm[size_t(i) * hw + p];
+      for (int c = 0; c < 8; ++c) px[4 + c] = diff_feats[(size_t(i) * 8 + c) * hw + p];
+    }
+  const long long stats = enc::depth_init_stats_doubles(*net, n, h, w);
+  const size_t bytes = enc::depth_init_workspace_bytes(*net, n, h, w);
+  std::vector<char> ws(bytes + 256);
+  char* base = (char*)((uintptr_t(ws.data()) + 255) & ~uintptr_t(255));
+  enc::Arena ar{base, bytes, 0, true};
+  HostOps ops;
+  const bool ok = stats > 0 && enc::depth_init_graph(ops, ar, *net, packed.data(), x16.data(), depth_norm, n, h, w, out, out_stride, out_off, stats, nullptr);
+  delete net;
+  return ok ? 0 : -2;
+}
+extern "C" int nr_cpu_depth_init_dims(int h, int w, int* fh, int* fw, int* tensors) {
+  const enc::ImageDims d = enc::depth_init_dims(h, w);
+  *fh = d.u2h; *fw = d.u2w;
+  enc::DepthInitNet* net = new enc::DepthInitNet;
+  enc::build_depth_init_net(*net);
+  *tensors = net->res.spec.count;
+  delete net;
+  return 0;
+}
+
 // one convolution: w [cout][cin][ks][ks] (PyTorch layout, packed here), x / y / res channel-last
 extern "C" int nr_cpu_conv2d(const float* x, const float* w, const float* bias, const float* res, float* y, double* stats, int n, int h, int wd,
-                             int cin, int cout, int ks, int stride, int reflect, int cin_rot, int x_stride, int x_off, int y_stride, int y_off) {
+                             int cin, int cout, int ks, int stride, int reflect, int cin_rot, int x_stride, int x_off, int y_stride, int y_off, int pad,
+                             int cin_ref) {
   enc::NetSpec* spec = new enc::NetSpec;
   spec->count = 0; spec->total = 0;
-  spec->conv(cout, cin, ks, cin_rot, 0);
+  spec->conv(cout, cin, ks, cin_rot, 0, cin_ref);
   std::vector<float> packed(spec->total);
   const float* params[1] = {w};
   host_pack(*spec, params, packed.data());
@@ -233,7 +283,8 @@ extern "C" int nr_cpu_conv2d(const float* x, const float* w, const float* bias, 
   ConvP p;
   p.x = x; p.w = packed.data(); p.bias = bias; p.res = res; p.y = y; p.stats = stats;
   p.N = n; p.H = h; p.W = wd; p.Cin = cin; p.Cout = cout; p.ks = ks; p.stride = stride; p.reflect = reflect;
-  p.Ho = enc::conv_out(h, ks, stride); p.Wo = enc::conv_out(wd, ks, stride);
+  p.pad = pad >= 0 ? pad : (ks - 1) / 2;
+  p.Ho = enc::conv_out(h, ks, stride, p.pad); p.Wo = enc::conv_out(wd, ks, stride, p.pad);
   p.x_stride = x_stride; p.x_off = x_off; p.y_stride = y_stride; p.y_off = y_off; p.res_stride = cout; p.res_off = 0;
   p.tf32x1 = 0;
   HostOps ops;

@@ -98,21 +98,25 @@ def test_layer_graphs_on_the_host_match_the_reference(harness, tag):
     assert float((feat[..., 32:].permute(0, 3, 1, 2) - c["img_feats"]).abs().max()) < 5e-5
 
 
-@pytest.mark.parametrize("n,h,w,cin,cout,ks,stride,reflect,rot", [
-    (2, 9, 11, 16, 32, 3, 2, 1, 0),      # Cin 16 (KC 16), stride 2, odd sizes, images share a CTA
-    (3, 7, 9, 32, 64, 3, 1, 0, 0),       # zero padding, a warp's rows straddle two images
-    (1, 12, 13, 64, 128, 3, 1, 1, 32),   # 128 outputs (4 m-tiles per warp), rotated input channels
-    (2, 8, 8, 32, 32, 1, 2, 1, 0),       # 1x1 stride 2 (the downsample branch)
-    (1, 20, 20, 128, 64, 3, 1, 1, 0),    # 4 CTAs, the last one partial
+@pytest.mark.parametrize("n,h,w,cin,cout,ks,stride,reflect,rot,pad,cin_ref", [
+    (2, 9, 11, 16, 32, 3, 2, 1, 0, -1, 0),      # Cin 16 (KC 16), stride 2, odd sizes, images share a CTA
+    (3, 7, 9, 32, 64, 3, 1, 0, 0, -1, 0),       # zero padding, a warp's rows straddle two images
+    (1, 12, 13, 64, 128, 3, 1, 1, 32, -1, 0),   # 128 outputs (4 m-tiles per warp), rotated input channels
+    (2, 8, 8, 32, 32, 1, 2, 1, 0, -1, 0),       # 1x1 stride 2 (the downsample branch)
+    (1, 20, 20, 128, 64, 3, 1, 1, 0, -1, 0),    # 4 CTAs, the last one partial
+    (2, 22, 26, 16, 32, 8, 2, 1, 0, 2, 12),     # ResEncoder.conv1: 8x8 stride 2 padding 2, 12 reference channels packed into 16
+    (1, 10, 12, 48, 32, 1, 1, 1, 0, -1, 0),     # DepthInitNet.conv_out: 48 inputs (three K steps of 16)
 ])
-def test_emulated_tensor_core_conv_matches_conv2d(harness, n, h, w, cin, cout, ks, stride, reflect, rot):
+def test_emulated_tensor_core_conv_matches_conv2d(harness, n, h, w, cin, cout, ks, stride, reflect, rot, pad, cin_ref):
     g = torch.Generator().manual_seed(cin * 1000 + cout + ks)
+    cr = cin_ref or cin
     x = torch.randn(n, cin, h, w, generator=g)
-    wt = torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5
+    x[:, cr:] = 0.0 if cr < cin else x[:, cr:]
+    wt = torch.randn(cout, cr, ks, ks, generator=g) / (cin * ks * ks) ** 0.5
     bias = torch.randn(cout, generator=g)
-    p = (ks - 1) // 2
+    p = (ks - 1) // 2 if pad < 0 else pad
     xin = x if rot == 0 else torch.roll(x, rot, 1)       # packed channel c reads reference channel (c + rot) % cin
-    xp = F.pad(x, (p, p, p, p), mode="reflect") if (reflect and p) else x
+    xp = F.pad(x[:, :cr], (p, p, p, p), mode="reflect") if (reflect and p) else x[:, :cr]
     want = F.conv2d(xp, wt, bias, stride=stride, padding=0 if (reflect or not p) else p)
     res = torch.randn(n, want.shape[2], want.shape[3], cout, generator=g)
     want = want + res.permute(0, 3, 1, 2)
@@ -120,14 +124,52 @@ def test_emulated_tensor_core_conv_matches_conv2d(harness, n, h, w, cin, cout, k
     xs, xo, ys, yo = cin + 8, 4, cout + 8, 4
     xbuf = torch.full((n, h, w, xs), 7.0)
     xbuf[..., xo:xo + cin] = _nhwc(xin if rot == 0 else torch.roll(x, -rot, 1))
+    if cr < cin:
+        xbuf[..., xo + cr:xo + cin] = 5.0        # the padding channels meet zero weight rows: their content must not matter
     ybuf = torch.full((n, want.shape[2], want.shape[3], ys), -3.0)
     stats = torch.zeros(n, cout, 2, dtype=torch.float64)
     wt_c, b_c, r_c = wt.contiguous(), bias.contiguous(), res.contiguous()
     rc = harness.nr_cpu_conv2d(C.c_void_p(xbuf.data_ptr()), C.c_void_p(wt_c.data_ptr()), C.c_void_p(b_c.data_ptr()), C.c_void_p(r_c.data_ptr()),
-                               C.c_void_p(ybuf.data_ptr()), C.c_void_p(stats.data_ptr()), n, h, w, cin, cout, ks, stride, reflect, rot, xs, xo, ys, yo)
+                               C.c_void_p(ybuf.data_ptr()), C.c_void_p(stats.data_ptr()), n, h, w, cin, cout, ks, stride, reflect, rot, xs, xo, ys, yo, pad, cin_ref)
     assert rc == 0
     got = ybuf[..., yo:yo + cout].permute(0, 3, 1, 2)
     assert float((got - want).abs().max()) < 2e-5
     assert torch.all(ybuf[..., :yo] == -3.0) and torch.all(ybuf[..., yo + cout:] == -3.0)       # nothing outside the slot
     assert torch.allclose(stats[..., 0], want.double().sum((2, 3)), atol=1e-4)
     assert torch.allclose(stats[..., 1], (want.double() ** 2).sum((2, 3)), rtol=1e-5, atol=1e-4)
+
+
+def depth_init_golden():
+    z = np.load(os.path.join(GOLDEN_DIR, "depth_init_net.npz"))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    ref = {k[4:]: t(z[k]) for k in z.files if k.startswith("ref_")}
+    return ref, t(z["out"]), orc.encoder_test_weights(json.loads(str(z["shapes"])), 13)
+
+
+def test_depth_init_net_oracle_matches_the_reference():
+    ref, out, W = depth_init_golden()
+    got = orc.depth_init_net(W, "", ref)
+    assert got.shape == out.shape
+    assert torch.allclose(got, out, atol=3e-5, rtol=1e-5), float((got - out).abs().max())
+
+
+def test_depth_init_net_graph_on_the_host_matches_the_reference(harness):
+    """DepthInitNet (init_net.py:76-101) after extract_depth / get_diff_feats: ResEncoder (8x8 first conv on 12 channels packed
+    into 16), depth_skip, conv_out -- the product's graph + packing on the host against the unmodified module's output."""
+    ref, out, W = depth_init_golden()
+    n, _, h, w = ref["imgs"].shape
+    depth = orc.extract_depth_for_init(ref["depth_range"], ref["depth"]).contiguous()
+    diff = orc.get_diff_feats(ref, depth).contiguous()
+    fh, fw, nt = C.c_int(), C.c_int(), C.c_int()
+    harness.nr_cpu_depth_init_dims(h, w, C.byref(fh), C.byref(fw), C.byref(nt))
+    assert (fh.value, fw.value) == tuple(out.shape[-2:]) and nt.value == len(W)
+    params = [t.contiguous() for t in W.values()]
+    buf = torch.full((n, fh.value, fw.value, 64), 9.0)
+    imgs = ref["imgs"].contiguous()
+    rc = harness.nr_cpu_depth_init(_ptrs(params), len(params), C.c_void_p(imgs.data_ptr()), C.c_void_p(depth.data_ptr()), C.c_void_p(diff.data_ptr()),
+                                   n, h, w, C.c_void_p(buf.data_ptr()), 64, 0)
+    assert rc == 0
+    got = buf[..., :32].permute(0, 3, 1, 2)
+    err = float((got - out).abs().max())
+    assert err < 1e-4, err
+    assert bool(torch.all(buf[..., 32:] == 9.0))

@@ -65,7 +65,7 @@ def test_conv2d_matches_torch(n, h, w, cin, cout, ks, stride, reflect, rot):
     c = _lib.NrConv2d()
     c.x, c.w_packed, c.bias, c.res, c.y, c.stats = xbuf.data_ptr(), packed.data_ptr(), b_d.data_ptr(), r_d.data_ptr(), ybuf.data_ptr(), stats.data_ptr()
     c.n, c.h, c.w, c.cin, c.cout, c.ks, c.stride, c.reflect = n, h, w, cin, cout, ks, stride, reflect
-    c.x_stride, c.x_off, c.y_stride, c.y_off, c.res_stride, c.res_off = xs, xo, ys, yo, cout, 0
+    c.x_stride, c.x_off, c.y_stride, c.y_off, c.res_stride, c.res_off, c.pad = xs, xo, ys, yo, cout, 0, -1
     _lib.check(_lib.lib().nr_conv2d_nhwc(C.byref(c), st), "nr_conv2d_nhwc")
     torch.cuda.synchronize()
     got = ybuf[..., yo:yo + cout].permute(0, 3, 1, 2).cpu().double()
@@ -179,3 +179,96 @@ def test_single_pass_tf32_option():
     assert float((r32.cpu() - c["ray_feats"]).abs().max()) < 1e-1
     with pytest.raises(ValueError):
         encoders.set_precision("bf16")
+
+
+# ---- DepthInitNet (reference init_net.py:63-101), the init net of the neuray_gen_depth model ------------------------------------
+
+def depth_init_golden():
+    z = np.load(os.path.join(GOLDEN_DIR, "depth_init_net.npz"))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    return {k[4:]: t(z[k]) for k in z.files if k.startswith("ref_")}, t(z["out"]), orc.encoder_test_weights(json.loads(str(z["shapes"])), 13)
+
+
+def test_depth_init_net_matches_the_reference_golden():
+    from neuray_b200 import init_nets
+    ref, out, W = depth_init_golden()
+    net = init_nets.DepthInitNet()
+    net.load_state_dict(W, strict=True)
+    net.cuda()
+    with torch.no_grad():
+        got = net(synthetic.to_device(ref, "cuda"), None, False)
+    torch.cuda.synchronize()
+    assert got.shape == out.shape
+    err = float((got.cpu() - out).abs().max())
+    assert err < 1e-4, err
+    with pytest.raises(_lib.NeurayB200Error):
+        net(synthetic.to_device(ref, "cuda"), None, True)          # forward-only
+
+
+def _smooth_depth(rs, rfn, h, w, lo, hi):
+    base = torch.from_numpy(rs.uniform(lo, hi, (rfn, 1, max(2, h // 16), max(2, w // 16))).astype(np.float32))
+    return F.interpolate(base, size=(h, w), mode="bilinear", align_corners=True)
+
+
+def test_depth_init_net_matches_the_oracle_at_the_training_image_size():
+    """cfg5: 8 views 300x400 padded to 304x400."""
+    from neuray_b200 import init_nets
+    _, _, W = depth_init_golden()
+    _, ref = synthetic.make_scene(300, 400, 8, seed=12, smooth=2, pad=16, depth_range=(0.8, 4.0))
+    rs = np.random.RandomState(3)
+    h, w = ref["imgs"].shape[-2:]
+    ref = {k: ref[k] for k in ("imgs", "poses", "Ks", "depth_range")}
+    ref["depth"] = _smooth_depth(rs, 8, h, w, 1.0, 3.5)
+    want = orc.depth_init_net(W, "", ref)
+    net = init_nets.DepthInitNet()
+    net.load_state_dict(W, strict=True)
+    net.cuda()
+    with torch.no_grad():
+        got = net(synthetic.to_device(ref, "cuda"), None, False)
+    torch.cuda.synchronize()
+    err = (got.cpu() - want).abs()
+    # reprojections within rounding of an image border flip a validity bit of get_diff_feats on isolated pixels (test_diff_feats.py);
+    # through the 3x3 / 8x8 receptive fields they touch a small neighbourhood
+    assert float((err > 2e-4 * max(1.0, float(want.abs().max()))).float().mean()) < 2e-3, float(err.max())
+    assert float(err.mean()) < 3e-5
+
+
+def test_gen_frame_renderer_end_to_end_matches_the_oracle():
+    """NeuralRayGenFrameRenderer.forward (reference renderer.py:318-327 in eval mode): DepthInitNet -> image_encoder + vis_encoder ->
+    coarse + fine render + predict_mean_for_depth_loss, every stage native, against the oracle's restatement of each stage."""
+    cfg = {"use_hierarchical_sampling": True, "dist_decoder_cfg": {"use_vis": False}, "depth_sample_num": 32, "fine_depth_sample_num": 32,
+           "agg_net_cfg": {"sample_num": 32}, "fine_agg_net_cfg": {"sample_num": 32}, "render_depth": True, "ray_batch_num": 160,
+           "depth_loss_coords_num": 64}
+    _, img_w, vis_w = golden()
+    _, _, init_w = depth_init_golden()
+    que, ref = synthetic.make_scene(64, 80, 4, seed=6, smooth=2)
+    que = synthetic.slice_rays(que, 1500, 1900)
+    rs = np.random.RandomState(6)
+    ref = {k: ref[k] for k in ("imgs", "poses", "Ks", "depth_range")}
+    ref["depth"] = _smooth_depth(rs, 4, 64, 80, 2.5, 5.0)
+    W = synthetic.make_weights(cfg, seed=6)
+    full = dict(W)
+    full.update({"image_encoder." + k: v for k, v in img_w.items()})
+    full.update({"vis_encoder." + k: v for k, v in vis_w.items()})
+    full.update({"init_net." + k: v for k, v in init_w.items()})
+    net = renderer.NeuralRayGenFrameRenderer(cfg)
+    net.load_state_dict(full, strict=True)
+    net.cuda().eval()
+    data = {"que_imgs_info": synthetic.to_device(que, "cuda"), "ref_imgs_info": synthetic.to_device(ref, "cuda"), "eval": True}
+    torch.manual_seed(1)
+    with torch.no_grad():
+        out = net(data)
+    torch.cuda.synchronize()
+    ray_in = orc.depth_init_net(init_w, "", ref)
+    img_feats = orc.res_unet_light(img_w, "", ref["imgs"])
+    ray_feats = orc.vis_encoder(vis_w, "", ray_in, img_feats)
+    gold = orc.render(W, flat_cfg({**renderer.base_cfg, **cfg}), que, dict(ref, ray_feats=ray_feats, img_feats=img_feats), False, ray_batch_num=160)
+    err = float((out["pixel_colors_nr"].cpu() - gold["pixel_colors_nr"]).abs().max())
+    assert err < 3e-4, err
+    fine = (out["pixel_colors_nr_fine"].cpu() - gold["pixel_colors_nr_fine"]).abs()
+    assert float(torch.quantile(fine.flatten(), 0.99)) < 3e-4 and float((fine > 1e-3).float().mean()) < 0.01
+    assert torch.equal(out["ray_mask"].cpu(), gold["ray_mask"])
+    mean = orc.predict_mean(W, "dist_decoder", ray_feats, out["depth_coords"].cpu(), 64, 80)
+    assert float((out["depth_mean"].cpu() - mean[..., 0]).abs().max()) < 2e-4
+    with pytest.raises(_lib.NeurayB200Error):
+        net({k: v for k, v in data.items() if k != "eval"})        # training is not this class' job
