@@ -325,6 +325,7 @@ typedef struct NrConv2d {
   int32_t x_stride, x_off, y_stride, y_off, res_stride, res_off;
   int32_t tf32x1;            /* 0: 3xTF32 (fp32 accuracy); 1: one TF32 pass */
   int32_t pad;               /* -1: (ks-1)/2 */
+  int32_t bm;                /* output pixels per CTA: 0 = chosen by the library, else 64 / 128 (cout 64, 128) or 128 / 256 (cout 32) */
 } NrConv2d;
 int nr_conv2d_nhwc(const NrConv2d* c, void* stream);
 /* [cout][cin][ks][ks] -> [tap][cin][cout]; packed input channel c reads reference channel (c + cin_rot) % cin */

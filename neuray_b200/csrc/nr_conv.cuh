@@ -26,9 +26,13 @@
 namespace nr {
 namespace cv {
 
-constexpr int BM = 128;        // output pixels per CTA
-constexpr int THREADS = 256;   // 8 warps: (8 / WN) along M x WN along N, WN = Cout / 32; a warp owns 16*MT pixels x 32 channels
-constexpr int STAGES = 3;
+constexpr int THREADS = 256;   // 8 warps: WM = 8 / WN along M x WN = Cout / 32 along N; a warp owns 16*MT pixels x 32 channels
+// Output pixels per CTA: BM in {64, 128, 256}, MT = BM / (16 WM) m16 tiles per warp.  128 is the default; 64 for Cout = 128 when
+// 128-pixel tiles would leave a nearly empty last wave (layer3 of an 800x800 frame: 157 tiles on 148 SMs); 256 for Cout = 32,
+// where a warp otherwise owns a single m16 tile and re-reads / re-splits the whole weight tile for 12 MMAs (2 pipeline stages
+// instead of 3, so that two CTAs still fit an SM).
+__host__ __device__ constexpr int mt_of(int BM, int BN) { return BM / (16 * (8 / (BN / 32))); }
+__host__ __device__ constexpr int stages_of(int BM) { return BM > 128 ? 2 : 3; }
 
 struct ConvP {
   const float* x;       // input: pixel (n, y, x) channel c at x[((n*H + y)*W + x) * x_stride + x_off + c]
@@ -39,8 +43,19 @@ struct ConvP {
   double* stats;        // [N][Cout][2]: sum, sum of squares (accumulated; the caller zeroes it) or null
   int N, H, W, Ho, Wo, Cin, Cout, ks, stride, pad, reflect;
   int x_stride, x_off, y_stride, y_off, res_stride, res_off;
+  int bm;               // output pixels per CTA: 0 = chosen by the launcher, else 64 / 128 / 256 (tests force every variant)
   int tf32x1;           // 0: 3xTF32 (fp32 accuracy, the default); 1: one TF32 pass, what cuDNN does under torch's default allow_tf32
 };
+
+// tile height the launcher uses when p.bm == 0: slots = CTAs the device runs at once for this Cout
+NR_HD int pick_bm(int Cout, long long M, int sms) {
+  if (Cout == 32) return M >= 2LL * 256 * sms ? 256 : 128;
+  if (Cout == 128) {
+    const long long w128 = (M + 128LL * sms - 1) / (128LL * sms), w64 = (M + 64LL * sms - 1) / (64LL * sms);
+    return w64 * 64 < w128 * 128 ? 64 : 128;          // rows an SM works through, one CTA per SM either way
+  }
+  return 128;
+}
 
 struct RowInfo {
   int n, y0, x0;        // image (-1: row beyond the last pixel), input coordinates of tap (0, 0)
@@ -123,10 +138,10 @@ NR_HD void atomic_add_f64(double* p, double v) {
 // the InstanceNorm sums.  When all rows of the warp lie in one image (`uniform`), the per-column partial sums come back in
 // s / q (the caller reduces them over the 8 row lanes and issues one atomic per column); otherwise every element is added
 // on its own.
-template <int BN>
-NR_HD void epilogue_thread(const ConvP& p, long long m0, int warp, int lane, const float (&acc)[BN / 32][4][4], bool uniform,
+template <int BM, int BN>
+NR_HD void epilogue_thread(const ConvP& p, long long m0, int warp, int lane, const float (&acc)[mt_of(BM, BN)][4][4], bool uniform,
                            float (&s)[4][2], float (&q)[4][2]) {
-  constexpr int MT = BN / 32, WN = BN / 32;
+  constexpr int MT = mt_of(BM, BN), WN = BN / 32;
   const int g = lane >> 2, t4 = lane & 3;
   const int warp_m = warp / WN, warp_n = warp - warp_m * WN;
   const long long M = (long long)p.N * p.Ho * p.Wo;
@@ -166,9 +181,9 @@ NR_HD void epilogue_thread(const ConvP& p, long long m0, int warp, int lane, con
 }
 
 // all valid rows of the warp's 16*MT rows in one image?
-template <int BN>
+template <int BM, int BN>
 NR_HD bool warp_rows_uniform(const ConvP& p, long long m0, int warp) {
-  constexpr int MT = BN / 32, WN = BN / 32;
+  constexpr int MT = mt_of(BM, BN), WN = BN / 32;
   const long long M = (long long)p.N * p.Ho * p.Wo;
   const long long first = m0 + (warp / WN) * (16 * MT);
   long long last = first + 16 * MT - 1;

@@ -34,10 +34,11 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {      // round to nearest 
 
 // FAST = one TF32 pass per product (operands rounded to TF32: ~1e-3 relative, torch's default for cuDNN convolutions);
 // otherwise the 3xTF32 split (fp32 accuracy, what the parity tests run)
-template <int BN, int KC, bool FAST>
+template <int BM, int BN, int KC, bool FAST>
 __global__ void __launch_bounds__(THREADS, BN >= 128 ? 1 : 2) conv_mma_kernel(const __grid_constant__ ConvP p) {
   extern __shared__ __align__(16) float sm[];
-  constexpr int MT = BN / 32, WN = BN / 32;
+  constexpr int MT = mt_of(BM, BN), WN = BN / 32, STAGES = stages_of(BM);
+  static_assert(MT >= 1 && MT <= 4 && MT * 16 * (8 / WN) == BM, "tile shape");
   constexpr int A_ST = BM * (KC + 4), B_ST = KC * (BN + 8), ST = A_ST + B_ST;
   constexpr int A_ROWS = THREADS / (KC / 4);      // rows of the A tile one pass of the 256 threads covers
   constexpr int A_PASSES = BM / A_ROWS;
@@ -153,9 +154,9 @@ __global__ void __launch_bounds__(THREADS, BN >= 128 ? 1 : 2) conv_mma_kernel(co
     for (int i = tid; i < 2 * BN; i += THREADS) cta_sums[i] = 0.0;
     __syncthreads();
   }
-  const bool uniform = warp_rows_uniform<BN>(p, m0, warp);
+  const bool uniform = warp_rows_uniform<BM, BN>(p, m0, warp);
   float s[4][2], q[4][2];
-  epilogue_thread<BN>(p, m0, warp, lane, acc, uniform, s, q);
+  epilogue_thread<BM, BN>(p, m0, warp, lane, acc, uniform, s, q);
   if (p.stats != nullptr && uniform) {
     const long long first = m0 + warp_m * (16 * MT);
     if (first < M) {                  // warp-uniform
@@ -382,18 +383,22 @@ __global__ void __launch_bounds__(256) pack_params_kernel(const __grid_constant_
   }
 }
 
-template <int BN, int KC, bool FAST>
+template <int BM, int BN, int KC, bool FAST>
 int launch_conv_f(const ConvP& p, cudaStream_t st) {
-  constexpr size_t smem = size_t(STAGES) * (BM * (KC + 4) + KC * (BN + 8)) * sizeof(float);
-  cudaFuncSetAttribute(conv_mma_kernel<BN, KC, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));   // per device, per launch
+  constexpr size_t smem = size_t(stages_of(BM)) * (BM * (KC + 4) + KC * (BN + 8)) * sizeof(float);
+  cudaFuncSetAttribute(conv_mma_kernel<BM, BN, KC, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));   // per device, per launch
   const long long M = (long long)p.N * p.Ho * p.Wo;
-  conv_mma_kernel<BN, KC, FAST><<<unsigned((M + BM - 1) / BM), THREADS, smem, st>>>(p);
+  conv_mma_kernel<BM, BN, KC, FAST><<<unsigned((M + BM - 1) / BM), THREADS, smem, st>>>(p);
   NR_CHECK_LAUNCH("conv_mma_kernel");
   return NR_OK;
 }
-template <int BN, int KC>
+template <int BM, int BN, int KC>
 int launch_conv_t(const ConvP& p, cudaStream_t st) {
-  return p.tf32x1 ? launch_conv_f<BN, KC, true>(p, st) : launch_conv_f<BN, KC, false>(p, st);
+  return p.tf32x1 ? launch_conv_f<BM, BN, KC, true>(p, st) : launch_conv_f<BM, BN, KC, false>(p, st);
+}
+template <int BM, int BN>
+int launch_conv_k(const ConvP& p, cudaStream_t st) {
+  return p.Cin % 32 == 0 ? launch_conv_t<BM, BN, 32>(p, st) : launch_conv_t<BM, BN, 16>(p, st);
 }
 
 int check_conv(const ConvP& p) {
@@ -409,14 +414,22 @@ int check_conv(const ConvP& p) {
   return NR_OK;
 }
 
+int sm_count();
+
 int launch_conv(const ConvP& p, cudaStream_t st) {
   const int rc = check_conv(p);
   if (rc != NR_OK) return rc;
-  const bool k32 = p.Cin % 32 == 0;
+  const int bm = p.bm != 0 ? p.bm : pick_bm(p.Cout, (long long)p.N * p.Ho * p.Wo, sm_count());
   switch (p.Cout) {
-    case 32: return k32 ? launch_conv_t<32, 32>(p, st) : launch_conv_t<32, 16>(p, st);
-    case 64: return k32 ? launch_conv_t<64, 32>(p, st) : launch_conv_t<64, 16>(p, st);
-    default: return k32 ? launch_conv_t<128, 32>(p, st) : launch_conv_t<128, 16>(p, st);
+    case 32:
+      NR_CHECK_ARG(bm == 128 || bm == 256, "conv: 128 or 256 pixels per CTA for 32 outputs");
+      return bm == 256 ? launch_conv_k<256, 32>(p, st) : launch_conv_k<128, 32>(p, st);
+    case 64:
+      NR_CHECK_ARG(bm == 64 || bm == 128, "conv: 64 or 128 pixels per CTA for 64 outputs");
+      return bm == 64 ? launch_conv_k<64, 64>(p, st) : launch_conv_k<128, 64>(p, st);
+    default:
+      NR_CHECK_ARG(bm == 64 || bm == 128, "conv: 64 or 128 pixels per CTA for 128 outputs");
+      return bm == 64 ? launch_conv_k<64, 128>(p, st) : launch_conv_k<128, 128>(p, st);
   }
 }
 
@@ -437,6 +450,7 @@ struct StreamOps {
     if (rc != NR_OK) return;
     ConvP q = p;
     q.tf32x1 = tf32x1;
+    q.bm = 0;
     rc = launch_conv(q, st);
   }
   void conv7(const Conv7P& p) {
@@ -660,6 +674,7 @@ extern "C" int nr_conv2d_nhwc(const NrConv2d* c, void* stream) {
   p.Ho = enc::conv_out(p.H, p.ks, p.stride, p.pad); p.Wo = enc::conv_out(p.W, p.ks, p.stride, p.pad);
   p.x_stride = c->x_stride; p.x_off = c->x_off; p.y_stride = c->y_stride; p.y_off = c->y_off; p.res_stride = c->res_stride; p.res_off = c->res_off;
   p.tf32x1 = c->tf32x1 != 0;
+  p.bm = c->bm;
   if (p.N == 0) return NR_OK;
   return cv::launch_conv(p, (cudaStream_t)stream);
 }

@@ -215,7 +215,7 @@ struct Builder {
     p.x = x; p.w = wt; p.bias = bias; p.res = res; p.y = y; p.stats = st;
     p.N = N; p.H = H; p.W = Wd; p.Ho = Ho; p.Wo = Wo; p.Cin = cin; p.Cout = cout; p.ks = ks; p.stride = stride; p.pad = pad; p.reflect = 1;
     p.x_stride = x_stride; p.x_off = x_off; p.y_stride = y_stride; p.y_off = y_off; p.res_stride = res_stride; p.res_off = res_off;
-    p.tf32x1 = 0;      // the backend decides (StreamOps)
+    p.tf32x1 = 0; p.bm = 0;      // the backend decides (StreamOps)
     ops.conv(p);
     return y;
   }

@@ -679,11 +679,13 @@ def extract_depth_for_init(depth_range, depth):
     return torch.clamp((d - near) / (far - near), min=0, max=1.0)
 
 
-def depth_init_net(W, pre, ref):
-    """DepthInitNet.forward (init_net.py:93-101); ref = {imgs, depth, depth_range, poses, Ks}; W under `pre` ('' or 'init_net.')."""
+def depth_init_net(W, pre, ref, diff=None):
+    """DepthInitNet.forward (init_net.py:93-101); ref = {imgs, depth, depth_range, poses, Ks}; W under `pre` ('' or 'init_net.').
+    diff: get_diff_feats' output when the caller already has it (tests that isolate the convolution stack)."""
     W = {k[len(pre):]: v for k, v in W.items() if k.startswith(pre)}
     depth = extract_depth_for_init(ref["depth_range"], ref["depth"])
-    diff = get_diff_feats(ref, depth)
+    if diff is None:
+        diff = get_diff_feats(ref, depth)
     feats = res_unet_light(W, "res_net.", torch.cat([ref["imgs"], depth, diff], 1), blocks=(2, 2, 2), first_pad=2)
     d = torch.relu(F.conv2d(depth, W["depth_skip.0.weight"], W["depth_skip.0.bias"], stride=2))
     d = F.conv2d(d, W["depth_skip.2.weight"], W["depth_skip.2.bias"], stride=2)

@@ -17,9 +17,9 @@ void set_error(const char*, ...) {}
 using namespace nr;
 using namespace nr::cv;
 
-template <int BN, int KC>
+template <int BM, int BN, int KC>
 static void host_conv(const ConvP& p) {
-  constexpr int MT = BN / 32, WN = BN / 32;
+  constexpr int MT = mt_of(BM, BN), WN = BN / 32;
   constexpr int A_ST = BM * (KC + 4), B_ST = KC * (BN + 8);
   constexpr int A_ROWS = THREADS / (KC / 4), A_PASSES = BM / A_ROWS;
   const long long M = (long long)p.N * p.Ho * p.Wo;
@@ -79,9 +79,9 @@ static void host_conv(const ConvP& p) {
       const int warp_m = warp / WN, warp_n = warp - warp_m * WN;
       float a[MT][4][4];
       memcpy(a, &acc[size_t(tid) * MT * 16], sizeof(a));
-      const bool uniform = warp_rows_uniform<BN>(p, m0, warp);
+      const bool uniform = warp_rows_uniform<BM, BN>(p, m0, warp);
       float s[4][2], q[4][2];
-      epilogue_thread<BN>(p, m0, warp, lane, a, uniform, s, q);
+      epilogue_thread<BM, BN>(p, m0, warp, lane, a, uniform, s, q);
       if (p.stats != nullptr && uniform) {
         const long long first = m0 + warp_m * (16 * MT);
         if (first < M) {
@@ -100,12 +100,14 @@ static void host_conv(const ConvP& p) {
 }
 
 struct HostOps {
-  void conv(const ConvP& p) {
-    const bool k32 = p.Cin % 32 == 0;
+  template <int BM, int BN>
+  static void conv_k(const ConvP& p) { p.Cin % 32 == 0 ? host_conv<BM, BN, 32>(p) : host_conv<BM, BN, 16>(p); }
+  void conv(const ConvP& p) {       // the launcher's dispatch (csrc/nr_encoder.cu launch_conv), 148 SMs assumed for the automatic choice
+    const int bm = p.bm != 0 ? p.bm : pick_bm(p.Cout, (long long)p.N * p.Ho * p.Wo, 148);
     switch (p.Cout) {
-      case 32: k32 ? host_conv<32, 32>(p) : host_conv<32, 16>(p); break;
-      case 64: k32 ? host_conv<64, 32>(p) : host_conv<64, 16>(p); break;
-      default: k32 ? host_conv<128, 32>(p) : host_conv<128, 16>(p); break;
+      case 32: bm == 256 ? conv_k<256, 32>(p) : conv_k<128, 32>(p); break;
+      case 64: bm == 64 ? conv_k<64, 64>(p) : conv_k<128, 64>(p); break;
+      default: bm == 64 ? conv_k<64, 128>(p) : conv_k<128, 128>(p); break;
     }
   }
   void conv7(const Conv7P& p) {
@@ -272,7 +274,7 @@ extern "C" int nr_cpu_depth_init_dims(int h, int w, int* fh, int* fw, int* tenso
 // one convolution: w [cout][cin][ks][ks] (PyTorch layout, packed here), x / y / res channel-last
 extern "C" int nr_cpu_conv2d(const float* x, const float* w, const float* bias, const float* res, float* y, double* stats, int n, int h, int wd,
                              int cin, int cout, int ks, int stride, int reflect, int cin_rot, int x_stride, int x_off, int y_stride, int y_off, int pad,
-                             int cin_ref) {
+                             int cin_ref, int bm) {
   enc::NetSpec* spec = new enc::NetSpec;
   spec->count = 0; spec->total = 0;
   spec->conv(cout, cin, ks, cin_rot, 0, cin_ref);
@@ -286,7 +288,7 @@ extern "C" int nr_cpu_conv2d(const float* x, const float* w, const float* bias, 
   p.pad = pad >= 0 ? pad : (ks - 1) / 2;
   p.Ho = enc::conv_out(h, ks, stride, p.pad); p.Wo = enc::conv_out(wd, ks, stride, p.pad);
   p.x_stride = x_stride; p.x_off = x_off; p.y_stride = y_stride; p.y_off = y_off; p.res_stride = cout; p.res_off = 0;
-  p.tf32x1 = 0;
+  p.tf32x1 = 0; p.bm = bm;
   HostOps ops;
   ops.conv(p);
   return 0;

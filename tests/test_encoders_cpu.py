@@ -98,16 +98,20 @@ def test_layer_graphs_on_the_host_match_the_reference(harness, tag):
     assert float((feat[..., 32:].permute(0, 3, 1, 2) - c["img_feats"]).abs().max()) < 5e-5
 
 
-@pytest.mark.parametrize("n,h,w,cin,cout,ks,stride,reflect,rot,pad,cin_ref", [
-    (2, 9, 11, 16, 32, 3, 2, 1, 0, -1, 0),      # Cin 16 (KC 16), stride 2, odd sizes, images share a CTA
-    (3, 7, 9, 32, 64, 3, 1, 0, 0, -1, 0),       # zero padding, a warp's rows straddle two images
-    (1, 12, 13, 64, 128, 3, 1, 1, 32, -1, 0),   # 128 outputs (4 m-tiles per warp), rotated input channels
-    (2, 8, 8, 32, 32, 1, 2, 1, 0, -1, 0),       # 1x1 stride 2 (the downsample branch)
-    (1, 20, 20, 128, 64, 3, 1, 1, 0, -1, 0),    # 4 CTAs, the last one partial
-    (2, 22, 26, 16, 32, 8, 2, 1, 0, 2, 12),     # ResEncoder.conv1: 8x8 stride 2 padding 2, 12 reference channels packed into 16
-    (1, 10, 12, 48, 32, 1, 1, 1, 0, -1, 0),     # DepthInitNet.conv_out: 48 inputs (three K steps of 16)
+@pytest.mark.parametrize("n,h,w,cin,cout,ks,stride,reflect,rot,pad,cin_ref,bm", [
+    (2, 9, 11, 16, 32, 3, 2, 1, 0, -1, 0, 128),      # Cin 16 (KC 16), stride 2, odd sizes, images share a CTA
+    (3, 7, 9, 32, 64, 3, 1, 0, 0, -1, 0, 128),       # zero padding, a warp's rows straddle two images
+    (1, 12, 13, 64, 128, 3, 1, 1, 32, -1, 0, 128),   # 128 outputs (4 m-tiles per warp), rotated input channels
+    (2, 8, 8, 32, 32, 1, 2, 1, 0, -1, 0, 128),       # 1x1 stride 2 (the downsample branch)
+    (1, 20, 20, 128, 64, 3, 1, 1, 0, -1, 0, 128),    # 4 CTAs, the last one partial
+    (2, 22, 26, 16, 32, 8, 2, 1, 0, 2, 12, 0),       # ResEncoder.conv1: 8x8 stride 2 padding 2, 12 reference channels packed into 16
+    (1, 10, 12, 48, 32, 1, 1, 1, 0, -1, 0, 0),       # DepthInitNet.conv_out: 48 inputs (three K steps of 16)
+    (3, 9, 10, 64, 128, 3, 1, 1, 0, -1, 0, 64),      # 64-pixel tiles, 128 outputs (two m-tiles per warp), images straddle CTAs and warps
+    (2, 7, 11, 32, 64, 3, 2, 1, 0, -1, 0, 64),       # 64-pixel tiles, 64 outputs (one m-tile per warp)
+    (3, 13, 15, 32, 32, 3, 1, 1, 0, -1, 0, 256),     # 256-pixel tiles, 32 outputs (two m-tiles per warp, two pipeline stages)
+    (2, 18, 20, 16, 32, 3, 2, 0, 0, -1, 0, 256),     # 256-pixel tiles, Cin 16, zero padding, stride 2
 ])
-def test_emulated_tensor_core_conv_matches_conv2d(harness, n, h, w, cin, cout, ks, stride, reflect, rot, pad, cin_ref):
+def test_emulated_tensor_core_conv_matches_conv2d(harness, n, h, w, cin, cout, ks, stride, reflect, rot, pad, cin_ref, bm):
     g = torch.Generator().manual_seed(cin * 1000 + cout + ks)
     cr = cin_ref or cin
     x = torch.randn(n, cin, h, w, generator=g)
@@ -130,7 +134,7 @@ def test_emulated_tensor_core_conv_matches_conv2d(harness, n, h, w, cin, cout, k
     stats = torch.zeros(n, cout, 2, dtype=torch.float64)
     wt_c, b_c, r_c = wt.contiguous(), bias.contiguous(), res.contiguous()
     rc = harness.nr_cpu_conv2d(C.c_void_p(xbuf.data_ptr()), C.c_void_p(wt_c.data_ptr()), C.c_void_p(b_c.data_ptr()), C.c_void_p(r_c.data_ptr()),
-                               C.c_void_p(ybuf.data_ptr()), C.c_void_p(stats.data_ptr()), n, h, w, cin, cout, ks, stride, reflect, rot, xs, xo, ys, yo, pad, cin_ref)
+                               C.c_void_p(ybuf.data_ptr()), C.c_void_p(stats.data_ptr()), n, h, w, cin, cout, ks, stride, reflect, rot, xs, xo, ys, yo, pad, cin_ref, bm)
     assert rc == 0
     got = ybuf[..., yo:yo + cout].permute(0, 3, 1, 2)
     assert float((got - want).abs().max()) < 2e-5
