@@ -734,6 +734,11 @@ def run_headline(ctx, args):
             enc["frame_with_encoders"] = {"ms_per_frame": frame_ms + enc["ms_per_frame"], "unit": "ray-samples/s",
                                           "value": samples_per_step / (frame_ms + enc["ms_per_frame"]) * 1e3,
                                           "what": "headline step (render, encoder outputs given) + native encoders of the 8 reference views"}
+            di = enc.get("depth_init_net", {}).get("ms_per_frame")
+            if di is not None:      # the whole per-frame path of the gen_depth model in inference: init net -> encoders -> render
+                tot = frame_ms + enc["ms_per_frame"] + di
+                enc["frame_gen_depth"] = {"ms_per_frame": tot, "unit": "ray-samples/s", "value": samples_per_step / tot * 1e3,
+                                          "what": "headline step + native encoders + native DepthInitNet (sum of the three device-timed stages)"}
             line["aux"]["encoders"] = enc
         except Exception as e:
             line["aux"]["encoders"] = {"error": f"{type(e).__name__}: {e}"}
