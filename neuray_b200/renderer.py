@@ -99,7 +99,10 @@ class FramePack:
             elif tuple(rf.shape[-2:]) != (fh, fw) or rf.shape[1] != 32:
                 raise _lib.NeurayB200Error(f"ray_feats {tuple(rf.shape)} do not match the image encoder's output size {(fh, fw)} for {h}x{w} images")
         else:
-            imf = ref_imgs_info["img_feats"]
+            imf = ref_imgs_info.get("img_feats")
+            if rf is None or imf is None:
+                raise _lib.NeurayB200Error("ref_imgs_info needs the encoder outputs 'ray_feats' and 'img_feats' [rfn,32,fh,fw] "
+                                           "(or render through an owner with native encoders: NeuralRayFrameRenderer)")
             if rf.shape != imf.shape or rf.shape[1] != 32:
                 raise _lib.NeurayB200Error(f"ray_feats {tuple(rf.shape)} and img_feats {tuple(imf.shape)} must both be [rfn,32,fh,fw]")
             fh, fw = rf.shape[-2:]
