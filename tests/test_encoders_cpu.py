@@ -177,3 +177,35 @@ def test_depth_init_net_graph_on_the_host_matches_the_reference(harness):
     err = float((got - out).abs().max())
     assert err < 1e-4, err
     assert bool(torch.all(buf[..., 32:] == 9.0))
+
+
+def test_parameter_containers_carry_the_reference_state_dicts():
+    """encoders.ImageEncoder / VisEncoder / init_nets.DepthInitNet: names, order and shapes of state_dict() equal the unmodified
+    reference modules' (recorded in the goldens), so a reference checkpoint loads strict=True; the library's layer tables have
+    the same tensor counts; and there is no CPU path."""
+    from neuray_b200 import _lib, encoders, init_nets
+    z = np.load(os.path.join(GOLDEN_DIR, "encoders.npz"))
+    zi = np.load(os.path.join(GOLDEN_DIR, "depth_init_net.npz"))
+    want = {"image": json.loads(str(z["image_shapes"])), "vis": json.loads(str(z["vis_shapes"])), "depth_init": json.loads(str(zi["shapes"]))}
+    mods = {"image": encoders.ImageEncoder(), "vis": encoders.VisEncoder(), "depth_init": init_nets.DepthInitNet()}
+    names = {"image": encoders.image_param_names(), "vis": encoders.vis_param_names(), "depth_init": init_nets.param_names()}
+    for k, m in mods.items():
+        sd = m.state_dict()
+        assert list(sd) == list(want[k]) == names[k], k
+        assert {n: list(v.shape) for n, v in sd.items()} == want[k], k
+        m.load_state_dict(orc.encoder_test_weights(want[k], 1), strict=True)
+    lay = _lib.NrEncoderLayout()
+    _lib.check(_lib.lib().nr_encoder_layout(C.byref(lay)), "nr_encoder_layout")
+    assert (lay.image_tensors, lay.vis_tensors, lay.depth_init_tensors) == (len(want["image"]), len(want["vis"]), len(want["depth_init"]))
+    # conv weights keep their element count in the packed buffers, except ResEncoder.conv1 (12 -> 16 input channels)
+    n_img = sum(int(np.prod(s)) for s in want["image"].values())
+    assert n_img <= lay.image_packed_floats <= n_img + 4 * len(want["image"])
+    n_di = sum(int(np.prod(s)) for s in want["depth_init"].values()) + 32 * 4 * 64
+    assert n_di <= lay.depth_init_packed_floats <= n_di + 4 * len(want["depth_init"])
+    with pytest.raises(_lib.NeurayB200Error):
+        with torch.no_grad():
+            mods["image"](torch.zeros(1, 3, 32, 32))
+    assert encoders.image_dims(800, 800) == (200, 200) and init_nets.dims(768, 1008) == (192, 252) and encoders.image_dims(40, 52) == (12, 16)
+    fh, fw = C.c_int(), C.c_int()
+    assert _lib.lib().nr_image_encoder_dims(16, 16, C.byref(fh), C.byref(fw)) != 0          # below the smallest supported image
+    assert _lib.lib().nr_image_encoder_workspace(8, 800, 800) > 0 and _lib.lib().nr_depth_init_workspace(8, 800, 800) > 0
