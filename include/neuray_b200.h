@@ -313,6 +313,39 @@ int nr_depth_init_pack(const float* const* params, int n_params, float* packed, 
 int nr_depth_init_fwd(const float* packed, const float* imgs, const float* depth_norm, const float* diff_feats, int n, int h, int w,
                       float* out, int out_stride, int out_off, int tf32x1, void* workspace, long long workspace_bytes, void* stream);
 
+/* ---- CostVolumeInitNet (reference network/init_net.py:113-254) ----------------------------------
+ * nr_mvsnet_*: the frozen MVSNet (network/mvsnet/mvsnet.py: FeatureNet, homography cost volume, CostRegNet) behind
+ * construct_cost_volume_with_src (init_net.py:113-160), inference.  `params`: the 89 tensors of MVSNet.state_dict() without
+ * num_batches_tracked, in order: per layer the conv weight, then the norm's weight, bias, running_mean, running_var (or the
+ * conv bias for feature.feature / cost_regularization.prob); BatchNorm is folded at pack time.  Outputs, channel-last:
+ * prob [rfn,ho,wo,dn] = softmax over the depth planes of the regularised cost volume (what volume_conv2d consumes) and
+ * depth [rfn,ho,wo] = the regressed metric depth, ho x wo from nr_mvsnet_dims (h/4 x w/4; evaluation at 800x800 / 768x1024
+ * runs the network at 640x640 / 576x768 and resizes the cost volume back, init_net.py:120-139,155). */
+typedef struct NrMvsIn {
+  const float* ref_imgs; const float* src_imgs;   /* [rfn,3,h,w], [sn,3,h,w], values in 0..1 */
+  const float* ref_Ks; const float* ref_poses;    /* [rfn,3,3], [rfn,3,4] */
+  const float* src_Ks; const float* src_poses;    /* [sn,3,3], [sn,3,4] */
+  const float* depth_range;                       /* [rfn,2] */
+  const int32_t* nn_ids;                          /* [rfn,nn]: the source views of each reference view */
+  int32_t rfn, sn, nn, h, w, dn, is_train;
+} NrMvsIn;
+int nr_mvsnet_layout(int* n_tensors, long long* packed_floats);
+int nr_mvsnet_pack(const float* const* params, int n_params, float* packed, void* stream);
+int nr_mvsnet_dims(int h, int w, int is_train, int* ho, int* wo);
+long long nr_mvsnet_workspace(const NrMvsIn* in);   /* bytes; 0: unsupported shape */
+int nr_mvsnet_fwd(const float* packed, const NrMvsIn* in, float* prob, float* depth, void* workspace, long long workspace_bytes, void* stream);
+
+/* nr_cost_volume_head_*: CostVolumeInitNet.forward after construct_cost_volume_with_src (init_net.py:247-254): res_net =
+ * ResUNetLight(out_dim=32) on the images, volume_conv2d on the softmaxed cost volume, depth_conv on the normalised regressed
+ * depth (nr_extract_depth of nr_mvsnet_fwd's depth), out_conv on their concatenation -> 32 channels into an output slot
+ * (e.g. channels 0..31 of the frame pack).  `params`: the module's tensors after `mvsnet.*` in state_dict() order (res_net.*,
+ * volume_conv2d.*, depth_conv.*, out_conv.*: 120 tensors).  prob / depth_norm: [n,h/4,w/4,cost_volume_sn] / [n,h/4,w/4]. */
+int nr_cost_volume_head_layout(int cost_volume_sn, int* n_tensors, long long* packed_floats);
+int nr_cost_volume_head_pack(int cost_volume_sn, const float* const* params, int n_params, float* packed, void* stream);
+long long nr_cost_volume_head_workspace(int cost_volume_sn, int n, int h, int w);
+int nr_cost_volume_head_fwd(int cost_volume_sn, const float* packed, const float* imgs, const float* prob, const float* depth_norm, int n, int h, int w,
+                            float* out, int out_stride, int out_off, int tf32x1, void* workspace, long long workspace_bytes, void* stream);
+
 /* Building blocks (channel-last).  nr_conv2d_nhwc: k x k convolution (k <= 8), stride 1 / 2, reflect or zero padding of
  * `pad` (-1: (ks-1)/2), cout in {32, 64, 128}, cin a multiple of 16, as an implicit GEMM on the tensor cores (3xTF32: fp32 accuracy);
  * y = conv(x) [+ bias] [+ res]; when `stats` is given, sum and sum of squares of y per (image, channel) are ADDED to

@@ -108,11 +108,25 @@ SIGNATURES = {
     "nr_depth_init_workspace": (C.c_longlong, [_i, _i, _i]),
     "nr_depth_init_pack": (C.c_int, [_vp, _i, _vp, _vp]),
     "nr_depth_init_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp, C.c_longlong, _vp]),
+    "nr_mvsnet_layout": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
+    "nr_mvsnet_pack": (C.c_int, [_vp, _i, _vp, _vp]),
+    "nr_mvsnet_dims": (C.c_int, [_i, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "nr_mvsnet_workspace": (C.c_longlong, [_vp]),
+    "nr_mvsnet_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_longlong, _vp]),
+    "nr_cost_volume_head_layout": (C.c_int, [_i, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
+    "nr_cost_volume_head_pack": (C.c_int, [_i, _vp, _i, _vp, _vp]),
+    "nr_cost_volume_head_workspace": (C.c_longlong, [_i, _i, _i, _i]),
+    "nr_cost_volume_head_fwd": (C.c_int, [_i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp, C.c_longlong, _vp]),
     "nr_depth_mean": (C.c_int, [_vp, _vp]),
     "nr_render_loss": (C.c_int, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "nr_depth_loss": (C.c_int, [_vp, _vp]),
     "nr_consistency_loss": (C.c_int, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
 }
+
+
+class NrMvsIn(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in "ref_imgs src_imgs ref_Ks ref_poses src_Ks src_poses depth_range nn_ids".split()] + \
+               [(n, C.c_int32) for n in "rfn sn nn h w dn is_train".split()]
 
 
 class NrDepthMeanParams(C.Structure):

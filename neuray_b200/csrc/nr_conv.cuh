@@ -193,19 +193,21 @@ NR_HD bool warp_rows_uniform(const ConvP& p, long long m0, int warp) {
   return first / plane == last / plane;
 }
 
-// ---- first layer: 7x7 stride-2 reflect conv of the NCHW image (Cin 3 -> 16), one thread per output pixel ----------
+// ---- first layer: 7x7 stride-2 reflect conv of the NCHW image (Cin 3 -> COUT = 16 | 32), one thread per output pixel -----
 struct Conv7P {
   const float* img;     // [N,3,H,W] (the reference's layout, read as is)
-  const float* w;       // packed [147][16]  (tap-major: (c*7 + dy)*7 + dx)
-  float* y;             // [N,Ho,Wo,16]
-  double* stats;        // [N][16][2]
-  int N, H, W, Ho, Wo;
+  const float* w;       // packed [147][Cout]  (tap-major: (c*7 + dy)*7 + dx)
+  float* y;             // [N,Ho,Wo,Cout]
+  double* stats;        // [N][Cout][2]
+  int N, H, W, Ho, Wo, Cout;
 };
 NR_HD int reflect_idx(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i); }
 
-NR_HD void conv7_pixel(const Conv7P& p, const float* w, int n, int pix, float (&out)[16]) {
+template <int COUT>
+NR_HD void conv7_pixel(const Conv7P& p, const float* w, int n, int pix, float (&out)[COUT]) {
   const int yo = pix / p.Wo, xo = pix - yo * p.Wo;
-  for (int c = 0; c < 16; ++c) out[c] = 0.f;
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) out[c] = 0.f;
   for (int c = 0; c < 3; ++c) {
     const float* im = p.img + ((long long)n * 3 + c) * p.H * p.W;
     for (int dy = 0; dy < 7; ++dy) {
@@ -213,8 +215,9 @@ NR_HD void conv7_pixel(const Conv7P& p, const float* w, int n, int pix, float (&
       for (int dx = 0; dx < 7; ++dx) {
         const int xi = reflect_idx(2 * xo - 3 + dx, p.W);
         const float v = im[(long long)yi * p.W + xi];
-        const float* wr = w + ((c * 7 + dy) * 7 + dx) * 16;
-        for (int o = 0; o < 16; ++o) out[o] = fmaf(v, wr[o], out[o]);
+        const float* wr = w + ((c * 7 + dy) * 7 + dx) * COUT;
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) out[o] = fmaf(v, wr[o], out[o]);
       }
     }
   }

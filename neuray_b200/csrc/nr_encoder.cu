@@ -192,28 +192,29 @@ __global__ void __launch_bounds__(THREADS, BN >= 128 ? 1 : 2) conv_mma_kernel(co
   }
 }
 
+template <int COUT>
 __global__ void __launch_bounds__(256) conv7_kernel(const __grid_constant__ Conv7P p) {
-  __shared__ __align__(16) float w[147 * 16];
-  for (int i = threadIdx.x; i < 147 * 16; i += 256) w[i] = p.w[i];
+  __shared__ __align__(16) float w[147 * COUT];
+  for (int i = threadIdx.x; i < 147 * COUT; i += 256) w[i] = p.w[i];
   __syncthreads();
   const int n = blockIdx.y, pix = blockIdx.x * 256 + threadIdx.x;
   const bool valid = pix < p.Ho * p.Wo;
-  float out[16];
+  float out[COUT];
 #pragma unroll
-  for (int c = 0; c < 16; ++c) out[c] = 0.f;
+  for (int c = 0; c < COUT; ++c) out[c] = 0.f;
   if (valid) {
-    conv7_pixel(p, w, n, pix, out);
-    float4* o = reinterpret_cast<float4*>(p.y + ((long long)n * p.Ho * p.Wo + pix) * 16);
+    conv7_pixel<COUT>(p, w, n, pix, out);
+    float4* o = reinterpret_cast<float4*>(p.y + ((long long)n * p.Ho * p.Wo + pix) * COUT);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) o[c] = make_float4(out[4 * c], out[4 * c + 1], out[4 * c + 2], out[4 * c + 3]);
+    for (int c = 0; c < COUT / 4; ++c) o[c] = make_float4(out[4 * c], out[4 * c + 1], out[4 * c + 2], out[4 * c + 3]);
   }
   // InstanceNorm sums of the block's pixels (one image per blockIdx.y): warp sums in fp32 -> block sums in shared memory ->
   // one fp64 atomic per channel, sum and block
-  __shared__ double cta_sums[32];
-  if (threadIdx.x < 32) cta_sums[threadIdx.x] = 0.0;
+  __shared__ double cta_sums[2 * COUT];
+  if (threadIdx.x < 2 * COUT) cta_sums[threadIdx.x] = 0.0;
   __syncthreads();
 #pragma unroll
-  for (int c = 0; c < 16; ++c) {
+  for (int c = 0; c < COUT; ++c) {
     float sv = out[c], qv = out[c] * out[c];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(256) conv7_kernel(const __grid_constant__ Conv
     }
   }
   __syncthreads();
-  if (threadIdx.x < 32) atomicAdd(p.stats + (long long)n * 32 + threadIdx.x, cta_sums[threadIdx.x]);
+  if (threadIdx.x < 2 * COUT) atomicAdd(p.stats + (long long)n * 2 * COUT + threadIdx.x, cta_sums[threadIdx.x]);
 }
 
 __global__ void __launch_bounds__(256) norm_act_kernel(const __grid_constant__ NormP p) {
@@ -370,7 +371,7 @@ struct PackJob {
   const float* src;
 };
 struct PackArgs {
-  PackJob job[96];
+  PackJob job[160];
   int count;
   float* out;
 };
@@ -455,7 +456,9 @@ struct StreamOps {
   }
   void conv7(const Conv7P& p) {
     if (rc != NR_OK) return;
-    conv7_kernel<<<dim3(unsigned((p.Ho * p.Wo + 255) / 256), p.N), 256, 0, st>>>(p);
+    const dim3 grid(unsigned((p.Ho * p.Wo + 255) / 256), p.N);
+    if (p.Cout == 16) conv7_kernel<16><<<grid, 256, 0, st>>>(p);
+    else conv7_kernel<32><<<grid, 256, 0, st>>>(p);
   }
   void norm(const NormP& p) {
     if (rc != NR_OK) return;
@@ -659,6 +662,66 @@ extern "C" int nr_depth_init_fwd(const float* packed, const float* imgs, const f
   NR_CHECK_ARG(stats > 0, "depth_init: image size whose depth_skip and ResEncoder outputs differ (init_net.py:101 would fail too)");
   NR_CHECK_ARG(ok, "depth_init: workspace too small (nr_depth_init_workspace)");
   NR_CHECK_LAUNCH("depth_init");
+  return NR_OK;
+}
+
+extern "C" int nr_cost_volume_head_layout(int cost_volume_sn, int* n_tensors, long long* packed_floats) {
+  NR_CHECK_ARG(n_tensors && packed_floats && cost_volume_sn >= 16 && cost_volume_sn % 16 == 0, "cost_volume_head_layout");
+  enc::CostVolumeHead* net = new enc::CostVolumeHead;
+  enc::build_cost_volume_head(*net, cost_volume_sn);
+  *n_tensors = net->res.spec.count;
+  *packed_floats = net->res.spec.total;
+  delete net;
+  return NR_OK;
+}
+extern "C" int nr_cost_volume_head_pack(int cost_volume_sn, const float* const* params, int n_params, float* packed, void* stream) {
+  NR_CHECK_ARG(cost_volume_sn >= 16 && cost_volume_sn % 16 == 0, "cost_volume_head_pack: cost_volume_sn must be a multiple of 16");
+  enc::CostVolumeHead* net = new enc::CostVolumeHead;
+  enc::build_cost_volume_head(*net, cost_volume_sn);
+  const int rc = cv::pack_params(net->res.spec, params, n_params, packed, (cudaStream_t)stream);
+  delete net;
+  return rc;
+}
+extern "C" long long nr_cost_volume_head_workspace(int cost_volume_sn, int n, int h, int w) {
+  if (n < 1 || h < 32 || w < 32 || cost_volume_sn < 16 || cost_volume_sn % 16 != 0) return 0;
+  enc::CostVolumeHead* net = new enc::CostVolumeHead;
+  enc::build_cost_volume_head(*net, cost_volume_sn);
+  const enc::ImageDims d = enc::image_dims(h, w);
+  const long long bytes = (long long)enc::cv_head_workspace_bytes(*net, n, h, w, d.u2h, d.u2w) + ((long long)n * d.u2h * d.u2w * 16 * 4 + 256);
+  delete net;
+  return bytes;
+}
+extern "C" int nr_cost_volume_head_fwd(int cost_volume_sn, const float* packed, const float* imgs, const float* prob, const float* depth_norm, int n,
+                                       int h, int w, float* out, int out_stride, int out_off, int tf32x1, void* workspace, long long workspace_bytes,
+                                       void* stream) {
+  if (n == 0) return NR_OK;
+  NR_CHECK_ARG(packed && imgs && prob && depth_norm && out && workspace, "cost_volume_head: null pointer");
+  NR_CHECK_ARG(n >= 1 && h >= 32 && w >= 32 && cost_volume_sn >= 16 && cost_volume_sn % 16 == 0, "cost_volume_head: shape");
+  NR_CHECK_ARG(out_stride >= 32 && out_stride % 4 == 0 && out_off % 4 == 0 && out_off + 32 <= out_stride, "cost_volume_head: output channel slot");
+  enc::CostVolumeHead* net = new enc::CostVolumeHead;
+  enc::build_cost_volume_head(*net, cost_volume_sn);
+  const enc::ImageDims d = enc::image_dims(h, w);
+  const long long stats = enc::cv_head_stats_doubles(*net, n, h, w, d.u2h, d.u2w);
+  int rc = NR_OK;
+  bool ok = false;
+  if (stats > 0) {
+    enc::Arena ar{(char*)workspace, size_t(workspace_bytes), 0, true};
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long hw = (long long)d.u2h * d.u2w;
+    float* d16 = ar.floats((long long)n * hw * 16);          // depth_conv's single input channel packed into 16 (zero weight rows for the rest)
+    if (ar.ok) {
+      cudaMemsetAsync(d16, 0, size_t(n) * hw * 16 * sizeof(float), st);
+      cv::nchw_to_nhwc_kernel<<<dim3(unsigned((hw + 31) / 32), 1, n), 256, 0, st>>>(depth_norm, d16, n, 1, hw, 16, 0);
+      cv::StreamOps ops{st, cv::sm_count(), NR_OK, tf32x1 != 0};
+      ok = enc::cost_volume_head_graph(ops, ar, *net, packed, imgs, prob, cost_volume_sn, d16, n, h, w, d.u2h, d.u2w, out, out_stride, out_off, stats, nullptr);
+      rc = ops.rc;
+    }
+  }
+  delete net;
+  if (rc != NR_OK) return rc;
+  NR_CHECK_ARG(stats > 0, "cost_volume_head: image size the decoder's skip connections cannot take");
+  NR_CHECK_ARG(ok, "cost_volume_head: workspace too small (nr_cost_volume_head_workspace)");
+  NR_CHECK_LAUNCH("cost_volume_head");
   return NR_OK;
 }
 

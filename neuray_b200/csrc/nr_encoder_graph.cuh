@@ -24,7 +24,7 @@ struct TensorSpec {
   long long n;     // elements
 };
 struct NetSpec {
-  TensorSpec t[96];
+  TensorSpec t[160];
   int count;
   long long total;
   int conv(int cout, int cin, int ks, int rot = 0, int cin_major = 0, int cin_ref = 0) {
@@ -150,6 +150,38 @@ inline void build_vis_net(VisNet& n) {
   n.conv_out = s.conv(32, 32, 1);
 }
 
+// conv3x3(cin, 32) -> ResidualBlock(32, 32) x nrb -> conv1x1(32, 32), all reflect / bias-free (the three heads of
+// CostVolumeInitNet, init_net.py:230-249; the vis encoder is the same stack with two blocks)
+struct StackNet { int conv0; ResidualIdx rb[2]; int nrb; int conv_out; int cin; };
+inline StackNet build_stack(NetSpec& s, int cin, int cin_ref, int nrb) {
+  StackNet n;
+  n.cin = cin; n.nrb = nrb;
+  n.conv0 = s.conv(32, cin, 3, 0, 0, cin_ref);
+  for (int i = 0; i < nrb; ++i) {
+    ResidualIdx& r = n.rb[i];
+    r.n0w = s.vec(32); r.n0b = s.vec(32); r.c0 = s.conv(32, 32, 3);
+    r.n1w = s.vec(32); r.n1b = s.vec(32); r.c1 = s.conv(32, 32, 3);
+  }
+  n.conv_out = s.conv(32, 32, 1);
+  return n;
+}
+// CostVolumeInitNet without its frozen MVSNet (init_net.py:227-254): res_net = ResUNetLight(out_dim=32) (3 -> 32, stages
+// [2,3,6]), volume_conv2d on the softmaxed cost volume (64 planes), depth_conv on the normalised regressed depth (1 channel,
+// packed into 16), out_conv on cat([ref_feats, volume_feats, depth_feats]); one spec, state_dict() order
+struct CostVolumeHead {
+  UNet res;
+  StackNet volume, depthc, outc;
+};
+inline void build_cost_volume_head(CostVolumeHead& n, int cost_volume_sn) {
+  NetSpec& s = n.res.spec;
+  s.count = 0; s.total = 0;
+  n.res.conv1 = s.conv(32, 3, 7, 0, 1); n.res.bn1w = s.vec(32); n.res.bn1b = s.vec(32);
+  build_unet_tail(n.res, 32, 2, 3, 6, 32);
+  n.volume = build_stack(s, cost_volume_sn, cost_volume_sn, 1);
+  n.depthc = build_stack(s, 16, 1, 1);
+  n.outc = build_stack(s, 96, 96, 1);
+}
+
 // ---- geometry ---------------------------------------------------------------------------------------------------------
 inline int conv_out(int n, int ks, int stride, int pad = -1) { return (n + 2 * (pad < 0 ? (ks - 1) / 2 : pad) - ks) / stride + 1; }
 struct ImageDims {
@@ -180,10 +212,12 @@ struct CopyP {     // y[n, yo, xo, y_off + c] = (yo - py, xo - px) inside the so
 struct Arena {
   char* base; size_t size, used;
   bool ok;
+  size_t peak = 0;     // high-water mark (graphs that release intermediates reset `used`)
   void* take(size_t bytes) {
     const size_t a = (used + 255) & ~size_t(255);
     if (base != nullptr && a + bytes > size) { ok = false; return base; }
     used = a + bytes;
+    if (used > peak) peak = used;
     return base != nullptr ? base + a : nullptr;
   }
   float* floats(long long n) { return (float*)take(size_t(n) * sizeof(float)); }
@@ -323,12 +357,13 @@ bool image_encoder_graph(Ops& ops, Arena& ar, const ImageNet& net, const float* 
     ops.zero(b.stats_base, size_t(stats_cap) * sizeof(double));
   }
   // conv1 + bn1 + relu
-  double* st0 = b.stats(16);
-  float* c1 = ar.floats((long long)N * d.h0 * d.w0 * 16);
+  const int c0 = net.inplanes;      // 16 (image_encoder) or 32 (CostVolumeInitNet.res_net)
+  double* st0 = b.stats(c0);
+  float* c1 = ar.floats((long long)N * d.h0 * d.w0 * c0);
   cv::Conv7P p7;
-  p7.img = imgs; p7.w = b.w(s, net.conv1); p7.y = c1; p7.stats = st0; p7.N = N; p7.H = H; p7.W = Wd; p7.Ho = d.h0; p7.Wo = d.w0;
+  p7.img = imgs; p7.w = b.w(s, net.conv1); p7.y = c1; p7.stats = st0; p7.N = N; p7.H = H; p7.W = Wd; p7.Ho = d.h0; p7.Wo = d.w0; p7.Cout = net.inplanes;
   ops.conv7(p7);
-  float* x = b.norm(c1, 16, d.h0 * d.w0, st0, b.w(s, net.bn1w), b.w(s, net.bn1b), nullptr, 0, 0, nullptr, nullptr, nullptr, 1, c1, 16, 0);
+  float* x = b.norm(c1, c0, d.h0 * d.w0, st0, b.w(s, net.bn1w), b.w(s, net.bn1b), nullptr, 0, 0, nullptr, nullptr, nullptr, 1, c1, c0, 0);
   unet_body(b, ar, net, d, x, out, out_stride, out_off);
   if (stats_used != nullptr) *stats_used = b.stats_used;
   return ar.ok;
@@ -394,6 +429,56 @@ bool vis_encoder_graph(Ops& ops, Arena& ar, const VisNet& net, const float* pack
   return ar.ok;
 }
 
+// x [N,H,W,cin] (stride / offset) -> conv0 -> residual blocks -> conv_out into the output slot
+template <class Ops>
+void run_stack(Builder<Ops>& b, const NetSpec& s, const StackNet& net, const float* xin, int x_stride, int x_off, int H, int Wd, float* y, int y_stride,
+               int y_off) {
+  int Ho, Wo;
+  const int HW = H * Wd;
+  double* st = b.stats(32);
+  float* x = b.conv(xin, x_stride, x_off, H, Wd, net.cin, 32, 3, 1, b.w(s, net.conv0), nullptr, nullptr, 0, 0, st, nullptr, 0, 0, Ho, Wo);
+  for (int i = 0; i < net.nrb; ++i) {       // ResidualBlock (ops.py:43-76)
+    const ResidualIdx& r = net.rb[i];
+    float* a0 = b.norm(x, 32, HW, st, b.w(s, r.n0w), b.w(s, r.n0b), nullptr, 0, 0, nullptr, nullptr, nullptr, 1, nullptr, 0, 0);
+    double* st1 = b.stats(32);
+    float* t = b.conv(a0, 32, 0, H, Wd, 32, 32, 3, 1, b.w(s, r.c0), nullptr, nullptr, 0, 0, st1, nullptr, 0, 0, Ho, Wo);
+    b.norm(t, 32, HW, st1, b.w(s, r.n1w), b.w(s, r.n1b), nullptr, 0, 0, nullptr, nullptr, nullptr, 1, t, 32, 0);
+    st = i + 1 < net.nrb ? b.stats(32) : nullptr;
+    x = b.conv(t, 32, 0, H, Wd, 32, 32, 3, 1, b.w(s, r.c1), nullptr, x, 32, 0, st, a0, 32, 0, Ho, Wo);
+  }
+  b.conv(x, 32, 0, H, Wd, 32, 32, 1, 1, b.w(s, net.conv_out), nullptr, nullptr, 0, 0, nullptr, y, y_stride, y_off, Ho, Wo);
+}
+
+// CostVolumeInitNet.forward after construct_cost_volume_with_src (init_net.py:247-254): imgs [N,3,H,W] (NCHW), prob
+// [N,fh,fw,sn] (softmaxed cost volume, channel-last), depth16 [N,fh,fw,16] (normalised regressed depth in channel 0, zeros
+// elsewhere) -> out[n, y, x, out_off + c], c < 32
+template <class Ops>
+bool cost_volume_head_graph(Ops& ops, Arena& ar, const CostVolumeHead& net, const float* packed, const float* imgs, const float* prob, int sn,
+                            const float* depth16, int N, int H, int Wd, int fh, int fw, float* out, int out_stride, int out_off, long long stats_cap,
+                            long long* stats_used) {
+  const NetSpec& s = net.res.spec;
+  const ImageDims d = image_dims(H, Wd);
+  if (!dims_ok(d) || d.u2h != fh || d.u2w != fw || sn != net.volume.cin) return false;
+  Builder<Ops> b{ops, ar, packed, N, nullptr, 0, stats_cap};
+  if (stats_cap > 0) {
+    b.stats_base = ar.doubles(stats_cap);
+    ops.zero(b.stats_base, size_t(stats_cap) * sizeof(double));
+  }
+  float* cat = ar.floats((long long)N * fh * fw * 96);           // [ref_feats 32 | volume_feats 32 | depth_feats 32]
+  double* st0 = b.stats(32);
+  float* c1 = ar.floats((long long)N * d.h0 * d.w0 * 32);
+  cv::Conv7P p7;
+  p7.img = imgs; p7.w = b.w(s, net.res.conv1); p7.y = c1; p7.stats = st0; p7.N = N; p7.H = H; p7.W = Wd; p7.Ho = d.h0; p7.Wo = d.w0; p7.Cout = 32;
+  ops.conv7(p7);
+  float* x = b.norm(c1, 32, d.h0 * d.w0, st0, b.w(s, net.res.bn1w), b.w(s, net.res.bn1b), nullptr, 0, 0, nullptr, nullptr, nullptr, 1, c1, 32, 0);
+  unet_body(b, ar, net.res, d, x, cat, 96, 0);
+  run_stack(b, s, net.volume, prob, sn, 0, fh, fw, cat, 96, 32);
+  run_stack(b, s, net.depthc, depth16, 16, 0, fh, fw, cat, 96, 64);
+  run_stack(b, s, net.outc, cat, 96, 0, fh, fw, out, out_stride, out_off);
+  if (stats_used != nullptr) *stats_used = b.stats_used;
+  return ar.ok;
+}
+
 // dry runs: the arena hands out fake (never dereferenced) addresses so that in-place reuse is counted once
 static char* const DRY_BASE = (char*)0x100000;
 struct NullOps {
@@ -431,6 +516,20 @@ inline size_t depth_init_workspace_bytes(const DepthInitNet& net, int N, int H, 
   NullOps ops;
   Arena ar{DRY_BASE, ~size_t(0) / 2, 0, true};
   depth_init_graph(ops, ar, net, nullptr, nullptr, nullptr, N, H, W, (float*)DRY_BASE, 32, 0, depth_init_stats_doubles(net, N, H, W), nullptr);
+  return ar.used + 256;
+}
+inline long long cv_head_stats_doubles(const CostVolumeHead& net, int N, int H, int W, int fh, int fw) {
+  NullOps ops;
+  Arena ar{DRY_BASE, ~size_t(0) / 2, 0, true};
+  long long used = 0;
+  cost_volume_head_graph(ops, ar, net, nullptr, nullptr, nullptr, net.volume.cin, nullptr, N, H, W, fh, fw, (float*)DRY_BASE, 32, 0, 0, &used);
+  return used;
+}
+inline size_t cv_head_workspace_bytes(const CostVolumeHead& net, int N, int H, int W, int fh, int fw) {
+  NullOps ops;
+  Arena ar{DRY_BASE, ~size_t(0) / 2, 0, true};
+  cost_volume_head_graph(ops, ar, net, nullptr, nullptr, nullptr, net.volume.cin, nullptr, N, H, W, fh, fw, (float*)DRY_BASE, 32, 0,
+                         cv_head_stats_doubles(net, N, H, W, fh, fw), nullptr);
   return ar.used + 256;
 }
 inline size_t image_workspace_bytes(const ImageNet& net, int N, int H, int W) {

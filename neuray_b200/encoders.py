@@ -285,7 +285,7 @@ def usable(owner, ref_imgs_info):
     rf = ref_imgs_info.get("ray_feats")
     if rf is None:
         from . import init_nets
-        if getattr(owner, "init_net", None) is None or not init_nets.usable(owner.init_net, ref_imgs_info):
+        if getattr(owner, "init_net", None) is None or not init_nets.init_usable(owner.init_net, ref_imgs_info):
             return False
     if torch.is_grad_enabled() and (any(p.requires_grad for p in ie.parameters()) or any(p.requires_grad for p in ve.parameters())
                                     or (rf is not None and rf.requires_grad)):
@@ -303,7 +303,7 @@ def encode_frame(owner, ref_imgs_info, feat):
         to_channel_last(ref_imgs_info["ray_feats"], feat, 0)
     else:                                  # renderer.py:269 -- the owner's init net, channel-last in place
         from . import init_nets
-        init_nets.forward_into(owner.init_net, ref_imgs_info, feat, 0)
+        init_nets.init_forward_into(owner.init_net, ref_imgs_info, feat, 0)
     image_encoder_into(owner.image_encoder, imgs, feat, 32)
     vis_encoder_inplace(owner.vis_encoder, feat)
     ref_imgs_info["img_feats"] = from_channel_last(feat, 32, 32)

@@ -10,7 +10,7 @@ What is rebound:
     network.init_net's namespaces, which star-/name-import them)
   * NeuralRayBaseRenderer.render_by_depth / fine_render_impl / render_impl / render -> neuray_b200.renderer
   * network.init_net.get_diff_feats (DepthInitNet, SURVEY.md 8f row 2) -> neuray_b200.init_ops.get_diff_feats;
-    DepthInitNet.forward -> neuray_b200.init_nets (inference: the whole init net natively)
+    DepthInitNet.forward / CostVolumeInitNet.forward -> neuray_b200.init_nets (inference: the whole init net natively, MVSNet included)
   * NeuralRayGenRenderer.predict_mean_for_depth_loss and network.loss.{RenderLoss, DepthLoss, ConsistencyLoss, name2loss}
      -> neuray_b200.losses
   * inference only: `render` runs image_encoder / vis_encoder natively into the frame pack (SURVEY.md 8f row 1,
@@ -51,6 +51,7 @@ def install():
         _rebind(ref_init, "get_diff_feats", init_ops.get_diff_feats)      # DepthInitNet's per-frame reprojection features
         # inference: the whole DepthInitNet natively (ResEncoder on the tensor cores); with a gradient wanted, the reference's
         _rebind(ref_init.DepthInitNet, "forward", init_nets.forward_or_reference(ref_init.DepthInitNet.forward))
+        _rebind(ref_init.CostVolumeInitNet, "forward", init_nets.cost_volume_forward_or_reference(ref_init.CostVolumeInitNet.forward))
     except Exception:      # init_net needs inplace_abn / kornia; the rendering path does not
         pass
     for name in render_ops.__all__:

@@ -94,7 +94,7 @@ class FramePack:
         if encoder_owner is not None:
             fh, fw = encoders.image_dims(h, w)
             if rf is None:       # the owner's init net writes its ray_feats straight into the pack (encoders.encode_frame)
-                if init_nets.dims(h, w) != (fh, fw):
+                if not hasattr(encoder_owner.init_net, "mvsnet") and init_nets.dims(h, w) != (fh, fw):
                     raise _lib.NeurayB200Error(f"init net and image encoder disagree on the map size for {h}x{w} images")
             elif tuple(rf.shape[-2:]) != (fh, fw) or rf.shape[1] != 32:
                 raise _lib.NeurayB200Error(f"ray_feats {tuple(rf.shape)} do not match the image encoder's output size {(fh, fw)} for {h}x{w} images")
@@ -482,21 +482,24 @@ class NeuralRayFrameRenderer(NeuralRayRenderPath):
 
 
 class NeuralRayGenFrameRenderer(NeuralRayFrameRenderer):
-    """The inference frame path of NeuralRayGenRenderer with init_net_type 'depth' (reference renderer.py:255-327, the
-    neuray_gen_depth model): DepthInitNet -> image_encoder + vis_encoder -> chunk loop, every stage native, the three front
+    """The inference frame path of NeuralRayGenRenderer (reference renderer.py:255-327; init_net_type 'depth' = the neuray_gen_depth
+    model, 'cost_volume' = neuray_gen_cost_volume with its MVSNet): init net -> image_encoder + vis_encoder -> chunk loop, every stage native, the three front
     stages writing the channel-last frame pack in place.  State-dict names are the reference's (`init_net.*`,
     `image_encoder.*`, `vis_encoder.*`, `dist_decoder.*`, ...), so a gen-model checkpoint loads unchanged.
-    ref_imgs_info carries imgs, depth, depth_range, poses, Ks (the init net's inputs); forward(data) like the reference."""
+    ref_imgs_info carries imgs, depth_range, poses, Ks and depth (DepthInitNet) or nn_ids + data['src_imgs_info'] (CostVolumeInitNet);
+    forward(data) like the reference."""
 
     def __init__(self, cfg):
         super().__init__(cfg)
-        if self.cfg.get("init_net_type", "depth") != "depth":
-            raise NotImplementedError("only init_net_type 'depth' (DepthInitNet) is native; CostVolumeInitNet / MVSNet is not built (DESIGN.md 7)")
-        self.init_net = init_nets.DepthInitNet(self.cfg.get("init_net_cfg", {}))
+        kind = self.cfg.get("init_net_type", "depth")
+        if kind not in ("depth", "cost_volume"):
+            raise ValueError(f"init_net_type {kind!r}")
+        self.init_net = (init_nets.DepthInitNet if kind == "depth" else init_nets.CostVolumeInitNet)(self.cfg.get("init_net_cfg", {}))
 
     def render_call(self, que_imgs_info, ref_imgs_info, is_train, src_imgs_info=None):
         """renderer.py:268-270: the init net's ray_feats go straight into the frame pack (no 'ray_feats' entry needed)."""
         ref_imgs_info.pop("ray_feats", None)
+        ref_imgs_info[init_nets.SRC_KEY] = src_imgs_info
         if not encoders.usable(self, ref_imgs_info):
             raise _lib.NeurayB200Error("NeuralRayGenFrameRenderer is the INFERENCE frame path (CUDA tensors, torch.no_grad() or frozen front-end "
                                        "parameters); training goes through patch.install() on the reference's NeuralRayGenRenderer")

@@ -690,3 +690,143 @@ def depth_init_net(W, pre, ref, diff=None):
     d = torch.relu(F.conv2d(depth, W["depth_skip.0.weight"], W["depth_skip.0.bias"], stride=2))
     d = F.conv2d(d, W["depth_skip.2.weight"], W["depth_skip.2.bias"], stride=2)
     return F.conv2d(torch.cat([d, feats], 1), W["conv_out.weight"], W["conv_out.bias"])
+
+
+# --------------------------------------------------------------------------------------------------
+# CostVolumeInitNet's frozen MVSNet: network/mvsnet/mvsnet.py:7-66,124-141,
+# network/mvsnet/modules.py:25-70, network/init_net.py:103-168; pinned by tests/golden/mvsnet.npz.
+# ABN / InPlaceABN in eval mode = batch_norm with the running statistics + leaky_relu(0.01) (oracle/ref_import.py).
+
+
+def _abn(W, pre, x):
+    x = F.batch_norm(x, W[pre + ".running_mean"], W[pre + ".running_var"], W[pre + ".weight"], W[pre + ".bias"], False, 0.0, 1e-5)
+    return F.leaky_relu(x, 0.01)
+
+
+def mvs_feature_net(W, pre, x):
+    """FeatureNet.forward (mvsnet.py:25-29): zero-padded 3x3 / 5x5 convolutions + ABN, a final biased 3x3."""
+    for name, stride, pad in (("conv0", 1, 1), ("conv1", 1, 1), ("conv2", 2, 2), ("conv3", 1, 1), ("conv4", 1, 1), ("conv5", 2, 2), ("conv6", 1, 1)):
+        x = _abn(W, f"{pre}{name}.bn", F.conv2d(x, W[f"{pre}{name}.conv.weight"], None, stride, pad))
+    return F.conv2d(x, W[pre + "feature.weight"], W[pre + "feature.bias"], 1, 1)
+
+
+def mvs_homo_warp(src_feat, src_proj, ref_proj_inv, depth_values):
+    """modules.py:25-63 for one reference view: src_feat [C,h,w], 4x4 matrices, depth_values [D] -> [C,D,h,w]."""
+    C, h, w = src_feat.shape
+    T = src_proj @ ref_proj_inv
+    R, t = T[:3, :3], T[:3, 3:]
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float32), torch.arange(w, dtype=torch.float32), indexing="ij")
+    grid = torch.stack([xs.reshape(-1), ys.reshape(-1), torch.ones(h * w)], 0)              # [3,hw]
+    pts = (R @ (grid[:, None, :] * depth_values.view(1, -1, 1)).reshape(3, -1)) + t            # [3,D*hw]
+    z = pts[2:].clone()
+    z[z < 1e-4] = 1e-4
+    xy = (pts[:2] / z).t()[None]                                                               # [1,D*hw,2] pixel coordinates
+    out = bilinear_sample(src_feat[None], xy, h, w, padding_mode="zeros", align_corners=True)  # [1,D*hw,C]
+    return out[0].t().reshape(C, -1, h, w)
+
+
+def mvs_cost_reg(W, pre, vol):
+    """CostRegNet.forward (mvsnet.py:52-66) on vol [1,32,D,h,w] -> [1,1,D,h,w]."""
+    c3 = lambda name, x, s: _abn(W, f"{pre}{name}.bn", F.conv3d(x, W[f"{pre}{name}.conv.weight"], None, s, 1))
+    up = lambda name, x: _abn(W, f"{pre}{name}.1", F.conv_transpose3d(x, W[f"{pre}{name}.0.weight"], None, 2, 1, 1))
+    conv0 = c3("conv0", vol, 1)
+    conv2 = c3("conv2", c3("conv1", conv0, 2), 1)
+    conv4 = c3("conv4", c3("conv3", conv2, 2), 1)
+    x = c3("conv6", c3("conv5", conv4, 2), 1)
+    x = conv4 + up("conv7", x)
+    x = conv2 + up("conv9", x)
+    x = conv0 + up("conv11", x)
+    return F.conv3d(x, W[pre + "prob.weight"], W[pre + "prob.bias"], 1, 1)
+
+
+def mvs_project_matrix(ratio, Ks, poses):
+    """init_net.py:103-111."""
+    S = torch.diag(torch.tensor([ratio, ratio, 1.0]))
+    P = S[None] @ Ks @ poses
+    return torch.cat([P, torch.tensor([0.0, 0.0, 0.0, 1.0]).view(1, 1, 4).repeat(P.shape[0], 1, 1)], 1)
+
+
+def mvs_depth_vals(depth_range, dn):
+    """init_net.py:162-168."""
+    near, far = depth_range[:, 0], depth_range[:, 1]
+    interval = (1 / far - 1 / near) / (dn - 1)
+    vals = 1 / (1 / near[:, None] + torch.arange(0, dn - 1)[None, :] * interval[:, None])
+    return torch.cat([vals, far[:, None]], 1)
+
+
+def mvs_cost_volume(W, pre, ref, src, dn, is_train):
+    """construct_cost_volume_with_src (init_net.py:113-160): returns (softmaxed cost volume [rfn,dn,h/4,w/4], depth [rfn,h/4,w/4])."""
+    imgs_r, imgs_s = ref["imgs"], src["imgs"]
+    rfn, _, h, w = imgs_r.shape
+    ratio = 1.0
+    if not is_train and max(h, w) >= 800:
+        size = (576, 768) if (h, w) == (768, 1024) else (640, 640) if (h, w) == (800, 800) else None
+        if size is not None:
+            imgs_r, imgs_s = F.interpolate(imgs_r, size, mode="bilinear"), F.interpolate(imgs_s, size, mode="bilinear")
+            ratio = size[0] / h
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    rf = mvs_feature_net(W, pre + "feature.", (imgs_r - mean) / std)
+    sf = mvs_feature_net(W, pre + "feature.", (imgs_s - mean) / std)
+    rp = mvs_project_matrix(0.25 * ratio, ref["Ks"], ref["poses"])
+    sp = mvs_project_matrix(0.25 * ratio, src["Ks"], src["poses"])
+    vals = mvs_depth_vals(ref["depth_range"], dn)
+    nn_ids = ref["nn_ids"]
+    out = []
+    for i in range(rfn):
+        s = rf[i][:, None].repeat(1, dn, 1, 1)
+        q = s ** 2
+        inv = torch.inverse(rp[i])
+        for k in nn_ids[i].tolist():
+            wv = mvs_homo_warp(sf[k], sp[k], inv, vals[i])
+            s = s + wv
+            q = q + wv ** 2
+        n = nn_ids.shape[1] + 1
+        var = q / n - (s / n) ** 2
+        out.append(mvs_cost_reg(W, pre + "cost_regularization.", var[None])[0, 0])
+    cost = torch.stack(out, 0)
+    cost[torch.isnan(cost)] = 0
+    if ratio != 1.0:
+        cost = F.interpolate(cost, (h // 4, w // 4), mode="bilinear")
+    cost = F.softmax(cost, 1)
+    return cost, torch.sum(cost * vals.view(rfn, dn, 1, 1), 1)
+
+
+def mvs_test_weights(template, seed):
+    """Seeded MVSNet parameters: conv weights ~ N(0, 2/fan_in), norm weights U(0.5,1.5), running_var U(0.5,1.5), rest N(0,0.1)."""
+    rs = np.random.RandomState(seed)
+    out = {}
+    for name, shape in template.items():
+        shape = tuple(shape)
+        if len(shape) >= 4:
+            a = rs.standard_normal(shape) * math.sqrt(2.0 / (int(np.prod(shape[1:])) if "conv" in name and ".0.weight" not in name else int(np.prod(shape[2:])) * shape[0]))
+        elif name.endswith("running_var") or (name.endswith(".weight") and len(shape) == 1):
+            a = rs.uniform(0.5, 1.5, shape)
+        else:
+            a = rs.standard_normal(shape) * 0.1
+        if "prob.weight" in name:
+            a = a * 0.05          # keep the logits of the depth softmax moderate: a saturated (one-hot) volume would test an argmax
+        out[name] = torch.from_numpy(a.astype(np.float32))
+    return out
+
+
+def _conv_stack(W, pre, x, nrb=1):
+    """conv3x3 -> ResidualBlock x nrb -> conv1x1 (init_net.py:230-249; ops.py:43-76), all reflect / bias-free."""
+    x = _conv2d(x, W[f"{pre}.0.weight"])
+    for i in range(1, nrb + 1):
+        p = f"{pre}.{i}.conv"
+        t = _conv2d(torch.relu(_inorm(W, p + ".0", x)), W[p + ".2.weight"])
+        t = _conv2d(torch.relu(_inorm(W, p + ".3", t)), W[p + ".5.weight"])
+        x = t + x
+    return F.conv2d(x, W[f"{pre}.{nrb + 1}.weight"])
+
+
+def cost_volume_init_net(W, pre, ref, src, is_train, sn=64):
+    """CostVolumeInitNet.forward (init_net.py:247-254); W under `pre` ('' or 'init_net.'), ref carries nn_ids."""
+    W = {k[len(pre):]: v for k, v in W.items() if k.startswith(pre)}
+    cost, depth = mvs_cost_volume(W, "mvsnet.", ref, src, sn, is_train)
+    ref_feats = res_unet_light(W, "res_net.", ref["imgs"], blocks=(2, 3, 6))
+    volume_feats = _conv_stack(W, "volume_conv2d", cost)
+    d = extract_depth_for_init(ref["depth_range"], depth[:, None])
+    depth_feats = _conv_stack(W, "depth_conv", d)
+    return _conv_stack(W, "out_conv", torch.cat([ref_feats, torch.cat([volume_feats, depth_feats], 1)], 1))

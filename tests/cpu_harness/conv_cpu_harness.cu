@@ -110,18 +110,20 @@ struct HostOps {
       default: bm == 64 ? conv_k<64, 128>(p) : conv_k<128, 128>(p); break;
     }
   }
-  void conv7(const Conv7P& p) {
+  template <int COUT>
+  static void conv7_t(const Conv7P& p) {
     for (int n = 0; n < p.N; ++n)
       for (int pix = 0; pix < p.Ho * p.Wo; ++pix) {
-        float out[16];
-        conv7_pixel(p, p.w, n, pix, out);
-        for (int c = 0; c < 16; ++c) {
-          p.y[((long long)n * p.Ho * p.Wo + pix) * 16 + c] = out[c];
-          p.stats[((long long)n * 16 + c) * 2] += out[c];
-          p.stats[((long long)n * 16 + c) * 2 + 1] += double(out[c]) * out[c];
+        float out[COUT];
+        conv7_pixel<COUT>(p, p.w, n, pix, out);
+        for (int c = 0; c < COUT; ++c) {
+          p.y[((long long)n * p.Ho * p.Wo + pix) * COUT + c] = out[c];
+          p.stats[((long long)n * COUT + c) * 2] += out[c];
+          p.stats[((long long)n * COUT + c) * 2 + 1] += double(out[c]) * out[c];
         }
       }
   }
+  void conv7(const Conv7P& p) { p.Cout == 16 ? conv7_t<16>(p) : conv7_t<32>(p); }
   void norm(const NormP& p) {
     for (int n = 0; n < p.N; ++n)
       for (int c = 0; c < p.C; ++c) {
@@ -269,6 +271,39 @@ extern "C" int nr_cpu_depth_init_dims(int h, int w, int* fh, int* fw, int* tenso
   *tensors = net->res.spec.count;
   delete net;
   return 0;
+}
+
+// CostVolumeInitNet's head: imgs [n,3,h,w] NCHW, prob [n,fh,fw,sn] channel-last, depth_norm [n,fh,fw] -> out slot
+extern "C" int nr_cpu_cost_volume_head(int sn, const float* const* params, int n_params, const float* imgs, const float* prob, const float* depth_norm,
+                                       int n, int h, int w, float* out, int out_stride, int out_off) {
+  enc::CostVolumeHead* net = new enc::CostVolumeHead;
+  enc::build_cost_volume_head(*net, sn);
+  if (n_params != net->res.spec.count) return -1;
+  std::vector<float> packed(net->res.spec.total);
+  host_pack(net->res.spec, params, packed.data());
+  const enc::ImageDims d = enc::image_dims(h, w);
+  const long long hw = (long long)d.u2h * d.u2w;
+  std::vector<float> d16(size_t(n) * hw * 16, 0.f);
+  for (long long i = 0; i < (long long)n * hw; ++i) d16[i * 16] = depth_norm[i];
+  const long long stats = enc::cv_head_stats_doubles(*net, n, h, w, d.u2h, d.u2w);
+  const size_t bytes = enc::cv_head_workspace_bytes(*net, n, h, w, d.u2h, d.u2w);
+  std::vector<char> ws(bytes + 256);
+  char* base = (char*)((uintptr_t(ws.data()) + 255) & ~uintptr_t(255));
+  enc::Arena ar{base, bytes, 0, true};
+  HostOps ops;
+  const bool ok = stats > 0 && enc::cost_volume_head_graph(ops, ar, *net, packed.data(), imgs, prob, sn, d16.data(), n, h, w, d.u2h, d.u2w, out, out_stride,
+                                                          out_off, stats, nullptr);
+  const int count = net->res.spec.count;
+  delete net;
+  (void)count;
+  return ok ? 0 : -2;
+}
+extern "C" int nr_cpu_cost_volume_head_tensors(int sn) {
+  enc::CostVolumeHead* net = new enc::CostVolumeHead;
+  enc::build_cost_volume_head(*net, sn);
+  const int c = net->res.spec.count;
+  delete net;
+  return c;
 }
 
 // one convolution: w [cout][cin][ks][ks] (PyTorch layout, packed here), x / y / res channel-last

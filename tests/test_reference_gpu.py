@@ -298,3 +298,45 @@ def test_losses_patched_equal_unpatched(ref_mod):
         assert gwant[k] is not None and ggot[k] is not None, k
         err, scale = float((ggot[k] - gwant[k]).abs().max()), float(gwant[k].abs().max())
         assert err <= 1e-4 * scale + 1e-9, (k, err, scale)
+
+
+def test_cost_volume_model_eval_forward_patched_equals_unpatched(ref_mod):
+    """The neuray_gen_cost_volume model (init_net_type 'cost_volume': CostVolumeInitNet with its frozen MVSNet, random-init here) in
+    eval mode, as is and after patch.install(): the patched run goes through nr_mvsnet_fwd + nr_cost_volume_head_fwd, the native
+    encoders and the render kernels."""
+    import os
+    cfg = dict(CFG, init_net_type="cost_volume")
+    que, ref = synthetic.make_scene(64, 96, 4, seed=5, smooth=2)
+    _, src = synthetic.make_scene(64, 96, 3, seed=6, smooth=2)
+    ref = dict(ref)
+    ref.pop("ray_feats"), ref.pop("img_feats")
+    rs = np.random.RandomState(5)
+    ref["imgs"] = _smooth(rs, tuple(ref["imgs"].shape), 0.0, 1.0)
+    src = {"imgs": _smooth(rs, tuple(src["imgs"].shape), 0.0, 1.0), "poses": src["poses"], "Ks": src["Ks"]}
+    ref["nn_ids"] = torch.from_numpy(np.stack([rs.permutation(3)[:2] for _ in range(4)]).astype(np.int64))
+    que = dict(que, imgs=_smooth(rs, tuple(que["imgs"].shape), 0.0, 1.0), coords=que["coords"][:, torch.from_numpy(rs.permutation(que["coords"].shape[1])[:384])].contiguous())
+    cwd = os.getcwd()
+    os.chdir(ref_import.REFERENCE_ROOT)          # CostVolumeInitNet opens network/mvsnet/mvsnet_pl.ckpt relative to the reference root
+    try:
+        net = build(ref_mod, cfg).eval()
+    finally:
+        os.chdir(cwd)
+    # soften the cost volume's logits so that the depth softmax is not an argmax (random-init / foreign-data weights saturate it)
+    with torch.no_grad():
+        net.init_net.mvsnet.cost_regularization.prob.weight.mul_(0.05)
+
+    def go():
+        data = {"que_imgs_info": synthetic.to_device(que, "cuda"), "ref_imgs_info": synthetic.to_device(ref, "cuda"),
+                "src_imgs_info": synthetic.to_device(src, "cuda"), "eval": True}
+        torch.manual_seed(7)
+        return net(data)
+
+    with torch.no_grad():
+        want = go()
+        patch.install()
+        try:
+            got = go()
+        finally:
+            patch.uninstall()
+    torch.cuda.synchronize()
+    compare_outputs(got, want, fine_bad_frac=0.01)
