@@ -541,7 +541,56 @@ def encoders_bench(dr, dev, reps=5):
         res["depth_init_net"] = init_net_bench(dr, dev, reps, timed)
     except Exception as e:
         res["depth_init_net"] = {"error": f"{type(e).__name__}: {e}"}
+    try:
+        res["cost_volume_init_net"] = cost_volume_bench(dr, dev, max(2, reps // 2), timed)
+    except Exception as e:
+        res["cost_volume_init_net"] = {"error": f"{type(e).__name__}: {e}"}
     return res
+
+
+def cost_volume_bench(dr, dev, reps, timed):
+    """CostVolumeInitNet of the same frame (init_net.py:205-254: MVSNet cost volumes of the 8 reference views from 3 neighbouring
+    source views each, 64 depth planes, evaluation resize 800 -> 640; ResUNetLight + the three conv heads), native against the
+    unmodified reference module (its frozen mvsnet_pl.ckpt weights in both) on the same GPU."""
+    from neuray_b200 import init_nets
+    imgs = dr["imgs"]
+    rfn, _, h, w = imgs.shape
+    nn_ids = torch.stack([torch.tensor([(i + 1) % rfn, (i + 2) % rfn, (i + 3) % rfn]) for i in range(rfn)]).to(dev)
+    ref = {"imgs": imgs, "depth_range": dr["depth_range"], "poses": dr["poses"], "Ks": dr["Ks"], "nn_ids": nn_ids}
+    src = {"imgs": imgs, "poses": dr["poses"], "Ks": dr["Ks"]}          # the reference views double as each other's source views
+    torch.manual_seed(0)
+    net = init_nets.CostVolumeInitNet().to(dev).eval()
+    ref_mod = _load_reference()
+    rnet = None
+    if ref_mod is not None:
+        import network.init_net as ref_init
+        import ref_import
+        cwd = os.getcwd()
+        os.chdir(ref_import.REFERENCE_ROOT)
+        try:
+            rnet = ref_init.CostVolumeInitNet({}).to(dev).eval()          # loads network/mvsnet/mvsnet_pl.ckpt
+        finally:
+            os.chdir(cwd)
+        sd = {k: v for k, v in rnet.state_dict().items()}
+        net.load_state_dict(sd, strict=False)                            # same weights in both (the head is random-init)
+    fh, fw = h // 4, w // 4
+    buf = torch.empty(rfn, fh, fw, 64, device=dev)
+    with torch.no_grad():
+        ms = timed(lambda: init_nets.cost_volume_forward_into(net, ref, src, False, buf, 0))
+        ms_mvs = timed(lambda: init_nets.mvsnet_cost_volume(net, ref, src, False))
+    out = {"ms_per_frame": ms, "ms_mvsnet_part": ms_mvs, "views": rfn, "neighbours": 3, "depth_planes": 64,
+           "what": "nr_mvsnet_fwd (FeatureNet on 16 images at 640x640, 8 variance volumes 64x160x160x32, CostRegNet, softmax + regression) + "
+                   "nr_extract_depth + nr_cost_volume_head_fwd into the frame pack"}
+    if rnet is None:
+        return out
+    with torch.no_grad():
+        ms_ref = timed(lambda: rnet(dict(ref), dict(src), False))
+        want = rnet(dict(ref), dict(src), False)
+    err = (buf[..., :32].permute(0, 3, 1, 2) - want).abs()
+    out["reference"] = {"ms_per_frame": ms_ref, "kind": "reference", "max_abs_diff": float(err.max()), "mean_abs_diff": float(err.mean()),
+                        "output_abs_max": float(want.abs().max()),
+                        "what": "the unmodified reference's CostVolumeInitNet (PyTorch eager / cuDNN, torch's default TF32 convolutions) on the same GPU"}
+    return out
 
 
 def init_net_bench(dr, dev, reps, timed):
@@ -734,6 +783,11 @@ def run_headline(ctx, args):
             enc["frame_with_encoders"] = {"ms_per_frame": frame_ms + enc["ms_per_frame"], "unit": "ray-samples/s",
                                           "value": samples_per_step / (frame_ms + enc["ms_per_frame"]) * 1e3,
                                           "what": "headline step (render, encoder outputs given) + native encoders of the 8 reference views"}
+            cvn = enc.get("cost_volume_init_net", {}).get("ms_per_frame")
+            if cvn is not None:
+                tot = frame_ms + enc["ms_per_frame"] + cvn
+                enc["frame_gen_cost_volume"] = {"ms_per_frame": tot, "unit": "ray-samples/s", "value": samples_per_step / tot * 1e3,
+                                                "what": "headline step + native encoders + native CostVolumeInitNet (MVSNet included)"}
             di = enc.get("depth_init_net", {}).get("ms_per_frame")
             if di is not None:      # the whole per-frame path of the gen_depth model in inference: init net -> encoders -> render
                 tot = frame_ms + enc["ms_per_frame"] + di
