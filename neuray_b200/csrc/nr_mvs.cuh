@@ -35,6 +35,24 @@ struct ConvP {
   const float* in_mean; const float* in_istd;   // first layer: input channels are (x - mean) * istd inside the image, 0 in the padding
 };
 
+// acc[0..COUT) += xv * w[0..COUT): the weights of one (tap, input channel) are COUT contiguous floats read by every lane of a warp
+// from the same address (one broadcast transaction); 128-bit loads keep it at one load instruction per four FMAs
+template <int COUT>
+NR_HD void axpy_row(float xv, const float* __restrict__ wr, float (&acc)[COUT]) {
+  if constexpr (COUT % 4 == 0) {
+    const float4* __restrict__ w4 = reinterpret_cast<const float4*>(wr);
+#pragma unroll
+    for (int j = 0; j < COUT / 4; ++j) {
+      const float4 w = w4[j];
+      acc[4 * j] = fmaf(xv, w.x, acc[4 * j]); acc[4 * j + 1] = fmaf(xv, w.y, acc[4 * j + 1]);
+      acc[4 * j + 2] = fmaf(xv, w.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(xv, w.w, acc[4 * j + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[o] = fmaf(xv, wr[o], acc[o]);
+  }
+}
+
 template <int COUT>
 NR_HD void conv_voxel(const ConvP& p, long long v, float (&acc)[COUT]) {
   const int wo = int(v % p.Wo);
@@ -42,29 +60,36 @@ NR_HD void conv_voxel(const ConvP& p, long long v, float (&acc)[COUT]) {
   const int ho = int(t % p.Ho), dz = int(t / p.Ho);
 #pragma unroll
   for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
-  for (int kd = 0; kd < p.kd; ++kd) {
-    int di;
-    if (p.transposed) { const int num = dz + p.pd - kd; if (num < 0 || (num % p.sd) != 0) continue; di = num / p.sd; }
-    else di = dz * p.sd - p.pd + kd;
+  // transposed (stride 2): output o gathers input i through tap k where o + pad - k = 2 i, i.e. only taps of one parity
+  const int kd0 = p.transposed ? (dz + p.pd) % p.sd : 0, kdstep = p.transposed ? p.sd : 1;
+  const int kh0 = p.transposed ? (ho + p.ph) % p.sh : 0, khstep = p.transposed ? p.sh : 1;
+  const int kw0 = p.transposed ? (wo + p.pw) % p.sw : 0, kwstep = p.transposed ? p.sw : 1;
+  const bool vec_x = (p.Cin % 4 == 0) && p.in_mean == nullptr;
+  for (int kd = kd0; kd < p.kd; kd += kdstep) {
+    const int di = p.transposed ? (dz + p.pd - kd) / p.sd : dz * p.sd - p.pd + kd;
     if (di < 0 || di >= p.D) continue;
-    for (int kh = 0; kh < p.kh; ++kh) {
-      int hi;
-      if (p.transposed) { const int num = ho + p.ph - kh; if (num < 0 || (num % p.sh) != 0) continue; hi = num / p.sh; }
-      else hi = ho * p.sh - p.ph + kh;
+    for (int kh = kh0; kh < p.kh; kh += khstep) {
+      const int hi = p.transposed ? (ho + p.ph - kh) / p.sh : ho * p.sh - p.ph + kh;
       if (hi < 0 || hi >= p.H) continue;
-      for (int kw = 0; kw < p.kw; ++kw) {
-        int wi;
-        if (p.transposed) { const int num = wo + p.pw - kw; if (num < 0 || (num % p.sw) != 0) continue; wi = num / p.sw; }
-        else wi = wo * p.sw - p.pw + kw;
+      for (int kw = kw0; kw < p.kw; kw += kwstep) {
+        const int wi = p.transposed ? (wo + p.pw - kw) / p.sw : wo * p.sw - p.pw + kw;
         if (wi < 0 || wi >= p.W) continue;
-        const float* xin = p.x + (((long long)di * p.H + hi) * p.W + wi) * p.Cin;
-        const float* wt = p.w + (long long)((kd * p.kh + kh) * p.kw + kw) * p.Cin * COUT;
-        for (int c = 0; c < p.Cin; ++c) {
-          float xv = xin[c];
-          if (p.in_mean != nullptr) xv = (xv - p.in_mean[c]) * p.in_istd[c];
-          const float* wr = wt + c * COUT;
-#pragma unroll
-          for (int o = 0; o < COUT; ++o) acc[o] = fmaf(xv, wr[o], acc[o]);
+        const float* __restrict__ xin = p.x + (((long long)di * p.H + hi) * p.W + wi) * p.Cin;
+        const float* __restrict__ wt = p.w + (long long)((kd * p.kh + kh) * p.kw + kw) * p.Cin * COUT;
+        if (vec_x) {
+          const float4* __restrict__ x4 = reinterpret_cast<const float4*>(xin);
+          for (int c4 = 0; c4 < p.Cin / 4; ++c4) {
+            const float4 xv = x4[c4];
+            const float* wr = wt + 4 * c4 * COUT;
+            axpy_row<COUT>(xv.x, wr, acc); axpy_row<COUT>(xv.y, wr + COUT, acc);
+            axpy_row<COUT>(xv.z, wr + 2 * COUT, acc); axpy_row<COUT>(xv.w, wr + 3 * COUT, acc);
+          }
+        } else {
+          for (int c = 0; c < p.Cin; ++c) {
+            float xv = xin[c];
+            if (p.in_mean != nullptr) xv = (xv - p.in_mean[c]) * p.in_istd[c];
+            axpy_row<COUT>(xv, wt + c * COUT, acc);
+          }
         }
       }
     }
@@ -93,9 +118,14 @@ NR_HD void volume_voxel(const VolumeP& p, long long v) {
   const int x = int(v % p.w);
   const long long t = v / p.w;
   const int y = int(t % p.h), d = int(t / p.h);
-  const float* rf = p.ref_feat + ((long long)y * p.w + x) * 32;
+  const float4* __restrict__ rf = reinterpret_cast<const float4*>(p.ref_feat + ((long long)y * p.w + x) * 32);
   float s[32], q[32];
-  for (int c = 0; c < 32; ++c) { s[c] = rf[c]; q[c] = rf[c] * rf[c]; }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float4 f = rf[c];
+    s[4 * c] = f.x; s[4 * c + 1] = f.y; s[4 * c + 2] = f.z; s[4 * c + 3] = f.w;
+    q[4 * c] = f.x * f.x; q[4 * c + 1] = f.y * f.y; q[4 * c + 2] = f.z * f.z; q[4 * c + 3] = f.w * f.w;
+  }
   const float depth = p.depth_vals[d];
   for (int k = 0; k < p.nn; ++k) {
     const float* T = p.transforms + 12 * k;
@@ -117,14 +147,26 @@ NR_HD void volume_voxel(const VolumeP& p, long long v) {
     for (int q4 = 0; q4 < 4; ++q4) {
       const float xf = x0f + float(q4 & 1), yf = y0f + float(q4 >> 1);
       if (!(xf >= 0.f && xf <= float(p.w - 1) && yf >= 0.f && yf <= float(p.h - 1))) continue;
-      const float* tap = sf + ((long long)int(yf) * p.w + int(xf)) * 32;
-      for (int c = 0; c < 32; ++c) wv[c] = fmaf(tap[c], wgt[q4], wv[c]);
+      const float4* __restrict__ tap = reinterpret_cast<const float4*>(sf + ((long long)int(yf) * p.w + int(xf)) * 32);
+      const float g = wgt[q4];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 f = tap[c];
+        wv[4 * c] = fmaf(f.x, g, wv[4 * c]); wv[4 * c + 1] = fmaf(f.y, g, wv[4 * c + 1]);
+        wv[4 * c + 2] = fmaf(f.z, g, wv[4 * c + 2]); wv[4 * c + 3] = fmaf(f.w, g, wv[4 * c + 3]);
+      }
     }
     for (int c = 0; c < 32; ++c) { s[c] += wv[c]; q[c] += wv[c] * wv[c]; }
   }
   const float inv = 1.f / float(p.nn + 1);
-  float* out = p.vol + v * 32;
-  for (int c = 0; c < 32; ++c) { const float m = s[c] * inv; out[c] = q[c] * inv - m * m; }
+  float4* out = reinterpret_cast<float4*>(p.vol + v * 32);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float r[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float m = s[4 * c + e] * inv; r[e] = q[4 * c + e] * inv - m * m; }
+    out[c] = make_float4(r[0], r[1], r[2], r[3]);
+  }
 }
 
 // ---- softmax over the depth planes + depth regression (init_net.py:155-159), with the optional bilinear resize of the logits
