@@ -5,12 +5,13 @@
 namespace nr {
 namespace mvs {
 
-template <int COUT>
+template <int CG>
 __global__ void __launch_bounds__(128) conv_kernel(const __grid_constant__ ConvP p) {
-  const long long total = (long long)p.Do * p.Ho * p.Wo;
-  for (long long v = (long long)blockIdx.x * 128 + threadIdx.x; v < total; v += (long long)gridDim.x * 128) {
-    float acc[COUT];
-    conv_voxel<COUT>(p, v, acc);
+  const int groups = p.Cout / CG;
+  const long long total = (long long)p.Do * p.Ho * p.Wo * groups;
+  for (long long i = (long long)blockIdx.x * 128 + threadIdx.x; i < total; i += (long long)gridDim.x * 128) {
+    float acc[CG];
+    conv_voxel<CG>(p, i / groups, int(i % groups), acc);       // the groups of a voxel sit in neighbouring lanes: its x loads coalesce
   }
 }
 __global__ void __launch_bounds__(128) volume_kernel(const __grid_constant__ VolumeP p) {
@@ -70,15 +71,11 @@ struct StreamOps {
   int sms, rc;
   void mvs_conv(const ConvP& p) {
     if (rc != NR_OK) return;
-    const unsigned g = grid_of((long long)p.Do * p.Ho * p.Wo, 128, 32 * sms);
-    switch (p.Cout) {
-      case 1: conv_kernel<1><<<g, 128, 0, st>>>(p); break;
-      case 8: conv_kernel<8><<<g, 128, 0, st>>>(p); break;
-      case 16: conv_kernel<16><<<g, 128, 0, st>>>(p); break;
-      case 32: conv_kernel<32><<<g, 128, 0, st>>>(p); break;
-      case 64: conv_kernel<64><<<g, 128, 0, st>>>(p); break;
-      default: rc = NR_E_UNSUPPORTED;
-    }
+    const int cg = group_size(p.Cout);
+    const unsigned g = grid_of((long long)p.Do * p.Ho * p.Wo * (p.Cout / cg), 128, 32 * sms);
+    if (cg == 1) conv_kernel<1><<<g, 128, 0, st>>>(p);
+    else if (cg == 8 && p.Cout % 8 == 0) conv_kernel<8><<<g, 128, 0, st>>>(p);
+    else rc = NR_E_UNSUPPORTED;
   }
   void mvs_volume(const VolumeP& p) { if (rc == NR_OK) volume_kernel<<<grid_of((long long)p.dn * p.h * p.w, 128, 32 * sms), 128, 0, st>>>(p); }
   void mvs_softmax(const SoftmaxP& p) { if (rc == NR_OK) softmax_kernel<<<(p.ho * p.wo + 127) / 128, 128, 0, st>>>(p); }

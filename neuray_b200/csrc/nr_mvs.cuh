@@ -35,6 +35,9 @@ struct ConvP {
   const float* in_mean; const float* in_istd;   // first layer: input channels are (x - mean) * istd inside the image, 0 in the padding
 };
 
+// output channels per thread: all of them up to 8, groups of 8 beyond
+NR_HD int group_size(int Cout) { return Cout <= 8 ? Cout : 8; }
+
 // acc[0..COUT) += xv * w[0..COUT): the weights of one (tap, input channel) are COUT contiguous floats read by every lane of a warp
 // from the same address (one broadcast transaction); 128-bit loads keep it at one load instruction per four FMAs
 template <int COUT>
@@ -53,8 +56,11 @@ NR_HD void axpy_row(float xv, const float* __restrict__ wr, float (&acc)[COUT]) 
   }
 }
 
+// One thread = one output voxel x one group of COUT consecutive output channels (group g of p.Cout / COUT): the layers with 32 / 64
+// outputs sit on 25 600 / 3 200 voxels, far too few threads for the machine if a thread carried all of a voxel's outputs
+// (profiles/r2_cost_volume_launches.md: 750 us for 110 592 serial FMAs per thread on 25 CTAs).
 template <int COUT>
-NR_HD void conv_voxel(const ConvP& p, long long v, float (&acc)[COUT]) {
+NR_HD void conv_voxel(const ConvP& p, long long v, int g, float (&acc)[COUT]) {
   const int wo = int(v % p.Wo);
   const long long t = v / p.Wo;
   const int ho = int(t % p.Ho), dz = int(t / p.Ho);
@@ -75,29 +81,29 @@ NR_HD void conv_voxel(const ConvP& p, long long v, float (&acc)[COUT]) {
         const int wi = p.transposed ? (wo + p.pw - kw) / p.sw : wo * p.sw - p.pw + kw;
         if (wi < 0 || wi >= p.W) continue;
         const float* __restrict__ xin = p.x + (((long long)di * p.H + hi) * p.W + wi) * p.Cin;
-        const float* __restrict__ wt = p.w + (long long)((kd * p.kh + kh) * p.kw + kw) * p.Cin * COUT;
+        const float* __restrict__ wt = p.w + (long long)((kd * p.kh + kh) * p.kw + kw) * p.Cin * p.Cout + g * COUT;
         if (vec_x) {
           const float4* __restrict__ x4 = reinterpret_cast<const float4*>(xin);
           for (int c4 = 0; c4 < p.Cin / 4; ++c4) {
             const float4 xv = x4[c4];
-            const float* wr = wt + 4 * c4 * COUT;
-            axpy_row<COUT>(xv.x, wr, acc); axpy_row<COUT>(xv.y, wr + COUT, acc);
-            axpy_row<COUT>(xv.z, wr + 2 * COUT, acc); axpy_row<COUT>(xv.w, wr + 3 * COUT, acc);
+            const float* wr = wt + 4 * c4 * p.Cout;
+            axpy_row<COUT>(xv.x, wr, acc); axpy_row<COUT>(xv.y, wr + p.Cout, acc);
+            axpy_row<COUT>(xv.z, wr + 2 * p.Cout, acc); axpy_row<COUT>(xv.w, wr + 3 * p.Cout, acc);
           }
         } else {
           for (int c = 0; c < p.Cin; ++c) {
             float xv = xin[c];
             if (p.in_mean != nullptr) xv = (xv - p.in_mean[c]) * p.in_istd[c];
-            axpy_row<COUT>(xv, wt + c * COUT, acc);
+            axpy_row<COUT>(xv, wt + c * p.Cout, acc);
           }
         }
       }
     }
   }
-  const long long yo = (long long)dz * p.y_sd + (long long)ho * p.y_sh + (long long)wo * p.y_sw;
+  const long long yo = (long long)dz * p.y_sd + (long long)ho * p.y_sh + (long long)wo * p.y_sw + g * COUT;
 #pragma unroll
   for (int o = 0; o < COUT; ++o) {
-    float r = acc[o] * p.scale[o] + p.shift[o];
+    float r = acc[o] * p.scale[g * COUT + o] + p.shift[g * COUT + o];
     r = r >= 0.f ? r : r * p.slope;
     if (p.skip != nullptr) r += p.skip[yo + o];
     p.y[yo + o] = r;

@@ -15,23 +15,16 @@ using namespace nr;
 using namespace nr::mvs;
 
 struct HostOps {
-  template <int COUT>
+  template <int CG>
   static void conv_t(const ConvP& p) {
-    const long long total = (long long)p.Do * p.Ho * p.Wo;
-    for (long long v = 0; v < total; ++v) {
-      float acc[COUT];
-      conv_voxel<COUT>(p, v, acc);
+    const int groups = p.Cout / CG;
+    const long long total = (long long)p.Do * p.Ho * p.Wo * groups;
+    for (long long i = 0; i < total; ++i) {
+      float acc[CG];
+      conv_voxel<CG>(p, i / groups, int(i % groups), acc);
     }
   }
-  void mvs_conv(const ConvP& p) {
-    switch (p.Cout) {
-      case 1: conv_t<1>(p); break;
-      case 8: conv_t<8>(p); break;
-      case 16: conv_t<16>(p); break;
-      case 32: conv_t<32>(p); break;
-      default: conv_t<64>(p); break;
-    }
-  }
+  void mvs_conv(const ConvP& p) { group_size(p.Cout) == 1 ? conv_t<1>(p) : conv_t<8>(p); }
   void mvs_volume(const VolumeP& p) { for (long long v = 0; v < (long long)p.dn * p.h * p.w; ++v) volume_voxel(p, v); }
   void mvs_softmax(const SoftmaxP& p) {
     std::vector<float> tmp(p.dn);
