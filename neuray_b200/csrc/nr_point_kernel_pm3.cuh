@@ -1,17 +1,19 @@
 // Point kernel (namespace nr::pkt::pm3): point-major rows, tcgen05 layers, THREE independent 128-row blocks per SM.
 //
 // Row = point * G + view inside a block (G lanes per point: 4, 5, 6, 8, 10, 16 or 32), thread r = row r = TMEM lane r; a thread
-// keeps its row in registers from the gather to the output record.  Resource plan (one CTA of 384 threads per SM):
+// keeps its row in registers from the gather to the output record.  Resource plan (one CTA per SM: 384 compute threads + a
+// 128-thread producer group whose lane 0 feeds the weight ring, see NR_PRODUCER_WARP below):
 //   * tensor memory: 160 columns per block.  Activations: hi parts at columns [0,64), lo parts at [64,128), accumulator at
 //     [128,160).  base_fc.0 (N = 64) is issued in K rounds into one accumulator at [96,160): round A (the 32 neuray_feat
 //     inputs) right after prob_embed.2 while they are still the only live A operand, round B (the 40 rgb_feat inputs, lo parts
 //     at [48,88)) after ray_dir_fc, then five rounds of view-pooled statistics (K 32 each).  Its epilogue reads the accumulator
 //     half by half and writes base_fc.2's operand over the columns it has already consumed.
-//   * shared memory (230 KB): 4 x 16 KB weight ring (TMA bulk copies, fed by thread 0), the resident tiles of the pooled
+//   * shared memory (230 KB): 4 x 16 KB weight ring (TMA bulk copies, fed by the producer group), the resident tiles of the pooled
 //     base_fc.0 inputs (80 KB) and of ray_dir_fc.2, small weights, camera blocks, and one [32][36] transposition buffer per warp:
 //     gather (two channel passes: ray_feats, then img_feats, which stay there until ray_dir_fc needs them), the cross-view
 //     pooling (pm::pool_rows) and the lane-group sums of the non-power-of-two groups all go through it.
-//   * 384 threads: three warps per SM sub-partition, i.e. at most 168 registers per thread.
+//   * 384 compute threads: three warps per SM sub-partition; the CTA launches at 512 x 128 registers and setmaxnreg moves the
+//     producer group's share to the compute groups (160 / 24 registers per thread).
 // The three blocks exist to fill each other's bubbles: a block has ~25 MMA round trips per tile during which its four warps
 // have nothing to do (profiles/r2_point_kernel_v4_lines.txt).
 #pragma once
