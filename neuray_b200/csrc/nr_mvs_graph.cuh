@@ -108,20 +108,23 @@ struct MvsBuilder {
   }
 };
 
-// FeatureNet.forward (mvsnet.py:25-29) on one image [hr,wr,3] (raw 0..1 values; ImageNet normalisation folded into conv0) -> [h4,w4,32]
+// FeatureNet.forward (mvsnet.py:25-29) on n images [n,hr,wr,3] (raw 0..1 values; ImageNet normalisation folded into conv0) ->
+// [n,h4,w4,32].  The batch rides on the depth axis of the direct convolution (kernel depth 1): eight launches for all images.
 template <class Ops>
-void feature_net(MvsBuilder<Ops>& b, const float* img, int hr, int wr, const float* mean, const float* istd, float* out) {
+void feature_net(MvsBuilder<Ops>& b, const float* imgs, int n, int hr, int wr, const float* mean, const float* istd, float* out) {
   int D, H, W;
   const size_t mark = b.ar.used;
-  float* x = b.layer(F0, img, 1, hr, wr, nullptr, nullptr, 0, 0, 0, D, H, W, mean, istd);
-  x = b.layer(F1, x, 1, H, W, nullptr, nullptr, 0, 0, 0, D, H, W);
-  x = b.layer(F2, x, 1, H, W, nullptr, nullptr, 0, 0, 0, D, H, W);
-  x = b.layer(F3, x, 1, H, W, nullptr, nullptr, 0, 0, 0, D, H, W);
-  x = b.layer(F4, x, 1, H, W, nullptr, nullptr, 0, 0, 0, D, H, W);
-  x = b.layer(F5, x, 1, H, W, nullptr, nullptr, 0, 0, 0, D, H, W);
-  x = b.layer(F6, x, 1, H, W, nullptr, nullptr, 0, 0, 0, D, H, W);
-  b.layer(FEAT, x, 1, H, W, nullptr, out, 0, (long long)W * 32, 32, D, H, W);
-  b.ar.used = mark;        // the intermediate maps are free again (stream order keeps the next image from overwriting them early)
+  float* x = b.layer(F0, imgs, n, hr, wr, nullptr, nullptr, 0, 0, 0, D, H, W, mean, istd);
+  x = b.layer(F1, x, n, H, W, nullptr, nullptr, 0, 0, 0, D, H, W);
+  x = b.layer(F2, x, n, H, W, nullptr, nullptr, 0, 0, 0, D, H, W);
+  x = b.layer(F3, x, n, H, W, nullptr, nullptr, 0, 0, 0, D, H, W);
+  x = b.layer(F4, x, n, H, W, nullptr, nullptr, 0, 0, 0, D, H, W);
+  x = b.layer(F5, x, n, H, W, nullptr, nullptr, 0, 0, 0, D, H, W);
+  x = b.layer(F6, x, n, H, W, nullptr, nullptr, 0, 0, 0, D, H, W);
+  int Ho, Wo;
+  Ho = H; Wo = W;
+  b.layer(FEAT, x, n, H, W, nullptr, out, (long long)Ho * Wo * 32, (long long)Wo * 32, 32, D, H, W);
+  b.ar.used = mark;        // the intermediate maps are free again (stream order keeps later layers from overwriting them early)
 }
 
 // CostRegNet.forward (mvsnet.py:52-66) on the variance volume [dn,h,w,32]; the logits go to out[(y*w + x)*dn + d]
@@ -172,9 +175,8 @@ bool mvsnet_graph(Ops& ops, enc::Arena& ar, const MvsNet& net, const float* pack
   ops.mvs_resize(rp);
   rp.img = in.src_imgs; rp.out = imgs_r + (long long)in.rfn * d.hr * d.wr * 3; rp.N = in.sn;
   ops.mvs_resize(rp);
-  for (int i = 0; i < in.rfn + in.sn; ++i)
-    feature_net(b, imgs_r + (long long)i * d.hr * d.wr * 3, d.hr, d.wr, consts, consts + 3,
-                i < in.rfn ? ref_feats + (long long)i * n4 * 32 : src_feats + (long long)(i - in.rfn) * n4 * 32);
+  feature_net(b, imgs_r, in.rfn, d.hr, d.wr, consts, consts + 3, ref_feats);
+  feature_net(b, imgs_r + (long long)in.rfn * d.hr * d.wr * 3, in.sn, d.hr, d.wr, consts, consts + 3, src_feats);
   TransformsP tp;
   tp.in = in; tp.ratio = 0.25f * d.ratio;
   tp.transforms = ar.floats((long long)in.rfn * in.nn * 12);
