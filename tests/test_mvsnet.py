@@ -233,3 +233,30 @@ def test_gen_frame_renderer_with_the_cost_volume_init_net():
     assert err < 5e-4, err
     assert torch.equal(out["ray_mask"].cpu(), gold["ray_mask"])
     assert "depth_mean" in out
+
+
+def test_evaluation_resize_path_on_the_host(harness):
+    """800x800 in eval mode (init_net.py:120-139,155): images resized to 640x640, MVSNet at 160x160, the cost volume resized back to
+    200x200 before the softmax -- the product's graph on the host against the oracle (8 depth planes, one neighbour)."""
+    from neuray_b200 import synthetic
+    _, ref = synthetic.make_scene(800, 800, 1, seed=51, smooth=2, pad=32, depth_range=(2.0, 6.0), arc_deg=20.0)
+    _, src = synthetic.make_scene(800, 800, 1, seed=52, smooth=2, pad=32, depth_range=(2.0, 6.0), arc_deg=26.0)
+    ref = {k: ref[k] for k in ("imgs", "poses", "Ks", "depth_range")}
+    src = {k: src[k] for k in ("imgs", "poses", "Ks")}
+    ref["nn_ids"] = torch.tensor([[0]])
+    _, _, W, _, _ = golden()
+    dn = 8
+    cost_o, depth_o = orc.mvs_cost_volume(W, "", ref, src, dn, False)
+    assert cost_o.shape == (1, dn, 200, 200)
+    params = [t.contiguous() for t in W.values()]
+    arr = (C.c_void_p * len(params))(*[t.data_ptr() for t in params])
+    f = lambda t: t.contiguous().float()
+    keep = [f(ref["imgs"]), f(src["imgs"]), f(ref["Ks"]), f(ref["poses"]), f(src["Ks"]), f(src["poses"]), f(ref["depth_range"]),
+            ref["nn_ids"].to(torch.int32).contiguous()]
+    prob, depth = torch.empty(1, 200, 200, dn), torch.empty(1, 200, 200)
+    rc = harness.nr_cpu_mvsnet(arr, len(params), *[C.c_void_p(t.data_ptr()) for t in keep], 1, 1, 1, 800, 800, dn, 0,
+                               C.c_void_p(prob.data_ptr()), C.c_void_p(depth.data_ptr()))
+    assert rc == 0
+    e1 = float((prob.permute(0, 3, 1, 2) - cost_o).abs().max())
+    e2 = float((depth - depth_o).abs().max())
+    assert e1 < 1e-4 and e2 < 1e-3, (e1, e2)
