@@ -9,10 +9,18 @@ nn.Module, no F.grid_sample) of the algorithm in the reference (liuyuan-pal/NeuR
     network/aggregate_net.py:8-68     aggregation front-end
     network/ibrnet.py:7-102,239-369   IBRNetWithNeuRay + ray self-attention
     network/renderer.py:67-83,127-254 render_by_depth / render_impl / render chunk loop
+and, next to the path (second half of this file):
+    network/init_net.py:29-101        get_diff_feats, DepthInitNet (extract_depth_for_init, ResEncoder, depth_skip, conv_out)
+    network/ops.py:43-312             ResidualBlock, BasicBlock, ResUNetLight / ResEncoder
+    network/vis_encoder.py:6-21       DefaultVisEncoder
+    network/renderer.py:280-316, network/loss.py:17-132   predict_mean_for_depth_loss and the three losses
+    network/init_net.py:103-254, network/mvsnet/          CostVolumeInitNet with its MVSNet (feature net, homography variance
+                                      volume, 3-D regulariser, softmax + depth regression)
 
 Pinning: the reference ships no tests or golden vectors for this path, so the
 oracle is pinned against outputs of the reference itself, run in the build container by
-oracle/gen_golden.py and committed under tests/golden/ (checked by tests/test_oracle_golden.py).
+oracle/gen_golden*.py and committed under tests/golden/ (checked by tests/test_oracle_golden.py,
+test_diff_feats.py, test_encoders_cpu.py, test_losses.py, test_mvsnet.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
 this file.  The product path (neuray_b200/) never does.
